@@ -1,0 +1,211 @@
+"""ORACLE tooling (test infrastructure): generate tests/golden/*.npz by running the UNMODIFIED
+reference (/root/reference) through oracle/shims in the build container.
+
+    python oracle/gen_golden.py            # writes tests/golden/
+
+The reference cannot travel to the GPU box, so its outputs are frozen here as small fixtures.
+Weights are NOT stored: both sides rebuild them with oracle.oa_ref.make_state_dict(seed).
+"""
+import json
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+sys.path.insert(1, "/root/reference")
+sys.path.insert(2, ROOT)
+
+from oa_reactdiff.model import LEFTNet  # noqa: E402
+from oa_reactdiff.dynamics import EGNNDynamics  # noqa: E402
+from oa_reactdiff.diffusion._schedule import DiffSchedule, PredefinedNoiseSchedule  # noqa: E402
+from oa_reactdiff.diffusion._normalizer import Normalizer  # noqa: E402
+from oa_reactdiff.diffusion.en_diffusion import EnVariationalDiffusion  # noqa: E402
+from oa_reactdiff.utils import get_edges_index, get_mask_for_frag, get_n_frag_switch, get_subgraph_mask  # noqa: E402
+
+from oracle import oa_ref  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+SMALL_CFG = dict(cutoff=5.0, num_layers=2, hidden_channels=32, num_radial=16, in_hidden_channels=8,
+                 reflect_equiv=True, legacy=True, update=True, object_aware=True)
+TRAINED_CFG = dict(oa_ref.TRAINED_CFG)
+
+
+def ref_cfg(cfg):
+    c = dict(cfg)
+    c.update(pos_require_grad=False, pos_grad=False, single_layer_output=True)
+    return c
+
+
+def build_dynamics(cfg, node_nfs, condition_nf, seed, dtype):
+    dyn = EGNNDynamics(model_config=ref_cfg(cfg), fragment_names=[f"f{i}" for i in range(len(node_nfs))],
+                       node_nfs=list(node_nfs), edge_nf=0, condition_nf=condition_nf, pos_dim=3,
+                       update_pocket_coords=True, condition_time=True, model=LEFTNet, device=torch.device("cpu"))
+    shapes = oa_ref.dynamics_param_shapes(cfg, node_nfs, condition_nf)
+    sd = oa_ref.make_state_dict(shapes, seed, cfg, prefix_model="model.")
+    missing, unexpected = dyn.load_state_dict(sd, strict=True), None
+    return dyn.to(dtype), sd
+
+
+def graph(fragments_nodes):
+    masks = [get_mask_for_frag(n) for n in fragments_nodes]
+    cm = torch.cat(masks)
+    return masks, cm, get_edges_index(cm, remove_self_edge=True), get_n_frag_switch(fragments_nodes)
+
+
+def capture_leftnet_intermediates(model, h, pos, edge_index, sub):
+    """Re-run pieces of the reference forward to expose integer artefacts (mask, group ids)."""
+    i, j = edge_index
+    dist = (pos[i] - pos[j]).pow(2).sum(dim=-1).sqrt()
+    mask = (dist < model.cutoff).to(pos.dtype)[:, None] * sub
+    ei = edge_index.T[torch.where(mask > 0)[0]].T
+    group = model.assemble_nodemask(edge_index=ei, pos=pos)
+    return mask.squeeze(-1), group.long()
+
+
+def case_dynamics(name, cfg, fragments_nodes, node_nfs, condition_nf, seed, pos_scale, t_vec=True):
+    g = torch.Generator().manual_seed(seed)
+    masks, cm, edge_index, nfs = graph(fragments_nodes)
+    B = fragments_nodes[0].numel()
+    xh = []
+    for f, m in enumerate(masks):
+        x = torch.randn(len(m), 3, generator=g, dtype=torch.float64) * pos_scale
+        hh = torch.randn(len(m), node_nfs[f] - 3, generator=g, dtype=torch.float64)
+        xh.append(torch.cat([x, hh], dim=1))
+    t = torch.rand(B, 1, generator=g, dtype=torch.float64) if t_vec else torch.tensor([0.314], dtype=torch.float64)
+    cond = torch.rand(B, condition_nf, generator=g, dtype=torch.float64)
+    out = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        dyn, sd = build_dynamics(cfg, node_nfs, condition_nf, seed, dt)
+        with torch.no_grad():
+            res, _ = dyn([x.to(dt) for x in xh], edge_index, t.to(dt), cond.to(dt), nfs, cm)
+        for f, r in enumerate(res):
+            out[f"out{f}_{tag}"] = r.numpy()
+        if dt == torch.float64:
+            pos = torch.cat([x[:, :3] for x in xh])
+            sub = get_subgraph_mask(edge_index, nfs)[:, None]
+            mask, group = capture_leftnet_intermediates(dyn.model, pos, pos, edge_index, sub.to(dt))
+            out["mask"] = mask.numpy().astype(np.int64)
+            out["group"] = group.numpy()
+    out.update({f"xh{f}": x.numpy() for f, x in enumerate(xh)})
+    out.update(t=t.numpy(), cond=cond.numpy(), edge_index=edge_index.numpy(), n_frag_switch=nfs.numpy(),
+               combined_mask=cm.numpy(), seed=np.int64(seed),
+               fragments_nodes=np.stack([n.numpy() for n in fragments_nodes]),
+               node_nfs=np.array(node_nfs), condition_nf=np.int64(condition_nf),
+               cfg=json.dumps(cfg))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N", cm.numel(), "E", edge_index.size(1), "active", int(out["mask"].sum()),
+          "groups", int(out["group"].max()) + 1)
+
+
+def case_leftnet(name, cfg, n_nodes, seed, cut=None, pos_scale=1.0):
+    """Raw LEFTNet.forward on one complete graph (reference tests/model fixtures style)."""
+    g = torch.Generator().manual_seed(seed)
+    ii, jj = torch.meshgrid(torch.arange(n_nodes), torch.arange(n_nodes), indexing="ij")
+    keep = ii != jj
+    edge_index = torch.stack([ii[keep], jj[keep]])
+    h = torch.rand(n_nodes, cfg["in_hidden_channels"], generator=g, dtype=torch.float64)
+    pos = torch.rand(n_nodes, 3, generator=g, dtype=torch.float64) * pos_scale
+    if cut is None:
+        sub = torch.ones(edge_index.size(1), 1, dtype=torch.long)
+    else:
+        s = (edge_index < cut).sum(0)
+        sub = ((s == 2) | (s == 0)).long()[:, None]
+    shapes = oa_ref.leftnet_param_shapes(cfg)
+    sd = oa_ref.make_state_dict(shapes, seed, cfg)
+    out = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        model = LEFTNet(**ref_cfg(cfg))
+        model.load_state_dict(sd, strict=True)
+        model = model.to(dt)
+        with torch.no_grad():
+            ho, po, _ = model(h.to(dt), pos.to(dt), edge_index, subgraph_mask=sub)
+        out[f"h_out_{tag}"] = ho.numpy()
+        out[f"dpos_{tag}"] = (po - pos.to(dt)).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), h=h.numpy(), pos=pos.numpy(),
+                        edge_index=edge_index.numpy(), subgraph_mask=sub.numpy(), seed=np.int64(seed),
+                        cfg=json.dumps(cfg), **out)
+    print(name, "ok")
+
+
+def build_ddpm(cfg, seed, T, dtype=torch.float32):
+    dyn, sd = build_dynamics(cfg, [9, 9, 9], 1, seed, dtype)
+    sched = DiffSchedule(PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=Normalizer(), size_histogram=None,
+                                  loss_type="l2", pos_only=True, fixed_idx=None)
+    return ddpm, sd
+
+
+def case_sample(name, cfg, sizes, seed, T):
+    ddpm, _ = build_ddpm(cfg, seed, T)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, seed)
+    torch.manual_seed(seed)
+    out, masks = ddpm.sample(n_samples=len(sizes), fragments_nodes=nodes, conditions=cond, return_frames=1,
+                             timesteps=None, h0=h0)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), sizes=np.array(sizes), seed=np.int64(seed), T=np.int64(T),
+                        cfg=json.dumps(cfg), gamma=ddpm.schedule.gamma_module.gamma.detach().numpy(),
+                        **{f"out{f}": o.numpy() for f, o in enumerate(out[0])})
+    print(name, "ok", [tuple(o.shape) for o in out[0]])
+
+
+def case_inpaint(name, cfg, sizes, seed, T, resamplings, jump_length):
+    ddpm, _ = build_ddpm(cfg, seed, T)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    xh_fixed = [torch.cat([torch.randn(h.size(0), 3, generator=g) * 1.5, h], dim=1) for h in h0]
+    torch.manual_seed(seed)
+    out, masks = ddpm.inpaint(n_samples=len(sizes), fragments_nodes=nodes, conditions=cond, return_frames=1,
+                              resamplings=resamplings, jump_length=jump_length, timesteps=None,
+                              xh_fixed=[x.clone() for x in xh_fixed], frag_fixed=[0, 2])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), sizes=np.array(sizes), seed=np.int64(seed), T=np.int64(T),
+                        resamplings=np.int64(resamplings), jump_length=np.int64(jump_length), cfg=json.dumps(cfg),
+                        **{f"xh_fixed{f}": x.numpy() for f, x in enumerate(xh_fixed)},
+                        **{f"out{f}": o.numpy() for f, o in enumerate(out[0])})
+    print(name, "ok")
+
+
+def t1x_histogram():
+    path = "/root/reference/oa_reactdiff/data/transition1x/train.pkl"
+    with open(path, "rb") as fh:
+        data = pickle.load(fh)
+    n_atoms = np.array([len(x) for x in data["transition_state"]["charges"]])
+    use = np.array(data["use_ind"]) if "use_ind" in data else np.arange(len(n_atoms))
+    n_use = n_atoms[use]
+    hist = np.bincount(n_use, minlength=24).tolist()
+    charges = np.concatenate([np.asarray(data["transition_state"]["charges"][k]) for k in use[:2000]])
+    zs, cnt = np.unique(charges, return_counts=True)
+    with open(os.path.join(OUT, "t1x_hist.json"), "w") as fh:
+        json.dump({"source": "oa_reactdiff/data/transition1x/train.pkl use_ind", "n_reactions": int(len(n_use)),
+                   "min": int(n_use.min()), "max": int(n_use.max()), "mean": float(n_use.mean()),
+                   "hist_by_natoms": hist,
+                   "element_freq": {str(int(z)): int(c) for z, c in zip(zs, cnt)}}, fh, indent=1)
+    print("t1x_hist", len(n_use), n_use.min(), n_use.max(), n_use.mean())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    t1x_histogram()
+    # raw LEFTNet.forward (reference tests/model style): full graph, and object-aware cut graph
+    case_leftnet("leftnet_small_full", SMALL_CFG, 9, seed=11, pos_scale=3.0)
+    case_leftnet("leftnet_small_cut", SMALL_CFG, 10, seed=12, cut=4, pos_scale=3.0)
+    case_leftnet("leftnet_small_split", SMALL_CFG, 12, seed=13, cut=5, pos_scale=9.0)  # cutoff splits groups
+    # dynamics: reference fixture shape (ragged, an EMPTY fragment, per-fragment node_nf) tests/dynamics/test_egnn_dynamics.py:99-104
+    case_dynamics("dyn_small_ragged", dict(SMALL_CFG, in_hidden_channels=8),
+                  [torch.tensor([2, 0]), torch.tensor([2, 3]), torch.tensor([1, 2])], [4, 5, 6], 3, seed=21,
+                  pos_scale=1.5)
+    # config 1: trained cfg, single 12-atom triple
+    case_dynamics("dyn_trained_cfg1", TRAINED_CFG, [torch.tensor([12])] * 3, [9, 9, 9], 1, seed=31, pos_scale=1.5)
+    # trained cfg, ragged B=4 incl. min/max sizes; pos_scale 4 => some pairs beyond the 10 A cutoff
+    case_dynamics("dyn_trained_b4", TRAINED_CFG, [torch.tensor([4, 9, 14, 23])] * 3, [9, 9, 9], 1, seed=32,
+                  pos_scale=1.5)
+    case_dynamics("dyn_trained_b3_far", TRAINED_CFG, [torch.tensor([5, 17, 11])] * 3, [9, 9, 9], 1, seed=33,
+                  pos_scale=4.0)
+    # sampler trajectories (fp32, reference RNG order)
+    case_sample("sample_small_T10", SMALL_CFG, [5, 3], seed=41, T=10)
+    case_sample("sample_trained_cfg1_T10", TRAINED_CFG, [12], seed=42, T=10)
+    case_inpaint("inpaint_small_T12_r2_j3", SMALL_CFG, [4, 6], seed=43, T=12, resamplings=2, jump_length=3)

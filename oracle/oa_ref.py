@@ -1,0 +1,649 @@
+"""ORACLE (test infrastructure, NOT product code).
+
+A plain-PyTorch CPU restatement of the OA-ReactDiff denoising hot path, written
+function-style over a flat state-dict whose keys are the reference's own
+parameter names.  It exists so that parity tests and the
+CPU-baseline leg of bench.py can run on the GPU box, where /root/reference does
+not exist.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this file; the product package
+(oareactdiff_b200/) never does and fails loudly without its CUDA library.
+
+Parity status: PINNED.  The reference has no stored numeric vectors for this
+path, so the restatement is pinned by (i) the reference's own
+integer known-answer tests (tests/utils/test_graph_tools.py:14-63,
+tests/dynamics/test_egnn_dynamics.py:142-153), re-stated in
+tests/test_oracle.py, and (ii) outputs of the UNMODIFIED reference imported in
+the build container through oracle/shims (script: oracle/gen_golden.py),
+committed as tests/golden/*.npz.  tests/test_oracle.py checks this file against
+those vectors to 1e-12 (fp64).
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference/oa_reactdiff/).  The op structure deliberately mirrors the
+reference's eager PyTorch ops (dense masked compute over ALL edges, cat ->
+Linear, scatter_add) so that timing it on host cores is a fair stand-in for the
+reference's own CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+EPS = 1e-6  # model/leftnet.py:15
+
+TRAINED_CFG = dict(  # trainer/train_ts1x.py:43-56
+    cutoff=10.0, num_layers=6, hidden_channels=196, num_radial=96, in_hidden_channels=8,
+    reflect_equiv=True, legacy=True, update=True, object_aware=True,
+)
+
+
+# --------------------------------------------------------------------------- graph tools
+def get_mask_for_frag(natm: Tensor) -> Tensor:
+    """utils/_graph_tools.py:84-96 — sample id of every node of one fragment."""
+    return torch.repeat_interleave(torch.arange(natm.size(0)), natm)
+
+
+def get_n_frag_switch(natm_list: Sequence[Tensor]) -> Tensor:
+    """utils/_graph_tools.py:62-81 — fragment id of every node."""
+    return torch.repeat_interleave(
+        torch.arange(len(natm_list)), torch.tensor([int(n.sum()) for n in natm_list])
+    )
+
+
+def get_edges_index(combined_mask: Tensor, remove_self_edge: bool = False) -> Tensor:
+    """utils/_graph_tools.py:9-36 — complete directed graph per sample, row-major (i, j) order."""
+    adj = combined_mask[:, None] == combined_mask[None, :]
+    if remove_self_edge:
+        adj = adj.clone()
+        adj.fill_diagonal_(False)
+    return torch.stack(torch.where(adj), dim=0)
+
+
+def get_subgraph_mask(edge_index: Tensor, n_frag_switch: Tensor) -> Tensor:
+    """utils/_graph_tools.py:39-59 — 1 where both ends lie in the same fragment."""
+    return (n_frag_switch[edge_index[0]] == n_frag_switch[edge_index[1]]).long()
+
+
+# --------------------------------------------------------------------------- parameters
+def leftnet_param_shapes(cfg: Dict) -> Dict[str, Tuple[int, ...]]:
+    """Names/shapes of LEFTNet's state-dict (model/leftnet.py:594-688)."""
+    H, R, C, L = cfg["hidden_channels"], cfg["num_radial"], cfg["in_hidden_channels"], cfg["num_layers"]
+    D = 3 * H + R
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def lin(name, out, inp, bias=True):
+        s[name + ".weight"] = (out, inp)
+        if bias:
+            s[name + ".bias"] = (out,)
+
+    lin("embedding", H, C)
+    lin("embedding_out", C, H)
+    s["radial_emb.means"] = (R,)
+    s["radial_emb.betas"] = (R,)
+    lin("neighbor_emb.embedding", H, C)
+    lin("s2v.lin1.0", H, H)
+    lin("radial_lin.0", H, R)
+    lin("radial_lin.2", H, H)
+    lin("lin3.0", H // 4, 3)
+    lin("lin3.2", 1, H // 4)
+    lin("pos_expansion.mlp.0.linear", H // 2, 3, bias=False)
+    lin("pos_expansion.mlp.1.linear", H, H // 2, bias=False)
+    lin("distance_embedding.mlp.0.linear", H // 2, R, bias=False)  # unused in forward
+    lin("distance_embedding.mlp.1.linear", H, H // 2, bias=False)  # unused in forward
+    for l in range(L):
+        g = f"gcl_layers.{l}."
+        lin(g + "edge_mlp.mlp.0.linear", H, 2 * H + D)
+        lin(g + "edge_mlp.mlp.1.linear", H, H)
+        lin(g + "node_mlp.mlp.0.linear", H, 2 * H)
+        lin(g + "node_mlp.mlp.1.linear", H, H)
+        lin(g + "edge_out_trans.mlp.0.linear", D, H)
+        lin(g + "att_mlp.mlp.0.linear", 1, H)
+        s[g + "x_layernorm.weight"] = (H,)
+        s[g + "x_layernorm.bias"] = (H,)
+        m = f"message_layers.{l}."
+        lin(m + "dir_proj.0", 3 * H, D)
+        lin(m + "dir_proj.2", 3 * H, 3 * H)
+        lin(m + "x_proj.0", H, H, bias=False)
+        lin(m + "x_proj.2", 3 * H, H, bias=False)
+        lin(m + "rbf_proj", 3 * H, R, bias=False)
+        s[m + "x_layernorm.weight"] = (H,)
+        s[m + "x_layernorm.bias"] = (H,)
+        u = f"update_layers.{l}."
+        lin(u + "vec_proj", 2 * H, H, bias=False)
+        lin(u + "xvec_proj.0", H, 2 * H, bias=False)
+        lin(u + "xvec_proj.2", 3 * H, H, bias=False)
+        lin(u + "lin3.0", 48, 3)
+        lin(u + "lin3.2", 8, 48)
+        lin(u + "lin3.4", 1, 8)
+    lin("last_layer", 1, H)  # unused in forward
+    o = "out_pos.output_network.0."
+    lin(o + "vec1_proj", H, H, bias=False)
+    lin(o + "vec2_proj", 1, H, bias=False)
+    lin(o + "update_net.0", H, 2 * H)
+    lin(o + "update_net.2", 2, H)
+    return s
+
+
+def dynamics_param_shapes(cfg: Dict, node_nfs: Sequence[int], condition_nf: int,
+                          pos_dim: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """EGNNDynamics state-dict: model.* + encoders.f.* + decoders.f.* (dynamics/_base.py:82-113)."""
+    s = {"model." + k: v for k, v in leftnet_param_shapes(cfg).items()}
+    embed = cfg["in_hidden_channels"] - 1 - condition_nf  # _base.py:69-77
+    for f, nf in enumerate(node_nfs):
+        d = nf - pos_dim
+        s[f"encoders.{f}.mlp.0.linear.weight"] = (2 * d, d)
+        s[f"encoders.{f}.mlp.0.linear.bias"] = (2 * d,)
+        s[f"encoders.{f}.mlp.1.linear.weight"] = (embed, 2 * d)
+        s[f"encoders.{f}.mlp.1.linear.bias"] = (embed,)
+        s[f"decoders.{f}.mlp.0.linear.weight"] = (2 * d, embed)
+        s[f"decoders.{f}.mlp.0.linear.bias"] = (2 * d,)
+        s[f"decoders.{f}.mlp.1.linear.weight"] = (d, 2 * d)
+        s[f"decoders.{f}.mlp.1.linear.bias"] = (d,)
+    return s
+
+
+def rbf_buffers(num_rbf: int, cutoff: float, dtype=torch.float32) -> Tuple[Tensor, Tensor]:
+    """model/leftnet.py:49-56 — computed in fp32 like the reference, then cast."""
+    start = torch.exp(torch.scalar_tensor(-float(cutoff)))
+    end = torch.exp(torch.scalar_tensor(-0.0))
+    means = torch.linspace(start, end, num_rbf)
+    betas = torch.tensor([(2 / num_rbf * (end - start)) ** -2] * num_rbf)
+    return means.to(dtype), betas.to(dtype)
+
+
+def make_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int, cfg: Dict,
+                    dtype=torch.float32, gain: float = 1.0, prefix_model: str = "") -> Dict[str, Tensor]:
+    """Deterministic, torch-version-independent weights (numpy RandomState), in the spirit of the
+    reference tests' `init_weights` (tests/model/utils.py:39-49): xavier-uniform weights and
+    NON-ZERO uniform biases.  LayerNorm affine params are perturbed too so they are exercised."""
+    rng = np.random.RandomState(seed)
+    sd: Dict[str, Tensor] = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if name.endswith("radial_emb.means") or name.endswith("radial_emb.betas"):
+            continue
+        if "x_layernorm.weight" in name:
+            v = 1.0 + 0.2 * rng.uniform(-1, 1, size=shp)
+        elif "x_layernorm.bias" in name:
+            v = 0.2 * rng.uniform(-1, 1, size=shp)
+        elif len(shp) == 2:
+            bound = gain * math.sqrt(6.0 / (shp[0] + shp[1]))
+            v = rng.uniform(-bound, bound, size=shp)
+        else:
+            v = rng.uniform(-0.5 * gain, 0.5 * gain, size=shp)
+        sd[name] = torch.from_numpy(np.asarray(v, dtype=np.float32)).to(dtype)
+    means, betas = rbf_buffers(cfg["num_radial"], cfg["cutoff"], dtype)
+    sd[prefix_model + "radial_emb.means"] = means
+    sd[prefix_model + "radial_emb.betas"] = betas
+    return sd
+
+
+# --------------------------------------------------------------------------- small layers
+def _lin(sd, name, x):
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _mlp(sd, name, x, n_layers, last_no_act=False):
+    """model/core.py:52-92 — OneLayerActivation stack with SiLU."""
+    for k in range(n_layers):
+        x = _lin(sd, f"{name}.mlp.{k}.linear", x)
+        if not (last_no_act and k == n_layers - 1):
+            x = F.silu(x)
+    return x
+
+
+def _scatter_add(src: Tensor, index: Tensor, n: int) -> Tensor:
+    out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype)
+    return out.index_add_(0, index, src)
+
+
+def _scatter_mean(src: Tensor, index: Tensor, n: int) -> Tensor:
+    tot = _scatter_add(src, index, n)
+    cnt = torch.zeros(n, dtype=src.dtype).index_add_(0, index, torch.ones(index.numel(), dtype=src.dtype))
+    cnt = cnt.clamp(min=1)
+    return tot / cnt.view((-1,) + (1,) * (src.dim() - 1))
+
+
+def remove_mean_batch(x: Tensor, indices: Tensor) -> Tensor:
+    """model/leftnet.py:26-29 == diffusion/_utils.py:9-12 == dynamics/egnn_dynamics.py:267-271."""
+    n = int(indices.max()) + 1 if indices.numel() else 0
+    return x - _scatter_mean(x, indices, n)[indices]
+
+
+def rbf_emb(dist: Tensor, means: Tensor, betas: Tensor, cutoff: float) -> Tensor:
+    """model/leftnet.py:63-69."""
+    d = dist.unsqueeze(-1)
+    rb = 0.5 * (torch.cos(d * math.pi / cutoff) + 1.0)
+    rb = rb * (d < cutoff).to(d.dtype)
+    return rb * torch.exp(-betas * torch.square(torch.exp(-d) - means))
+
+
+def assemble_nodemask(edge_index: Tensor, n_nodes: int) -> Tensor:
+    """model/leftnet.py:707-722 — greedy labelling with overwrite semantics; returns int64 ids."""
+    lab = np.full(n_nodes, -1, dtype=np.int64)
+    ei = edge_index.numpy()
+    order = np.argsort(ei[0], kind="stable")
+    src, dst = ei[0][order], ei[1][order]
+    starts = np.searchsorted(src, np.arange(n_nodes + 1))
+    ind = 0
+    for c in range(n_nodes):
+        if lab[c] > -1:
+            continue
+        lab[dst[starts[c]:starts[c + 1]]] = ind
+        lab[c] = ind
+        ind += 1
+    return torch.from_numpy(lab)
+
+
+def scalarization(pos: Tensor, edge_index: Tensor):
+    """model/leftnet.py:693-705 (torch.cross there is called without dim; we use dim=-1, which is
+    what it resolves to whenever neither N nor E equals 3 — SURVEY §8c 'known quirks')."""
+    i, j = edge_index
+    dist = (pos[i] - pos[j]).pow(2).sum(dim=-1).sqrt()
+    coord_diff = pos[i] - pos[j]
+    radial = torch.sum(coord_diff ** 2, 1).unsqueeze(1)
+    coord_cross = torch.cross(pos[i], pos[j], dim=-1)
+    coord_diff = coord_diff / (torch.sqrt(radial) + EPS)
+    cross_norm = torch.sqrt(torch.sum(coord_cross ** 2, 1).unsqueeze(1)) + EPS
+    coord_cross = coord_cross / cross_norm
+    coord_vertical = torch.cross(coord_diff, coord_cross, dim=-1)
+    return dist, coord_diff, coord_cross, coord_vertical
+
+
+# --------------------------------------------------------------------------- LEFTNet forward
+def leftnet_forward(sd: Dict[str, Tensor], cfg: Dict, h: Tensor, pos: Tensor, edge_index: Tensor,
+                    subgraph_mask: Optional[Tensor] = None, dbg: Optional[Dict] = None,
+                    prefix: str = "") -> Tuple[Tensor, Tensor]:
+    """model/leftnet.py:724-891 for legacy=True, update=True, pos_grad=False, single_layer_output=True.
+    Returns (h_out [N,C], dpos [N,3]); the reference returns pos + dpos."""
+    p = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)} if prefix else sd
+    H, L, cutoff = cfg["hidden_channels"], cfg["num_layers"], float(cfg["cutoff"])
+    reflect = cfg.get("reflect_equiv", True)
+    if not cfg.get("object_aware", True):
+        subgraph_mask = None
+    N = pos.size(0)
+    dt = pos.dtype
+    i, j = edge_index
+
+    z_emb = _lin(p, "embedding", h)  # :744
+    dist_raw = (pos[i] - pos[j]).pow(2).sum(dim=-1).sqrt()  # :747
+    mask = (dist_raw < cutoff).to(dt).unsqueeze(-1)  # :748-749
+    if subgraph_mask is not None:
+        mask = mask * subgraph_mask.reshape(-1, 1).to(dt)  # :751-753
+    ei_cut = edge_index[:, mask.squeeze(-1) > 0]  # :755
+    group = assemble_nodemask(ei_cut, N)  # :756-758
+    pos_frame = remove_mean_batch(pos.clone(), group)  # :760-761
+
+    dist, cdiff, ccross, cvert = scalarization(pos_frame, edge_index)  # :764-766
+    dist = dist * mask.squeeze(-1)
+    cdiff, ccross, cvert = cdiff * mask, ccross * mask, cvert * mask  # :768-771
+    frame = torch.stack((cdiff, ccross, cvert), dim=-1)  # :773-780  [E,3(xyz),3(k)]
+    rbf = rbf_emb(dist, p["radial_emb.means"], p["radial_emb.betas"], cutoff) * mask  # :781-782
+    f = _lin(p, "radial_lin.2", F.silu(_lin(p, "radial_lin.0", rbf)))  # :784
+    rbounds = 0.5 * (torch.cos(dist * math.pi / cutoff) + 1.0)  # :785
+    f = rbounds.unsqueeze(-1) * f  # :786
+
+    # NeighborEmb :81-89 (gather at edge_index[0], aggregate at edge_index[1])
+    ne = F.layer_norm(_lin(p, "neighbor_emb.embedding", h), (H,))
+    s = z_emb + _scatter_add(f * ne[i], j, N)
+    # CFConvS2V :104-125
+    q = F.silu(F.layer_norm(_lin(p, "s2v.lin1.0", s), (H,)))
+    emb = f.unsqueeze(1) * cdiff.unsqueeze(-1)  # [E,3,H]
+    NE1 = _scatter_add(emb * q[i].unsqueeze(1), j, N)  # [N,3,H]
+    if dbg is not None:
+        dbg.update(mask=mask.squeeze(-1).clone(), group=group.clone(), pos_frame=pos_frame.clone(),
+                   dist=dist.clone(), coord_diff=cdiff.clone(), rbf=rbf.clone(), f=f.clone(),
+                   s0=s.clone(), NE1=NE1.clone())
+
+    S1 = torch.sum(NE1[i].unsqueeze(2) * frame.unsqueeze(-1), dim=1)  # :792 [E,3(k),H]
+    S2 = torch.sum(NE1[j].unsqueeze(2) * frame.unsqueeze(-1), dim=1)  # :793
+    if reflect:
+        S1[:, 1, :] = S1[:, 1, :].abs()
+        S2[:, 1, :] = S2[:, 1, :].abs()  # :794-796
+
+    def lin3(x):
+        return _lin(p, "lin3.2", F.silu(_lin(p, "lin3.0", x)))
+
+    S1p, S2p = S1.permute(0, 2, 1), S2.permute(0, 2, 1)
+    sc3 = (lin3(S1p) + S1p[:, :, 0].unsqueeze(2)).squeeze(-1)  # :798-801
+    sc4 = (lin3(S2p) + S2p[:, :, 0].unsqueeze(2)).squeeze(-1)  # :802-805
+    e = torch.cat((sc3, sc4), dim=-1) * rbounds.unsqueeze(-1)
+    e = torch.cat((e, f, rbf), dim=-1)  # :806-809  [E, 3H+R]
+
+    # node frame, legacy :812-834 ; `vector` :421-428 = mean of neighbours' pos_frame at edge_index[1]
+    a = pos_frame
+    b = _scatter_mean(pos_frame[i], j, N)
+    x1 = (a - b) / (torch.sqrt(torch.sum((a - b) ** 2, 1).unsqueeze(1)) + EPS)
+    y1 = torch.cross(a, b, dim=-1)
+    y1 = y1 / (torch.sqrt(torch.sum(y1 ** 2, 1).unsqueeze(1)) + EPS)
+    z1 = torch.cross(x1, y1, dim=-1)
+    nodeframe = torch.stack((x1, y1, z1), dim=-1)  # [N,3(xyz),3(k)]
+    pos_prjt = torch.sum(pos_frame.unsqueeze(-1) * nodeframe, dim=1)  # :834
+    if dbg is not None:
+        dbg.update(e0=e.clone(), nodeframe=nodeframe.clone(), pos_prjt=pos_prjt.clone())
+
+    vec = torch.zeros(N, 3, H, dtype=dt)
+    inv_sqrt_2, inv_sqrt_3, inv_sqrt_h = 1 / math.sqrt(2.0), 1 / math.sqrt(3.0), 1 / math.sqrt(H)
+    for l in range(L):
+        s = s + _mlp(p, "pos_expansion", pos_prjt, 2, last_no_act=True)  # :840-841 (legacy: every layer)
+        # ---- GCLMessage :157-183
+        g = f"gcl_layers.{l}."
+        xh = F.layer_norm(s, (H,), p[g + "x_layernorm.weight"], p[g + "x_layernorm.bias"])
+        m = _mlp(p, g + "edge_mlp", torch.cat([xh[i], xh[j], e], dim=1), 2)
+        m = m * _mlp(p, g + "att_mlp", m, 1)
+        agg = _scatter_mean(m, i, N)  # util_funcs.py:27-45, aggregate at edge_index[0]
+        xh = xh + _mlp(p, g + "node_mlp", torch.cat([xh, agg], dim=1), 2,
+                       last_no_act=cfg.get("legacy", True))
+        e = e + _mlp(p, g + "edge_out_trans", m, 1)
+        s = xh
+        # ---- EquiMessage :244-289
+        ml = f"message_layers.{l}."
+        X = F.layer_norm(s, (H,), p[ml + "x_layernorm.weight"], p[ml + "x_layernorm.bias"])
+        X = _lin(p, ml + "x_proj.2", F.silu(_lin(p, ml + "x_proj.0", X)))
+        G = _lin(p, ml + "rbf_proj", rbf) * _lin(p, ml + "dir_proj.2", F.silu(_lin(p, ml + "dir_proj.0", e)))
+        al, be, ga = torch.split((X[i] + X[j]) * G, H, dim=-1)  # xh_j = X[edge_index[0]], xh_i = X[edge_index[1]]
+        be = be * inv_sqrt_3
+        vmsg = vec[i] * be.unsqueeze(1) + ga.unsqueeze(1) * cdiff.unsqueeze(2)
+        if not reflect:
+            vmsg = vmsg + al.unsqueeze(1) * ccross.unsqueeze(2)
+        vmsg = vmsg * inv_sqrt_h
+        dx = _scatter_add(al, j, N)
+        dvec = _scatter_add(vmsg, j, N)
+        s = (s + dx) * inv_sqrt_2  # :857-859
+        vec = vec + dvec
+        if dbg is not None:
+            dbg[f"s_msg{l}"] = s.clone()
+            dbg[f"vec_msg{l}"] = vec.clone()
+            dbg[f"e{l + 1}"] = e.clone()
+        # ---- EquiUpdate :325-346
+        if cfg.get("update", True):
+            u = f"update_layers.{l}."
+            vp = _lin(p, u + "vec_proj", vec)
+            v1, v2 = torch.split(vp, H, dim=-1)
+            Sc = torch.sum(v1.unsqueeze(2) * nodeframe.unsqueeze(-1), dim=1)  # [N,3(k),H]
+            if reflect:
+                Sc[:, 1, :] = Sc[:, 1, :].abs()
+            t = Sc.permute(0, 2, 1)
+            t = F.silu(_lin(p, u + "lin3.0", t))
+            t = F.silu(_lin(p, u + "lin3.2", t))
+            scalar = _lin(p, u + "lin3.4", t).squeeze(-1)
+            vdot = (v1 * v2).sum(dim=1) * inv_sqrt_h
+            xv = _lin(p, u + "xvec_proj.2", F.silu(_lin(p, u + "xvec_proj.0", torch.cat([s, scalar], dim=-1))))
+            xv1, xv2, xv3 = torch.split(xv, H, dim=-1)
+            s = s + (xv1 + xv2 + vdot) * inv_sqrt_2
+            vec = vec + xv3.unsqueeze(1) * v2
+        if dbg is not None:
+            dbg[f"s{l + 1}"] = s.clone()
+            dbg[f"vec{l + 1}"] = vec.clone()
+
+    # EquiOutput / GatedEquivariantBlock :566-576
+    o = "out_pos.output_network.0."
+    n1 = torch.norm(_lin(p, o + "vec1_proj", vec), dim=-2)
+    v2 = _lin(p, o + "vec2_proj", vec)  # [N,3,1]
+    upd = _lin(p, o + "update_net.2", F.silu(_lin(p, o + "update_net.0", torch.cat([s, n1], dim=-1))))
+    gate = upd[:, 1:2]
+    dpos = (gate.unsqueeze(1) * v2).squeeze(-1)  # [N,3]
+    h_out = _lin(p, "embedding_out", s)  # :887
+    return h_out, dpos
+
+
+# --------------------------------------------------------------------------- dynamics wrapper
+def dynamics_forward(sd: Dict[str, Tensor], cfg: Dict, xh: List[Tensor], edge_index: Tensor, t: Tensor,
+                     conditions: Optional[Tensor], n_frag_switch: Tensor, combined_mask: Tensor,
+                     pos_dim: int = 3, condition_nf: int = 1, dbg: Optional[Dict] = None) -> List[Tensor]:
+    """dynamics/egnn_dynamics.py:63-168 (condition_time=True, edge_nf=0, update_pocket_coords=True)."""
+    nf = len(xh)
+    pos = torch.cat([x[:, :pos_dim].clone() for x in xh], dim=0)  # :91-94
+    h = torch.cat([_mlp(sd, f"encoders.{f}", xh[f][:, pos_dim:].clone(), 2, last_no_act=True)
+                   for f in range(nf)], dim=0)  # :95-101
+    if t.dim() == 1:
+        h_time = torch.empty_like(h[:, 0:1]).fill_(float(t.item()))  # :107-109
+    else:
+        h_time = t[combined_mask]  # :112
+    h = torch.cat([h, h_time.to(h.dtype)], dim=1)
+    cdim = 1
+    if condition_nf > 0:
+        h = torch.cat([h, conditions[combined_mask].to(h.dtype)], dim=1)  # :116-119
+        cdim += condition_nf
+    sub = get_subgraph_mask(edge_index, n_frag_switch)  # :121
+    h_final, dpos = leftnet_forward(sd, cfg, h, pos, edge_index, sub[:, None], dbg=dbg, prefix="model.")
+    vel = (pos + dpos) - pos  # :137 (pos_final - pos)
+    h_final = h_final[:, :-cdim]  # :145
+    counts = [int((n_frag_switch == f).sum()) for f in torch.unique(n_frag_switch).tolist()]  # :177-182
+    fi = np.concatenate([[0], np.cumsum(counts)])
+    out = []
+    for f in range(nf):
+        sl = slice(int(fi[f]), int(fi[f + 1]))
+        out.append(torch.cat([remove_mean_batch(vel[sl], combined_mask[sl]),
+                              _mlp(sd, f"decoders.{f}", h_final[sl], 2, last_no_act=True)], dim=-1))  # :147-160
+    return out
+
+
+# --------------------------------------------------------------------------- noise schedule
+def polynomial_schedule(timesteps: int, s: float = 1e-4, power: float = 3.0) -> np.ndarray:
+    """diffusion/_schedule.py:60-74 with clip_noise_schedule :43-57."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    alphas2 = (1 - np.power(x / steps, power)) ** 2
+    alphas2 = np.concatenate([np.ones(1), alphas2], axis=0)
+    step = np.clip(alphas2[1:] / alphas2[:-1], a_min=0.001, a_max=1.0)
+    alphas2 = np.cumprod(step, axis=0)
+    return (1 - 2 * s) * alphas2 + s
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008, raise_to_power: float = 1) -> np.ndarray:
+    """diffusion/_schedule.py:9-26."""
+    steps = timesteps + 2
+    x = np.linspace(0, steps, steps)
+    ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = np.clip(1 - (ac[1:] / ac[:-1]), a_min=0, a_max=0.999)
+    ac = np.cumprod(1.0 - betas, axis=0)
+    if raise_to_power != 1:
+        ac = np.power(ac, raise_to_power)
+    return ac
+
+
+def gamma_table(noise_schedule: str, timesteps: int, precision: float) -> Tensor:
+    """diffusion/_schedule.py:77-125 — float32 lookup table gamma[0..T]."""
+    if "cosine" in noise_schedule:
+        sp = noise_schedule.split("_")
+        alphas2 = cosine_beta_schedule(timesteps, raise_to_power=1 if len(sp) == 1 else float(sp[1]))
+    elif "polynomial" in noise_schedule:
+        alphas2 = polynomial_schedule(timesteps, s=precision, power=float(noise_schedule.split("_")[1]))
+    else:
+        raise ValueError(noise_schedule)
+    sigmas2 = 1 - alphas2
+    return torch.from_numpy(-(np.log(alphas2) - np.log(sigmas2))).float()
+
+
+def get_repaint_schedule(resamplings: int, jump_length: int, timesteps: int) -> List[int]:
+    """diffusion/_schedule.py:206-232."""
+    sched: List[int] = []
+    cur = 0
+    while cur < timesteps:
+        if cur + jump_length < timesteps:
+            if sched:
+                sched[-1] += jump_length
+                sched.extend([jump_length] * (resamplings - 1))
+            else:
+                sched.extend([jump_length] * resamplings)
+            cur += jump_length
+        else:
+            res = timesteps - cur
+            if sched:
+                sched[-1] += res
+            else:
+                sched.append(res)
+            cur += res
+    return list(reversed(sched))
+
+
+class Sampler:
+    """diffusion/en_diffusion.py sample()/inpaint() for pos_only=True, identity Normalizer,
+    with the reference's RNG draw order (per fragment: positions [N_f,3], then features [N_f,nf-3])."""
+
+    def __init__(self, sd, cfg, gamma: Tensor, node_nfs=(9, 9, 9), condition_nf=1, pos_dim=3, dtype=torch.float32):
+        self.sd, self.cfg, self.gamma = sd, cfg, gamma
+        self.T = gamma.numel() - 1
+        self.node_nfs, self.condition_nf, self.pos_dim, self.dtype = list(node_nfs), condition_nf, pos_dim, dtype
+        self.n_evals = 0
+
+    # _schedule.py:127-129,149-187
+    def _gamma(self, t):
+        return self.gamma[torch.round(t * self.T).long()]
+
+    @staticmethod
+    def _sigma(g):
+        return torch.sqrt(torch.sigmoid(g))
+
+    @staticmethod
+    def _alpha(g):
+        return torch.sqrt(torch.sigmoid(-g))
+
+    @staticmethod
+    def _sigma_alpha_t_given_s(gt, gs):
+        s2 = -torch.expm1(F.softplus(gs) - F.softplus(gt))
+        a = torch.exp(0.5 * (F.logsigmoid(-gt) - F.logsigmoid(-gs)))
+        return s2, torch.sqrt(s2), a
+
+    def _noise(self, masks):
+        """en_diffusion.py:281-304 with pos_only=True."""
+        out = []
+        for ii, m in enumerate(masks):
+            x = remove_mean_batch(torch.randn(len(m), self.pos_dim), m)
+            hh = torch.randn(len(m), self.node_nfs[ii] - self.pos_dim)
+            out.append(torch.cat([x, torch.zeros_like(hh)], dim=1).to(self.dtype))
+        return out
+
+    def _dyn(self, z, edge_index, t, cond, nfs, masks):
+        self.n_evals += 1
+        return dynamics_forward(self.sd, self.cfg, z, edge_index, t.to(self.dtype), cond, nfs, torch.cat(masks),
+                                self.pos_dim, self.condition_nf)
+
+    def _p_zs_given_zt(self, s, t, z, edge_index, nfs, masks, cond):
+        """en_diffusion.py:562-632."""
+        gs, gt = self._gamma(s), self._gamma(t)
+        s2ts, sts, ats = self._sigma_alpha_t_given_s(gt, gs)
+        sig_s, sig_t = self._sigma(gs), self._sigma(gt)
+        eps = self._dyn(z, edge_index, t, cond, nfs, masks)
+        mu = [z[ii] / ats[masks[ii]] - eps[ii] * (s2ts / ats / sig_t)[masks[ii]] for ii in range(len(z))]
+        sigma = sts * sig_s / sig_t
+        n = self._noise(masks)
+        zs = [mu[ii] + sigma[masks[ii]] * n[ii] for ii in range(len(z))]
+        for ii in range(len(z)):
+            zs[ii][:, :self.pos_dim] = remove_mean_batch(zs[ii][:, :self.pos_dim], masks[ii])
+        return zs
+
+    def _p_xh_given_z0(self, z0, edge_index, nfs, masks, B, cond):
+        """en_diffusion.py:649-702 (positions only; pos_only overrides the h part)."""
+        t0 = torch.zeros(B, 1)
+        g0 = self._gamma(t0)
+        sigma_x = torch.exp(-(-0.5 * g0))
+        eps = self._dyn(z0, edge_index, t0, cond, nfs, masks)
+        sig, al = self._sigma(g0), self._alpha(g0)
+        mu = [1.0 / al[masks[ii]] * (z0[ii] - sig[masks[ii]] * eps[ii]) for ii in range(len(z0))]
+        n = self._noise(masks)
+        return [(mu[ii] + sigma_x[masks[ii]] * n[ii])[:, :self.pos_dim] for ii in range(len(z0))]
+
+    def _graph(self, fragments_nodes):
+        masks = [get_mask_for_frag(n) for n in fragments_nodes]
+        cm = torch.cat(masks)
+        return masks, cm, get_edges_index(cm, remove_self_edge=True), get_n_frag_switch(fragments_nodes)
+
+    @torch.no_grad()
+    def sample(self, n_samples, fragments_nodes, conditions, h0, timesteps=None, max_steps=None):
+        """en_diffusion.py:459-560.  `max_steps` (oracle-only) stops after that many reverse steps so a
+        bounded slice of the loop can be timed; the final p(x|z0) evaluation is always run."""
+        T = self.T if timesteps is None else timesteps
+        masks, cm, edge_index, nfs = self._graph(fragments_nodes)
+        z = self._noise(masks)
+        z = [torch.cat([z[ii][:, :self.pos_dim], h0[ii].to(self.dtype)], dim=1) for ii in range(len(h0))]
+        done = 0
+        for s in reversed(range(0, T)):
+            s_arr = torch.full((n_samples, 1), fill_value=s)
+            t_arr = (s_arr + 1) / T
+            s_arr = s_arr / T
+            z = self._p_zs_given_zt(s_arr, t_arr, z, edge_index, nfs, masks, conditions)
+            z = [torch.cat([z[ii][:, :self.pos_dim], h0[ii].to(self.dtype)], dim=1) for ii in range(len(h0))]
+            done += 1
+            if max_steps is not None and done >= max_steps:
+                break
+        pos = self._p_xh_given_z0(z, edge_index, nfs, masks, n_samples, conditions)
+        return [torch.cat([pos[ii], h0[ii].to(self.dtype)], dim=1) for ii in range(len(pos))], masks
+
+    @torch.no_grad()
+    def inpaint(self, n_samples, fragments_nodes, conditions, xh_fixed, frag_fixed, resamplings=1,
+                jump_length=1, timesteps=None):
+        """en_diffusion.py:722-883."""
+        T = self.T if timesteps is None else timesteps
+        masks, cm, edge_index, nfs = self._graph(fragments_nodes)
+        xh_fixed = [x.clone().to(self.dtype) for x in xh_fixed]
+        h0 = [x[:, self.pos_dim:].long().to(self.dtype) for x in xh_fixed]
+        for ii in range(len(xh_fixed)):
+            xh_fixed[ii][:, :self.pos_dim] = remove_mean_batch(xh_fixed[ii][:, :self.pos_dim], masks[ii])
+        z = self._noise(masks)
+        z = [torch.cat([z[ii][:, :self.pos_dim], h0[ii]], dim=1) for ii in range(len(h0))]
+        sched = get_repaint_schedule(resamplings, jump_length, T)
+        s = T - 1
+        for i, n_denoise in enumerate(sched):
+            for j in range(n_denoise):
+                s_arr = torch.full((n_samples, 1), fill_value=s)
+                t_arr = (s_arr + 1) / T
+                s_arr = s_arr / T
+                gs = self._gamma(s_arr)
+                al, sg = self._alpha(gs), self._sigma(gs)
+                n = self._noise(masks)  # noised_representation :260-279
+                z_known = [al[masks[ii]] * xh_fixed[ii] + sg[masks[ii]] * n[ii] for ii in range(len(masks))]
+                z_unknown = self._p_zs_given_zt(s_arr, t_arr, z, edge_index, nfs, masks, conditions)
+                z_known = [torch.cat([z_known[ii][:, :self.pos_dim], h0[ii]], dim=1) for ii in range(len(h0))]
+                z_unknown = [torch.cat([z_unknown[ii][:, :self.pos_dim], h0[ii]], dim=1) for ii in range(len(h0))]
+                z = [z_known[ii] if ii in frag_fixed else z_unknown[ii] for ii in range(len(h0))]
+                if j == n_denoise - 1 and i < len(sched) - 1:
+                    t = s + jump_length
+                    gt = self._gamma(torch.full((n_samples, 1), fill_value=t) / T)
+                    s2, st, at = self._sigma_alpha_t_given_s(gt, gs)  # :1050-1074
+                    n = self._noise(masks)
+                    z = [at[masks[ii]] * z[ii] + st[masks[ii]] * n[ii] for ii in range(len(masks))]
+                    for ii in range(len(masks)):
+                        z[ii][:, :self.pos_dim] = remove_mean_batch(z[ii][:, :self.pos_dim], masks[ii])
+                    s = t
+                s = s - 1
+        pos = self._p_xh_given_z0(z, edge_index, nfs, masks, n_samples, conditions)
+        return [torch.cat([pos[ii], h0[ii]], dim=1) for ii in range(len(pos))], masks
+
+
+# --------------------------------------------------------------------------- synthetic workloads
+# Atom-count histogram of Transition1x `use_ind` reactions (index = atoms per reaction), measured from the
+# in-tree pickle by oracle/gen_golden.py (tests/golden/t1x_hist.json: 9000 reactions, min 4, max 23,
+# mean 13.57) and frozen here so the GPU box needs no data.
+T1X_SIZE_HIST = [0, 0, 0, 0, 1, 4, 15, 36, 157, 261, 599, 947, 1155, 1207, 1461, 1051, 907, 636, 200, 280, 25, 55,
+                 0, 3]
+
+
+def t1x_sizes(B: int, seed: int = 0) -> List[int]:
+    """B reaction sizes drawn i.i.d. from the Transition1x histogram."""
+    p = np.asarray(T1X_SIZE_HIST, dtype=np.float64)
+    return [int(x) for x in np.random.RandomState(seed).choice(len(p), size=B, p=p / p.sum())]
+
+
+def synthetic_batch(B: int, sizes: Sequence[int], seed: int = 0):
+    """SURVEY §8d synthetic inputs: fragments_nodes=[n,n,n], h0 = [onehot(5) | Z] from {H,C,N,O},
+    conditions = zeros[B,1]."""
+    rng = np.random.RandomState(seed)
+    sizes = list(sizes)
+    assert len(sizes) == B
+    nodes = torch.tensor(sizes, dtype=torch.long)
+    z_table = np.array([1, 6, 7, 8, 9])
+    probs = np.array([0.445, 0.290, 0.149, 0.116, 0.0])  # tests/golden/t1x_hist.json element_freq
+    types = [rng.choice(5, size=n, p=probs) for n in sizes]
+    t = np.concatenate(types)
+    h = np.zeros((t.size, 6), dtype=np.float32)
+    h[np.arange(t.size), t] = 1
+    h[:, 5] = z_table[t]
+    h0 = torch.from_numpy(h)
+    return [nodes, nodes.clone(), nodes.clone()], [h0, h0.clone(), h0.clone()], torch.zeros(B, 1)
