@@ -1,0 +1,92 @@
+/* oard.h — C ABI of the B200-native OA-ReactDiff denoising hot path (liboard_b200.so).
+ *
+ * The library replaces, for this path only, what the reference delegates to eager PyTorch + torch_scatter + PyG:
+ *   oa_reactdiff/model/leftnet.py:724-891   LEFTNet.forward            -> oard_forward
+ *   oa_reactdiff/model/leftnet.py:594-688   LEFTNet.__init__ / weights  -> oard_create, oard_set_weight, oard_commit_weights
+ *   oa_reactdiff/utils/_graph_tools.py:9-36 edge list of the batch      -> oard_plan (consumes that edge list)
+ * The reference has no FFI of its own (it is pure Python); the seam a maintainer binds is the `model=` plugin
+ * argument of EGNNDynamics (oa_reactdiff/dynamics/_base.py:21,62-64).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: plain C, no exceptions across the boundary; every entry point returns 0 on success or a negative
+ * OARD_E* code and records a message retrievable with oard_last_error().  All tensor pointers passed to
+ * oard_forward are DEVICE pointers owned by the caller, fp32 row-major, valid until the stream reaches the end of the
+ * call's work; the call is asynchronous on `stream` (a cudaStream_t passed as void*).  One handle per device; a handle
+ * is not thread-safe.  There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * OARD_ECUDA.
+ */
+#ifndef OARD_H
+#define OARD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OARD_OK 0
+#define OARD_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define OARD_ECUDA (-2)       /* CUDA runtime error (message holds cudaGetErrorString) */
+#define OARD_ESTATE (-3)      /* call order violated (e.g. forward before plan / commit) */
+#define OARD_EGRAPH (-4)      /* edge list is not CSR-sorted / not symmetric / component too large */
+#define OARD_EMISSING (-5)    /* a required weight was not provided */
+
+typedef struct oard_handle oard_handle;
+
+/* Mirror of LEFTNet.__init__ kwargs (leftnet.py:594-611).  Only legacy=1, pos_grad=0, single_layer_output=1,
+ * for_conf=0, ff=0 are implemented (the trained configuration, trainer/train_ts1x.py:43-56). */
+typedef struct oard_cfg {
+  int32_t hidden_channels;    /* H, <= 256 */
+  int32_t num_radial;         /* R */
+  int32_t num_layers;         /* L */
+  int32_t in_hidden_channels; /* C, <= 32 */
+  float cutoff;
+  int32_t reflect_equiv;
+  int32_t legacy;
+  int32_t update;
+  int32_t object_aware;
+} oard_cfg;
+
+int oard_abi_version(void);
+const char* oard_last_error(void);
+
+int oard_create(const oard_cfg* cfg, int device, oard_handle** out);
+void oard_destroy(oard_handle* h);
+
+/* Number of weights the configuration requires and their reference state-dict names,
+ * e.g. "gcl_layers.0.edge_mlp.mlp.0.linear.weight". */
+int oard_num_weights(const oard_handle* h);
+const char* oard_weight_name(const oard_handle* h, int i);
+int64_t oard_weight_numel(const oard_handle* h, int i);
+
+/* Copy one named fp32 tensor (row-major, exactly oard_weight_numel elements) into the handle.
+ * `is_device` != 0: `data` is a device pointer on the handle's device; else a host pointer. */
+int oard_set_weight(oard_handle* h, const char* name, const float* data, int64_t numel, int is_device, void* stream);
+/* Verify that every required weight was set; derive packed forms.  Must be called after (re)setting weights. */
+int oard_commit_weights(oard_handle* h, void* stream);
+
+/* Build the static per-batch plan from the HOST edge list edge_index[2][E] (int64, edge_index[0] = source):
+ * CSR rows, transposed-edge map, connected components (= reactions).  Requirements: edges grouped by source in
+ * non-decreasing order, the graph symmetric, no duplicates, components of <= 256 nodes.  Allocates the workspace. */
+int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const int64_t* edge_index_host);
+size_t oard_workspace_bytes(const oard_handle* h);
+
+/* LEFTNet.forward (leftnet.py:724-891).  h_in[N,C], pos[N,3], subgraph_mask[E] (int64, may be NULL = all ones),
+ * h_out[N,C], dpos[N,3] (the reference returns pos + dpos).  Device pointers; asynchronous on `stream`. */
+int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* subgraph_mask, float* h_out,
+                 float* dpos, void* stream);
+
+/* Parity instrumentation.  With debug on, oard_forward keeps snapshots of intermediates; oard_debug_read copies a
+ * named snapshot to host (synchronises).  Names: mask(u8[E]) group(i32[N]) act_idx(i32[n_act]) n_act(i32[1])
+ * pos_frame(f32[N,3]) geo(f32[E,4]) rb f_act rbf_act s0 NE1 e0 nodeframe pos_prjt s_msg{l} vec_msg{l} e{l} s{l} vec{l}. */
+int oard_set_debug(oard_handle* h, int on);
+int64_t oard_debug_bytes(oard_handle* h, const char* name);
+int oard_debug_read(oard_handle* h, const char* name, void* host_dst, size_t bytes);
+
+/* Kernel launches issued by the last oard_forward call (for bench.py's gpu_launches). */
+int64_t oard_last_launch_count(const oard_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OARD_H */

@@ -1,0 +1,22 @@
+"""oareactdiff_b200 — B200-native drop-in for OA-ReactDiff's denoising hot path.
+
+Public names mirror the reference (`oa_reactdiff.model.LEFTNet`, `oa_reactdiff.dynamics.EGNNDynamics`,
+`oa_reactdiff.diffusion.*`, `oa_reactdiff.utils.*`).  All LEFTNet arithmetic runs in liboard_b200.so (CUDA, sm_100a,
+C ABI in include/oard.h); importing the package without the built library raises.
+"""
+from . import _lib
+
+_lib.load()  # fail loudly if the CUDA library has not been built: there is no fallback path
+
+from .leftnet import LEFTNetB200  # noqa: E402
+from .dynamics import EGNNDynamics  # noqa: E402
+from .diffusion import EnVariationalDiffusion  # noqa: E402
+from .schedule import DiffSchedule, PredefinedNoiseSchedule, get_repaint_schedule  # noqa: E402
+from .normalizer import Normalizer  # noqa: E402
+from .graph_tools import get_edges_index, get_mask_for_frag, get_n_frag_switch, get_subgraph_mask  # noqa: E402
+
+LEFTNet = LEFTNetB200
+
+__all__ = ["LEFTNetB200", "LEFTNet", "EGNNDynamics", "EnVariationalDiffusion", "DiffSchedule",
+           "PredefinedNoiseSchedule", "get_repaint_schedule", "Normalizer", "get_edges_index", "get_mask_for_frag",
+           "get_n_frag_switch", "get_subgraph_mask"]

@@ -1,0 +1,43 @@
+// Shared device helpers for the OA-ReactDiff B200 hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define OARD_EPS 1e-6f  // reference model/leftnet.py:15
+#define OARD_PI 3.14159265358979323846
+
+namespace oard {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the whole block; every thread gets the total.  `sm` needs >= 33 floats.  Deterministic.
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect sm reuse across consecutive calls
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? sm[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) sm[32] = t;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+// LayerNorm statistics of one row held one-element-per-thread (threads >= H idle with v = 0, valid=false).
+__device__ __forceinline__ void block_ln_stats(float v, bool valid, int H, float* sm, float& mean, float& rstd) {
+  mean = block_sum(valid ? v : 0.f, sm) / (float)H;
+  const float d = valid ? v - mean : 0.f;
+  const float var = block_sum(d * d, sm) / (float)H;  // biased, like torch.nn.LayerNorm
+  rstd = rsqrtf(var + 1e-5f);
+}
+
+}  // namespace oard

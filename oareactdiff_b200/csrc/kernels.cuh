@@ -1,0 +1,535 @@
+// Message-passing / geometry / node kernels of the object-aware LEFTNet forward (sm_100a).
+// Citations: reference oa_reactdiff/model/leftnet.py (file:line in each kernel's comment).
+//
+// Conventions: edges are CSR-ordered by source (row_ptr/esrc/ecol), rev[e] is the position of the transposed edge,
+// "channel kernels" run one block per node (or edge) with one thread per hidden channel h < H (blockDim = H rounded
+// up to a warp multiple).  Aggregations at edge_index[1] (PyG 'target') are done as row sums over transposed edges,
+// so every reduction is a fixed-order segmented sum: no atomics, bitwise reproducible.
+#pragma once
+#include "common.cuh"
+
+namespace oard {
+
+// ---------------------------------------------------------------------------------------------------------------
+// (B) raw distance + cutoff/same-fragment edge mask.  leftnet.py:747-753
+__global__ void k_edge_mask(int E, const int* __restrict__ esrc, const int* __restrict__ ecol,
+                            const float* __restrict__ pos, const int64_t* __restrict__ sub, float cutoff,
+                            uint8_t* __restrict__ mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int i = esrc[e], j = ecol[e];
+  const float dx = pos[i * 3 + 0] - pos[j * 3 + 0], dy = pos[i * 3 + 1] - pos[j * 3 + 1],
+              dz = pos[i * 3 + 2] - pos[j * 3 + 2];
+  // same rounding sequence as torch: pow(2) (separately rounded), sequential sum, sqrt
+  const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  mask[e] = (d < cutoff) && (sub == nullptr || sub[e] > 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (C)+(D)+(J) per connected component of the unmasked graph (= one reaction): greedy group labelling with the
+// reference's overwrite semantics (leftnet.py:707-722), per-group centre-of-mass removal (:760-761, :26-29) and the
+// legacy node frame (:812-834).  CoM and node frame are evaluated in fp64: in exact arithmetic b = -a/(n-1) and
+// y1 = a x b vanishes, so the reference's fp32 y1 is pure rounding noise; fp64 here tracks the fp64
+// oracle instead of inventing different noise.
+template <int MAXC>
+__global__ void __launch_bounds__(128) k_group_frame(
+    const int* __restrict__ comp_ptr, const int* __restrict__ comp_nodes, const int* __restrict__ node_local,
+    const int* __restrict__ row_ptr, const int* __restrict__ ecol, const uint8_t* __restrict__ mask,
+    const float* __restrict__ pos, float* __restrict__ pf, float* __restrict__ nodeframe,
+    float* __restrict__ pos_prjt, int* __restrict__ owner, uint8_t* __restrict__ opener) {
+  __shared__ int lab[MAXC];
+  __shared__ double p[MAXC][3];
+  __shared__ double q[MAXC][3];
+  const int c = blockIdx.x, base = comp_ptr[c], nc = comp_ptr[c + 1] - base;
+  const int* nodes = comp_nodes + base;
+  for (int n = threadIdx.x; n < nc; n += blockDim.x) {
+    lab[n] = -1;
+    const int t = nodes[n];
+    p[n][0] = pos[t * 3 + 0]; p[n][1] = pos[t * 3 + 1]; p[n][2] = pos[t * 3 + 2];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    for (int a = 0; a < nc; a++) {  // centres in ascending global node id
+      if (lab[a] < 0) {
+        const int t = nodes[a];
+        for (int e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32)
+          if (mask[e]) lab[node_local[ecol[e]]] = a;
+        if (lane == 0) lab[a] = a;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < nc; n += blockDim.x) {
+    const int own = lab[n];
+    double sx = 0, sy = 0, sz = 0;
+    int cnt = 0;
+    for (int m = 0; m < nc; m++)
+      if (lab[m] == own) { sx += p[m][0]; sy += p[m][1]; sz += p[m][2]; cnt++; }
+    q[n][0] = p[n][0] - sx / cnt; q[n][1] = p[n][1] - sy / cnt; q[n][2] = p[n][2] - sz / cnt;
+    const int t = nodes[n];
+    pf[t * 3 + 0] = (float)q[n][0]; pf[t * 3 + 1] = (float)q[n][1]; pf[t * 3 + 2] = (float)q[n][2];
+    owner[t] = nodes[own];
+    opener[t] = (own == n);
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < nc; n += blockDim.x) {
+    const int t = nodes[n];
+    double b0 = 0, b1 = 0, b2 = 0;
+    const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+    for (int e = r0; e < r1; e++) {
+      const int m = node_local[ecol[e]];
+      b0 += q[m][0]; b1 += q[m][1]; b2 += q[m][2];
+    }
+    const double cnt = (r1 - r0) > 0 ? (double)(r1 - r0) : 1.0;
+    b0 /= cnt; b1 /= cnt; b2 /= cnt;
+    const double a0 = q[n][0], a1 = q[n][1], a2 = q[n][2];
+    double x0 = a0 - b0, x1 = a1 - b1, x2 = a2 - b2;
+    const double nx = sqrt(x0 * x0 + x1 * x1 + x2 * x2) + (double)OARD_EPS;
+    x0 /= nx; x1 /= nx; x2 /= nx;
+    double y0 = a1 * b2 - a2 * b1, y1 = a2 * b0 - a0 * b2, y2 = a0 * b1 - a1 * b0;
+    const double ny = sqrt(y0 * y0 + y1 * y1 + y2 * y2) + (double)OARD_EPS;
+    y0 /= ny; y1 /= ny; y2 /= ny;
+    const double z0 = x1 * y2 - x2 * y1, z1 = x2 * y0 - x0 * y2, z2 = x0 * y1 - x1 * y0;
+    float* nf = nodeframe + (size_t)t * 9;  // [xyz c][k]: k = 0:x1, 1:y1, 2:z1
+    nf[0] = (float)x0; nf[1] = (float)y0; nf[2] = (float)z0;
+    nf[3] = (float)x1; nf[4] = (float)y1; nf[5] = (float)z1;
+    nf[6] = (float)x2; nf[7] = (float)y2; nf[8] = (float)z2;
+    pos_prjt[t * 3 + 0] = (float)(a0 * x0 + a1 * x1 + a2 * x2);
+    pos_prjt[t * 3 + 1] = (float)(a0 * y0 + a1 * y1 + a2 * y2);
+    pos_prjt[t * 3 + 2] = (float)(a0 * z0 + a1 * z1 + a2 * z2);
+  }
+}
+
+// group ids in the reference's numbering: rank of the opening centre among all opening centres (debug/parity only)
+__global__ void k_group_ids(int N, const int* __restrict__ owner, const uint8_t* __restrict__ opener,
+                            int* __restrict__ rank_tmp, int* __restrict__ group) {
+  // single block
+  __shared__ int sm[1025];
+  const int T = blockDim.x, tid = threadIdx.x, per = (N + T - 1) / T;
+  const int b = tid * per, e = min(N, b + per);
+  int s = 0;
+  for (int i = b; i < e; i++) s += opener[i];
+  sm[tid + 1] = s;
+  if (tid == 0) sm[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= T; i++) sm[i] += sm[i - 1];
+  __syncthreads();
+  int run = sm[tid];
+  for (int i = b; i < e; i++) { rank_tmp[i] = run; run += opener[i]; }
+  __syncthreads();
+  __threadfence_block();
+  for (int i = tid; i < N; i += T) group[i] = rank_tmp[owner[i]];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (E) edge geometry on pos_frame, masked (leftnet.py:693-705,764-771,785): geo[e] = (u_x,u_y,u_z,dist), rb[e];
+// also counts the row's active edges.  One warp per CSR row.
+__global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
+                            const uint8_t* __restrict__ mask, const float* __restrict__ pf, float cutoff,
+                            float4* __restrict__ geo, float* __restrict__ rb, int* __restrict__ row_cnt) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= N) return;
+  const float ax = pf[t * 3 + 0], ay = pf[t * 3 + 1], az = pf[t * 3 + 2];
+  int cnt = 0;
+  for (int e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float r = 1.0f;  // 0.5*(cos(0)+1)
+    if (mask[e]) {
+      const int j = ecol[e];
+      const float dx = ax - pf[j * 3 + 0], dy = ay - pf[j * 3 + 1], dz = az - pf[j * 3 + 2];
+      const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      const float inv = 1.0f / (d + OARD_EPS);
+      g = make_float4(dx * inv, dy * inv, dz * inv, d);
+      r = 0.5f * (cosf(d * (float)OARD_PI / cutoff) + 1.0f);
+      cnt++;
+    }
+    geo[e] = g;
+    rb[e] = r;
+  }
+  cnt = (int)warp_sum((float)cnt);
+  if (lane == 0) row_cnt[t] = cnt;
+}
+
+// exclusive scan of row_cnt -> row_act_ptr[N+1], n_act = total.  Single block.
+__global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restrict__ row_act_ptr,
+                            int* __restrict__ n_act) {
+  __shared__ int sm[1025];
+  const int T = blockDim.x, tid = threadIdx.x, per = (N + T - 1) / T;
+  const int b = min(N, tid * per), e = min(N, b + per);
+  int s = 0;
+  for (int i = b; i < e; i++) s += row_cnt[i];
+  sm[tid + 1] = s;
+  if (tid == 0) sm[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= T; i++) sm[i] += sm[i - 1];
+  __syncthreads();
+  int run = sm[tid];
+  for (int i = b; i < e; i++) { row_act_ptr[i] = run; run += row_cnt[i]; }
+  if (tid == T - 1) { row_act_ptr[N] = sm[T]; *n_act = sm[T]; }
+}
+
+// ordered compaction of active edges: act_idx[p] = e, act_pos[e] = p or -1.  One warp per row.
+__global__ void k_compact(int N, const int* __restrict__ row_ptr, const uint8_t* __restrict__ mask,
+                          const int* __restrict__ row_act_ptr, int* __restrict__ act_idx, int* __restrict__ act_pos) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= N) return;
+  int base = row_act_ptr[t];
+  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  for (int e0 = r0; e0 < r1; e0 += 32) {
+    const int e = e0 + lane;
+    const bool a = e < r1 && mask[e];
+    const unsigned bal = __ballot_sync(0xffffffffu, a);
+    const int off = __popc(bal & ((1u << lane) - 1u));
+    if (e < r1) {
+      if (a) { act_idx[base + off] = e; act_pos[e] = base + off; }
+      else act_pos[e] = -1;
+    }
+    base += __popc(bal);
+  }
+}
+
+// (F) radial basis on active edges (leftnet.py:63-69; mask == 1 there): rbf_act[p, r]
+__global__ void k_rbf(const int* __restrict__ n_act, int cap, int R, const int* __restrict__ act_idx,
+                      const float4* __restrict__ geo, const float* __restrict__ means, const float* __restrict__ betas,
+                      float cutoff, float* __restrict__ rbf_act) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (int)(idx / R), r = (int)(idx % R);
+  if (p >= min(*n_act, cap)) return;
+  const float d = geo[act_idx[p]].w;
+  float rbc = 0.5f * (cosf(d * (float)OARD_PI / cutoff) + 1.0f);
+  rbc = d < cutoff ? rbc : 0.f;
+  const float x = expf(-d) - means[r];
+  rbf_act[idx] = rbc * expf(-betas[r] * x * x);
+}
+
+// constants of masked edges: f0 = radial_lin(0) (leftnet.py:784-786 with rbf = 0, rbounds = 1),
+// c3 = lin3(0) (leftnet.py:798-805 with zero frame).  Single block, one thread per channel.
+__global__ void k_masked_consts(int H, int Hq, const float* __restrict__ rl0_b, const float* __restrict__ rl2_w,
+                                const float* __restrict__ rl2_b, const float* __restrict__ l3_b0,
+                                const float* __restrict__ l3_w2, const float* __restrict__ l3_b2,
+                                float* __restrict__ f0, float* __restrict__ c3) {
+  extern __shared__ float t1[];
+  const int h = threadIdx.x;
+  if (h < H) t1[h] = silu(rl0_b[h]);
+  __syncthreads();
+  if (h < H) {
+    float a = rl2_b[h];
+    for (int k = 0; k < H; k++) a = fmaf(rl2_w[h * H + k], t1[k], a);
+    f0[h] = a;
+  }
+  if (h == 0) {
+    float a = l3_b2[0];
+    for (int q = 0; q < Hq; q++) a = fmaf(l3_w2[q], silu(l3_b0[q]), a);
+    *c3 = a;
+  }
+}
+
+// (A)+(G prologue) z_emb = embedding(h); ne = LN0(neighbor_emb.embedding(h)).  leftnet.py:744, 82
+__global__ void k_node_init(int H, int C, const float* __restrict__ hin, const float* __restrict__ w_emb,
+                            const float* __restrict__ b_emb, const float* __restrict__ w_ne,
+                            const float* __restrict__ b_ne, float* __restrict__ z_emb, float* __restrict__ ne) {
+  __shared__ float sm[40];
+  __shared__ float x[32];
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h < C) x[h] = hin[(size_t)t * C + h];
+  __syncthreads();
+  const bool ok = h < H;
+  float z = 0.f, n = 0.f;
+  if (ok) {
+    z = b_emb[h]; n = b_ne[h];
+    for (int c = 0; c < C; c++) { z = fmaf(w_emb[h * C + c], x[c], z); n = fmaf(w_ne[h * C + c], x[c], n); }
+    z_emb[(size_t)t * H + h] = z;
+  }
+  float mean, rstd;
+  block_ln_stats(n, ok, H, sm, mean, rstd);
+  if (ok) ne[(size_t)t * H + h] = (n - mean) * rstd;
+}
+
+// (G) NeighborEmb: s_t = z_emb_t + sum_{e: tgt = t} f_e * ne[src]   (leftnet.py:81-89), all edges incl. masked (f = f0)
+__global__ void k_neighbor(int H, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
+                           const int* __restrict__ rev, const int* __restrict__ act_pos,
+                           const float* __restrict__ f_act, const float* __restrict__ f0,
+                           const float* __restrict__ z_emb, const float* __restrict__ ne, float* __restrict__ s) {
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  float acc = z_emb[(size_t)t * H + h];
+  const float f0h = f0[h];
+  for (int e = row_ptr[t]; e < row_ptr[t + 1]; e++) {
+    const int p = act_pos[rev[e]];
+    const float fv = p >= 0 ? f_act[(size_t)p * H + h] : f0h;
+    acc = fmaf(fv, ne[(size_t)ecol[e] * H + h], acc);
+  }
+  s[(size_t)t * H + h] = acc;
+}
+
+// row-wise LayerNorm variants.  x: [rows, H] (ldx).  y = act(LN(x (+ add)) * gamma + beta) -> out (ldo)
+__global__ void k_layernorm(int H, const float* __restrict__ x, int ldx, const float* __restrict__ add,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, int act_silu,
+                            float* __restrict__ out, int ldo) {
+  __shared__ float sm[40];
+  const int t = blockIdx.x, h = threadIdx.x;
+  const bool ok = h < H;
+  float v = 0.f;
+  if (ok) {
+    v = x[(size_t)t * ldx + h];
+    if (add) v += add[(size_t)t * H + h];
+  }
+  float mean, rstd;
+  block_ln_stats(v, ok, H, sm, mean, rstd);
+  if (ok) {
+    float y = (v - mean) * rstd;
+    if (gamma) y = y * gamma[h] + beta[h];
+    if (act_silu) y = silu(y);
+    out[(size_t)t * ldo + h] = y;
+  }
+}
+
+// (H) CFConvS2V aggregation: NE1_t[c,:] = sum_{e: tgt = t, active} f_e * u_e[c] * q[src]   (leftnet.py:116-125)
+__global__ void k_s2v(int H, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
+                      const int* __restrict__ rev, const int* __restrict__ act_pos, const float* __restrict__ f_act,
+                      const float4* __restrict__ geo, const float* __restrict__ q, float* __restrict__ NE1) {
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int e = row_ptr[t]; e < row_ptr[t + 1]; e++) {
+    const int r = rev[e], p = act_pos[r];
+    if (p < 0) continue;
+    const float fq = f_act[(size_t)p * H + h] * q[(size_t)ecol[e] * H + h];
+    const float4 g = geo[r];
+    a0 = fmaf(fq, g.x, a0); a1 = fmaf(fq, g.y, a1); a2 = fmaf(fq, g.z, a2);
+  }
+  float* o = NE1 + (size_t)t * 3 * H;
+  o[h] = a0; o[H + h] = a1; o[2 * H + h] = a2;
+}
+
+// (I) initial edge state e0 = [ (sc3 | sc4) * rb | f | rbf ]  (leftnet.py:792-809).  One block per edge.
+// Masked edges carry the constant [c3 .. | f0 | 0].
+__global__ void k_edge_init(int H, int R, int Hq, int reflect, const int* __restrict__ esrc,
+                            const int* __restrict__ ecol, const int* __restrict__ act_pos,
+                            const float* __restrict__ pf, const float4* __restrict__ geo, const float* __restrict__ rb,
+                            const float* __restrict__ NE1, const float* __restrict__ f_act,
+                            const float* __restrict__ rbf_act, const float* __restrict__ f0,
+                            const float* __restrict__ c3, const float* __restrict__ l3_w0,
+                            const float* __restrict__ l3_b0, const float* __restrict__ l3_w2,
+                            const float* __restrict__ l3_b2, float* __restrict__ ew) {
+  extern __shared__ float sw[];  // w0[Hq*3], b0[Hq], w2[Hq]
+  const int e = blockIdx.x, h = threadIdx.x, D = 3 * H + R;
+  float* out = ew + (size_t)e * D;
+  const int p = act_pos[e];
+  if (p < 0) {
+    if (h < H) { const float c = *c3; out[h] = c; out[H + h] = c; out[2 * H + h] = f0[h]; }
+    for (int r = h; r < R; r += blockDim.x) out[3 * H + r] = 0.f;
+    return;
+  }
+  for (int k = h; k < Hq * 3; k += blockDim.x) sw[k] = l3_w0[k];
+  for (int k = h; k < Hq; k += blockDim.x) { sw[Hq * 3 + k] = l3_b0[k]; sw[Hq * 4 + k] = l3_w2[k]; }
+  __syncthreads();
+  for (int r = h; r < R; r += blockDim.x) out[3 * H + r] = rbf_act[(size_t)p * R + r];
+  if (h >= H) return;
+  const int i = esrc[e], j = ecol[e];
+  const float4 g = geo[e];
+  // edge frame columns: u (unit diff), c (unit cross of pos_frame_i x pos_frame_j), v = u x c   (:693-705)
+  const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2];
+  const float bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
+  float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+  const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
+  cx *= cinv; cy *= cinv; cz *= cinv;
+  const float vx = g.y * cz - g.z * cy, vy = g.z * cx - g.x * cz, vz = g.x * cy - g.y * cx;
+  const float rbe = rb[e], b2 = l3_b2[0];
+  const float* ni = NE1 + (size_t)i * 3 * H;
+  const float* nj = NE1 + (size_t)j * 3 * H;
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    const float* n = side ? nj : ni;
+    const float n0 = n[h], n1 = n[H + h], n2 = n[2 * H + h];
+    const float s0 = n0 * g.x + n1 * g.y + n2 * g.z;
+    float s1 = n0 * cx + n1 * cy + n2 * cz;
+    const float s2 = n0 * vx + n1 * vy + n2 * vz;
+    if (reflect) s1 = fabsf(s1);
+    float acc = b2;
+    for (int k = 0; k < Hq; k++) {
+      const float u = fmaf(sw[k * 3], s0, fmaf(sw[k * 3 + 1], s1, fmaf(sw[k * 3 + 2], s2, sw[Hq * 3 + k])));
+      acc = fmaf(sw[Hq * 4 + k], silu(u), acc);
+    }
+    out[side * H + h] = (acc + s0) * rbe;
+  }
+  out[2 * H + h] = f_act[(size_t)p * H + h];
+}
+
+// GCL attention gate + mean aggregation at the edge source (leftnet.py:169-183, util_funcs.py:27-45).
+// One block per node; warps take the row's edges round-robin.  m2 is scaled in place by its gate.
+__global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restrict__ m2,
+                          const float* __restrict__ w_att, const float* __restrict__ b_att, float* __restrict__ xa,
+                          int ldxa) {
+  extern __shared__ float part[];  // [nw][H]
+  const int t = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.f;
+  const float ba = b_att[0];
+  for (int e = r0 + w; e < r1; e += nw) {
+    float* row = m2 + (size_t)e * H;
+    float v[8], d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int h = lane + 32 * k;
+      v[k] = h < H ? row[h] : 0.f;
+      d = fmaf(v[k], h < H ? w_att[h] : 0.f, d);
+    }
+    d = warp_sum(d);
+    const float att = silu(d + ba);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int h = lane + 32 * k;
+      if (h < H) { const float m = v[k] * att; row[h] = m; acc[k] += m; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int h = lane + 32 * k;
+    if (h < H) part[w * H + h] = acc[k];
+  }
+  __syncthreads();
+  const int h = threadIdx.x;
+  if (h < H) {
+    float s = 0.f;
+    for (int ww = 0; ww < nw; ww++) s += part[ww * H + h];
+    const int cnt = r1 - r0;
+    xa[(size_t)t * ldxa + H + h] = s / (float)(cnt > 0 ? cnt : 1);
+  }
+}
+
+// EquiMessage message + aggregation at the edge target + residual (leftnet.py:263-284, 857-859).
+// One block per target node t; walks row t and uses the transposed edge r = (a -> t).
+__global__ void k_equi_reduce(int H, int reflect, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
+                              const int* __restrict__ rev, const int* __restrict__ act_pos,
+                              const float* __restrict__ G, const float* __restrict__ X,
+                              const float4* __restrict__ geo, const float* __restrict__ pf,
+                              const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
+  const float* Xt = X + (size_t)t * 3 * H;
+  const float x0 = Xt[h], x1 = Xt[H + h], x2 = Xt[2 * H + h];
+  float dx = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  for (int e = row_ptr[t]; e < row_ptr[t + 1]; e++) {
+    const int r = rev[e], p = act_pos[r];
+    if (p < 0) continue;  // masked edges contribute exactly 0 (rbf_proj has no bias, rbf = 0)
+    const int a = ecol[e];
+    const float* g = G + (size_t)p * 3 * H;
+    const float* Xa = X + (size_t)a * 3 * H;
+    const float al = (Xa[h] + x0) * g[h];
+    const float be = (Xa[H + h] + x1) * g[H + h] * inv_sqrt_3;
+    const float ga = (Xa[2 * H + h] + x2) * g[2 * H + h];
+    const float4 u = geo[r];
+    const float* va = vec_in + (size_t)a * 3 * H;
+    float m0 = fmaf(va[h], be, ga * u.x), m1 = fmaf(va[H + h], be, ga * u.y), m2 = fmaf(va[2 * H + h], be, ga * u.z);
+    if (!reflect) {  // + x * edge_cross (leftnet.py:268-269); cross of pos_frame_a x pos_frame_t, unit
+      const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
+      const float bx = pf[t * 3], by = pf[t * 3 + 1], bz = pf[t * 3 + 2];
+      float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
+      m0 = fmaf(al, cx * cinv, m0); m1 = fmaf(al, cy * cinv, m1); m2 = fmaf(al, cz * cinv, m2);
+    }
+    dx += al;
+    d0 = fmaf(m0, inv_sqrt_h, d0); d1 = fmaf(m1, inv_sqrt_h, d1); d2 = fmaf(m2, inv_sqrt_h, d2);
+  }
+  const size_t o = (size_t)t * 3 * H;
+  s[(size_t)t * H + h] = (s[(size_t)t * H + h] + dx) * inv_sqrt_2;
+  vec_out[o + h] = vec_in[o + h] + d0;
+  vec_out[o + H + h] = vec_in[o + H + h] + d1;
+  vec_out[o + 2 * H + h] = vec_in[o + 2 * H + h] + d2;
+}
+
+// EquiUpdate scalarisation on the node frame + lin3 (3->48->8->1) + vec_dot  (leftnet.py:326-336)
+__global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, const float* __restrict__ nodeframe,
+                             const float* __restrict__ s, const float* __restrict__ w0, const float* __restrict__ b0,
+                             const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w4,
+                             const float* __restrict__ b4, float* __restrict__ sx, float* __restrict__ vd) {
+  __shared__ float W0[48 * 3], B0[48], W2[8 * 48], B2[8], W4[8];
+  for (int k = threadIdx.x; k < 144; k += blockDim.x) W0[k] = w0[k];
+  for (int k = threadIdx.x; k < 48; k += blockDim.x) B0[k] = b0[k];
+  for (int k = threadIdx.x; k < 384; k += blockDim.x) W2[k] = w2[k];
+  for (int k = threadIdx.x; k < 8; k += blockDim.x) { B2[k] = b2[k]; W4[k] = w4[k]; }
+  __syncthreads();
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  const float* nf = nodeframe + (size_t)t * 9;
+  const float* vp = VP + (size_t)t * 3 * 2 * H;
+  const float v10 = vp[h], v11 = vp[2 * H + h], v12 = vp[4 * H + h];
+  const float v20 = vp[H + h], v21 = vp[3 * H + h], v22 = vp[5 * H + h];
+  const float s0 = v10 * nf[0] + v11 * nf[3] + v12 * nf[6];
+  float s1 = v10 * nf[1] + v11 * nf[4] + v12 * nf[7];
+  const float s2 = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
+  if (reflect) s1 = fabsf(s1);
+  float u[48];
+#pragma unroll
+  for (int k = 0; k < 48; k++)
+    u[k] = silu(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
+  float out = b4[0];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float a = B2[q];
+#pragma unroll
+    for (int k = 0; k < 48; k++) a = fmaf(W2[q * 48 + k], u[k], a);
+    out = fmaf(W4[q], silu(a), out);
+  }
+  sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
+  sx[(size_t)t * 2 * H + H + h] = out;
+  vd[(size_t)t * H + h] = (v10 * v20 + v11 * v21 + v12 * v22) * rsqrtf((float)H);
+}
+
+// EquiUpdate apply: s += (xv1 + xv2 + vec_dot)/sqrt2 ; vec += xv3 * vec2   (leftnet.py:338-346, 863-864)
+__global__ void k_upd_apply(int H, const float* __restrict__ XV, const float* __restrict__ VP,
+                            const float* __restrict__ vd, float* __restrict__ s, float* __restrict__ vec) {
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  const float* xv = XV + (size_t)t * 3 * H;
+  const float* vp = VP + (size_t)t * 3 * 2 * H;
+  s[(size_t)t * H + h] += (xv[h] + xv[H + h] + vd[(size_t)t * H + h]) * 0.70710678118654752f;
+  const float x3 = xv[2 * H + h];
+  float* v = vec + (size_t)t * 3 * H;
+  v[h] = fmaf(x3, vp[H + h], v[h]);
+  v[H + h] = fmaf(x3, vp[3 * H + h], v[H + h]);
+  v[2 * H + h] = fmaf(x3, vp[5 * H + h], v[2 * H + h]);
+}
+
+// GatedEquivariantBlock prologue: sn = [ s | ||vec1_proj(vec)||_xyz ]   (leftnet.py:567-570)
+__global__ void k_out_norm(int H, const float* __restrict__ O1, const float* __restrict__ s, float* __restrict__ sn) {
+  const int t = blockIdx.x, h = threadIdx.x;
+  if (h >= H) return;
+  const float* o = O1 + (size_t)t * 3 * H;
+  const float a = o[h], b = o[H + h], c = o[2 * H + h];
+  sn[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
+  sn[(size_t)t * 2 * H + H + h] = sqrtf(a * a + b * b + c * c);
+}
+
+// Output head: gate = update_net.2(t)[1]; dpos = gate * vec2_proj(vec); h_out = embedding_out(s)  (:571-572, 878-887)
+__global__ void k_final(int H, int C, const float* __restrict__ tu, const float* __restrict__ w_u2,
+                        const float* __restrict__ b_u2, const float* __restrict__ vec, const float* __restrict__ w_o2,
+                        const float* __restrict__ s, const float* __restrict__ w_eout, const float* __restrict__ b_eout,
+                        float* __restrict__ dpos, float* __restrict__ h_out) {
+  __shared__ float sm[40];
+  const int t = blockIdx.x, h = threadIdx.x;
+  const bool ok = h < H;
+  const float tv = ok ? tu[(size_t)t * H + h] : 0.f;
+  const float gate = block_sum(ok ? tv * w_u2[H + h] : 0.f, sm) + b_u2[1];
+  const float* v = vec + (size_t)t * 3 * H;
+  const float wo = ok ? w_o2[h] : 0.f;
+  for (int c = 0; c < 3; c++) {
+    const float d = block_sum(ok ? v[c * H + h] * wo : 0.f, sm);
+    if (h == 0) dpos[t * 3 + c] = gate * d;
+  }
+  const float sv = ok ? s[(size_t)t * H + h] : 0.f;
+  for (int c = 0; c < C; c++) {
+    const float d = block_sum(ok ? sv * w_eout[c * H + h] : 0.f, sm);
+    if (h == 0) h_out[(size_t)t * C + c] = d + b_eout[c];
+  }
+}
+
+}  // namespace oard

@@ -1,0 +1,624 @@
+// liboard_b200.so — host orchestration + C ABI (include/oard.h) of the OA-ReactDiff LEFTNet hot path on B200.
+// No torch types here: plain pointers, cudart only.
+#include "../../include/oard.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+using namespace oard;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+struct WeightSpec { std::string name; int64_t numel; };
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct LayerW {
+  const float *e0w, *e0b, *e1w, *e1b, *n0w, *n0b, *n1w, *n1b, *eow, *eob, *attw, *attb, *glnw, *glnb;
+  const float *d0w, *d0b, *d2w, *d2b, *x0w, *x2w, *rbfw, *mlnw, *mlnb;
+  const float *vpw, *xv0w, *xv2w, *l0w, *l0b, *l2w, *l2b, *l4w, *l4b;
+};
+
+}  // namespace
+
+struct oard_handle {
+  oard_cfg cfg{};
+  int device = 0;
+  std::vector<WeightSpec> specs;
+  std::unordered_map<std::string, int> spec_idx;
+  std::vector<float*> wdev;
+  std::vector<char> wset;
+  bool committed = false;
+  // resolved weights
+  const float *emb_w, *emb_b, *eout_w, *eout_b, *means, *betas, *ne_w, *ne_b, *s2v_w, *s2v_b, *rl0_w, *rl0_b, *rl2_w,
+      *rl2_b, *l3_w0, *l3_b0, *l3_w2, *l3_b2, *pe0_w, *pe1_w, *o_v1w, *o_v2w, *o_u0w, *o_u0b, *o_u2w, *o_u2b;
+  std::vector<LayerW> L;
+  // plan
+  bool planned = false;
+  int N = 0, E = 0, NC = 0;
+  std::map<std::string, DevBuf> ws;  // named workspace buffers
+  size_t ws_bytes = 0;
+  // debug
+  bool debug = false;
+  std::map<std::string, DevBuf> snaps;
+  int64_t launches = 0;
+
+  template <typename T>
+  T* buf(const char* name) { return reinterpret_cast<T*>(ws.at(name).p); }
+};
+
+static void build_specs(oard_handle* h) {
+  const int H = h->cfg.hidden_channels, R = h->cfg.num_radial, C = h->cfg.in_hidden_channels, D = 3 * H + R;
+  auto add = [&](const std::string& n, int64_t numel) {
+    h->spec_idx[n] = (int)h->specs.size();
+    h->specs.push_back({n, numel});
+  };
+  auto lin = [&](const std::string& n, int out, int in, bool bias = true) {
+    add(n + ".weight", (int64_t)out * in);
+    if (bias) add(n + ".bias", out);
+  };
+  lin("embedding", H, C);
+  lin("embedding_out", C, H);
+  add("radial_emb.means", R);
+  add("radial_emb.betas", R);
+  lin("neighbor_emb.embedding", H, C);
+  lin("s2v.lin1.0", H, H);
+  lin("radial_lin.0", H, R);
+  lin("radial_lin.2", H, H);
+  lin("lin3.0", H / 4, 3);
+  lin("lin3.2", 1, H / 4);
+  lin("pos_expansion.mlp.0.linear", H / 2, 3, false);
+  lin("pos_expansion.mlp.1.linear", H, H / 2, false);
+  for (int l = 0; l < h->cfg.num_layers; l++) {
+    const std::string g = "gcl_layers." + std::to_string(l) + ".";
+    lin(g + "edge_mlp.mlp.0.linear", H, 2 * H + D);
+    lin(g + "edge_mlp.mlp.1.linear", H, H);
+    lin(g + "node_mlp.mlp.0.linear", H, 2 * H);
+    lin(g + "node_mlp.mlp.1.linear", H, H);
+    lin(g + "edge_out_trans.mlp.0.linear", D, H);
+    lin(g + "att_mlp.mlp.0.linear", 1, H);
+    add(g + "x_layernorm.weight", H);
+    add(g + "x_layernorm.bias", H);
+    const std::string m = "message_layers." + std::to_string(l) + ".";
+    lin(m + "dir_proj.0", 3 * H, D);
+    lin(m + "dir_proj.2", 3 * H, 3 * H);
+    lin(m + "x_proj.0", H, H, false);
+    lin(m + "x_proj.2", 3 * H, H, false);
+    lin(m + "rbf_proj", 3 * H, R, false);
+    add(m + "x_layernorm.weight", H);
+    add(m + "x_layernorm.bias", H);
+    const std::string u = "update_layers." + std::to_string(l) + ".";
+    lin(u + "vec_proj", 2 * H, H, false);
+    lin(u + "xvec_proj.0", H, 2 * H, false);
+    lin(u + "xvec_proj.2", 3 * H, H, false);
+    lin(u + "lin3.0", 48, 3);
+    lin(u + "lin3.2", 8, 48);
+    lin(u + "lin3.4", 1, 8);
+  }
+  const std::string o = "out_pos.output_network.0.";
+  lin(o + "vec1_proj", H, H, false);
+  lin(o + "vec2_proj", 1, H, false);
+  lin(o + "update_net.0", H, 2 * H);
+  lin(o + "update_net.2", 2, H);
+  h->wdev.assign(h->specs.size(), nullptr);
+  h->wset.assign(h->specs.size(), 0);
+}
+
+extern "C" int oard_abi_version(void) { return 1; }
+extern "C" const char* oard_last_error(void) { return g_err.c_str(); }
+
+extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
+  if (!cfg || !out) return fail(OARD_EINVAL, "null argument");
+  if (cfg->hidden_channels <= 0 || cfg->hidden_channels > 256 || cfg->hidden_channels % 4)
+    return fail(OARD_EINVAL, "hidden_channels must be a multiple of 4 in (0,256], got %d", cfg->hidden_channels);
+  if (cfg->in_hidden_channels <= 0 || cfg->in_hidden_channels > 32)
+    return fail(OARD_EINVAL, "in_hidden_channels must be in (0,32]");
+  if (cfg->num_radial <= 0 || cfg->num_layers <= 0) return fail(OARD_EINVAL, "num_radial/num_layers must be > 0");
+  if (!cfg->legacy) return fail(OARD_EINVAL, "legacy=False (nn_vector node frame) is not implemented");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(OARD_ECUDA, "device %d not available (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  auto* h = new oard_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  build_specs(h);
+  for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
+  *out = h;
+  return OARD_OK;
+}
+
+static void free_map(std::map<std::string, DevBuf>& m) {
+  for (auto& kv : m)
+    if (kv.second.p) cudaFree(kv.second.p);
+  m.clear();
+}
+
+extern "C" void oard_destroy(oard_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (float* p : h->wdev)
+    if (p) cudaFree(p);
+  free_map(h->ws);
+  free_map(h->snaps);
+  delete h;
+}
+
+extern "C" int oard_num_weights(const oard_handle* h) { return h ? (int)h->specs.size() : 0; }
+extern "C" const char* oard_weight_name(const oard_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->specs.size()) ? h->specs[i].name.c_str() : nullptr;
+}
+extern "C" int64_t oard_weight_numel(const oard_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->specs.size()) ? h->specs[i].numel : -1;
+}
+
+extern "C" int oard_set_weight(oard_handle* h, const char* name, const float* data, int64_t numel, int is_device,
+                               void* stream) {
+  if (!h || !name || !data) return fail(OARD_EINVAL, "null argument");
+  auto it = h->spec_idx.find(name);
+  if (it == h->spec_idx.end()) return fail(OARD_EINVAL, "unknown weight '%s'", name);
+  const WeightSpec& s = h->specs[it->second];
+  if (numel != s.numel) return fail(OARD_EINVAL, "weight '%s': expected %lld elements, got %lld", name,
+                                    (long long)s.numel, (long long)numel);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->wdev[it->second], data, numel * sizeof(float),
+                     is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  h->wset[it->second] = 1;
+  h->committed = false;
+  return OARD_OK;
+}
+
+extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  for (size_t i = 0; i < h->specs.size(); i++)
+    if (!h->wset[i]) return fail(OARD_EMISSING, "weight '%s' was never set", h->specs[i].name.c_str());
+  auto W = [&](const std::string& n) -> const float* { return h->wdev[h->spec_idx.at(n)]; };
+  h->emb_w = W("embedding.weight"); h->emb_b = W("embedding.bias");
+  h->eout_w = W("embedding_out.weight"); h->eout_b = W("embedding_out.bias");
+  h->means = W("radial_emb.means"); h->betas = W("radial_emb.betas");
+  h->ne_w = W("neighbor_emb.embedding.weight"); h->ne_b = W("neighbor_emb.embedding.bias");
+  h->s2v_w = W("s2v.lin1.0.weight"); h->s2v_b = W("s2v.lin1.0.bias");
+  h->rl0_w = W("radial_lin.0.weight"); h->rl0_b = W("radial_lin.0.bias");
+  h->rl2_w = W("radial_lin.2.weight"); h->rl2_b = W("radial_lin.2.bias");
+  h->l3_w0 = W("lin3.0.weight"); h->l3_b0 = W("lin3.0.bias");
+  h->l3_w2 = W("lin3.2.weight"); h->l3_b2 = W("lin3.2.bias");
+  h->pe0_w = W("pos_expansion.mlp.0.linear.weight"); h->pe1_w = W("pos_expansion.mlp.1.linear.weight");
+  const std::string o = "out_pos.output_network.0.";
+  h->o_v1w = W(o + "vec1_proj.weight"); h->o_v2w = W(o + "vec2_proj.weight");
+  h->o_u0w = W(o + "update_net.0.weight"); h->o_u0b = W(o + "update_net.0.bias");
+  h->o_u2w = W(o + "update_net.2.weight"); h->o_u2b = W(o + "update_net.2.bias");
+  h->L.resize(h->cfg.num_layers);
+  for (int l = 0; l < h->cfg.num_layers; l++) {
+    LayerW& w = h->L[l];
+    const std::string g = "gcl_layers." + std::to_string(l) + ".";
+    w.e0w = W(g + "edge_mlp.mlp.0.linear.weight"); w.e0b = W(g + "edge_mlp.mlp.0.linear.bias");
+    w.e1w = W(g + "edge_mlp.mlp.1.linear.weight"); w.e1b = W(g + "edge_mlp.mlp.1.linear.bias");
+    w.n0w = W(g + "node_mlp.mlp.0.linear.weight"); w.n0b = W(g + "node_mlp.mlp.0.linear.bias");
+    w.n1w = W(g + "node_mlp.mlp.1.linear.weight"); w.n1b = W(g + "node_mlp.mlp.1.linear.bias");
+    w.eow = W(g + "edge_out_trans.mlp.0.linear.weight"); w.eob = W(g + "edge_out_trans.mlp.0.linear.bias");
+    w.attw = W(g + "att_mlp.mlp.0.linear.weight"); w.attb = W(g + "att_mlp.mlp.0.linear.bias");
+    w.glnw = W(g + "x_layernorm.weight"); w.glnb = W(g + "x_layernorm.bias");
+    const std::string m = "message_layers." + std::to_string(l) + ".";
+    w.d0w = W(m + "dir_proj.0.weight"); w.d0b = W(m + "dir_proj.0.bias");
+    w.d2w = W(m + "dir_proj.2.weight"); w.d2b = W(m + "dir_proj.2.bias");
+    w.x0w = W(m + "x_proj.0.weight"); w.x2w = W(m + "x_proj.2.weight");
+    w.rbfw = W(m + "rbf_proj.weight");
+    w.mlnw = W(m + "x_layernorm.weight"); w.mlnb = W(m + "x_layernorm.bias");
+    const std::string u = "update_layers." + std::to_string(l) + ".";
+    w.vpw = W(u + "vec_proj.weight"); w.xv0w = W(u + "xvec_proj.0.weight"); w.xv2w = W(u + "xvec_proj.2.weight");
+    w.l0w = W(u + "lin3.0.weight"); w.l0b = W(u + "lin3.0.bias");
+    w.l2w = W(u + "lin3.2.weight"); w.l2b = W(u + "lin3.2.bias");
+    w.l4w = W(u + "lin3.4.weight"); w.l4b = W(u + "lin3.4.bias");
+  }
+  (void)stream;
+  h->committed = true;
+  return OARD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+static int ws_alloc(oard_handle* h, const char* name, size_t bytes) {
+  DevBuf b;
+  b.bytes = bytes ? bytes : 16;
+  cudaError_t e = cudaMalloc(&b.p, b.bytes);
+  if (e != cudaSuccess) return fail(OARD_ECUDA, "cudaMalloc(%s, %zu): %s", name, b.bytes, cudaGetErrorString(e));
+  h->ws[name] = b;
+  h->ws_bytes += b.bytes;
+  return OARD_OK;
+}
+
+extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const int64_t* ei) {
+  if (!h || (!ei && n_edges > 0)) return fail(OARD_EINVAL, "null argument");
+  if (n_nodes <= 0 || n_nodes > (1 << 28) || n_edges < 0 || n_edges > (int64_t)1 << 30)
+    return fail(OARD_EINVAL, "bad sizes N=%lld E=%lld", (long long)n_nodes, (long long)n_edges);
+  CU(cudaSetDevice(h->device));
+  const int N = (int)n_nodes, E = (int)n_edges;
+  const int64_t* src = ei;
+  const int64_t* dst = ei + n_edges;
+  std::vector<int> row_ptr(N + 1, 0), esrc(E), ecol(E), rev(E);
+  for (int e = 0; e < E; e++) {
+    if (src[e] < 0 || src[e] >= N || dst[e] < 0 || dst[e] >= N)
+      return fail(OARD_EGRAPH, "edge %d (%lld,%lld) out of range", e, (long long)src[e], (long long)dst[e]);
+    if (e > 0 && src[e] < src[e - 1]) return fail(OARD_EGRAPH, "edge list not grouped by source at edge %d", e);
+    esrc[e] = (int)src[e];
+    ecol[e] = (int)dst[e];
+    row_ptr[src[e] + 1]++;
+  }
+  for (int i = 0; i < N; i++) row_ptr[i + 1] += row_ptr[i];
+  {
+    std::unordered_map<uint64_t, int> pos;
+    pos.reserve((size_t)E * 2);
+    for (int e = 0; e < E; e++) {
+      const uint64_t key = ((uint64_t)esrc[e] << 32) | (uint32_t)ecol[e];
+      if (!pos.emplace(key, e).second) return fail(OARD_EGRAPH, "duplicate edge (%d,%d)", esrc[e], ecol[e]);
+    }
+    for (int e = 0; e < E; e++) {
+      auto it = pos.find(((uint64_t)ecol[e] << 32) | (uint32_t)esrc[e]);
+      if (it == pos.end()) return fail(OARD_EGRAPH, "graph not symmetric: (%d,%d) has no transpose", esrc[e], ecol[e]);
+      rev[e] = it->second;
+    }
+  }
+  // connected components of the unmasked graph (union-find); a reaction = one component
+  std::vector<int> parent(N);
+  std::iota(parent.begin(), parent.end(), 0);
+  auto find = [&](int x) {
+    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+    return x;
+  };
+  for (int e = 0; e < E; e++) {
+    const int a = find(esrc[e]), b = find(ecol[e]);
+    if (a != b) parent[std::max(a, b)] = std::min(a, b);
+  }
+  std::vector<int> comp_of(N, -1), comp_ptr, comp_nodes(N), node_local(N);
+  int NC = 0;
+  std::vector<int> root_comp(N, -1), count;
+  for (int i = 0; i < N; i++) {
+    const int r = find(i);
+    if (root_comp[r] < 0) { root_comp[r] = NC++; count.push_back(0); }
+    comp_of[i] = root_comp[r];
+    count[comp_of[i]]++;
+  }
+  comp_ptr.assign(NC + 1, 0);
+  for (int c = 0; c < NC; c++) {
+    if (count[c] > 256) return fail(OARD_EGRAPH, "component %d has %d nodes (max 256)", c, count[c]);
+    comp_ptr[c + 1] = comp_ptr[c] + count[c];
+  }
+  std::vector<int> fill(comp_ptr.begin(), comp_ptr.end() - 1);
+  for (int i = 0; i < N; i++) {  // ascending node id inside each component
+    const int c = comp_of[i];
+    node_local[i] = fill[c] - comp_ptr[c];
+    comp_nodes[fill[c]++] = i;
+  }
+
+  free_map(h->ws);
+  free_map(h->snaps);
+  h->ws_bytes = 0;
+  h->planned = false;
+  const size_t H = h->cfg.hidden_channels, R = h->cfg.num_radial, D = 3 * H + R, Nn = N, Ee = E > 0 ? E : 1;
+  struct { const char* n; size_t b; } allocs[] = {
+      {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
+      {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
+      {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"row_cnt", Nn * 4},
+      {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
+      {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
+      {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
+      {"NE1", Nn * 3 * H * 4}, {"pe_t", Nn * (H / 2) * 4}, {"pe", Nn * H * 4}, {"xa", Nn * 2 * H * 4},
+      {"PQ", Nn * 2 * H * 4}, {"tN", Nn * H * 4}, {"X", Nn * 3 * H * 4}, {"vecA", Nn * 3 * H * 4},
+      {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
+      {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
+      {"ew", Ee * D * 4}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"d1", Ee * 3 * H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
+  };
+  for (auto& a : allocs) {
+    const int rc = ws_alloc(h, a.n, a.b);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpy(h->buf<int>("row_ptr"), row_ptr.data(), (Nn + 1) * 4, cudaMemcpyHostToDevice));
+  if (E) {
+    CU(cudaMemcpy(h->buf<int>("esrc"), esrc.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->buf<int>("ecol"), ecol.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->buf<int>("rev"), rev.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+  }
+  CU(cudaMemcpy(h->buf<int>("comp_ptr"), comp_ptr.data(), (size_t)(NC + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->buf<int>("comp_nodes"), comp_nodes.data(), Nn * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->buf<int>("node_local"), node_local.data(), Nn * 4, cudaMemcpyHostToDevice));
+  h->N = N; h->E = E; h->NC = NC;
+  h->planned = true;
+  return OARD_OK;
+}
+
+extern "C" size_t oard_workspace_bytes(const oard_handle* h) { return h ? h->ws_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------ forward
+static int snap(oard_handle* h, const std::string& name, const void* p, size_t bytes, cudaStream_t st) {
+  if (!h->debug) return OARD_OK;
+  auto it = h->snaps.find(name);
+  if (it == h->snaps.end() || it->second.bytes < bytes) {
+    if (it != h->snaps.end() && it->second.p) cudaFree(it->second.p);
+    DevBuf b;
+    b.bytes = bytes ? bytes : 16;
+    CU(cudaMalloc(&b.p, b.bytes));
+    h->snaps[name] = b;
+    it = h->snaps.find(name);
+  }
+  it->second.bytes = bytes ? bytes : 16;
+  CU(cudaMemcpyAsync(it->second.p, p, bytes, cudaMemcpyDeviceToDevice, st));
+  return OARD_OK;
+}
+
+#define KCHECK()                                                                                            \
+  do {                                                                                                      \
+    cudaError_t e_ = cudaGetLastError();                                                                    \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    h->launches++;                                                                                          \
+  } while (0)
+#define SNAP(name, ptr, bytes)                                       \
+  do {                                                               \
+    const int rc_ = snap(h, name, ptr, bytes, st);                   \
+    if (rc_) return rc_;                                             \
+  } while (0)
+
+static GemmArgs mk(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K) {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
+                            float* dpos, void* stream) {
+  if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
+  if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
+  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  const oard_cfg& c = h->cfg;
+  const int N = h->N, E = h->E, H = c.hidden_channels, R = c.num_radial, C = c.in_hidden_channels, D = 3 * H + R;
+  const int HB = (H + 31) / 32 * 32, Hq = H / 4;
+  if (!c.object_aware) sub = nullptr;
+
+  int *row_ptr = h->buf<int>("row_ptr"), *esrc = h->buf<int>("esrc"), *ecol = h->buf<int>("ecol"),
+      *rev = h->buf<int>("rev");
+  uint8_t* mask = h->buf<uint8_t>("mask");
+  float4* geo = h->buf<float4>("geo");
+  float* rb = h->buf<float>("rb");
+  int *act_idx = h->buf<int>("act_idx"), *act_pos = h->buf<int>("act_pos"), *n_act = h->buf<int>("n_act");
+  float *pf = h->buf<float>("pf"), *nodeframe = h->buf<float>("nodeframe"), *pos_prjt = h->buf<float>("pos_prjt");
+  float *f0 = h->buf<float>("f0"), *c3 = h->buf<float>("c3");
+  float *z_emb = h->buf<float>("z_emb"), *ne = h->buf<float>("ne"), *s = h->buf<float>("s"),
+        *tmpH = h->buf<float>("tmpH"), *q = h->buf<float>("q"), *NE1 = h->buf<float>("NE1"),
+        *pe_t = h->buf<float>("pe_t"), *pe = h->buf<float>("pe"), *xa = h->buf<float>("xa"), *PQ = h->buf<float>("PQ"),
+        *tN = h->buf<float>("tN"), *X = h->buf<float>("X"), *VP = h->buf<float>("VP"), *sx = h->buf<float>("sx"),
+        *vd = h->buf<float>("vd"), *XV = h->buf<float>("XV"), *O1 = h->buf<float>("O1"), *sn = h->buf<float>("sn"),
+        *tu = h->buf<float>("tu");
+  float *vec = h->buf<float>("vecA"), *vec2 = h->buf<float>("vecB");
+  float *ew = h->buf<float>("ew"), *hid1 = h->buf<float>("hid1"), *m2 = h->buf<float>("m2"),
+        *rbf_act = h->buf<float>("rbf_act"), *f_act = h->buf<float>("f_act"), *d1 = h->buf<float>("d1"),
+        *RB = h->buf<float>("RB"), *G = h->buf<float>("G");
+#define GEMM(g)                                                                                              \
+  do {                                                                                                       \
+    cudaError_t e_ = launch_gemm_simt(g, st);                                                                \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    h->launches++;                                                                                           \
+  } while (0)
+
+  // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
+  if (E) { k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
+  k_group_frame<256><<<h->NC, 128, 0, st>>>(h->buf<int>("comp_ptr"), h->buf<int>("comp_nodes"),
+                                            h->buf<int>("node_local"), row_ptr, ecol, mask, pos, pf, nodeframe, pos_prjt,
+                                            h->buf<int>("owner"), h->buf<uint8_t>("opener"));
+  KCHECK();
+  if (h->debug) {
+    k_group_ids<<<1, 1024, 0, st>>>(N, h->buf<int>("owner"), h->buf<uint8_t>("opener"), h->buf<int>("rank_tmp"),
+                                    h->buf<int>("group"));
+    KCHECK();
+  }
+  k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, pf, c.cutoff, geo, rb,
+                                                    h->buf<int>("row_cnt"));
+  KCHECK();
+  k_scan_rows<<<1, 1024, 0, st>>>(N, h->buf<int>("row_cnt"), h->buf<int>("row_act_ptr"), n_act);
+  KCHECK();
+  k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
+  KCHECK();
+  if (E) {
+    const size_t tot = (size_t)E * R;
+    k_rbf<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_act, E, R, act_idx, geo, h->means, h->betas, c.cutoff,
+                                                         rbf_act);
+    KCHECK();
+    // radial_lin on active edges: f = rb * (W2 SiLU(W1 rbf + b1) + b2)   (leftnet.py:784-786)
+    GemmArgs g = mk(rbf_act, R, h->rl0_w, R, hid1, H, E, H, R);
+    g.m_dev = n_act; g.bias = h->rl0_b; g.act = 1;
+    GEMM(g);
+    g = mk(hid1, H, h->rl2_w, H, f_act, H, E, H, H);
+    g.m_dev = n_act; g.bias = h->rl2_b; g.rowscale = rb; g.rsidx = act_idx;
+    GEMM(g);
+  }
+  k_masked_consts<<<1, HB, H * sizeof(float), st>>>(H, Hq, h->rl0_b, h->rl2_w, h->rl2_b, h->l3_b0, h->l3_w2, h->l3_b2,
+                                                    f0, c3);
+  KCHECK();
+  k_node_init<<<N, HB, 0, st>>>(H, C, h_in, h->emb_w, h->emb_b, h->ne_w, h->ne_b, z_emb, ne);
+  KCHECK();
+  k_neighbor<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, f0, z_emb, ne, s);
+  KCHECK();
+  {
+    GemmArgs g = mk(s, H, h->s2v_w, H, tmpH, H, N, H, H);
+    g.bias = h->s2v_b;
+    GEMM(g);
+  }
+  k_layernorm<<<N, HB, 0, st>>>(H, tmpH, H, nullptr, nullptr, nullptr, 1, q, H);
+  KCHECK();
+  k_s2v<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, geo, q, NE1);
+  KCHECK();
+  if (E) {
+    k_edge_init<<<E, HB, Hq * 5 * sizeof(float), st>>>(H, R, Hq, c.reflect_equiv, esrc, ecol, act_pos, pf, geo, rb, NE1,
+                                                       f_act, rbf_act, f0, c3, h->l3_w0, h->l3_b0, h->l3_w2, h->l3_b2,
+                                                       ew);
+    KCHECK();
+  }
+  {  // pos_expansion(pos_prjt): shared weights and a layer-independent input -> evaluated once (leftnet.py:840-841)
+    GemmArgs g = mk(pos_prjt, 3, h->pe0_w, 3, pe_t, H / 2, N, H / 2, 3);
+    g.act = 1;
+    GEMM(g);
+    g = mk(pe_t, H / 2, h->pe1_w, H / 2, pe, H, N, H, H / 2);
+    GEMM(g);
+  }
+  if (h->debug) {
+    SNAP("mask", mask, (size_t)E); SNAP("group", h->buf<int>("group"), (size_t)N * 4);
+    SNAP("act_idx", act_idx, (size_t)E * 4); SNAP("n_act", n_act, 4); SNAP("pos_frame", pf, (size_t)N * 12);
+    SNAP("geo", geo, (size_t)E * 16); SNAP("rb", rb, (size_t)E * 4); SNAP("f_act", f_act, (size_t)E * H * 4);
+    SNAP("rbf_act", rbf_act, (size_t)E * R * 4); SNAP("s0", s, (size_t)N * H * 4);
+    SNAP("NE1", NE1, (size_t)N * 3 * H * 4); SNAP("e0", ew, (size_t)E * D * 4);
+    SNAP("nodeframe", nodeframe, (size_t)N * 36); SNAP("pos_prjt", pos_prjt, (size_t)N * 12);
+  }
+  CU(cudaMemsetAsync(vec, 0, (size_t)N * 3 * H * sizeof(float), st));
+
+  for (int l = 0; l < c.num_layers; l++) {
+    const LayerW& w = h->L[l];
+    const int ldw0 = 2 * H + D;
+    // ---- GCLMessage (leftnet.py:157-183).  W_a = [W_ai | W_aj | W_ae]: the x_i / x_j parts are per-node GEMMs.
+    k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
+    KCHECK();
+    GemmArgs g = mk(xa, 2 * H, w.e0w, ldw0, PQ, 2 * H, N, H, H);
+    g.bias = w.e0b;
+    GEMM(g);
+    g = mk(xa, 2 * H, w.e0w + H, ldw0, PQ + H, 2 * H, N, H, H);
+    GEMM(g);
+    if (E) {
+      g = mk(ew, D, w.e0w + 2 * H, ldw0, hid1, H, E, H, D);
+      g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
+      g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
+      g.act = 1;
+      GEMM(g);
+      g = mk(hid1, H, w.e1w, H, m2, H, E, H, H);
+      g.bias = w.e1b; g.act = 1;
+      GEMM(g);
+    }
+    k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
+    KCHECK();
+    g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
+    g.bias = w.n0b; g.act = 1;
+    GEMM(g);
+    g = mk(tN, H, w.n1w, H, s, H, N, H, H);
+    g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
+    GEMM(g);
+    if (E) {
+      g = mk(m2, H, w.eow, H, ew, D, E, D, H);
+      g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
+      GEMM(g);
+    }
+    // ---- EquiMessage (leftnet.py:244-289) on active edges only
+    k_layernorm<<<N, HB, 0, st>>>(H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
+    KCHECK();
+    g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
+    g.act = 1;
+    GEMM(g);
+    g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
+    GEMM(g);
+    if (E) {
+      g = mk(ew, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
+      g.aidx = act_idx; g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
+      GEMM(g);
+      g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
+      g.m_dev = n_act;
+      GEMM(g);
+      g = mk(d1, 3 * H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
+      g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
+      GEMM(g);
+    }
+    k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
+    KCHECK();
+    std::swap(vec, vec2);
+    if (h->debug) {
+      const std::string ls = std::to_string(l), l1 = std::to_string(l + 1);
+      SNAP("s_msg" + ls, s, (size_t)N * H * 4); SNAP("vec_msg" + ls, vec, (size_t)N * 3 * H * 4);
+      SNAP("e" + l1, ew, (size_t)E * D * 4);
+    }
+    // ---- EquiUpdate (leftnet.py:325-346)
+    if (c.update) {
+      g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
+      GEMM(g);
+      k_upd_scalar<<<N, HB, 0, st>>>(H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
+                                     vd);
+      KCHECK();
+      g = mk(sx, 2 * H, w.xv0w, 2 * H, tN, H, N, H, 2 * H);
+      g.act = 1;
+      GEMM(g);
+      g = mk(tN, H, w.xv2w, H, XV, 3 * H, N, 3 * H, H);
+      GEMM(g);
+      k_upd_apply<<<N, HB, 0, st>>>(H, XV, VP, vd, s, vec);
+      KCHECK();
+    }
+    if (h->debug) {
+      const std::string l1 = std::to_string(l + 1);
+      SNAP("s" + l1, s, (size_t)N * H * 4); SNAP("vec" + l1, vec, (size_t)N * 3 * H * 4);
+    }
+  }
+  // ---- output head (leftnet.py:566-576, 878-887)
+  GemmArgs g = mk(vec, H, h->o_v1w, H, O1, H, 3 * N, H, H);
+  GEMM(g);
+  k_out_norm<<<N, HB, 0, st>>>(H, O1, s, sn);
+  KCHECK();
+  g = mk(sn, 2 * H, h->o_u0w, 2 * H, tu, H, N, H, 2 * H);
+  g.bias = h->o_u0b; g.act = 1;
+  GEMM(g);
+  k_final<<<N, HB, 0, st>>>(H, C, tu, h->o_u2w, h->o_u2b, vec, h->o_v2w, s, h->eout_w, h->eout_b, dpos, h_out);
+  KCHECK();
+  return OARD_OK;
+}
+
+extern "C" int oard_set_debug(oard_handle* h, int on) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  h->debug = on != 0;
+  if (!on) free_map(h->snaps);
+  return OARD_OK;
+}
+
+extern "C" int64_t oard_debug_bytes(oard_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  auto it = h->snaps.find(name);
+  return it == h->snaps.end() ? -1 : (int64_t)it->second.bytes;
+}
+
+extern "C" int oard_debug_read(oard_handle* h, const char* name, void* dst, size_t bytes) {
+  if (!h || !name || !dst) return fail(OARD_EINVAL, "null argument");
+  auto it = h->snaps.find(name);
+  if (it == h->snaps.end()) return fail(OARD_EINVAL, "no snapshot '%s' (debug off or forward not run)", name);
+  if (bytes > it->second.bytes) return fail(OARD_EINVAL, "snapshot '%s' has %zu bytes, asked %zu", name, it->second.bytes, bytes);
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(dst, it->second.p, bytes, cudaMemcpyDeviceToHost));
+  return OARD_OK;
+}
+
+extern "C" int64_t oard_last_launch_count(const oard_handle* h) { return h ? h->launches : 0; }

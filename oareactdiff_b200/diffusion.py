@@ -1,0 +1,232 @@
+"""`EnVariationalDiffusion` sampling API with the reference's names and signatures
+(oa_reactdiff/diffusion/en_diffusion.py:26-52, 260-304, 459-718, 722-883, 1050-1074).
+
+Host-side PyTorch, as the north star prescribes: tensor plumbing and the noise schedule live here, the denoiser
+evaluated at every step is the CUDA LEFTNet behind `dynamics`.  The reverse loop issues no host<->device sync:
+the reference's per-step `assert_mean_zero_with_mask` (4 `.item()` calls per step, _utils.py:15-19) runs only at the
+start and end of a trajectory unless `debug_asserts=True`.  The RNG draw order of the reference is kept (per
+fragment: positions, then features).  Training `forward()` (loss terms) is a later row of SURVEY §8f.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .dynamics import EGNNDynamics
+from .graph_tools import get_edges_index, get_mask_for_frag, get_n_frag_switch
+from .normalizer import Normalizer
+from .schedule import DiffSchedule, get_repaint_schedule
+
+
+def remove_mean_batch(x: Tensor, indices: Tensor, n_seg: int) -> Tensor:
+    """x - segment_mean(x)[indices]  (diffusion/_utils.py:9-12), with the segment count supplied (no sync)."""
+    tot = torch.zeros(n_seg, x.size(1), device=x.device, dtype=x.dtype).index_add_(0, indices, x)
+    cnt = torch.zeros(n_seg, device=x.device, dtype=x.dtype).index_add_(0, indices, torch.ones_like(indices, dtype=x.dtype))
+    return x - (tot / cnt.clamp(min=1)[:, None])[indices]
+
+
+def assert_mean_zero_with_mask(x: Tensor, node_mask: Tensor, n_seg: int, eps: float = 1e-10):
+    """diffusion/_utils.py:15-19."""
+    largest = x.abs().max().item()
+    err = torch.zeros(n_seg, x.size(1), device=x.device, dtype=x.dtype).index_add_(0, node_mask, x).abs().max().item()
+    rel = err / (largest + eps)
+    assert rel < 1e-2, f"Mean is not zero, relative_error {rel}"
+
+
+class EnVariationalDiffusion(nn.Module):
+    def __init__(self, dynamics: EGNNDynamics, schdule: DiffSchedule, normalizer: Normalizer,
+                 size_histogram: Optional[Dict] = None, loss_type: str = "l2", pos_only: bool = False,
+                 fixed_idx: Optional[List] = None, debug_asserts: bool = False):
+        super().__init__()
+        assert loss_type in {"vlb", "l2"}
+        self.dynamics, self.schedule, self.normalizer = dynamics, schdule, normalizer
+        self.size_histogram, self.loss_type, self.pos_only = size_histogram, loss_type, pos_only
+        self.fixed_idx = fixed_idx or []
+        self.pos_dim, self.node_nfs, self.fragment_names = dynamics.pos_dim, dynamics.node_nfs, dynamics.fragment_names
+        self.T = schdule.gamma_module.timesteps
+        self.norm_values, self.norm_biases = normalizer.norm_values, normalizer.norm_biases
+        self.debug_asserts = debug_asserts
+        self.n_evals = 0  # denoiser evaluations of the last sample()/inpaint() call
+
+    def forward(self, representations, conditions, return_pred: bool = False):
+        raise NotImplementedError("training loss (en_diffusion.py:56-248) is outside round 1's hot path (SURVEY §8f)")
+
+    # ---------------------------------------------------------------- noise
+    def sample_combined_position_feature_noise(self, masks: List[Tensor]) -> List[Tensor]:
+        """CoM-free Gaussian for positions, standard normal (zero if pos_only) for features (en_diffusion.py:281-304)."""
+        out = []
+        for ii, mask in enumerate(masks):
+            x = remove_mean_batch(torch.randn((len(mask), self.pos_dim), device=mask.device), mask, self._B)
+            hh = torch.randn((len(mask), self.node_nfs[ii] - self.pos_dim), device=mask.device)
+            if self.pos_only:
+                hh = torch.zeros_like(hh)
+            out.append(torch.cat([x, hh], dim=1))
+        for idx in self.fixed_idx:
+            out[idx] = torch.zeros_like(out[idx])
+        return out
+
+    def noised_representation(self, xh: List[Tensor], masks: List[Tensor], gamma_t: Tensor):
+        """z_t = alpha_t x + sigma_t eps (en_diffusion.py:260-279)."""
+        alpha_t, sigma_t = self.schedule.alpha(gamma_t, xh[0]), self.schedule.sigma(gamma_t, xh[0])
+        eps = self.sample_combined_position_feature_noise(masks)
+        return [alpha_t[masks[ii]] * xh[ii] + sigma_t[masks[ii]] * eps[ii] for ii in range(len(masks))], eps
+
+    def sample_normal(self, mu: List[Tensor], sigma: Tensor, masks: List[Tensor], fix_noise: bool = False):
+        if fix_noise:
+            raise NotImplementedError("fix_noise option isn't implemented yet")  # en_diffusion.py:642-644
+        eps = self.sample_combined_position_feature_noise(masks)
+        return [mu[ii] + sigma[masks[ii]] * eps[ii] for ii in range(len(masks))]
+
+    # ---------------------------------------------------------------- reverse kernels
+    def _dyn(self, z, edge_index, t, conditions, n_frag_switch, masks):
+        self.n_evals += 1
+        eps, _ = self.dynamics(xh=z, edge_index=edge_index, t=t, conditions=conditions, n_frag_switch=n_frag_switch,
+                               combined_mask=self._combined, edge_attr=None)
+        return eps
+
+    def sample_p_zs_given_zt(self, s, t, zt_xh, edge_index, n_frag_switch, masks, conditions=None, fix_noise=False):
+        """One reverse step z_t -> z_s (en_diffusion.py:562-632)."""
+        gamma_s, gamma_t = self.schedule.gamma_module(s), self.schedule.gamma_module(t)
+        sigma2_ts, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(gamma_t, gamma_s, zt_xh[0])
+        sigma_s = self.schedule.sigma(gamma_s, target_tensor=zt_xh[0])
+        sigma_t = self.schedule.sigma(gamma_t, target_tensor=zt_xh[0])
+        eps = self._dyn(zt_xh, edge_index, t, conditions, n_frag_switch, masks)
+        if self.debug_asserts:
+            for zz in (zt_xh, eps):
+                assert_mean_zero_with_mask(torch.cat([z[:, :self.pos_dim] for z in zz]), self._combined, self._B)
+        coef = sigma2_ts / alpha_ts / sigma_t
+        mu = [zt_xh[ii] / alpha_ts[masks[ii]] - eps[ii] * coef[masks[ii]] for ii in range(len(zt_xh))]
+        zs = self.sample_normal(mu=mu, sigma=sigma_ts * sigma_s / sigma_t, masks=masks, fix_noise=fix_noise)
+        for ii in range(len(masks)):  # project the CoM out again
+            zs[ii][:, :self.pos_dim] = remove_mean_batch(zs[ii][:, :self.pos_dim], masks[ii], self._B)
+        return zs
+
+    def compute_x_pred(self, net_eps_xh, zt_xh, gamma_t, masks):
+        """en_diffusion.py:704-718."""
+        sigma_t = self.schedule.sigma(gamma_t, target_tensor=net_eps_xh[0])
+        alpha_t = self.schedule.alpha(gamma_t, target_tensor=net_eps_xh[0])
+        return [1.0 / alpha_t[masks[ii]] * (zt_xh[ii] - sigma_t[masks[ii]] * net_eps_xh[ii]) for ii in range(len(masks))]
+
+    def sample_p_xh_given_z0(self, z0_xh, edge_index, n_frag_switch, masks, batch_size, conditions=None,
+                             fix_noise=False):
+        """Final decode x ~ p(x | z0) (en_diffusion.py:649-702)."""
+        t0 = torch.zeros(size=(batch_size, 1), device=z0_xh[0].device)
+        gamma_0 = self.schedule.gamma_module(t0)
+        sigma_x = self.schedule.SNR(-0.5 * gamma_0)
+        eps = self._dyn(z0_xh, edge_index, t0, conditions, n_frag_switch, masks)
+        mu_x = self.compute_x_pred(eps, z0_xh, gamma_0, masks)
+        x0 = self.sample_normal(mu=mu_x, sigma=sigma_x, masks=masks, fix_noise=fix_noise)
+        p = self.pos_dim
+        pos = [self.normalizer.unnormalize(x0[ii][:, :p], 0) for ii in range(len(masks))]
+        cat = [self.normalizer.unnormalize(x0[ii][:, p:-1], 1) for ii in range(len(masks))]
+        charge = [torch.round(self.normalizer.unnormalize(x0[ii][:, -1:], 2)).long() for ii in range(len(masks))]
+        cat = [F.one_hot(torch.argmax(cat[ii], dim=1), self.node_nfs[ii] - 4).long() for ii in range(len(masks))]
+        return pos, cat, charge
+
+    def sample_p_zt_given_zs(self, zs, masks, gamma_t, gamma_s, fix_noise=False):
+        """Forward jump z_s -> z_t used by RePaint (en_diffusion.py:1050-1074)."""
+        _, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(gamma_t, gamma_s, zs[0])
+        zt = self.sample_normal(mu=[alpha_ts[masks[ii]] * zs[ii] for ii in range(len(masks))], sigma=sigma_ts,
+                                masks=masks, fix_noise=fix_noise)
+        for ii in range(len(masks)):
+            zt[ii][:, :self.pos_dim] = remove_mean_batch(zt[ii][:, :self.pos_dim], masks[ii], self._B)
+        return zt
+
+    # ---------------------------------------------------------------- drivers
+    def _setup(self, n_samples, fragments_nodes):
+        masks = [get_mask_for_frag(n) for n in fragments_nodes]
+        self._combined = torch.cat(masks)
+        self._B = n_samples
+        self.n_evals = 0
+        return masks, get_edges_index(self._combined, remove_self_edge=True), get_n_frag_switch(fragments_nodes)
+
+    def _with_h0(self, z, h0):
+        return [torch.cat([z[ii][:, :self.pos_dim], h0[ii]], dim=1) for ii in range(len(h0))]
+
+    def _check_com(self, zz):
+        assert_mean_zero_with_mask(torch.cat([z[:, :self.pos_dim] for z in zz]), self._combined, self._B)
+
+    @torch.no_grad()
+    def sample(self, n_samples: int, fragments_nodes: List[Tensor], conditions: Optional[Tensor] = None,
+               return_frames: int = 1, timesteps: Optional[int] = None, h0: Optional[List[Tensor]] = None):
+        """Unconditional reverse diffusion (en_diffusion.py:459-560).  Returns (out_samples, fragments_masks) with
+        out_samples[0] = list of [N_f, pos | one-hot | charge]."""
+        timesteps = self.T if timesteps is None else timesteps
+        assert 0 < return_frames <= timesteps and timesteps % return_frames == 0
+        assert h0 is not None if self.pos_only else True
+        masks, edge_index, nfs = self._setup(n_samples, fragments_nodes)
+        z = self.sample_combined_position_feature_noise(masks)
+        if self.pos_only:
+            z = self._with_h0(z, h0)
+        self._check_com(z)
+        out_samples = [[torch.zeros((return_frames,) + zz.size(), device=zz.device) for zz in z]
+                       for _ in range(return_frames)]
+        dev = z[0].device
+        for s in reversed(range(0, timesteps)):
+            s_arr = torch.full((n_samples, 1), fill_value=s, device=dev)
+            t_arr = (s_arr + 1) / timesteps
+            s_arr = s_arr / timesteps
+            z = self.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z, edge_index=edge_index, n_frag_switch=nfs,
+                                          masks=masks, conditions=conditions, fix_noise=False)
+            if self.pos_only:
+                z = self._with_h0(z, h0)
+            if (s * return_frames) % timesteps == 0:
+                out_samples[(s * return_frames) // timesteps] = self.normalizer.unnormalize_z(z)
+        pos, cat, charge = self.sample_p_xh_given_z0(z, edge_index, nfs, masks, n_samples, conditions)
+        if self.pos_only:
+            cat = [_h0[:, :-1] for _h0 in h0]
+            charge = [_h0[:, -1:] for _h0 in h0]
+        self._check_com(pos)
+        out_samples[0] = [torch.cat([pos[ii], cat[ii], charge[ii]], dim=1) for ii in range(len(pos))]
+        return out_samples, masks
+
+    @torch.no_grad()
+    def inpaint(self, n_samples: int, fragments_nodes: List[Tensor], conditions: Optional[Tensor] = None,
+                return_frames: int = 1, resamplings: int = 1, jump_length: int = 1, timesteps: Optional[int] = None,
+                xh_fixed: Optional[List[Tensor]] = None, frag_fixed: Optional[List] = None):
+        """RePaint-style conditional generation with the fragments in `frag_fixed` clamped to `xh_fixed`
+        (en_diffusion.py:722-883)."""
+        timesteps = self.T if timesteps is None else timesteps
+        assert 0 < return_frames <= timesteps and timesteps % return_frames == 0
+        assert len(xh_fixed)
+        masks, edge_index, nfs = self._setup(n_samples, fragments_nodes)
+        p = self.pos_dim
+        h0 = [x[:, p:].long() for x in xh_fixed]
+        for ii in range(len(xh_fixed)):
+            xh_fixed[ii][:, :p] = remove_mean_batch(xh_fixed[ii][:, :p], masks[ii], n_samples)
+        self._check_com(xh_fixed)
+        z = self.sample_combined_position_feature_noise(masks)
+        if self.pos_only:
+            z = self._with_h0(z, h0)
+        out_samples = [[torch.zeros((return_frames,) + zz.size(), device=zz.device) for zz in z]
+                       for _ in range(return_frames)]
+        dev = z[0].device
+        schedule = get_repaint_schedule(resamplings, jump_length, timesteps)
+        s = timesteps - 1
+        for i, n_denoise_steps in enumerate(schedule):
+            for j in range(n_denoise_steps):
+                s_arr = torch.full((n_samples, 1), fill_value=s, device=dev)
+                t_arr = (s_arr + 1) / timesteps
+                s_arr = s_arr / timesteps
+                gamma_s = self.schedule.inflate_batch_array(self.schedule.gamma_module(s_arr), xh_fixed[0])
+                z_known, _ = self.noised_representation(xh_fixed, masks, gamma_s)
+                z_unknown = self.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z, edge_index=edge_index,
+                                                      n_frag_switch=nfs, masks=masks, conditions=conditions)
+                if self.pos_only:
+                    z_known, z_unknown = self._with_h0(z_known, h0), self._with_h0(z_unknown, h0)
+                z = [z_known[ii] if ii in frag_fixed else z_unknown[ii] for ii in range(len(h0))]
+                if j == n_denoise_steps - 1 and i < len(schedule) - 1:  # jump back `jump_length` steps
+                    t = s + jump_length
+                    t_arr = torch.full((n_samples, 1), fill_value=t, device=dev) / timesteps
+                    gamma_t = self.schedule.inflate_batch_array(self.schedule.gamma_module(t_arr), xh_fixed[0])
+                    z = self.sample_p_zt_given_zs(z, masks, gamma_t, gamma_s)
+                    s = t
+                s = s - 1
+        pos, cat, charge = self.sample_p_xh_given_z0(z, edge_index, nfs, masks, n_samples, conditions)
+        if self.pos_only:
+            cat = [_h0[:, :-1] for _h0 in h0]
+            charge = [_h0[:, -1:] for _h0 in h0]
+        self._check_com(pos)
+        out_samples[0] = [torch.cat([pos[ii], cat[ii], charge[ii]], dim=1) for ii in range(len(pos))]
+        return out_samples, masks

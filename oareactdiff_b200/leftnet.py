@@ -1,0 +1,271 @@
+"""`LEFTNetB200`: drop-in for the reference's `oa_reactdiff.model.LEFTNet` (model/leftnet.py:579-891).
+
+Same constructor kwargs, same parameter/buffer names (SURVEY.md App. B — checkpoints load with
+`load_state_dict`), same `forward` signature and return triple; it is accepted by the reference's plugin seam
+`EGNNDynamics(model=LEFTNetB200, model_config=...)` (dynamics/_base.py:62-64).
+
+The torch modules below only HOLD parameters; all arithmetic of `forward` runs in hand-written CUDA kernels
+(csrc/) behind the C ABI of include/oard.h.  Inference only: outputs are detached (no autograd through the kernels).
+"""
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+# ---- parameter containers reproducing the reference's module tree (names only; no math here) ----
+class _One(nn.Module):  # model/core.py:36-49  OneLayerActivation
+    def __init__(self, i, o, bias=True):
+        super().__init__()
+        self.linear = nn.Linear(i, o, bias=bias)
+
+
+class _MLP(nn.Module):  # model/core.py:52-92
+    def __init__(self, in_dim, out_dims, bias=True):
+        super().__init__()
+        mods, d = [], in_dim
+        for o in out_dims:
+            mods.append(_One(d, o, bias))
+            d = o
+        self.mlp = nn.Sequential(*mods)
+
+
+def _seq(*mods):
+    return nn.Sequential(*mods)
+
+
+class _RBF(nn.Module):  # model/leftnet.py:32-61
+    def __init__(self, num_rbf, cutoff):
+        super().__init__()
+        start = torch.exp(torch.scalar_tensor(-float(cutoff)))
+        end = torch.exp(torch.scalar_tensor(-0.0))
+        self.register_buffer("means", torch.linspace(start, end, num_rbf))
+        self.register_buffer("betas", torch.tensor([(2 / num_rbf * (end - start)) ** -2] * num_rbf))
+
+
+class _NeighborEmb(nn.Module):  # :72-79
+    def __init__(self, H, C_in):
+        super().__init__()
+        self.embedding = nn.Linear(C_in, H)
+
+
+class _S2V(nn.Module):  # :92-102
+    def __init__(self, H):
+        super().__init__()
+        self.lin1 = _seq(nn.Linear(H, H))
+
+
+class _GCL(nn.Module):  # :128-155
+    def __init__(self, H, R):
+        super().__init__()
+        self.edge_mlp = _MLP(5 * H + R, [H, H])
+        self.node_mlp = _MLP(2 * H, [H, H])
+        self.edge_out_trans = _MLP(H, [3 * H + R])
+        self.att_mlp = _MLP(H, [1])
+        self.x_layernorm = nn.LayerNorm(H)
+
+
+class _EquiMessage(nn.Module):  # :186-242
+    def __init__(self, H, R):
+        super().__init__()
+        self.dir_proj = _seq(nn.Linear(3 * H + R, 3 * H), nn.Identity(), nn.Linear(3 * H, 3 * H))
+        self.x_proj = _seq(nn.Linear(H, H, bias=False), nn.Identity(), nn.Linear(H, 3 * H, bias=False))
+        self.rbf_proj = nn.Linear(R, 3 * H, bias=False)
+        self.x_layernorm = nn.LayerNorm(H)
+        nn.init.xavier_uniform_(self.x_proj[0].weight)
+        nn.init.xavier_uniform_(self.x_proj[2].weight)
+        nn.init.xavier_uniform_(self.rbf_proj.weight)
+
+
+class _EquiUpdate(nn.Module):  # :292-323
+    def __init__(self, H):
+        super().__init__()
+        self.vec_proj = nn.Linear(H, 2 * H, bias=False)
+        self.xvec_proj = _seq(nn.Linear(2 * H, H, bias=False), nn.Identity(), nn.Linear(H, 3 * H, bias=False))
+        self.lin3 = _seq(nn.Linear(3, 48), nn.Identity(), nn.Linear(48, 8), nn.Identity(), nn.Linear(8, 1))
+        nn.init.xavier_uniform_(self.vec_proj.weight)
+        nn.init.xavier_uniform_(self.xvec_proj[0].weight)
+        nn.init.xavier_uniform_(self.xvec_proj[2].weight)
+
+
+class _Gated(nn.Module):  # :531-564
+    def __init__(self, H, out):
+        super().__init__()
+        self.vec1_proj = nn.Linear(H, H, bias=False)
+        self.vec2_proj = nn.Linear(H, out, bias=False)
+        self.update_net = _seq(nn.Linear(2 * H, H), nn.Identity(), nn.Linear(H, 2 * out))
+        nn.init.xavier_uniform_(self.vec1_proj.weight)
+        nn.init.xavier_uniform_(self.vec2_proj.weight)
+        nn.init.xavier_uniform_(self.update_net[0].weight)
+        self.update_net[0].bias.data.fill_(0)
+        nn.init.xavier_uniform_(self.update_net[2].weight)
+        self.update_net[2].bias.data.fill_(0)
+
+
+class _EquiOutput(nn.Module):  # :500-519
+    def __init__(self, H):
+        super().__init__()
+        self.output_network = nn.ModuleList([_Gated(H, 1)])
+
+
+class _Engine:
+    """One C-ABI handle (device workspace + weights + plan) for one module on one device."""
+
+    def __init__(self, cfg: Dict, device: torch.device):
+        self.lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("LEFTNetB200 runs only on CUDA tensors (no CPU fallback); got device " + str(device))
+        self.device = device
+        c = _lib.OardCfg(cfg["hidden_channels"], cfg["num_radial"], cfg["num_layers"], cfg["in_hidden_channels"],
+                         float(cfg["cutoff"]), int(cfg["reflect_equiv"]), int(cfg["legacy"]), int(cfg["update"]),
+                         int(cfg["object_aware"]))
+        self.h = C.c_void_p()
+        _lib.check(self.lib.oard_create(C.byref(c), device.index or 0, C.byref(self.h)))
+        self.names = [self.lib.oard_weight_name(self.h, i).decode() for i in range(self.lib.oard_num_weights(self.h))]
+        self.weights_key = None
+        self.plan_key = None
+        self.N = self.E = 0
+        self.debug = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.oard_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream(device):
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def sync_weights(self, module: nn.Module, force=False):
+        sd = module._oard_tensors()
+        key = tuple((t.data_ptr(), t._version) for t in sd.values())
+        if not force and key == self.weights_key:
+            return
+        st = self._stream(self.device)
+        for name in self.names:
+            t = sd[name]
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            _lib.check(self.lib.oard_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), 1, st))
+        _lib.check(self.lib.oard_commit_weights(self.h, st))
+        self.weights_key = key
+
+    def plan(self, edge_index: Tensor, n_nodes: int):
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n_nodes)
+        if key == self.plan_key:
+            return
+        ei = edge_index.detach().to("cpu", torch.int64).contiguous()
+        _lib.check(self.lib.oard_plan(self.h, n_nodes, ei.size(1), C.c_void_p(ei.data_ptr())))
+        self.plan_key, self.N, self.E = key, n_nodes, ei.size(1)
+
+    def forward(self, h: Tensor, pos: Tensor, sub: Optional[Tensor]):
+        h = h.detach().to(torch.float32).contiguous()
+        pos = pos.detach().to(torch.float32).contiguous()
+        h_out = torch.empty_like(h)
+        dpos = torch.empty_like(pos)
+        sp = None
+        if sub is not None:
+            sub = sub.detach().reshape(-1).to(torch.int64).contiguous()
+            if sub.numel() != self.E:
+                raise ValueError(f"subgraph_mask has {sub.numel()} entries, edge_index has {self.E} edges")
+            sp = C.c_void_p(sub.data_ptr())
+        _lib.check(self.lib.oard_forward(self.h, C.c_void_p(h.data_ptr()), C.c_void_p(pos.data_ptr()), sp,
+                                         C.c_void_p(h_out.data_ptr()), C.c_void_p(dpos.data_ptr()),
+                                         self._stream(self.device)))
+        return h_out, dpos
+
+    # ---- parity instrumentation
+    def set_debug(self, on: bool):
+        _lib.check(self.lib.oard_set_debug(self.h, int(on)))
+        self.debug = on
+
+    def read(self, name: str, dtype=torch.float32) -> Tensor:
+        nb = self.lib.oard_debug_bytes(self.h, name.encode())
+        if nb < 0:
+            raise KeyError(name)
+        out = torch.empty(nb // torch.empty(0, dtype=dtype).element_size(), dtype=dtype)
+        _lib.check(self.lib.oard_debug_read(self.h, name.encode(), C.c_void_p(out.data_ptr()), nb))
+        return out
+
+    def launches(self) -> int:
+        return int(self.lib.oard_last_launch_count(self.h))
+
+
+class LEFTNetB200(nn.Module):
+    """See module docstring.  Constructor mirrors model/leftnet.py:594-611."""
+
+    def __init__(self, pos_require_grad=False, cutoff=10.0, num_layers=4, hidden_channels=128, num_radial=96,
+                 in_hidden_channels: int = 8, reflect_equiv: bool = True, legacy: bool = True, update: bool = True,
+                 pos_grad: bool = False, single_layer_output: bool = True, for_conf: bool = False, ff: bool = False,
+                 object_aware: bool = True, **kwargs):
+        super().__init__()
+        unsupported = dict(pos_grad=pos_grad, for_conf=for_conf, ff=ff, not_legacy=not legacy,
+                           multi_layer_output=not single_layer_output)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"LEFTNetB200 implements the trained OA-ReactDiff configuration only; "
+                                      f"unsupported options: {bad}")
+        H, R, Cin = hidden_channels, num_radial, in_hidden_channels
+        self.num_layers, self.hidden_channels, self.cutoff = num_layers, H, cutoff
+        self.pos_require_grad, self.reflect_equiv, self.legacy, self.update = pos_require_grad, reflect_equiv, legacy, update
+        self.pos_grad, self.for_conf, self.ff, self.object_aware = pos_grad, for_conf, ff, object_aware
+        self.cfg = dict(hidden_channels=H, num_radial=R, num_layers=num_layers, in_hidden_channels=Cin,
+                        cutoff=float(cutoff), reflect_equiv=bool(reflect_equiv), legacy=bool(legacy),
+                        update=bool(update), object_aware=bool(object_aware))
+
+        self.embedding = nn.Linear(Cin, H)
+        self.embedding_out = nn.Linear(H, Cin)
+        self.radial_emb = _RBF(R, cutoff)
+        self.neighbor_emb = _NeighborEmb(H, Cin)
+        self.s2v = _S2V(H)
+        self.radial_lin = _seq(nn.Linear(R, H), nn.Identity(), nn.Linear(H, H))
+        self.lin3 = _seq(nn.Linear(3, H // 4), nn.Identity(), nn.Linear(H // 4, 1))
+        self.pos_expansion = _MLP(3, [H // 2, H], bias=False)
+        if legacy:
+            self.distance_embedding = _MLP(R, [H // 2, H], bias=False)  # present in checkpoints, unused in forward
+        self.gcl_layers = nn.ModuleList([_GCL(H, R) for _ in range(num_layers)])
+        self.message_layers = nn.ModuleList([_EquiMessage(H, R) for _ in range(num_layers)])
+        self.update_layers = nn.ModuleList([_EquiUpdate(H) for _ in range(num_layers)])
+        self.last_layer = nn.Linear(H, 1)  # present in checkpoints, unused in forward
+        self.out_pos = _EquiOutput(H)
+        self.inv_sqrt_2 = 1 / math.sqrt(2.0)
+        self._engines: Dict[torch.device, _Engine] = {}
+        self.assume_static_weights = False  # set True to skip the per-call weight-version check
+
+    # tensors the C library needs, keyed by reference state-dict name
+    def _oard_tensors(self) -> Dict[str, Tensor]:
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return sd
+
+    def engine(self, device: torch.device) -> _Engine:
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        eng = self._engines.get(device)
+        if eng is None:
+            eng = self._engines[device] = _Engine(self.cfg, device)
+        return eng
+
+    @torch.no_grad()
+    def forward(self, h: Tensor, pos: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None,
+                node_mask: Optional[Tensor] = None, edge_mask: Optional[Tensor] = None,
+                update_coords_mask: Optional[Tensor] = None, subgraph_mask: Optional[Tensor] = None):
+        eng = self.engine(pos.device)
+        if not (self.assume_static_weights and eng.weights_key is not None):
+            eng.sync_weights(self)
+        eng.plan(edge_index, pos.size(0))
+        h_out, dpos = eng.forward(h, pos, subgraph_mask if self.object_aware else None)
+        if update_coords_mask is not None:
+            dpos = update_coords_mask * dpos
+        pos_out = pos.to(torch.float32) + dpos
+        if node_mask is not None:
+            h_out = h_out * node_mask
+        return h_out, pos_out, None

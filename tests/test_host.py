@@ -1,0 +1,87 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the drop-in modules carry
+the reference's state-dict names, host helpers agree with the oracle, and the product fails loudly without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oareactdiff_b200 as ob
+from oareactdiff_b200 import _lib
+from oracle import oa_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "oard.h")).read()
+    declared = set(re.findall(r"\b(oard_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert _lib.load().oard_abi_version() == 1
+
+
+@pytest.mark.parametrize("cfg", [oa_ref.TRAINED_CFG, dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2)])
+def test_state_dict_names_match_reference(cfg):
+    # oracle shapes were strict-loaded into the reference LEFTNet/EGNNDynamics by oracle/gen_golden.py
+    model = ob.LEFTNetB200(**cfg)
+    want = oa_ref.leftnet_param_shapes(cfg)
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0,
+                          condition_nf=1, model=ob.LEFTNetB200, device=torch.device("cpu"))
+    want = oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1)
+    got = {k: tuple(v.shape) for k, v in dyn.state_dict().items()}
+    assert got == want
+    n_params = sum(p.numel() for p in dyn.parameters())
+    if cfg["hidden_channels"] == 196:
+        assert n_params == 10_645_719  # SURVEY App. B (probe-verified on the reference)
+
+
+def test_unsupported_options_raise():
+    with pytest.raises(NotImplementedError):
+        ob.LEFTNetB200(legacy=False)
+    with pytest.raises(NotImplementedError):
+        ob.LEFTNetB200(pos_grad=True)
+
+
+def test_no_cpu_fallback():
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1)
+    m = ob.LEFTNetB200(**cfg)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 8), torch.zeros(2, 3), ei)
+
+
+def test_graph_tools_kats():
+    # reference tests/utils/test_graph_tools.py:14-63
+    assert ob.get_mask_for_frag(torch.tensor([2, 0, 3])).tolist() == [0, 0, 2, 2, 2]
+    assert ob.get_n_frag_switch([torch.tensor([2, 0]), torch.tensor([1, 3]), torch.tensor([3, 2])]).tolist() == \
+        [0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 2]
+    ei = torch.tensor([[0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]])
+    assert ob.get_subgraph_mask(ei, torch.tensor([0, 0, 1])).tolist() == [1, 0, 1, 0, 0, 0]
+    frags = [torch.tensor([2, 0]), torch.tensor([2, 3]), torch.tensor([1, 2])]
+    cm = torch.cat([ob.get_mask_for_frag(n) for n in frags])
+    assert ob.get_edges_index(cm).shape == (2, 50)
+    ei = ob.get_edges_index(cm, remove_self_edge=True)
+    assert ei.shape == (2, 40)
+    assert int(ob.get_subgraph_mask(ei, ob.get_n_frag_switch(frags)).sum()) == 12
+
+
+def test_edges_index_bit_exact_vs_oracle():
+    sizes = oa_ref.t1x_sizes(16, seed=3)
+    nodes = [torch.tensor(sizes)] * 3
+    cm = torch.cat([ob.get_mask_for_frag(n) for n in nodes])
+    assert torch.equal(ob.get_edges_index(cm, remove_self_edge=True), oa_ref.get_edges_index(cm, remove_self_edge=True))
+
+
+def test_schedule_matches_oracle():
+    for name, T in [("polynomial_2", 1000), ("cosine", 5000), ("polynomial_2", 10)]:
+        assert torch.equal(ob.PredefinedNoiseSchedule(name, T, 1e-5).gamma.data, oa_ref.gamma_table(name, T, 1e-5))
+    for r, j, T in [(1, 1, 1000), (5, 5, 150), (5, 5, 1000), (2, 3, 12), (3, 7, 20), (1, 5, 3)]:
+        assert ob.get_repaint_schedule(r, j, T) == oa_ref.get_repaint_schedule(r, j, T)
