@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — reactions/sec for a full 1000-step reverse diffusion on Transition1x-shaped batches (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host cores (oracle port)
+
+One "step" = one full `EnVariationalDiffusion.sample()` of a B=64 batch: 1000 reverse steps + the final p(x|z0)
+decode = 1001 denoiser evaluations (config.workload names it).  Weak scaling: every rank samples its own B=64 batch.
+`value` = reactions per second with inputs resident in HBM; `e2e` = the same through the public API with HOST (pinned)
+inputs copied in and results copied out inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reactions/sec full 1000-step reverse diffusion, Transition1x-shaped batch"
+UNIT = "reactions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="reactions per GPU")
+    ap.add_argument("--denoise-steps", type=int, default=1000, help="T of the reverse diffusion (BASELINE: 1000)")
+    ap.add_argument("--profile-every", type=int, default=97, help="bracket kernels with CUDA events every n-th forward")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-evals", type=int, default=2, help="denoiser evaluations timed for cpu_baseline")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference algorithm on the host cores: oracle/oa_ref.py (a torch-CPU restatement with the reference's op
+    structure; /root/reference itself cannot travel to the GPU box).  One step = ONE reverse-diffusion step (one
+    denoiser evaluation + posterior sampling) on the full batch, extrapolated x1001 to a full trajectory: the cost per
+    step is constant (dense masked compute over all edges)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import oa_ref
+    from oareactdiff_b200 import workloads
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = dict(oa_ref.TRAINED_CFG)
+    T = args.denoise_steps
+    sizes = workloads.t1x_sizes(args.batch, seed=0)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 0)
+    sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 0, cfg, prefix_model="model.")
+    smp = oa_ref.Sampler(sd, cfg, oa_ref.gamma_table("polynomial_2", T, 1e-5))
+    masks, cm, ei, nfs = smp._graph(nodes)
+    torch.manual_seed(0)
+    z = smp._noise(masks)
+    z = [torch.cat([z[i][:, :3], h0[i]], dim=1) for i in range(3)]
+    times = []
+    with torch.no_grad():
+        for it in range(args.warmup + args.steps):
+            s = T - 1 - it
+            s_arr = torch.full((len(sizes), 1), float(s))
+            t0 = time.perf_counter()
+            z = smp._p_zs_given_zt(s_arr / T, (s_arr + 1) / T, z, ei, nfs, masks, cond)
+            z = [torch.cat([z[i][:, :3], h0[i]], dim=1) for i in range(3)]
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    per_eval = sum(times) / len(times)
+    traj = per_eval * (T + 1)
+    val = len(sizes) / traj
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": traj * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch={args.batch} Transition1x-shaped reactions (<=23 atoms), {T} steps, CPU",
+                       "global_batch": args.batch, "denoise_steps": T, "nodes": int(cm.numel()), "edges": int(ei.size(1))},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} reverse steps (1 denoiser evaluation each, {per_eval:.2f} s/eval) on the "
+                                       f"full batch, extrapolated x{T + 1}; torch {torch.__version__} CPU fp32"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def cpu_baseline(args, T):
+    import torch
+    from oracle import oa_ref
+    from oareactdiff_b200 import workloads
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = dict(oa_ref.TRAINED_CFG)
+    sizes = workloads.t1x_sizes(args.batch, seed=0)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 0)
+    sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 0, cfg, prefix_model="model.")
+    smp = oa_ref.Sampler(sd, cfg, oa_ref.gamma_table("polynomial_2", T, 1e-5))
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    smp.sample(len(sizes), nodes, cond, h0, max_steps=max(args.cpu_evals - 1, 1))
+    dt = time.perf_counter() - t0
+    per_eval = dt / smp.n_evals
+    val = len(sizes) / (per_eval * (T + 1))
+    return {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{smp.n_evals} denoiser evaluations of the same B={args.batch} batch via oracle Sampler.sample "
+                      f"({per_eval:.2f} s/eval), extrapolated to {T + 1}"}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import oareactdiff_b200 as ob
+    from oareactdiff_b200 import workloads
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, B = args.denoise_steps, args.batch
+    cfg = dict(cutoff=10.0, num_layers=6, hidden_channels=196, num_radial=96, in_hidden_channels=8, reflect_equiv=True,
+               legacy=True, update=True, object_aware=True)  # trainer/train_ts1x.py:43-56
+    torch.manual_seed(0)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0,
+                          condition_nf=1, model=ob.LEFTNetB200, device=dev).to(dev)
+    if world > 1:  # the one collective of the path: broadcast rank 0's weights (42.6 MB) over NCCL
+        flat = torch.cat([p.data.reshape(-1) for p in dyn.parameters()])
+        dist.broadcast(flat, 0)
+        o = 0
+        for p in dyn.parameters():
+            p.data.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+    sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True).to(dev)
+    dyn.model.assume_static_weights = True
+
+    sizes = workloads.t1x_sizes(B, seed=rank)  # every rank its own batch (weak scaling)
+    nodes_h, h0_h, cond_h = workloads.reaction_batch(sizes, seed=rank)
+    pin = lambda t: t.pin_memory()
+    nodes_h, h0_h, cond_h = [pin(x) for x in nodes_h], [pin(x) for x in h0_h], pin(cond_h)
+    nodes_d, h0_d, cond_d = [x.to(dev) for x in nodes_h], [x.to(dev) for x in h0_h], cond_h.to(dev)
+    eng = dyn.model.engine(dev)
+
+    def step_resident():
+        torch.manual_seed(1234 + rank)
+        out, _ = ddpm.sample(B, nodes_d, cond_d, h0=h0_d)
+        return out[0]
+
+    out_host = [torch.empty(h.size(0), 9).pin_memory() for h in h0_h]
+
+    def step_e2e():
+        torch.manual_seed(1234 + rank)
+        nd = [x.to(dev, non_blocking=True) for x in nodes_h]
+        hd = [x.to(dev, non_blocking=True) for x in h0_h]
+        cd = cond_h.to(dev, non_blocking=True)
+        out, _ = ddpm.sample(B, nd, cd, h0=hd)
+        for dst, src in zip(out_host, out[0]):
+            dst.copy_(src.to(torch.float32), non_blocking=True)
+        return out[0]
+
+    h2d = sum(x.numel() * x.element_size() for x in nodes_h + h0_h + [cond_h])
+    d2h = sum(x.numel() * x.element_size() for x in out_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    eng.set_profile(args.profile_every)
+    l0 = eng.total_launches()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms = timed(step_resident, args.steps)
+    clk = clocks.stop()
+    launches = eng.total_launches() - l0
+    prof = eng.profile()
+    eng.set_profile(0)
+    ms_e2e = timed(step_e2e, args.steps)
+    finite = all(bool(torch.isfinite(o).all()) for o in out_host)
+
+    total_reactions = B * world * args.steps
+    value = total_reactions / (ms / 1e3)
+    e2e_v = total_reactions / (ms_e2e / 1e3)
+    if rank != 0:
+        return
+    pk = peaks()
+    kernels = {k: dict(ms_per_launch=v["ms"] / max(v["launches"], 1), launches=v["launches"],
+                       tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
+                       gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                       share=v["ms"]) for k, v in prof.items()}
+    tot = sum(v["share"] for v in kernels.values()) or 1.0
+    for v in kernels.values():
+        v["share"] = v["share"] / tot
+    dom = max(kernels, key=lambda k: kernels[k]["share"]) if kernels else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roof = None
+    if dom:
+        kd = kernels[dom]
+        if dom.startswith("gemm"):
+            roof = {"kernel": dom, "bound": "tensor", "achieved": kd["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": kd["tflops"] / pk["tflops"], "traffic": traffic,
+                    "note": f"algorithmic fp32-equivalent flops (2MNK, inactive edges skipped) / CUDA-event launch time; "
+                            f"peak = bf16 cuBLAS sustained ({pk['src']})", "share_of_step": kd["share"]}
+        else:
+            roof = {"kernel": dom, "bound": "hbm", "achieved": kd["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": kd["gbs"] / pk["hbm_gbs"], "traffic": traffic, "share_of_step": kd["share"],
+                    "note": f"algorithmic bytes / CUDA-event launch time; peak = copy bandwidth ({pk['src']})"}
+    mp = kernels.get("k_equi_reduce")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch={B} Transition1x-shaped reactions (<=23 atoms) per GPU, {T} steps "
+                                   f"(sample(): {T + 1} LEFTNet evaluations), trained LEFTNet config (6 layers, H=196, R=96)",
+                       "global_batch": B * world, "denoise_steps": T, "nodes_per_gpu": int(sum(sizes) * 3),
+                       "edges_per_gpu": workloads.edge_count(sizes), "parallelism": f"dp{world} (reactions sharded, no "
+                       "per-step collective)", "l2": "working set per evaluation (edge state 4*E*684 B = "
+                       f"{workloads.edge_count(sizes) * 684 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
+                       "weights": "torch.manual_seed(0) default init (checkpoint is a git-LFS pointer)"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps, "outputs_finite": finite},
+            "roofline": roof,
+            "message_passing_roofline": None if not mp else {
+                "kernel": "k_equi_reduce", "bound": "hbm", "achieved": mp["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": mp["gbs"] / pk["hbm_gbs"]},
+            "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share"])[:12]}}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, T)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world == 1 and args.gpus > 1:
+            print(f"note: --gpus {args.gpus} requested without torchrun; running 1 rank", file=sys.stderr)
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

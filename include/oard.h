@@ -83,8 +83,17 @@ int oard_set_debug(oard_handle* h, int on);
 int64_t oard_debug_bytes(oard_handle* h, const char* name);
 int oard_debug_read(oard_handle* h, const char* name, void* host_dst, size_t bytes);
 
-/* Kernel launches issued by the last oard_forward call (for bench.py's gpu_launches). */
+/* Kernel launches issued by the last oard_forward call / by all calls so far (for bench.py's gpu_launches). */
 int64_t oard_last_launch_count(const oard_handle* h);
+int64_t oard_total_launch_count(const oard_handle* h);
+
+/* Live per-kernel-class timing for the roofline: with every_n > 0, every every_n-th oard_forward brackets each launch
+ * with CUDA events on the caller's stream and (synchronising at the end of that call) accumulates, per class tag,
+ * device milliseconds, launches, algorithmic flops and algorithmic bytes.  every_n = 0 switches it off and clears. */
+int oard_set_profile(oard_handle* h, int every_n);
+int oard_profile_count(const oard_handle* h);
+int oard_profile_get(const oard_handle* h, int i, const char** tag, double* ms, int64_t* launches, double* flops,
+                     double* bytes);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,11 @@ SYMBOLS = {
     "oard_debug_bytes": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "oard_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "oard_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "oard_total_launch_count": (C.c_int64, [C.c_void_p]),
+    "oard_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "oard_profile_count": (C.c_int, [C.c_void_p]),
+    "oard_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

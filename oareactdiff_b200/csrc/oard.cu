@@ -69,6 +69,18 @@ struct oard_handle {
   int N = 0, E = 0, NC = 0;
   std::map<std::string, DevBuf> ws;  // named workspace buffers
   size_t ws_bytes = 0;
+  // profiling: CUDA-event timing per kernel class on sampled forwards
+  int prof_every = 0;
+  int64_t fwd_count = 0;
+  bool prof_now = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; bool dyn; };
+  std::vector<ProfRec> prof_recs;
+  struct ProfCls { std::string tag; double ms = 0, flops = 0, bytes = 0; int64_t launches = 0; };
+  std::vector<ProfCls> prof_cls;
+  std::unordered_map<std::string, int> prof_idx;
+  int64_t total_launches = 0;
   // debug
   bool debug = false;
   std::map<std::string, DevBuf> snaps;
@@ -359,6 +371,54 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
 
 extern "C" size_t oard_workspace_bytes(const oard_handle* h) { return h ? h->ws_bytes : 0; }
 
+// ------------------------------------------------------------------------------------------------ profiling
+static cudaEvent_t prof_event(oard_handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+// flops/bytes: algorithmic work of this launch; dyn: scale by n_act / E at harvest (active-edge kernels sized by cap)
+static void prof_begin(oard_handle* h, const char* tag, double flops, double bytes, bool dyn, cudaStream_t st) {
+  if (!h->prof_now) return;
+  auto it = h->prof_idx.find(tag);
+  int cls;
+  if (it == h->prof_idx.end()) {
+    cls = (int)h->prof_cls.size();
+    h->prof_idx[tag] = cls;
+    h->prof_cls.push_back({});
+    h->prof_cls.back().tag = tag;
+  } else cls = it->second;
+  oard_handle::ProfRec r{cls, prof_event(h), prof_event(h), flops, bytes, dyn};
+  cudaEventRecord(r.a, st);
+  h->prof_recs.push_back(r);
+}
+static void prof_end(oard_handle* h, cudaStream_t st) {
+  if (!h->prof_now) return;
+  cudaEventRecord(h->prof_recs.back().b, st);
+}
+static int prof_harvest(oard_handle* h, cudaStream_t st) {
+  if (!h->prof_now) return OARD_OK;
+  CU(cudaStreamSynchronize(st));
+  int n_act = 0;
+  CU(cudaMemcpy(&n_act, h->buf<int>("n_act"), 4, cudaMemcpyDeviceToHost));
+  const double frac = h->E > 0 ? (double)n_act / (double)h->E : 0.0;
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.a, r.b));
+    auto& c = h->prof_cls[r.cls];
+    c.ms += ms; c.launches++;
+    c.flops += r.dyn ? r.flops * frac : r.flops;
+    c.bytes += r.dyn ? r.bytes * frac : r.bytes;
+  }
+  h->prof_recs.clear();
+  h->ev_used = 0;
+  h->prof_now = false;
+  return OARD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 static int snap(oard_handle* h, const std::string& name, const void* p, size_t bytes, cudaStream_t st) {
   if (!h->debug) return OARD_OK;
@@ -381,7 +441,9 @@ static int snap(oard_handle* h, const std::string& name, const void* p, size_t b
     cudaError_t e_ = cudaGetLastError();                                                                    \
     if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
     h->launches++;                                                                                          \
+    prof_end(h, st);                                                                                        \
   } while (0)
+#define PB(tag, flops, bytes, dyn) prof_begin(h, tag, (double)(flops), (double)(bytes), dyn, st)
 #define SNAP(name, ptr, bytes)                                       \
   do {                                                               \
     const int rc_ = snap(h, name, ptr, bytes, st);                   \
@@ -403,6 +465,8 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   CU(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   h->launches = 0;
+  h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
+  h->fwd_count++;
   const oard_cfg& c = h->cfg;
   const int N = h->N, E = h->E, H = c.hidden_channels, R = c.num_radial, C = c.in_hidden_channels, D = 3 * H + R;
   const int HB = (H + 31) / 32 * 32, Hq = H / 4;
@@ -426,61 +490,77 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   float *ew = h->buf<float>("ew"), *hid1 = h->buf<float>("hid1"), *m2 = h->buf<float>("m2"),
         *rbf_act = h->buf<float>("rbf_act"), *f_act = h->buf<float>("f_act"), *d1 = h->buf<float>("d1"),
         *RB = h->buf<float>("RB"), *G = h->buf<float>("G");
-#define GEMM(g)                                                                                              \
+#define GEMM(tag, g)                                                                                         \
   do {                                                                                                       \
+    prof_begin(h, tag, 2.0 * (g).M * (g).N * (g).K, 4.0 * (g).M * ((g).K + (g).N + ((g).resid ? (g).N : 0)),   \
+               (g).m_dev != nullptr, st);                                                                    \
     cudaError_t e_ = launch_gemm_simt(g, st);                                                                \
     if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
     h->launches++;                                                                                           \
+    prof_end(h, st);                                                                                         \
   } while (0)
 
   // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
-  if (E) { k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
+  if (E) { PB("k_edge_mask", 0, E*29.0, 0);
+    k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
+  PB("k_group_frame", 0, N*64.0, 0);
   k_group_frame<256><<<h->NC, 128, 0, st>>>(h->buf<int>("comp_ptr"), h->buf<int>("comp_nodes"),
                                             h->buf<int>("node_local"), row_ptr, ecol, mask, pos, pf, nodeframe, pos_prjt,
                                             h->buf<int>("owner"), h->buf<uint8_t>("opener"));
   KCHECK();
   if (h->debug) {
+    PB("k_group_ids", 0, N*12.0, 0);
     k_group_ids<<<1, 1024, 0, st>>>(N, h->buf<int>("owner"), h->buf<uint8_t>("opener"), h->buf<int>("rank_tmp"),
                                     h->buf<int>("group"));
     KCHECK();
   }
+  PB("k_edge_geom", 0, E*25.0, 0);
   k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, pf, c.cutoff, geo, rb,
                                                     h->buf<int>("row_cnt"));
   KCHECK();
+  PB("k_scan_rows", 0, N*8.0, 0);
   k_scan_rows<<<1, 1024, 0, st>>>(N, h->buf<int>("row_cnt"), h->buf<int>("row_act_ptr"), n_act);
   KCHECK();
+  PB("k_compact", 0, E*9.0, 0);
   k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
   KCHECK();
   if (E) {
     const size_t tot = (size_t)E * R;
+    PB("k_rbf", 0, (double)E*(R*4.0+20), 1);
     k_rbf<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_act, E, R, act_idx, geo, h->means, h->betas, c.cutoff,
                                                          rbf_act);
     KCHECK();
     // radial_lin on active edges: f = rb * (W2 SiLU(W1 rbf + b1) + b2)   (leftnet.py:784-786)
     GemmArgs g = mk(rbf_act, R, h->rl0_w, R, hid1, H, E, H, R);
     g.m_dev = n_act; g.bias = h->rl0_b; g.act = 1;
-    GEMM(g);
+    GEMM("gemm_radial_lin0", g);
     g = mk(hid1, H, h->rl2_w, H, f_act, H, E, H, H);
     g.m_dev = n_act; g.bias = h->rl2_b; g.rowscale = rb; g.rsidx = act_idx;
-    GEMM(g);
+    GEMM("gemm_radial_lin2", g);
   }
+  PB("k_masked_consts", 0, H*H*4.0, 0);
   k_masked_consts<<<1, HB, H * sizeof(float), st>>>(H, Hq, h->rl0_b, h->rl2_w, h->rl2_b, h->l3_b0, h->l3_w2, h->l3_b2,
                                                     f0, c3);
   KCHECK();
+  PB("k_node_init", 0, N*(C+2.0*H)*4, 0);
   k_node_init<<<N, HB, 0, st>>>(H, C, h_in, h->emb_w, h->emb_b, h->ne_w, h->ne_b, z_emb, ne);
   KCHECK();
+  PB("k_neighbor", 0, (double)E*(H*8.0+12), 0);
   k_neighbor<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, f0, z_emb, ne, s);
   KCHECK();
   {
     GemmArgs g = mk(s, H, h->s2v_w, H, tmpH, H, N, H, H);
     g.bias = h->s2v_b;
-    GEMM(g);
+    GEMM("gemm_s2v_lin", g);
   }
+  PB("k_layernorm", 0, N*H*8.0, 0);
   k_layernorm<<<N, HB, 0, st>>>(H, tmpH, H, nullptr, nullptr, nullptr, 1, q, H);
   KCHECK();
+  PB("k_s2v", 0, (double)E*(H*8.0+28), 1);
   k_s2v<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, geo, q, NE1);
   KCHECK();
   if (E) {
+    PB("k_edge_init", 0, (double)E*D*4.0, 0);
     k_edge_init<<<E, HB, Hq * 5 * sizeof(float), st>>>(H, R, Hq, c.reflect_equiv, esrc, ecol, act_pos, pf, geo, rb, NE1,
                                                        f_act, rbf_act, f0, c3, h->l3_w0, h->l3_b0, h->l3_w2, h->l3_b2,
                                                        ew);
@@ -489,9 +569,9 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   {  // pos_expansion(pos_prjt): shared weights and a layer-independent input -> evaluated once (leftnet.py:840-841)
     GemmArgs g = mk(pos_prjt, 3, h->pe0_w, 3, pe_t, H / 2, N, H / 2, 3);
     g.act = 1;
-    GEMM(g);
+    GEMM("gemm_pos_exp0", g);
     g = mk(pe_t, H / 2, h->pe1_w, H / 2, pe, H, N, H, H / 2);
-    GEMM(g);
+    GEMM("gemm_pos_exp1", g);
   }
   if (h->debug) {
     SNAP("mask", mask, (size_t)E); SNAP("group", h->buf<int>("group"), (size_t)N * 4);
@@ -507,55 +587,59 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     const LayerW& w = h->L[l];
     const int ldw0 = 2 * H + D;
     // ---- GCLMessage (leftnet.py:157-183).  W_a = [W_ai | W_aj | W_ae]: the x_i / x_j parts are per-node GEMMs.
+    PB("k_layernorm", 0, N*H*8.0, 0);
     k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
     KCHECK();
     GemmArgs g = mk(xa, 2 * H, w.e0w, ldw0, PQ, 2 * H, N, H, H);
     g.bias = w.e0b;
-    GEMM(g);
+    GEMM("gemm_gcl_P", g);
     g = mk(xa, 2 * H, w.e0w + H, ldw0, PQ + H, 2 * H, N, H, H);
-    GEMM(g);
+    GEMM("gemm_gcl_Q", g);
     if (E) {
       g = mk(ew, D, w.e0w + 2 * H, ldw0, hid1, H, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
-      GEMM(g);
+      GEMM("gemm_gcl_edge1", g);
       g = mk(hid1, H, w.e1w, H, m2, H, E, H, H);
       g.bias = w.e1b; g.act = 1;
-      GEMM(g);
+      GEMM("gemm_gcl_edge2", g);
     }
+    PB("k_att_agg", 0, (double)E*H*8.0, 0);
     k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
     KCHECK();
     g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
     g.bias = w.n0b; g.act = 1;
-    GEMM(g);
+    GEMM("gemm_gcl_node0", g);
     g = mk(tN, H, w.n1w, H, s, H, N, H, H);
     g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
-    GEMM(g);
+    GEMM("gemm_gcl_node1", g);
     if (E) {
       g = mk(m2, H, w.eow, H, ew, D, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
-      GEMM(g);
+      GEMM("gemm_gcl_edge_out", g);
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
+    PB("k_layernorm", 0, N*H*8.0, 0);
     k_layernorm<<<N, HB, 0, st>>>(H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
     KCHECK();
     g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
     g.act = 1;
-    GEMM(g);
+    GEMM("gemm_xproj0", g);
     g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
-    GEMM(g);
+    GEMM("gemm_xproj2", g);
     if (E) {
       g = mk(ew, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
       g.aidx = act_idx; g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
-      GEMM(g);
+      GEMM("gemm_dir_proj0", g);
       g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
       g.m_dev = n_act;
-      GEMM(g);
+      GEMM("gemm_rbf_proj", g);
       g = mk(d1, 3 * H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
-      GEMM(g);
+      GEMM("gemm_dir_proj2", g);
     }
+    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+16), 1);
     k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
     KCHECK();
     std::swap(vec, vec2);
@@ -567,15 +651,17 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     // ---- EquiUpdate (leftnet.py:325-346)
     if (c.update) {
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
-      GEMM(g);
+      GEMM("gemm_vec_proj", g);
+      PB("k_upd_scalar", 0, N*H*4.0*9, 0);
       k_upd_scalar<<<N, HB, 0, st>>>(H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
                                      vd);
       KCHECK();
       g = mk(sx, 2 * H, w.xv0w, 2 * H, tN, H, N, H, 2 * H);
       g.act = 1;
-      GEMM(g);
+      GEMM("gemm_xvec0", g);
       g = mk(tN, H, w.xv2w, H, XV, 3 * H, N, 3 * H, H);
-      GEMM(g);
+      GEMM("gemm_xvec2", g);
+      PB("k_upd_apply", 0, N*H*4.0*14, 0);
       k_upd_apply<<<N, HB, 0, st>>>(H, XV, VP, vd, s, vec);
       KCHECK();
     }
@@ -586,15 +672,18 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   }
   // ---- output head (leftnet.py:566-576, 878-887)
   GemmArgs g = mk(vec, H, h->o_v1w, H, O1, H, 3 * N, H, H);
-  GEMM(g);
+  GEMM("gemm_out_vec1", g);
+  PB("k_out_norm", 0, N*H*4.0*6, 0);
   k_out_norm<<<N, HB, 0, st>>>(H, O1, s, sn);
   KCHECK();
   g = mk(sn, 2 * H, h->o_u0w, 2 * H, tu, H, N, H, 2 * H);
   g.bias = h->o_u0b; g.act = 1;
-  GEMM(g);
+  GEMM("gemm_out_upd0", g);
+  PB("k_final", 0, N*H*4.0*5, 0);
   k_final<<<N, HB, 0, st>>>(H, C, tu, h->o_u2w, h->o_u2b, vec, h->o_v2w, s, h->eout_w, h->eout_b, dpos, h_out);
   KCHECK();
-  return OARD_OK;
+  h->total_launches += h->launches;
+  return prof_harvest(h, st);
 }
 
 extern "C" int oard_set_debug(oard_handle* h, int on) {
@@ -622,3 +711,25 @@ extern "C" int oard_debug_read(oard_handle* h, const char* name, void* dst, size
 }
 
 extern "C" int64_t oard_last_launch_count(const oard_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t oard_total_launch_count(const oard_handle* h) { return h ? h->total_launches : 0; }
+
+extern "C" int oard_set_profile(oard_handle* h, int every_n) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  h->prof_every = every_n > 0 ? every_n : 0;
+  h->fwd_count = 0;
+  h->prof_cls.clear();
+  h->prof_idx.clear();
+  return OARD_OK;
+}
+extern "C" int oard_profile_count(const oard_handle* h) { return h ? (int)h->prof_cls.size() : 0; }
+extern "C" int oard_profile_get(const oard_handle* h, int i, const char** tag, double* ms, int64_t* launches,
+                                double* flops, double* bytes) {
+  if (!h || i < 0 || i >= (int)h->prof_cls.size()) return fail(OARD_EINVAL, "bad profile index");
+  const auto& c = h->prof_cls[i];
+  if (tag) *tag = c.tag.c_str();
+  if (ms) *ms = c.ms;
+  if (launches) *launches = c.launches;
+  if (flops) *flops = c.flops;
+  if (bytes) *bytes = c.bytes;
+  return OARD_OK;
+}

@@ -197,6 +197,21 @@ class _Engine:
     def launches(self) -> int:
         return int(self.lib.oard_last_launch_count(self.h))
 
+    def total_launches(self) -> int:
+        return int(self.lib.oard_total_launch_count(self.h))
+
+    def set_profile(self, every_n: int):
+        _lib.check(self.lib.oard_set_profile(self.h, int(every_n)))
+
+    def profile(self):
+        """{tag: dict(ms, launches, flops, bytes)} accumulated over the profiled forwards."""
+        out = {}
+        for i in range(self.lib.oard_profile_count(self.h)):
+            tag, ms, n, fl, by = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            _lib.check(self.lib.oard_profile_get(self.h, i, C.byref(tag), C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)))
+            out[tag.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+        return out
+
 
 class LEFTNetB200(nn.Module):
     """See module docstring.  Constructor mirrors model/leftnet.py:594-611."""
