@@ -95,6 +95,11 @@ int oard_profile_count(const oard_handle* h);
 int oard_profile_get(const oard_handle* h, int i, const char** tag, double* ms, int64_t* launches, double* flops,
                      double* bytes);
 
+/* Unit-test entry for the two GEMM implementations: C[M,N] = act(A[M,K] W[N,K]^T + bias), device pointers.
+ * use_tc = 0: exact-fp32 SIMT kernel; 1: tcgen05 bf16x3 kernel (sm_100 only).  Synchronises `stream` when use_tc. */
+int oard_test_gemm(int device, int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
+                   int use_tc, int act, int swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,8 @@ SYMBOLS = {
     "oard_total_launch_count": (C.c_int64, [C.c_void_p]),
     "oard_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "oard_profile_count": (C.c_int, [C.c_void_p]),
+    "oard_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "oard_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

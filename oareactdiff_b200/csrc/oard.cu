@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 using namespace oard;
@@ -64,6 +66,13 @@ struct oard_handle {
   const float *emb_w, *emb_b, *eout_w, *eout_b, *means, *betas, *ne_w, *ne_b, *s2v_w, *s2v_b, *rl0_w, *rl0_b, *rl2_w,
       *rl2_b, *l3_w0, *l3_b0, *l3_w2, *l3_b2, *pe0_w, *pe1_w, *o_v1w, *o_v2w, *o_u0w, *o_u0b, *o_u2w, *o_u2b;
   std::vector<LayerW> L;
+  // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
+  bool use_tc = false;
+  int num_sms = 148;
+  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf; };
+  std::vector<LayerTc> T;
+  TcWeight tc_rl0{}, tc_rl2{};
+  std::vector<void*> tc_bufs;
   // plan
   bool planned = false;
   int N = 0, E = 0, NC = 0;
@@ -166,6 +175,15 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   build_specs(h);
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    const char* env = getenv("OARD_GEMM");  // "simt" forces the exact-fp32 SIMT GEMMs everywhere
+    const bool want_tc = !(env && strcmp(env, "simt") == 0);
+    const bool dims_ok = cfg->hidden_channels % 4 == 0 && cfg->num_radial % 4 == 0;
+    h->use_tc = want_tc && dims_ok && prop.major == 10;  // tcgen05 exists on sm_100 only
+  }
   for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
   *out = h;
   return OARD_OK;
@@ -182,6 +200,7 @@ extern "C" void oard_destroy(oard_handle* h) {
   cudaSetDevice(h->device);
   for (float* p : h->wdev)
     if (p) cudaFree(p);
+  for (void* p : h->tc_bufs) cudaFree(p);
   free_map(h->ws);
   free_map(h->snaps);
   delete h;
@@ -253,7 +272,39 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     w.l2w = W(u + "lin3.2.weight"); w.l2b = W(u + "lin3.2.bias");
     w.l4w = W(u + "lin3.4.weight"); w.l4b = W(u + "lin3.4.bias");
   }
-  (void)stream;
+  if (h->use_tc) {
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (void* p : h->tc_bufs) cudaFree(p);
+    h->tc_bufs.clear();
+    auto pack = [&](const float* Wp, int ldw, int N, int K, TcWeight* out) -> int {
+      const int n_tiles = (N + 255) / 256;
+      const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+      const size_t elems = tc_weight_elems(N, K, BN);
+      __nv_bfloat16* buf = nullptr;
+      CU(cudaMalloc(&buf, elems * sizeof(__nv_bfloat16)));
+      h->tc_bufs.push_back(buf);
+      k_tc_pack_weight<<<256, 256, 0, st>>>(Wp, ldw, N, K, BN, buf);
+      CU(cudaGetLastError());
+      *out = TcWeight{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
+      return OARD_OK;
+    };
+    const int H = h->cfg.hidden_channels, R = h->cfg.num_radial, D = 3 * H + R;
+    int rc;
+    if ((rc = pack(h->rl0_w, R, H, R, &h->tc_rl0))) return rc;
+    if ((rc = pack(h->rl2_w, H, H, H, &h->tc_rl2))) return rc;
+    h->T.resize(h->cfg.num_layers);
+    for (int l = 0; l < h->cfg.num_layers; l++) {
+      const LayerW& w = h->L[l];
+      auto& t = h->T[l];
+      if ((rc = pack(w.e0w + 2 * H, 2 * H + D, H, D, &t.e0))) return rc;
+      if ((rc = pack(w.e1w, H, H, H, &t.e1))) return rc;
+      if ((rc = pack(w.eow, H, D, H, &t.eo))) return rc;
+      if ((rc = pack(w.d0w, D, 3 * H, D, &t.d0))) return rc;
+      if ((rc = pack(w.d2w, 3 * H, 3 * H, 3 * H, &t.d2))) return rc;
+      if ((rc = pack(w.rbfw, R, 3 * H, R, &t.rbf))) return rc;
+    }
+  }
   h->committed = true;
   return OARD_OK;
 }
@@ -500,6 +551,17 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     prof_end(h, st);                                                                                         \
   } while (0)
 
+#define GEMM_TC(tag, g, tw)                                                                                  \
+  do {                                                                                                       \
+    if (!h->use_tc) { GEMM(tag, g); break; }                                                                 \
+    prof_begin(h, tag, 2.0 * (g).M * (g).N * (g).K, 4.0 * (g).M * ((g).K + (g).N + ((g).resid ? (g).N : 0)),   \
+               (g).m_dev != nullptr, st);                                                                    \
+    cudaError_t e_ = launch_gemm_tc(g, tw, h->num_sms, st);                                                  \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm_tc: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    h->launches++;                                                                                           \
+    prof_end(h, st);                                                                                         \
+  } while (0)
+
   // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
   if (E) { PB("k_edge_mask", 0, E*29.0, 0);
     k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
@@ -533,10 +595,10 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     // radial_lin on active edges: f = rb * (W2 SiLU(W1 rbf + b1) + b2)   (leftnet.py:784-786)
     GemmArgs g = mk(rbf_act, R, h->rl0_w, R, hid1, H, E, H, R);
     g.m_dev = n_act; g.bias = h->rl0_b; g.act = 1;
-    GEMM("gemm_radial_lin0", g);
+    GEMM_TC("gemm_radial_lin0", g, h->tc_rl0);
     g = mk(hid1, H, h->rl2_w, H, f_act, H, E, H, H);
     g.m_dev = n_act; g.bias = h->rl2_b; g.rowscale = rb; g.rsidx = act_idx;
-    GEMM("gemm_radial_lin2", g);
+    GEMM_TC("gemm_radial_lin2", g, h->tc_rl2);
   }
   PB("k_masked_consts", 0, H*H*4.0, 0);
   k_masked_consts<<<1, HB, H * sizeof(float), st>>>(H, Hq, h->rl0_b, h->rl2_w, h->rl2_b, h->l3_b0, h->l3_w2, h->l3_b2,
@@ -600,10 +662,10 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
-      GEMM("gemm_gcl_edge1", g);
+      GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
       g = mk(hid1, H, w.e1w, H, m2, H, E, H, H);
       g.bias = w.e1b; g.act = 1;
-      GEMM("gemm_gcl_edge2", g);
+      GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
     }
     PB("k_att_agg", 0, (double)E*H*8.0, 0);
     k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
@@ -617,7 +679,7 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     if (E) {
       g = mk(m2, H, w.eow, H, ew, D, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
-      GEMM("gemm_gcl_edge_out", g);
+      GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
     PB("k_layernorm", 0, N*H*8.0, 0);
@@ -631,13 +693,13 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     if (E) {
       g = mk(ew, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
       g.aidx = act_idx; g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
-      GEMM("gemm_dir_proj0", g);
+      GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
       g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
       g.m_dev = n_act;
-      GEMM("gemm_rbf_proj", g);
+      GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
       g = mk(d1, 3 * H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
-      GEMM("gemm_dir_proj2", g);
+      GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
     PB("k_equi_reduce", 0, (double)E*(3.0*H*4+16), 1);
     k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
@@ -684,6 +746,34 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   KCHECK();
   h->total_launches += h->launches;
   return prof_harvest(h, st);
+}
+
+// Bring-up / unit-test entry: C = act(A W^T + bias) with either GEMM implementation (device pointers).
+extern "C" int oard_test_gemm(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
+                              float* C, int use_tc, int act, int swap_lbo_sbo, void* stream) {
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmArgs g = mk(A, K, W, K, C, N, M, N, K);
+  g.bias = bias; g.act = act;
+  if (!use_tc) {
+    CU(launch_gemm_simt(g, st));
+    return OARD_OK;
+  }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
+  const int n_tiles = (N + 255) / 256;
+  const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  __nv_bfloat16* buf = nullptr;
+  CU(cudaMalloc(&buf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
+  k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, buf);
+  TcWeight tw{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
+  cudaError_t e = launch_gemm_tc(g, tw, prop.multiProcessorCount, st, swap_lbo_sbo);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(OARD_ECUDA, "gemm_tc launch: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(OARD_ECUDA, "gemm_tc run: %s", cudaGetErrorString(e2));
+  return OARD_OK;
 }
 
 extern "C" int oard_set_debug(oard_handle* h, int on) {

@@ -1,0 +1,19 @@
+"""GPU unit test of the tcgen05 bf16x3 GEMM against an fp64 matmul (tolerance 3e-5 of max|ref|: the split keeps
+~16 mantissa bits per operand) and of the exact-fp32 SIMT GEMM (1e-6)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (300, 196, 684), (1000, 684, 196), (257, 588, 588), (5000, 588, 96),
+                                   (33, 32, 112), (20000, 196, 684)])
+def test_gemm_tc_and_simt(M, N, K):
+    from tests.bringup_tc import run
+    tc = run(M, N, K, 1)
+    simt = run(M, N, K, 0)
+    tcs = run(M, N, K, 1, act=1)
+    print(M, N, K, "tc", tc, "simt", simt, "tc+silu", tcs)
+    for res, tol in ((tc, 3e-5), (tcs, 3e-5), (simt, 2e-6)):
+        assert res.startswith("rel_err="), res
+        assert float(res.split()[0].split("=")[1]) < tol and res.endswith("nan=0"), res
