@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--denoise-steps", type=int, default=1000, help="T of the reverse diffusion (BASELINE: 1000)")
     ap.add_argument("--profile-every", type=int, default=97, help="bracket kernels with CUDA events every n-th forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-replay", action="store_true", help="skip the realistic-geometry replay line")
     ap.add_argument("--cpu-evals", type=int, default=2, help="denoiser evaluations timed for cpu_baseline")
     return ap.parse_args()
 
@@ -195,6 +196,38 @@ def run_b200(args, rank, world, local_rank):
         out, _ = ddpm.sample(B, nodes_d, cond_d, h0=h0_d)
         return out[0]
 
+    # Replay (SURVEY §8d realism caveat): the same per-step work (denoiser + posterior sampling) on states
+    # z_t = alpha_t x + sigma_t eps built from compact synthetic geometries, i.e. what a TRAINED model sees: every
+    # same-fragment edge stays inside the 10 A cutoff.  With random weights the literal sample() drifts to |x| ~ 1e2 A.
+    gen = torch.Generator().manual_seed(99 + rank)
+    geo = []
+    for n in sizes:
+        r = 1.2 * n ** (1.0 / 3.0)
+        pts = torch.randn(n, 3, generator=gen)
+        pts = pts / pts.norm(dim=1, keepdim=True) * (torch.rand(n, 1, generator=gen) ** (1 / 3)) * r
+        geo.append(pts - pts.mean(0, keepdim=True))
+    x_frag = []
+    for f in range(3):
+        xs = [gp + 0.3 * torch.randn(gp.shape, generator=gen) for gp in geo]
+        x_frag.append(torch.cat([x - x.mean(0, keepdim=True) for x in xs]).to(dev))
+    xh0_d = [torch.cat([x_frag[f], h0_d[f]], dim=1) for f in range(3)]
+
+    def step_replay():
+        torch.manual_seed(4321 + rank)
+        masks, edge_index, nfs = ddpm._setup(B, nodes_d)
+        for s_int in reversed(range(T)):
+            s_arr = torch.full((B, 1), fill_value=s_int, device=dev)
+            t_arr = (s_arr + 1) / T
+            s_arr = s_arr / T
+            gamma_t = ddpm.schedule.inflate_batch_array(ddpm.schedule.gamma_module(t_arr), xh0_d[0])
+            z_t, _ = ddpm.noised_representation(xh0_d, masks, gamma_t)
+            z_t = ddpm._with_h0(z_t, h0_d)
+            ddpm.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z_t, edge_index=edge_index, n_frag_switch=nfs,
+                                      masks=masks, conditions=cond_d)
+        gamma_0 = ddpm.schedule.inflate_batch_array(ddpm.schedule.gamma_module(torch.zeros(B, 1, device=dev)), xh0_d[0])
+        z_0, _ = ddpm.noised_representation(xh0_d, masks, gamma_0)
+        return ddpm.sample_p_xh_given_z0(ddpm._with_h0(z_0, h0_d), edge_index, nfs, masks, B, cond_d)[0]
+
     out_host = [torch.empty(h.size(0), 9).pin_memory() for h in h0_h]
 
     def step_e2e():
@@ -241,6 +274,20 @@ def run_b200(args, rank, world, local_rank):
     eng.set_profile(0)
     ms_e2e = timed(step_e2e, args.steps)
     finite = all(bool(torch.isfinite(o).all()) for o in out_host)
+    replay = None
+    if not args.no_replay:
+        step_replay()
+        eng.set_profile(args.profile_every)
+        ms_rp = timed(step_replay, 1)
+        prof_rp = eng.profile()
+        eng.set_profile(0)
+        af = prof_rp.get("_active_fraction")
+        replay = {"value": B * world / (ms_rp / 1e3), "unit": UNIT, "ms_per_step": ms_rp, "steps": 1,
+                  "active_edge_fraction": (af["flops"] / max(af["launches"], 1)) if af else None,
+                  "note": "same per-step work on z_t = alpha_t x + sigma_t eps from compact synthetic geometries "
+                          "(what a trained model sees; every same-fragment edge inside the cutoff)",
+                  "kernels_ms_per_launch": {k: round(v["ms"] / max(v["launches"], 1), 5) for k, v in
+                                            sorted(prof_rp.items(), key=lambda kv: -kv[1]["ms"])[:10] if not k.startswith("_")}}
 
     total_reactions = B * world * args.steps
     value = total_reactions / (ms / 1e3)
@@ -248,6 +295,7 @@ def run_b200(args, rank, world, local_rank):
     if rank != 0:
         return
     pk = peaks()
+    af_lit = prof.pop("_active_fraction", None)
     kernels = {k: dict(ms_per_launch=v["ms"] / max(v["launches"], 1), launches=v["launches"],
                        tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
                        gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
@@ -286,6 +334,8 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps, "outputs_finite": finite},
+            "active_edge_fraction": (af_lit["flops"] / max(af_lit["launches"], 1)) if af_lit else None,
+            "replay": replay,
             "roofline": roof,
             "message_passing_roofline": None if not mp else {
                 "kernel": "k_equi_reduce", "bound": "hbm", "achieved": mp["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -10,6 +10,9 @@ namespace oard {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
+// ex2.approx / rcp.approx based SiLU (relative error ~1e-6): used where thousands of activations per thread dominate
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

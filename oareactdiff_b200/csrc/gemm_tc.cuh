@@ -150,13 +150,15 @@ __host__ __device__ inline uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 struct TcDebugOpts {  // layout experiments for bring-up (normally all zero)
   int swap_lbo_sbo;
 };
 
-template <int STAGES>
+// Epilogue modes (compile-time, keeps the register ring of each variant small):
+//   0 plain: bias / SiLU / row scale      1: + two gathered row adds (GCL: P[src] + Q[dst])
+//   2: * mul[m, n] (EquiMessage: rbf_proj gate)      3: + resid[m, n] (edge-state residual, may alias C)
+template <int STAGES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -198,46 +200,63 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 6) {
-    // ===================== A producer: one row per thread =====================
+    // ===================== A producer: one row per thread, loads run 2 chunks ahead of the conversion =====================
     const int p = threadIdx.x - 192;  // 0..127
-    uint32_t gchunk = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m = (tile / w.n_tiles) * TC_BM + p;
-      const bool ok = m < M;
-      const float* arow = g.A + (size_t)(ok ? (g.aidx ? g.aidx[m] : m) : 0) * g.lda;
-      const int row_off = (p >> 3) * TC_SBO + (p & 7) * 16;
-      for (int kc = 0; kc < k_chunks; kc++, gchunk++) {
-        const int s = gchunk % STAGES;
-        const uint32_t ph = (gchunk / STAGES) & 1;
-        float4 v[TC_KC / 4];
+    const int row_off = (p >> 3) * TC_SBO + (p & 7) * 16;
+    struct It { int tile, kc; const float* arow; bool ok; };
+    auto init_row = [&](It& it) {
+      const int m = (it.tile / w.n_tiles) * TC_BM + p;
+      it.ok = it.tile < total_tiles && m < M;
+      it.arow = g.A + (size_t)(it.ok ? (g.aidx ? g.aidx[m] : m) : 0) * g.lda;
+    };
+    auto advance = [&](It& it) {
+      if (++it.kc == k_chunks) { it.kc = 0; it.tile += gridDim.x; init_row(it); }
+    };
+    auto issue = [&](const It& it, float4* v) {
 #pragma unroll
-        for (int j = 0; j < TC_KC / 4; j++) {
-          const int k = kc * TC_KC + j * 4;
-          v[j] = (ok && k < g.K) ? __ldg(reinterpret_cast<const float4*>(arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* a_hi = smem + (size_t)s * STAGE_BYTES + row_off;
-        uint8_t* a_lo = a_hi + A_PART;
-#pragma unroll
-        for (int j = 0; j < TC_KC / 8; j++) {  // one 16-byte unit (8 bf16) per core-matrix column
-          const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
-                              v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
-            const float2 hf = __bfloat1622float2(h2);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
-            hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
-            lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
-          }
-          *reinterpret_cast<uint4*>(a_hi + j * TC_CORE_BYTES) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(a_lo + j * TC_CORE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&full_a[s]);
+      for (int j = 0; j < TC_KC / 4; j++) {
+        const int k = it.kc * TC_KC + j * 4;
+        v[j] = (it.ok && k < g.K) ? __ldg(reinterpret_cast<const float4*>(it.arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto consume = [&](uint32_t gchunk, const float4* v) {
+      const int s = gchunk % STAGES;
+      const uint32_t ph = (gchunk / STAGES) & 1;
+      ptx::mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* a_hi = smem + (size_t)s * STAGE_BYTES + row_off;
+      uint8_t* a_lo = a_hi + A_PART;
+#pragma unroll
+      for (int j = 0; j < TC_KC / 8; j++) {  // one 16-byte unit (8 bf16) per core-matrix column
+        const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
+                            v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+          const float2 hf = __bfloat1622float2(h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
+          hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        *reinterpret_cast<uint4*>(a_hi + j * TC_CORE_BYTES) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_lo + j * TC_CORE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_a[s]);
+    };
+    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t nchunks = (uint32_t)my_tiles * k_chunks;
+    It ld{(int)blockIdx.x, 0, nullptr, false};
+    init_row(ld);
+    float4 b0[TC_KC / 4], b1[TC_KC / 4], b2[TC_KC / 4];
+    issue(ld, b0); advance(ld);
+    issue(ld, b1); advance(ld);
+    for (uint32_t c = 0; c < nchunks; c += 3) {
+      issue(ld, b2); advance(ld);
+      consume(c, b0);
+      if (c + 1 < nchunks) { issue(ld, b0); advance(ld); consume(c + 1, b1); }
+      if (c + 2 < nchunks) { issue(ld, b1); advance(ld); consume(c + 2, b2); }
     }
   } else if (warp == 5) {
     // ===================== W loader: TMA bulk copies of pre-tiled slabs =====================
@@ -290,26 +309,42 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       }
     }
   } else {
-    // ===================== epilogue warps 0-3: TMEM lane quarter = warp =====================
+    // ===================== epilogue warps 0-3: TMEM lane quarter = warp; one output row per thread =====================
+    // 16-column groups; the row-wise operands of the epilogue (gathered adds / mul / resid) are fetched RING-1 groups
+    // ahead into a register ring so their HBM/L2 latency overlaps the math of earlier groups.
+    constexpr int NA = MODE == 1 ? 2 : (MODE == 0 ? 0 : 1);  // row-operand arrays per group
+    constexpr int RING = 4;
+    const int ngroups = BN / 16;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
       const int m = (tile / w.n_tiles) * TC_BM + warp * 32 + lane;
       const int n0 = (tile % w.n_tiles) * BN;
       const bool ok = m < M;
-      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(warp * 32) << 16);
-      const float* r1 = (ok && g.radd1) ? g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1 : nullptr;
-      const float* r2 = (ok && g.radd2) ? g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2 : nullptr;
+      const float* ra = nullptr;
+      const float* rb2 = nullptr;
+      if (ok) {
+        if (MODE == 1) { ra = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1; rb2 = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2; }
+        if (MODE == 2) ra = g.mul + (size_t)m * g.ldmul;
+        if (MODE == 3) ra = g.resid + (size_t)m * g.ldres;
+      }
       const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
-      const float* mulr = (ok && g.mul) ? g.mul + (size_t)m * g.ldmul : nullptr;
-      const float* resr = (ok && g.resid) ? g.resid + (size_t)m * g.ldres : nullptr;
       float* crow = g.C + (size_t)(ok ? m : 0) * g.ldc;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      float4 aux[RING][NA > 0 ? NA * 4 : 1];
+      auto issue = [&](int grp, float4* a) {
+        if (NA == 0) return;
+        const int n = n0 + grp * 16;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const bool in = ok && grp < ngroups && (n + q * 4) < g.N;
+          a[q] = in ? *reinterpret_cast<const float4*>(ra + n + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NA == 2) a[4 + q] = in ? *reinterpret_cast<const float4*>(rb2 + n + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto process = [&](int grp, const float4* a) {
         float v[16];
-        ptx::tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes even for rows >= M
-        const int n = n0 + c0;
+        ptx::tmem_ld16(tmem_base + buf * 256 + ((uint32_t)(warp * 32) << 16) + grp * 16, v);  // warp-collective
+        const int n = n0 + grp * 16;
         if (ok && n < g.N) {
 #pragma unroll
           for (int q = 0; q < 4; q++) {
@@ -317,17 +352,32 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
             if (nq < g.N) {  // N % 4 == 0 (checked on the host)
               float4 x = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nq)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-              if (r1) { const float4 b = __ldg(reinterpret_cast<const float4*>(r1 + nq)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-              if (r2) { const float4 b = __ldg(reinterpret_cast<const float4*>(r2 + nq)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+              if (MODE == 1) {
+                x.x += a[q].x + a[4 + q].x; x.y += a[q].y + a[4 + q].y; x.z += a[q].z + a[4 + q].z; x.w += a[q].w + a[4 + q].w;
+              }
               if (g.act == 1) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
               x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-              if (mulr) { const float4 b = *reinterpret_cast<const float4*>(mulr + nq); x.x *= b.x; x.y *= b.y; x.z *= b.z; x.w *= b.w; }
-              if (resr) { const float4 b = *reinterpret_cast<const float4*>(resr + nq); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+              if (MODE == 2) { x.x *= a[q].x; x.y *= a[q].y; x.z *= a[q].z; x.w *= a[q].w; }
+              if (MODE == 3) { x.x += a[q].x; x.y += a[q].y; x.z += a[q].z; x.w += a[q].w; }
               *reinterpret_cast<float4*>(crow + nq) = x;
             }
           }
         }
         __syncwarp();
+      };
+      // the row operands do not depend on the accumulator: start fetching before waiting for the MMAs
+#pragma unroll
+      for (int u = 0; u < RING - 1; u++) issue(u, aux[u]);
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int g0 = 0; g0 < ngroups; g0 += RING) {
+#pragma unroll
+        for (int u = 0; u < RING; u++) {
+          if (g0 + u < ngroups) {
+            issue(g0 + u + RING - 1, aux[(u + RING - 1) % RING]);
+            process(g0 + u, aux[u]);
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -347,29 +397,42 @@ inline size_t tc_smem_bytes(int BN, int stages) {
   return (size_t)stages * (2 * TC_BM * TC_KC * 2 + 2 * BN * TC_KC * 2) + (3 * stages + 4) * 8 + 16;
 }
 
-// Requirements (checked): K % 4 == 0, lda % 4 == 0, N % 4 == 0, 16-byte aligned operands, BN % 16 == 0, BN <= 256.
+// Requirements (checked): K % 4 == 0, lda % 4 == 0, N % 4 == 0, 16-byte aligned operands, BN % 16 == 0, BN <= 256,
+// at most one of {radd1+radd2, mul, resid}.
+template <int STAGES, int MODE>
+inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, TcDebugOpts dbg,
+                                       cudaStream_t st) {
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  gemm_tc_kernel<STAGES, MODE><<<grid, TC_THREADS, smem, st>>>(g, w, dbg);
+  return cudaGetLastError();
+}
+
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_sms, cudaStream_t st,
                                   int swap_lbo_sbo = 0) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   if (g.K % 4 || g.lda % 4 || g.N % 4 || g.ldc % 4 || w.BN % 16 || w.BN > 256 || w.BN < 16 || g.K != w.K || g.N != w.N)
     return cudaErrorInvalidValue;
+  const int nmode = (g.radd1 ? 1 : 0) + (g.mul ? 1 : 0) + (g.resid ? 1 : 0);
+  if (nmode > 1 || (g.radd1 && !g.radd2) || (!g.radd1 && g.radd2)) return cudaErrorInvalidValue;
+  const int mode = g.radd1 ? 1 : (g.mul ? 2 : (g.resid ? 3 : 0));
   const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
   const int total = m_tiles * w.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   TcDebugOpts dbg{swap_lbo_sbo};
   const int stages = tc_smem_bytes(w.BN, 4) <= 227 * 1024 ? 4 : 3;
   const size_t smem = tc_smem_bytes(w.BN, stages);
-  cudaError_t e;
-  if (stages == 4) {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(g, w, dbg);
-  } else {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(g, w, dbg);
-  }
-  return cudaGetLastError();
+#define OARD_TC_CASE(S, MD) \
+  if (stages == S && mode == MD) return launch_gemm_tc_inst<S, MD>(g, w, grid, smem, dbg, st);
+  OARD_TC_CASE(4, 0) OARD_TC_CASE(4, 1) OARD_TC_CASE(4, 2) OARD_TC_CASE(4, 3)
+  OARD_TC_CASE(3, 0) OARD_TC_CASE(3, 1) OARD_TC_CASE(3, 2) OARD_TC_CASE(3, 3)
+#undef OARD_TC_CASE
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace oard

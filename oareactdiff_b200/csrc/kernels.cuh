@@ -353,7 +353,7 @@ __global__ void k_edge_init(int H, int R, int Hq, int reflect, const int* __rest
     float acc = b2;
     for (int k = 0; k < Hq; k++) {
       const float u = fmaf(sw[k * 3], s0, fmaf(sw[k * 3 + 1], s1, fmaf(sw[k * 3 + 2], s2, sw[Hq * 3 + k])));
-      acc = fmaf(sw[Hq * 4 + k], silu(u), acc);
+      acc = fmaf(sw[Hq * 4 + k], silu_fast(u), acc);
     }
     out[side * H + h] = (acc + s0) * rbe;
   }
@@ -470,14 +470,14 @@ __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, c
   float u[48];
 #pragma unroll
   for (int k = 0; k < 48; k++)
-    u[k] = silu(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
+    u[k] = silu_fast(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
   float out = b4[0];
 #pragma unroll
   for (int q = 0; q < 8; q++) {
     float a = B2[q];
 #pragma unroll
     for (int k = 0; k < 48; k++) a = fmaf(W2[q * 48 + k], u[k], a);
-    out = fmaf(W4[q], silu(a), out);
+    out = fmaf(W4[q], silu_fast(a), out);
   }
   sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
   sx[(size_t)t * 2 * H + H + h] = out;

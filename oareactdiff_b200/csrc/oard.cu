@@ -69,9 +69,9 @@ struct oard_handle {
   // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
   bool use_tc = false;
   int num_sms = 148;
-  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf; };
+  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pi, pj, n0, n1, x0, x2, vp, xv0, xv2; };
   std::vector<LayerTc> T;
-  TcWeight tc_rl0{}, tc_rl2{};
+  TcWeight tc_rl0{}, tc_rl2{}, tc_s2v{}, tc_ov1{}, tc_ou0{};
   std::vector<void*> tc_bufs;
   // plan
   bool planned = false;
@@ -293,6 +293,9 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     int rc;
     if ((rc = pack(h->rl0_w, R, H, R, &h->tc_rl0))) return rc;
     if ((rc = pack(h->rl2_w, H, H, H, &h->tc_rl2))) return rc;
+    if ((rc = pack(h->s2v_w, H, H, H, &h->tc_s2v))) return rc;
+    if ((rc = pack(h->o_v1w, H, H, H, &h->tc_ov1))) return rc;
+    if ((rc = pack(h->o_u0w, 2 * H, H, 2 * H, &h->tc_ou0))) return rc;
     h->T.resize(h->cfg.num_layers);
     for (int l = 0; l < h->cfg.num_layers; l++) {
       const LayerW& w = h->L[l];
@@ -303,6 +306,15 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.d0w, D, 3 * H, D, &t.d0))) return rc;
       if ((rc = pack(w.d2w, 3 * H, 3 * H, 3 * H, &t.d2))) return rc;
       if ((rc = pack(w.rbfw, R, 3 * H, R, &t.rbf))) return rc;
+      if ((rc = pack(w.e0w, 2 * H + D, H, H, &t.pi))) return rc;
+      if ((rc = pack(w.e0w + H, 2 * H + D, H, H, &t.pj))) return rc;
+      if ((rc = pack(w.n0w, 2 * H, H, 2 * H, &t.n0))) return rc;
+      if ((rc = pack(w.n1w, H, H, H, &t.n1))) return rc;
+      if ((rc = pack(w.x0w, H, H, H, &t.x0))) return rc;
+      if ((rc = pack(w.x2w, H, 3 * H, H, &t.x2))) return rc;
+      if ((rc = pack(w.vpw, H, 2 * H, H, &t.vp))) return rc;
+      if ((rc = pack(w.xv0w, 2 * H, H, 2 * H, &t.xv0))) return rc;
+      if ((rc = pack(w.xv2w, H, 3 * H, H, &t.xv2))) return rc;
     }
   }
   h->committed = true;
@@ -464,6 +476,18 @@ static int prof_harvest(oard_handle* h, cudaStream_t st) {
     c.flops += r.dyn ? r.flops * frac : r.flops;
     c.bytes += r.dyn ? r.bytes * frac : r.bytes;
   }
+  {  // pseudo-class: mean active-edge fraction over the profiled forwards (flops field = sum, launches = count)
+    auto it = h->prof_idx.find("_active_fraction");
+    int cls;
+    if (it == h->prof_idx.end()) {
+      cls = (int)h->prof_cls.size();
+      h->prof_idx["_active_fraction"] = cls;
+      h->prof_cls.push_back({});
+      h->prof_cls.back().tag = "_active_fraction";
+    } else cls = it->second;
+    h->prof_cls[cls].flops += frac;
+    h->prof_cls[cls].launches++;
+  }
   h->prof_recs.clear();
   h->ev_used = 0;
   h->prof_now = false;
@@ -613,7 +637,7 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   {
     GemmArgs g = mk(s, H, h->s2v_w, H, tmpH, H, N, H, H);
     g.bias = h->s2v_b;
-    GEMM("gemm_s2v_lin", g);
+    GEMM_TC("gemm_s2v_lin", g, h->tc_s2v);
   }
   PB("k_layernorm", 0, N*H*8.0, 0);
   k_layernorm<<<N, HB, 0, st>>>(H, tmpH, H, nullptr, nullptr, nullptr, 1, q, H);
@@ -654,9 +678,9 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     KCHECK();
     GemmArgs g = mk(xa, 2 * H, w.e0w, ldw0, PQ, 2 * H, N, H, H);
     g.bias = w.e0b;
-    GEMM("gemm_gcl_P", g);
+    GEMM_TC("gemm_gcl_P", g, h->T[l].pi);
     g = mk(xa, 2 * H, w.e0w + H, ldw0, PQ + H, 2 * H, N, H, H);
-    GEMM("gemm_gcl_Q", g);
+    GEMM_TC("gemm_gcl_Q", g, h->T[l].pj);
     if (E) {
       g = mk(ew, D, w.e0w + 2 * H, ldw0, hid1, H, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
@@ -672,10 +696,10 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     KCHECK();
     g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
     g.bias = w.n0b; g.act = 1;
-    GEMM("gemm_gcl_node0", g);
+    GEMM_TC("gemm_gcl_node0", g, h->T[l].n0);
     g = mk(tN, H, w.n1w, H, s, H, N, H, H);
     g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
-    GEMM("gemm_gcl_node1", g);
+    GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
     if (E) {
       g = mk(m2, H, w.eow, H, ew, D, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
@@ -687,9 +711,9 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     KCHECK();
     g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
     g.act = 1;
-    GEMM("gemm_xproj0", g);
+    GEMM_TC("gemm_xproj0", g, h->T[l].x0);
     g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
-    GEMM("gemm_xproj2", g);
+    GEMM_TC("gemm_xproj2", g, h->T[l].x2);
     if (E) {
       g = mk(ew, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
       g.aidx = act_idx; g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
@@ -713,16 +737,16 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     // ---- EquiUpdate (leftnet.py:325-346)
     if (c.update) {
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
-      GEMM("gemm_vec_proj", g);
+      GEMM_TC("gemm_vec_proj", g, h->T[l].vp);
       PB("k_upd_scalar", 0, N*H*4.0*9, 0);
       k_upd_scalar<<<N, HB, 0, st>>>(H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
                                      vd);
       KCHECK();
       g = mk(sx, 2 * H, w.xv0w, 2 * H, tN, H, N, H, 2 * H);
       g.act = 1;
-      GEMM("gemm_xvec0", g);
+      GEMM_TC("gemm_xvec0", g, h->T[l].xv0);
       g = mk(tN, H, w.xv2w, H, XV, 3 * H, N, 3 * H, H);
-      GEMM("gemm_xvec2", g);
+      GEMM_TC("gemm_xvec2", g, h->T[l].xv2);
       PB("k_upd_apply", 0, N*H*4.0*14, 0);
       k_upd_apply<<<N, HB, 0, st>>>(H, XV, VP, vd, s, vec);
       KCHECK();
@@ -734,13 +758,13 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   }
   // ---- output head (leftnet.py:566-576, 878-887)
   GemmArgs g = mk(vec, H, h->o_v1w, H, O1, H, 3 * N, H, H);
-  GEMM("gemm_out_vec1", g);
+  GEMM_TC("gemm_out_vec1", g, h->tc_ov1);
   PB("k_out_norm", 0, N*H*4.0*6, 0);
   k_out_norm<<<N, HB, 0, st>>>(H, O1, s, sn);
   KCHECK();
   g = mk(sn, 2 * H, h->o_u0w, 2 * H, tu, H, N, H, 2 * H);
   g.bias = h->o_u0b; g.act = 1;
-  GEMM("gemm_out_upd0", g);
+  GEMM_TC("gemm_out_upd0", g, h->tc_ou0);
   PB("k_final", 0, N*H*4.0*5, 0);
   k_final<<<N, HB, 0, st>>>(H, C, tu, h->o_u2w, h->o_u2b, vec, h->o_v2w, s, h->eout_w, h->eout_b, dpos, h_out);
   KCHECK();
