@@ -1,4 +1,4 @@
-// tcgen05 / TMEM GEMM for the per-edge contractions of LEFTNet (sm_100a only).
+// tcgen05 / TMEM GEMM for the dense contractions of LEFTNet (sm_100a only).
 //
 //   C[m, n] = epi( sum_k A[arow(m), k] * W[n, k] )      A: fp32 in HBM (edge state / activations), W: nn.Linear weight
 //
@@ -6,13 +6,17 @@
 //   a = a_hi + a_lo, w = w_hi + w_lo (bf16 each);  a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi   (dropped term ~2^-16)
 // accumulated in fp32 in TMEM by three tcgen05.mma.kind::f16 per K step.
 //
-// Persistent, warp-specialised CTA (320 threads, 1 CTA/SM):
-//   warps 0-3  epilogue : tcgen05.ld accumulator -> bias / gathered row adds / SiLU / scale / mul / residual -> HBM
-//   warp  4    MMA      : one elected lane issues tcgen05.mma; owns TMEM alloc/dealloc (2 accumulators, double buffered)
-//   warp  5    W loader : cp.async.bulk (TMA bulk copy, UBLKCP) of pre-split, pre-tiled weight slabs, mbarrier complete_tx
-//   warps 6-9  A producer: fp32 rows (optionally gathered) from HBM/L2 -> bf16 hi/lo -> shared memory in the UMMA
-//                          K-major core-matrix layout (no swizzle): 8 rows x 16 B per core matrix, K-adjacent contiguous
+// Persistent, warp-specialised CTA (576 threads, 1 CTA/SM):
+//   warps 0-7   epilogue : tcgen05.ld accumulator (thread = row) -> smem transpose staging -> coalesced
+//                          bias / gathered row adds / SiLU / scale / mul / residual -> coalesced float4 stores
+//   warp  8     MMA      : one elected lane issues tcgen05.mma; owns TMEM alloc/dealloc (2 accumulators, double buffered)
+//   warp  9     W loader : cp.async.bulk (TMA bulk copy, UBLKCP) of pre-split, pre-tiled weight slabs, mbarrier complete_tx
+//   warps 10-17 A producer: coalesced float4 loads of fp32 rows (optionally gathered) -> bf16 hi/lo -> shared memory in the
+//                          UMMA K-major core-matrix layout (SWIZZLE_NONE), K-stride padded to 144 B so the 8-byte
+//                          stores of a warp are bank-conflict free; loads run two K-chunks ahead of the conversion
 // Pipelines: S-stage smem ring (full_a / full_w / empty mbarriers) and a 2-deep TMEM ring (acc_full / acc_empty).
+// Every global access of the kernel is a full 128-byte line per 8 threads: the first version (row per thread) was bound
+// by L1 tag throughput (32 lines per warp instruction), see profiles/.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -23,9 +27,15 @@ namespace oard {
 
 constexpr int TC_BM = 128;      // rows per tile (UMMA M)
 constexpr int TC_KC = 32;       // K elements per pipeline stage (2 x UMMA_K)
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;  // 576
 constexpr int TC_CORE_BYTES = 128;                   // one 8x8 bf16 core matrix
-constexpr int TC_SBO = (TC_KC / 8) * TC_CORE_BYTES;  // byte stride between 8-row groups (K-adjacent cores contiguous)
+constexpr int TC_SBO = (TC_KC / 8) * TC_CORE_BYTES;  // W operand: byte stride between 8-row groups (K-adjacent cores contiguous)
+constexpr int TC_A_LBO = 144;                        // A operand: K-adjacent core matrices 144 B apart (bank-conflict-free stores)
+constexpr int TC_A_SBO = (TC_KC / 8) * TC_A_LBO;     // 576
+constexpr int TC_A_PART = (TC_BM / 8) * TC_A_SBO;    // 9216 bytes per A part (hi or lo)
+constexpr int TC_STG_LD = 36;                        // epilogue staging row pitch in floats (32 + 4 pad)
+constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_LD * 4;
 
 // Pre-split, pre-tiled weight: [n_tiles][k_chunks][hi, lo][BN x KC in core-matrix layout], zero padded.
 struct TcWeight {
@@ -38,7 +48,7 @@ __host__ __device__ inline size_t tc_weight_elems(int N, int K, int BN) {
   return (size_t)n_tiles * k_chunks * 2 * BN * TC_KC;
 }
 
-// byte offset of element (r, k) inside one [rows x KC] operand block
+// byte offset of element (r, k) inside one [rows x KC] W operand block
 __host__ __device__ inline int tc_core_off(int r, int k) {
   return (r >> 3) * TC_SBO + (k >> 3) * TC_CORE_BYTES + (r & 7) * 16 + (k & 7) * 2;
 }
@@ -137,6 +147,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
 }  // namespace ptx
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
@@ -150,12 +176,11 @@ __host__ __device__ inline uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-
-struct TcDebugOpts {  // layout experiments for bring-up (normally all zero)
+struct TcDebugOpts {  // bring-up knobs (normally zero)
   int swap_lbo_sbo;
 };
 
-// Epilogue modes (compile-time, keeps the register ring of each variant small):
+// Epilogue modes (compile-time):
 //   0 plain: bias / SiLU / row scale      1: + two gathered row adds (GCL: P[src] + Q[dst])
 //   2: * mul[m, n] (EquiMessage: rbf_proj gate)      3: + resid[m, n] (edge-state residual, may alias C)
 template <int STAGES, int MODE>
@@ -163,10 +188,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int BN = w.BN;
-  const int A_PART = TC_BM * TC_KC * 2;  // bytes of one A part (hi or lo)
   const int W_PART = BN * TC_KC * 2;
-  const int STAGE_BYTES = 2 * A_PART + 2 * W_PART;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const int STAGE_BYTES = 2 * TC_A_PART + 2 * W_PART;
+  float* stg_all = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + TC_STG_BYTES);
   uint64_t* full_a = bars;
   uint64_t* full_w = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
@@ -183,73 +208,81 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      ptx::mbar_init(&full_a[s], 4);  // one elected lane per producer warp
-      ptx::mbar_init(&full_w[s], 1);  // arrive.expect_tx by the loader lane
-      ptx::mbar_init(&empty[s], 1);   // tcgen05.commit
+      ptx::mbar_init(&full_a[s], TC_PROD_WARPS);  // one elected lane per producer warp
+      ptx::mbar_init(&full_w[s], 1);              // arrive.expect_tx by the loader lane
+      ptx::mbar_init(&empty[s], 1);               // tcgen05.commit
     }
     for (int b = 0; b < 2; b++) {
-      ptx::mbar_init(&acc_full[b], 1);   // tcgen05.commit
-      ptx::mbar_init(&acc_empty[b], 4);  // one elected lane per epilogue warp
+      ptx::mbar_init(&acc_full[b], 1);              // tcgen05.commit
+      ptx::mbar_init(&acc_empty[b], TC_EPI_WARPS);  // one elected lane per epilogue warp
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 4) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == TC_EPI_WARPS) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 6) {
-    // ===================== A producer: one row per thread, loads run 2 chunks ahead of the conversion =====================
-    const int p = threadIdx.x - 192;  // 0..127
-    const int row_off = (p >> 3) * TC_SBO + (p & 7) * 16;
-    struct It { int tile, kc; const float* arow; bool ok; };
-    auto init_row = [&](It& it) {
-      const int m = (it.tile / w.n_tiles) * TC_BM + p;
-      it.ok = it.tile < total_tiles && m < M;
-      it.arow = g.A + (size_t)(it.ok ? (g.aidx ? g.aidx[m] : m) : 0) * g.lda;
-    };
-    auto advance = [&](It& it) {
-      if (++it.kc == k_chunks) { it.kc = 0; it.tile += gridDim.x; init_row(it); }
-    };
-    auto issue = [&](const It& it, float4* v) {
+  if (warp >= TC_EPI_WARPS + 2) {
+    // ===================== A producer =====================
+    // warp pw owns rows 16*pw .. 16*pw+15 of the tile.  One warp-wide float4 load covers 4 rows x 128 contiguous bytes
+    // (rows r0, r0+2, r0+4, r0+6 so that, with the 144-byte K pitch, the 8-byte smem stores hit each bank group twice).
+    const int pw = warp - (TC_EPI_WARPS + 2);
+    const int kq = lane & 7;
+    struct It { int tile, kc; const float* rp[4]; };
+    auto row_of = [&](int i) { return 16 * pw + ((i >> 1) << 3) + (i & 1) + 2 * (lane >> 3); };
+    auto init_rows = [&](It& it) {
 #pragma unroll
-      for (int j = 0; j < TC_KC / 4; j++) {
-        const int k = it.kc * TC_KC + j * 4;
-        v[j] = (it.ok && k < g.K) ? __ldg(reinterpret_cast<const float4*>(it.arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 4; i++) {
+        const int m = (it.tile / w.n_tiles) * TC_BM + row_of(i);
+        const bool ok = it.tile < total_tiles && m < M;
+        it.rp[i] = ok ? g.A + (size_t)(g.aidx ? g.aidx[m] : m) * g.lda + kq * 4 : nullptr;
       }
     };
+    auto advance = [&](It& it) {
+      if (++it.kc == k_chunks) { it.kc = 0; it.tile += gridDim.x; init_rows(it); }
+    };
+    auto issue = [&](const It& it, float4* v) {
+      const int k = it.kc * TC_KC + kq * 4;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        v[i] = (it.rp[i] && k < g.K) ? __ldg(reinterpret_cast<const float4*>(it.rp[i] + it.kc * TC_KC))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = row_of(i);
+      soff[i] = (r >> 3) * TC_A_SBO + (kq >> 1) * TC_A_LBO + (r & 7) * 16 + (kq & 1) * 8;
+    }
     auto consume = [&](uint32_t gchunk, const float4* v) {
       const int s = gchunk % STAGES;
       const uint32_t ph = (gchunk / STAGES) & 1;
       ptx::mbar_wait(&empty[s], ph ^ 1);
-      uint8_t* a_hi = smem + (size_t)s * STAGE_BYTES + row_off;
-      uint8_t* a_lo = a_hi + A_PART;
+      uint8_t* a_hi = smem + (size_t)s * STAGE_BYTES;
+      uint8_t* a_lo = a_hi + TC_A_PART;
 #pragma unroll
-      for (int j = 0; j < TC_KC / 8; j++) {  // one 16-byte unit (8 bf16) per core-matrix column
-        const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
-                            v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
-          const float2 hf = __bfloat1622float2(h2);
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
-          hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-        *reinterpret_cast<uint4*>(a_hi + j * TC_CORE_BYTES) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a_lo + j * TC_CORE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int i = 0; i < 4; i++) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i].x, v[i].y), h1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[i].x - f0.x, v[i].y - f0.y);
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(v[i].z - f1.x, v[i].w - f1.y);
+        *reinterpret_cast<uint2*>(a_hi + soff[i]) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(a_lo + soff[i]) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
       }
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
     };
-    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t nchunks = (uint32_t)my_tiles * k_chunks;
-    It ld{(int)blockIdx.x, 0, nullptr, false};
-    init_row(ld);
-    float4 b0[TC_KC / 4], b1[TC_KC / 4], b2[TC_KC / 4];
+    It ld;
+    ld.tile = blockIdx.x; ld.kc = 0;
+    init_rows(ld);
+    float4 b0[4], b1[4], b2[4];
     issue(ld, b0); advance(ld);
     issue(ld, b1); advance(ld);
     for (uint32_t c = 0; c < nchunks; c += 3) {
@@ -258,7 +291,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       if (c + 1 < nchunks) { issue(ld, b0); advance(ld); consume(c + 1, b1); }
       if (c + 2 < nchunks) { issue(ld, b1); advance(ld); consume(c + 2, b2); }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== W loader: TMA bulk copies of pre-tiled slabs =====================
     if (lane == 0) {
       uint32_t gchunk = 0;
@@ -270,16 +303,16 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
           const uint32_t ph = (gchunk / STAGES) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
           ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W_PART);
-          ptx::bulk_g2s(smem + (size_t)s * STAGE_BYTES + 2 * A_PART, src + (size_t)kc * 2 * W_PART, 2 * W_PART,
+          ptx::bulk_g2s(smem + (size_t)s * STAGE_BYTES + 2 * TC_A_PART, src + (size_t)kc * 2 * W_PART, 2 * W_PART,
                         &full_w[s]);
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_EPI_WARPS) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = tc_idesc(TC_BM, BN);
-      const uint32_t lbo = dbg.swap_lbo_sbo ? TC_SBO : TC_CORE_BYTES, sbo = dbg.swap_lbo_sbo ? TC_CORE_BYTES : TC_SBO;
+      const uint32_t wl = dbg.swap_lbo_sbo ? TC_SBO : TC_CORE_BYTES, ws = dbg.swap_lbo_sbo ? TC_CORE_BYTES : TC_SBO;
       uint32_t gchunk = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
         const int buf = it & 1;
@@ -292,13 +325,13 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
           ptx::mbar_wait(&full_a[s], ph);
           ptx::mbar_wait(&full_w[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_PART;
-          const uint32_t w_hi = a_hi + 2 * A_PART, w_lo = w_hi + W_PART;
+          const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TC_A_PART;
+          const uint32_t w_hi = a_hi + 2 * TC_A_PART, w_lo = w_hi + W_PART;
           const int steps = min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
-          for (int j = 0; j < steps; j++) {
-            const uint32_t ko = j * 2 * TC_CORE_BYTES;  // two K-adjacent core matrices per UMMA_K = 16
-            const uint64_t dah = tc_smem_desc(a_hi + ko, lbo, sbo), dal = tc_smem_desc(a_lo + ko, lbo, sbo);
-            const uint64_t dwh = tc_smem_desc(w_hi + ko, lbo, sbo), dwl = tc_smem_desc(w_lo + ko, lbo, sbo);
+          for (int j = 0; j < steps; j++) {  // two K-adjacent core matrices per UMMA_K = 16
+            const uint32_t ka = j * 2 * TC_A_LBO, kw = j * 2 * TC_CORE_BYTES;
+            const uint64_t dah = tc_smem_desc(a_hi + ka, TC_A_LBO, TC_A_SBO), dal = tc_smem_desc(a_lo + ka, TC_A_LBO, TC_A_SBO);
+            const uint64_t dwh = tc_smem_desc(w_hi + kw, wl, ws), dwl = tc_smem_desc(w_lo + kw, wl, ws);
             ptx::umma_bf16(d_tmem, dah, dwh, idesc, (kc | j) != 0);
             ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
             ptx::umma_bf16(d_tmem, dal, dwh, idesc, 1);
@@ -309,75 +342,80 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       }
     }
   } else {
-    // ===================== epilogue warps 0-3: TMEM lane quarter = warp; one output row per thread =====================
-    // 16-column groups; the row-wise operands of the epilogue (gathered adds / mul / resid) are fetched RING-1 groups
-    // ahead into a register ring so their HBM/L2 latency overlaps the math of earlier groups.
-    constexpr int NA = MODE == 1 ? 2 : (MODE == 0 ? 0 : 1);  // row-operand arrays per group
-    constexpr int RING = 4;
-    const int ngroups = BN / 16;
+    // ===================== epilogue warps 0-7 =====================
+    // warp e reads TMEM lanes 32*(e%4).. (its row quarter) and takes the 32-column blocks with parity e/4.
+    // thread = row after tcgen05.ld; a padded smem transpose turns that into 4 rows x 128 contiguous bytes per warp access.
+    const int rq = warp & 3, half = warp >> 2;
+    float* stg = stg_all + warp * 32 * TC_STG_LD;
+    const int nblocks = (BN + 31) / 32;
+    const int cq = lane & 7, rsub = lane >> 3;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
-      const int m = (tile / w.n_tiles) * TC_BM + warp * 32 + lane;
+      const int m_base = (tile / w.n_tiles) * TC_BM + rq * 32;
       const int n0 = (tile % w.n_tiles) * BN;
-      const bool ok = m < M;
-      const float* ra = nullptr;
-      const float* rb2 = nullptr;
-      if (ok) {
-        if (MODE == 1) { ra = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1; rb2 = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2; }
-        if (MODE == 2) ra = g.mul + (size_t)m * g.ldmul;
-        if (MODE == 3) ra = g.resid + (size_t)m * g.ldres;
-      }
-      const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
-      float* crow = g.C + (size_t)(ok ? m : 0) * g.ldc;
-      float4 aux[RING][NA > 0 ? NA * 4 : 1];
-      auto issue = [&](int grp, float4* a) {
-        if (NA == 0) return;
-        const int n = n0 + grp * 16;
+      // row-wise operands of this thread's 8 rows (rows rsub + 4 j)
+      const float* ra[8];
+      const float* rb[MODE == 1 ? 8 : 1];
+      float rs[8];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const bool in = ok && grp < ngroups && (n + q * 4) < g.N;
-          a[q] = in ? *reinterpret_cast<const float4*>(ra + n + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (NA == 2) a[4 + q] = in ? *reinterpret_cast<const float4*>(rb2 + n + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; j++) {
+        const int m = m_base + rsub + 4 * j;
+        const bool ok = m < M;
+        ra[j] = nullptr;
+        if (MODE == 1) rb[j] = nullptr;
+        rs[j] = 1.f;
+        if (ok) {
+          if (MODE == 1) { ra[j] = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1; rb[j] = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2; }
+          if (MODE == 2) ra[j] = g.mul + (size_t)m * g.ldmul;
+          if (MODE == 3) ra[j] = g.resid + (size_t)m * g.ldres;
+          if (g.rowscale) rs[j] = g.rowscale[g.rsidx ? g.rsidx[m] : m];
         }
-      };
-      auto process = [&](int grp, const float4* a) {
-        float v[16];
-        ptx::tmem_ld16(tmem_base + buf * 256 + ((uint32_t)(warp * 32) << 16) + grp * 16, v);  // warp-collective
-        const int n = n0 + grp * 16;
-        if (ok && n < g.N) {
+      }
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int blk = half; blk < nblocks; blk += 2) {
+        float v[32];
+        ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int nq = n + q * 4;
-            if (nq < g.N) {  // N % 4 == 0 (checked on the host)
-              float4 x = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + nq)); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = n0 + blk * 32 + cq * 4;
+        const bool ncol = n < g.N && (blk * 32 + cq * 4) < BN;  // N % 4 == 0 (checked on the host)
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ncol && g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+        for (int jh = 0; jh < 2; jh++) {
+          float4 a1[4], a2[MODE == 1 ? 4 : 1];
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {  // issue the row-operand loads of four rows, then do the math
+            const int j = jh * 4 + jj;
+            const bool in = ncol && (m_base + rsub + 4 * j) < M;
+            a1[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE != 0 && in) a1[jj] = *reinterpret_cast<const float4*>(ra[j] + n);
+            if (MODE == 1) a2[jj] = in ? *reinterpret_cast<const float4*>(rb[j] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int j = jh * 4 + jj;
+            const int m = m_base + rsub + 4 * j;
+            if (ncol && m < M) {
+              float4 x = *reinterpret_cast<const float4*>(stg + (rsub + 4 * j) * TC_STG_LD + cq * 4);
+              x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
               if (MODE == 1) {
-                x.x += a[q].x + a[4 + q].x; x.y += a[q].y + a[4 + q].y; x.z += a[q].z + a[4 + q].z; x.w += a[q].w + a[4 + q].w;
+                x.x += a1[jj].x + a2[jj].x; x.y += a1[jj].y + a2[jj].y; x.z += a1[jj].z + a2[jj].z; x.w += a1[jj].w + a2[jj].w;
               }
               if (g.act == 1) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
-              x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-              if (MODE == 2) { x.x *= a[q].x; x.y *= a[q].y; x.z *= a[q].z; x.w *= a[q].w; }
-              if (MODE == 3) { x.x += a[q].x; x.y += a[q].y; x.z += a[q].z; x.w += a[q].w; }
-              *reinterpret_cast<float4*>(crow + nq) = x;
+              const float r = rs[j];
+              x.x *= r; x.y *= r; x.z *= r; x.w *= r;
+              if (MODE == 2) { x.x *= a1[jj].x; x.y *= a1[jj].y; x.z *= a1[jj].z; x.w *= a1[jj].w; }
+              if (MODE == 3) { x.x += a1[jj].x; x.y += a1[jj].y; x.z += a1[jj].z; x.w += a1[jj].w; }
+              *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = x;
             }
           }
         }
-        __syncwarp();
-      };
-      // the row operands do not depend on the accumulator: start fetching before waiting for the MMAs
-#pragma unroll
-      for (int u = 0; u < RING - 1; u++) issue(u, aux[u]);
-      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      for (int g0 = 0; g0 < ngroups; g0 += RING) {
-#pragma unroll
-        for (int u = 0; u < RING; u++) {
-          if (g0 + u < ngroups) {
-            issue(g0 + u + RING - 1, aux[(u + RING - 1) % RING]);
-            process(g0 + u, aux[u]);
-          }
-        }
+        __syncwarp();  // staging is reused by the next block
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -387,14 +425,14 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
 inline size_t tc_smem_bytes(int BN, int stages) {
-  return (size_t)stages * (2 * TC_BM * TC_KC * 2 + 2 * BN * TC_KC * 2) + (3 * stages + 4) * 8 + 16;
+  return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + TC_STG_BYTES + (3 * stages + 4) * 8 + 16;
 }
 
 // Requirements (checked): K % 4 == 0, lda % 4 == 0, N % 4 == 0, 16-byte aligned operands, BN % 16 == 0, BN <= 256,
@@ -425,7 +463,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
   const int total = m_tiles * w.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   TcDebugOpts dbg{swap_lbo_sbo};
-  const int stages = tc_smem_bytes(w.BN, 4) <= 227 * 1024 ? 4 : 3;
+  const int stages = tc_smem_bytes(w.BN, 4) <= 226 * 1024 ? 4 : 3;
   const size_t smem = tc_smem_bytes(w.BN, stages);
 #define OARD_TC_CASE(S, MD) \
   if (stages == S && mode == MD) return launch_gemm_tc_inst<S, MD>(g, w, grid, smem, dbg, st);
