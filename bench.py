@@ -174,17 +174,18 @@ def run_b200(args, rank, world, local_rank):
     torch.manual_seed(0)
     dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0,
                           condition_nf=1, model=ob.LEFTNetB200, device=dev).to(dev)
-    if world > 1:  # the one collective of the path: broadcast rank 0's weights (42.6 MB) over NCCL
-        flat = torch.cat([p.data.reshape(-1) for p in dyn.parameters()])
-        dist.broadcast(flat, 0)
-        o = 0
-        for p in dyn.parameters():
-            p.data.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+    from oareactdiff_b200 import parallel
+    bcast_bytes = parallel.broadcast_module_(dyn, src=0)  # the one collective of the path: rank 0's weights (42.6 MB), NCCL
     sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
     ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True).to(dev)
     dyn.model.assume_static_weights = True
 
-    sizes = workloads.t1x_sizes(B, seed=rank)  # every rank its own batch (weak scaling)
+    # weak scaling: a global batch of B*world Transition1x-shaped reactions, sharded into contiguous chunks balanced by
+    # edge count; no per-step communication (reactions are independent)
+    all_sizes = workloads.t1x_sizes(B * world, seed=0)
+    lo, hi = parallel.shard_reactions(all_sizes, world)[rank]
+    sizes = all_sizes[lo:hi]
+    B = len(sizes)
     nodes_h, h0_h, cond_h = workloads.reaction_batch(sizes, seed=rank)
     pin = lambda t: t.pin_memory()
     nodes_h, h0_h, cond_h = [pin(x) for x in nodes_h], [pin(x) for x in h0_h], pin(cond_h)
@@ -256,10 +257,7 @@ def run_b200(args, rank, world, local_rank):
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
     for _ in range(args.warmup):
         step_resident()
@@ -282,14 +280,14 @@ def run_b200(args, rank, world, local_rank):
         prof_rp = eng.profile()
         eng.set_profile(0)
         af = prof_rp.get("_active_fraction")
-        replay = {"value": B * world / (ms_rp / 1e3), "unit": UNIT, "ms_per_step": ms_rp, "steps": 1,
+        replay = {"value": len(all_sizes) / (ms_rp / 1e3), "unit": UNIT, "ms_per_step": ms_rp, "steps": 1,
                   "active_edge_fraction": (af["flops"] / max(af["launches"], 1)) if af else None,
                   "note": "same per-step work on z_t = alpha_t x + sigma_t eps from compact synthetic geometries "
                           "(what a trained model sees; every same-fragment edge inside the cutoff)",
                   "kernels_ms_per_launch": {k: round(v["ms"] / max(v["launches"], 1), 5) for k, v in
                                             sorted(prof_rp.items(), key=lambda kv: -kv[1]["ms"])[:10] if not k.startswith("_")}}
 
-    total_reactions = B * world * args.steps
+    total_reactions = len(all_sizes) * args.steps
     value = total_reactions / (ms / 1e3)
     e2e_v = total_reactions / (ms_e2e / 1e3)
     if rank != 0:
@@ -324,9 +322,9 @@ def run_b200(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batch={B} Transition1x-shaped reactions (<=23 atoms) per GPU, {T} steps "
+            "config": {"workload": f"batch={args.batch} Transition1x-shaped reactions (<=23 atoms) per GPU, {T} steps "
                                    f"(sample(): {T + 1} LEFTNet evaluations), trained LEFTNet config (6 layers, H=196, R=96)",
-                       "global_batch": B * world, "denoise_steps": T, "nodes_per_gpu": int(sum(sizes) * 3),
+                       "global_batch": len(all_sizes), "denoise_steps": T, "weights_broadcast_bytes": int(bcast_bytes), "nodes_per_gpu": int(sum(sizes) * 3),
                        "edges_per_gpu": workloads.edge_count(sizes), "parallelism": f"dp{world} (reactions sharded, no "
                        "per-step collective)", "l2": "working set per evaluation (edge state 4*E*684 B = "
                        f"{workloads.edge_count(sizes) * 684 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",

@@ -227,11 +227,13 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   if (warp >= TC_EPI_WARPS + 2) {
     // ===================== A producer =====================
     // warp pw owns rows 16*pw .. 16*pw+15 of the tile.  One warp-wide float4 load covers 4 rows x 128 contiguous bytes
-    // (rows r0, r0+2, r0+4, r0+6 so that, with the 144-byte K pitch, the 8-byte smem stores hit each bank group twice).
+    // (rows r0, r0+4, r0+2, r0+6 so that, with the 144-byte K pitch, the 8-byte smem stores are bank-conflict free).
     const int pw = warp - (TC_EPI_WARPS + 2);
     const int kq = lane & 7;
     struct It { int tile, kc; const float* rp[4]; };
-    auto row_of = [&](int i) { return 16 * pw + ((i >> 1) << 3) + (i & 1) + 2 * (lane >> 3); };
+    // row offsets {0,4,2,6} per 8-lane group: the two groups of each half-warp (the unit a 64-bit shared store is
+    // processed in) then land in disjoint bank groups with the 144-byte K pitch
+    auto row_of = [&](int i) { return 16 * pw + ((i >> 1) << 3) + (i & 1) + (((lane >> 3) & 1) << 2) + ((lane >> 4) << 1); };
     auto init_rows = [&](It& it) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -282,6 +284,8 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
     It ld;
     ld.tile = blockIdx.x; ld.kc = 0;
     init_rows(ld);
+    // (an explicit prefetch.global.L2 of the next tile was tried and REMOVED: DRAM reads rose 65 % — lines were
+    //  evicted before use — and the kernel slowed down; see profiles/r1_tc_notes.md)
     float4 b0[4], b1[4], b2[4];
     issue(ld, b0); advance(ld);
     issue(ld, b1); advance(ld);
@@ -375,26 +379,36 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       for (int blk = half; blk < nblocks; blk += 2) {
-        float v[32];
-        ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-          *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
         const int n = n0 + blk * 32 + cq * 4;
         const bool ncol = n < g.N && (blk * 32 + cq * 4) < BN;  // N % 4 == 0 (checked on the host)
+        // single-operand modes: all 8 row-operand loads (HBM for the residual) fly while TMEM is read and transposed
+        float4 a1[8];
+        if (MODE == 2 || MODE == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            a1[j] = (ncol && ra[j]) ? *reinterpret_cast<const float4*>(ra[j] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ncol && g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        {
+          float v[32];
+          ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __syncwarp();
 #pragma unroll
         for (int jh = 0; jh < 2; jh++) {
-          float4 a1[4], a2[MODE == 1 ? 4 : 1];
+          float4 p1[MODE == 1 ? 4 : 1], p2[MODE == 1 ? 4 : 1];
+          if (MODE == 1) {
 #pragma unroll
-          for (int jj = 0; jj < 4; jj++) {  // issue the row-operand loads of four rows, then do the math
-            const int j = jh * 4 + jj;
-            const bool in = ncol && (m_base + rsub + 4 * j) < M;
-            a1[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE != 0 && in) a1[jj] = *reinterpret_cast<const float4*>(ra[j] + n);
-            if (MODE == 1) a2[jj] = in ? *reinterpret_cast<const float4*>(rb[j] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < 4; jj++) {  // gathered rows are L1/L2 resident: four rows in flight suffice
+              const int j = jh * 4 + jj;
+              const bool in = ncol && ra[j];
+              p1[jj] = in ? *reinterpret_cast<const float4*>(ra[j] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              p2[jj] = in ? *reinterpret_cast<const float4*>(rb[j] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
 #pragma unroll
           for (int jj = 0; jj < 4; jj++) {
@@ -404,13 +418,13 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
               float4 x = *reinterpret_cast<const float4*>(stg + (rsub + 4 * j) * TC_STG_LD + cq * 4);
               x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
               if (MODE == 1) {
-                x.x += a1[jj].x + a2[jj].x; x.y += a1[jj].y + a2[jj].y; x.z += a1[jj].z + a2[jj].z; x.w += a1[jj].w + a2[jj].w;
+                x.x += p1[jj].x + p2[jj].x; x.y += p1[jj].y + p2[jj].y; x.z += p1[jj].z + p2[jj].z; x.w += p1[jj].w + p2[jj].w;
               }
               if (g.act == 1) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
               const float r = rs[j];
               x.x *= r; x.y *= r; x.z *= r; x.w *= r;
-              if (MODE == 2) { x.x *= a1[jj].x; x.y *= a1[jj].y; x.z *= a1[jj].z; x.w *= a1[jj].w; }
-              if (MODE == 3) { x.x += a1[jj].x; x.y += a1[jj].y; x.z += a1[jj].z; x.w += a1[jj].w; }
+              if (MODE == 2) { x.x *= a1[j].x; x.y *= a1[j].y; x.z *= a1[j].z; x.w *= a1[j].w; }
+              if (MODE == 3) { x.x += a1[j].x; x.y += a1[j].y; x.z += a1[j].z; x.w += a1[j].w; }
               *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = x;
             }
           }

@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing for the sampling path: reactions are independent, so a batch shards across ranks with
+no per-step collective.  One process per GPU (`torch.distributed`, NCCL on GPUs / gloo in CPU tests); the only
+communication is one broadcast of the weights at start-up and small reductions of timings/outputs."""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+def shard_reactions(sizes: Sequence[int], world: int, n_frag: int = 3) -> List[Tuple[int, int]]:
+    """Split reactions 0..B-1 into `world` contiguous chunks balanced by edge count sum(3n(3n-1)) (the cost driver),
+    never leaving a rank empty when B >= world.  Returns [(start, stop)] per rank."""
+    B = len(sizes)
+    cost = [n_frag * n * (n_frag * n - 1) + 1 for n in sizes]
+    total = float(sum(cost))
+    bounds, acc, r = [0], 0.0, 1
+    for i, c in enumerate(cost):
+        acc += c
+        remaining_ranks = world - r
+        remaining_items = B - (i + 1)
+        if r < world and (acc >= total * r / world or remaining_items == remaining_ranks) and remaining_items >= remaining_ranks:
+            bounds.append(i + 1)
+            r += 1
+    while len(bounds) < world:
+        bounds.append(B)
+    bounds.append(B)
+    return [(bounds[k], bounds[k + 1]) for k in range(world)]
+
+
+@torch.no_grad()
+def broadcast_module_(module: nn.Module, src: int = 0) -> int:
+    """Make every rank's parameters and buffers equal to rank `src`'s with ONE flat broadcast; returns bytes sent."""
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    floats = [t for t in tensors if t.is_floating_point()]
+    if not floats or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in floats])
+    dist.broadcast(flat, src)
+    o = 0
+    for t in floats:
+        t.copy_(flat[o:o + t.numel()].view_as(t).to(t.dtype))
+        o += t.numel()
+    return flat.numel() * 4
+
+
+def max_over_ranks(value: float, device) -> float:
+    t = torch.tensor([float(value)], device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
