@@ -99,6 +99,11 @@ int oard_profile_get(const oard_handle* h, int i, const char** tag, double* ms, 
  * use_tc = 0: exact-fp32 SIMT kernel; 1: tcgen05 bf16x3 kernel (sm_100 only).  Synchronises `stream` when use_tc. */
 int oard_test_gemm(int device, int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
                    int use_tc, int act, int swap_lbo_sbo, void* stream);
+/* Extended form: epilogue mode (0 plain, 1 two gathered adds from aux[M,2N], 2 multiply by aux[M,N], 3 residual
+ * aux[M,N]), ablation bits for roofline studies (see gemm_tc.cuh TcDebugOpts), event-timed repetitions. */
+int oard_test_gemm_ex(int device, int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
+                      int use_tc, int act, int swap_lbo_sbo, int mode, const float* aux, int ablate, int reps,
+                      float* ms_out, void* stream);
 
 #ifdef __cplusplus
 }

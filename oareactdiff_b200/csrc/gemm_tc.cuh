@@ -176,8 +176,9 @@ __host__ __device__ inline uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct TcDebugOpts {  // bring-up knobs (normally zero)
+struct TcDebugOpts {  // bring-up / ablation knobs (normally zero)
   int swap_lbo_sbo;
+  int ablate;  // bit 0: no A global loads, bit 1: no epilogue global traffic, bit 2: no W bulk copies, bit 3: no MMAs
 };
 
 // Epilogue modes (compile-time):
@@ -249,7 +250,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       const int k = it.kc * TC_KC + kq * 4;
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        v[i] = (it.rp[i] && k < g.K) ? __ldg(reinterpret_cast<const float4*>(it.rp[i] + it.kc * TC_KC))
+        v[i] = (it.rp[i] && k < g.K && !(dbg.ablate & 1)) ? __ldg(reinterpret_cast<const float4*>(it.rp[i] + it.kc * TC_KC))
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     int soff[4];
@@ -306,6 +307,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
           const int s = gchunk % STAGES;
           const uint32_t ph = (gchunk / STAGES) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
+          if (dbg.ablate & 4) { ptx::mbar_arrive(&full_w[s]); continue; }
           ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W_PART);
           ptx::bulk_g2s(smem + (size_t)s * STAGE_BYTES + 2 * TC_A_PART, src + (size_t)kc * 2 * W_PART, 2 * W_PART,
                         &full_w[s]);
@@ -332,7 +334,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
           const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TC_A_PART;
           const uint32_t w_hi = a_hi + 2 * TC_A_PART, w_lo = w_hi + W_PART;
           const int steps = min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
-          for (int j = 0; j < steps; j++) {  // two K-adjacent core matrices per UMMA_K = 16
+          for (int j = 0; j < ((dbg.ablate & 8) ? 0 : steps); j++) {  // two K-adjacent core matrices per UMMA_K = 16
             const uint32_t ka = j * 2 * TC_A_LBO, kw = j * 2 * TC_CORE_BYTES;
             const uint64_t dah = tc_smem_desc(a_hi + ka, TC_A_LBO, TC_A_SBO), dal = tc_smem_desc(a_lo + ka, TC_A_LBO, TC_A_SBO);
             const uint64_t dwh = tc_smem_desc(w_hi + kw, wl, ws), dwl = tc_smem_desc(w_lo + kw, wl, ws);
@@ -380,7 +382,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       ptx::tc_fence_after();
       for (int blk = half; blk < nblocks; blk += 2) {
         const int n = n0 + blk * 32 + cq * 4;
-        const bool ncol = n < g.N && (blk * 32 + cq * 4) < BN;  // N % 4 == 0 (checked on the host)
+        const bool ncol = n < g.N && (blk * 32 + cq * 4) < BN && !(dbg.ablate & 2);  // N % 4 == 0 (checked on the host)
         // single-operand modes: all 8 row-operand loads (HBM for the residual) fly while TMEM is read and transposed
         float4 a1[8];
         if (MODE == 2 || MODE == 3) {
@@ -466,7 +468,7 @@ inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int
 }
 
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_sms, cudaStream_t st,
-                                  int swap_lbo_sbo = 0) {
+                                  int swap_lbo_sbo = 0, int ablate = 0) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   if (g.K % 4 || g.lda % 4 || g.N % 4 || g.ldc % 4 || w.BN % 16 || w.BN > 256 || w.BN < 16 || g.K != w.K || g.N != w.N)
     return cudaErrorInvalidValue;
@@ -476,7 +478,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
   const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
   const int total = m_tiles * w.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  TcDebugOpts dbg{swap_lbo_sbo};
+  TcDebugOpts dbg{swap_lbo_sbo, ablate};
   const int stages = tc_smem_bytes(w.BN, 4) <= 226 * 1024 ? 4 : 3;
   const size_t smem = tc_smem_bytes(w.BN, stages);
 #define OARD_TC_CASE(S, MD) \

@@ -772,31 +772,53 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   return prof_harvest(h, st);
 }
 
-// Bring-up / unit-test entry: C = act(A W^T + bias) with either GEMM implementation (device pointers).
+extern "C" int oard_test_gemm_ex(int, int, int, int, const float*, const float*, const float*, float*, int, int, int, int,
+                                 const float*, int, int, float*, void*);
+// Bring-up / unit-test / ablation entry: C = epi(A W^T + bias) with either GEMM implementation (device pointers).
+// mode: 0 plain, 1 gather adds (aux = [M,2N] used as radd1/radd2 with identity rows), 2 mul by aux[M,N], 3 residual aux[M,N].
+// reps > 1 times the launch with CUDA events (ms_out = mean ms); ablate: see TcDebugOpts.
 extern "C" int oard_test_gemm(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
                               float* C, int use_tc, int act, int swap_lbo_sbo, void* stream) {
+  return oard_test_gemm_ex(device, M, N, K, A, W, bias, C, use_tc, act, swap_lbo_sbo, 0, nullptr, 0, 1, nullptr, stream);
+}
+extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
+                                 float* C, int use_tc, int act, int swap_lbo_sbo, int mode, const float* aux, int ablate,
+                                 int reps, float* ms_out, void* stream) {
   CU(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   GemmArgs g = mk(A, K, W, K, C, N, M, N, K);
   g.bias = bias; g.act = act;
-  if (!use_tc) {
-    CU(launch_gemm_simt(g, st));
-    return OARD_OK;
-  }
+  if (mode == 1) { g.radd1 = aux; g.ld1 = 2 * N; g.radd2 = aux + N; g.ld2 = 2 * N; }
+  if (mode == 2) { g.mul = aux; g.ldmul = N; }
+  if (mode == 3) { g.resid = aux; g.ldres = N; }
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
-  const int n_tiles = (N + 255) / 256;
-  const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  TcWeight tw{};
   __nv_bfloat16* buf = nullptr;
-  CU(cudaMalloc(&buf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
-  k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, buf);
-  TcWeight tw{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
-  cudaError_t e = launch_gemm_tc(g, tw, prop.multiProcessorCount, st, swap_lbo_sbo);
+  if (use_tc) {
+    if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
+    const int n_tiles = (N + 255) / 256;
+    const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+    CU(cudaMalloc(&buf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
+    k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, buf);
+    tw = TcWeight{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < (reps > 1 ? reps + 1 : 1) && e == cudaSuccess; r++) {
+    if (r == (reps > 1 ? 1 : 0)) cudaEventRecord(e0, st);
+    e = use_tc ? launch_gemm_tc(g, tw, prop.multiProcessorCount, st, swap_lbo_sbo, ablate) : launch_gemm_simt(g, st);
+  }
+  cudaEventRecord(e1, st);
   cudaError_t e2 = cudaStreamSynchronize(st);
-  cudaFree(buf);
-  if (e != cudaSuccess) return fail(OARD_ECUDA, "gemm_tc launch: %s", cudaGetErrorString(e));
-  if (e2 != cudaSuccess) return fail(OARD_ECUDA, "gemm_tc run: %s", cudaGetErrorString(e2));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / (reps > 1 ? reps : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (buf) cudaFree(buf);
+  if (e != cudaSuccess) return fail(OARD_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(OARD_ECUDA, "gemm run: %s", cudaGetErrorString(e2));
   return OARD_OK;
 }
 
