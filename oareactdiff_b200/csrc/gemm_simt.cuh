@@ -22,6 +22,8 @@ struct GemmArgs {
   const float* rowscale; const int* rsidx;           // * rowscale[rsidx ? rsidx[m] : m]
   const float* mul; int ldmul;                       // * mul[m, n]
   const float* resid; int ldres;                     // + resid[m, n]   (may alias C)
+  // optional second, row-scattered copy of the result: C2[c2idx[m], n] = C[m, n] for rows with c2idx[m] >= 0
+  float* C2; const int* c2idx; int ldc2;
 };
 
 constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_simt_kernel(const GemmArgs g) {
       if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
       if (g.resid) v += g.resid[(size_t)m * g.ldres + n];
       g.C[(size_t)m * g.ldc + n] = v;
+      if (g.C2 && g.c2idx[m] >= 0) g.C2[(size_t)g.c2idx[m] * g.ldc2 + n] = v;
     }
   }
 }

@@ -18,6 +18,7 @@
 // Every global access of the kernel is a full 128-byte line per 8 threads: the first version (row per thread) was bound
 // by L1 tag throughput (32 lines per warp instruction), see profiles/.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -28,7 +29,9 @@ namespace oard {
 constexpr int TC_BM = 128;      // rows per tile (UMMA M)
 constexpr int TC_KC = 32;       // K elements per pipeline stage (2 x UMMA_K)
 constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;  // 576
+constexpr int TC_CTRL_WARPS = 3;  // MMA issuer, W loader, A loader (TMA)
+constexpr int TC_THREADS = (TC_EPI_WARPS + TC_CTRL_WARPS + TC_PROD_WARPS) * 32;  // 608
+constexpr int TC_RAW_BYTES = TC_BM * TC_KC * 4;  // one raw fp32 A box (128 rows x 32 floats) as landed by TMA
 constexpr int TC_CORE_BYTES = 128;                   // one 8x8 bf16 core matrix
 constexpr int TC_SBO = (TC_KC / 8) * TC_CORE_BYTES;  // W operand: byte stride between 8-row groups (K-adjacent cores contiguous)
 constexpr int TC_A_LBO = 144;                        // A operand: K-adjacent core matrices 144 B apart (bank-conflict-free stores)
@@ -108,6 +111,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// 2-D TMA tile load (SASS: UTMALDG): box {32 floats, 128 rows} at element coordinates (k, row); out-of-bounds -> zeros
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -184,21 +199,26 @@ struct TcDebugOpts {  // bring-up / ablation knobs (normally zero)
 // Epilogue modes (compile-time):
 //   0 plain: bias / SiLU / row scale      1: + two gathered row adds (GCL: P[src] + Q[dst])
 //   2: * mul[m, n] (EquiMessage: rbf_proj gate)      3: + resid[m, n] (edge-state residual, may alias C)
-template <int STAGES, int MODE>
+// RAW > 0: the A operand is contiguous (no row gather) and arrives by 2-D TMA into a RAW-deep ring of raw fp32 boxes;
+// RAW == 0: gathered / unaligned A through the LSU (coalesced float4 loads, register ring).
+template <int STAGES, int RAW, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
+gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const __grid_constant__ CUtensorMap tmA) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int BN = w.BN;
   const int W_PART = BN * TC_KC * 2;
   const int STAGE_BYTES = 2 * TC_A_PART + 2 * W_PART;
-  float* stg_all = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + TC_STG_BYTES);
+  uint8_t* raw_base = smem + (size_t)STAGES * STAGE_BYTES;
+  float* stg_all = reinterpret_cast<float*>(raw_base + (size_t)RAW * TC_RAW_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_all) + TC_STG_BYTES);
   uint64_t* full_a = bars;
   uint64_t* full_w = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
   uint64_t* acc_full = bars + 3 * STAGES;
   uint64_t* acc_empty = bars + 3 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint64_t* raw_full = bars + 3 * STAGES + 4;
+  uint64_t* raw_empty = raw_full + (RAW > 0 ? RAW : 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + (RAW > 0 ? RAW : 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
@@ -217,6 +237,10 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       ptx::mbar_init(&acc_full[b], 1);              // tcgen05.commit
       ptx::mbar_init(&acc_empty[b], TC_EPI_WARPS);  // one elected lane per epilogue warp
     }
+    for (int r = 0; r < RAW; r++) {
+      ptx::mbar_init(&raw_full[r], 1);               // arrive.expect_tx by the A loader lane
+      ptx::mbar_init(&raw_empty[r], TC_PROD_WARPS);  // one elected lane per producer warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == TC_EPI_WARPS) ptx::tmem_alloc(tmem_slot, 512);
@@ -225,11 +249,11 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= TC_EPI_WARPS + 2) {
+  if (warp >= TC_EPI_WARPS + TC_CTRL_WARPS) {
     // ===================== A producer =====================
     // warp pw owns rows 16*pw .. 16*pw+15 of the tile.  One warp-wide float4 load covers 4 rows x 128 contiguous bytes
     // (rows r0, r0+4, r0+2, r0+6 so that, with the 144-byte K pitch, the 8-byte smem stores are bank-conflict free).
-    const int pw = warp - (TC_EPI_WARPS + 2);
+    const int pw = warp - (TC_EPI_WARPS + TC_CTRL_WARPS);
     const int kq = lane & 7;
     struct It { int tile, kc; const float* rp[4]; };
     // row offsets {0,4,2,6} per 8-lane group: the two groups of each half-warp (the unit a 64-bit shared store is
@@ -280,6 +304,25 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
     };
+    if constexpr (RAW > 0) {
+      // TMA path: the raw fp32 box is already in shared memory; read it (one 128-byte row segment per 8 lanes), split, store
+      const int my_tiles_r = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const uint32_t nchunks_r = (uint32_t)my_tiles_r * k_chunks;
+      int roff[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) roff[i] = row_of(i) * (TC_KC * 4) + kq * 16;
+      for (uint32_t c = 0; c < nchunks_r; c++) {
+        const int r = c % RAW;
+        ptx::mbar_wait(&raw_full[r], (c / RAW) & 1);
+        const uint8_t* raw = raw_base + (size_t)r * TC_RAW_BYTES;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float4*>(raw + roff[i]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);  // box consumed (values are in registers)
+        consume(c, v);
+      }
+    } else {
     const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t nchunks = (uint32_t)my_tiles * k_chunks;
     It ld;
@@ -296,6 +339,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       if (c + 1 < nchunks) { issue(ld, b0); advance(ld); consume(c + 1, b1); }
       if (c + 2 < nchunks) { issue(ld, b1); advance(ld); consume(c + 2, b2); }
     }
+    }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== W loader: TMA bulk copies of pre-tiled slabs =====================
     if (lane == 0) {
@@ -311,6 +355,22 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
           ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W_PART);
           ptx::bulk_g2s(smem + (size_t)s * STAGE_BYTES + 2 * TC_A_PART, src + (size_t)kc * 2 * W_PART, 2 * W_PART,
                         &full_w[s]);
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 2) {
+    // ===================== A loader: 2-D TMA boxes {32 floats, 128 rows} into the raw ring =====================
+    if (RAW > 0 && lane == 0) {
+      ptx::tma_prefetch_desc(&tmA);
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / w.n_tiles) * TC_BM;
+        for (int kc = 0; kc < k_chunks; kc++, c++) {
+          const int r = c % (RAW > 0 ? RAW : 1);
+          ptx::mbar_wait(&raw_empty[r], ((c / (RAW > 0 ? RAW : 1)) & 1) ^ 1);
+          if (dbg.ablate & 1) { ptx::mbar_arrive(&raw_full[r]); continue; }
+          ptx::mbar_arrive_expect_tx(&raw_full[r], TC_RAW_BYTES);
+          ptx::tma_load_2d(raw_base + (size_t)r * TC_RAW_BYTES, &tmA, kc * TC_KC, m0, &raw_full[r]);
         }
       }
     }
@@ -364,10 +424,12 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
       const float* ra[8];
       const float* rb[MODE == 1 ? 8 : 1];
       float rs[8];
+      int c2row[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int m = m_base + rsub + 4 * j;
         const bool ok = m < M;
+        c2row[j] = (ok && g.C2) ? g.c2idx[m] : -1;
         ra[j] = nullptr;
         if (MODE == 1) rb[j] = nullptr;
         rs[j] = 1.f;
@@ -428,6 +490,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
               if (MODE == 2) { x.x *= a1[j].x; x.y *= a1[j].y; x.z *= a1[j].z; x.w *= a1[j].w; }
               if (MODE == 3) { x.x += a1[j].x; x.y += a1[j].y; x.z += a1[j].z; x.w += a1[j].w; }
               *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = x;
+              if (c2row[j] >= 0) *reinterpret_cast<float4*>(g.C2 + (size_t)c2row[j] * g.ldc2 + n) = x;
             }
           }
         }
@@ -447,23 +510,53 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg) {
   }
 }
 
-inline size_t tc_smem_bytes(int BN, int stages) {
-  return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + TC_STG_BYTES + (3 * stages + 4) * 8 + 16;
+inline size_t tc_smem_bytes(int BN, int stages, int raw) {
+  return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + (size_t)raw * TC_RAW_BYTES + TC_STG_BYTES +
+         (3 * stages + 4 + 2 * (raw > 0 ? raw : 1)) * 8 + 16;
+}
+
+// cuTensorMapEncodeTiled through the runtime (no libcuda link): fp32 [rows, K] row-major, box {32, 128}, no swizzle
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline tc_encode_fn tc_get_encoder() {
+  static tc_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tc_encode_fn>(p);
+  }
+  return fn;
+}
+inline bool tc_make_a_map(CUtensorMap* tm, const float* A, int rows, int K, int lda) {
+  tc_encode_fn enc = tc_get_encoder();
+  if (!enc || (reinterpret_cast<uintptr_t>(A) & 15) || ((size_t)lda * 4) % 16) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Requirements (checked): K % 4 == 0, lda % 4 == 0, N % 4 == 0, 16-byte aligned operands, BN % 16 == 0, BN <= 256,
 // at most one of {radd1+radd2, mul, resid}.
-template <int STAGES, int MODE>
+template <int STAGES, int RAW, int MODE>
 inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, TcDebugOpts dbg,
-                                       cudaStream_t st) {
+                                       const CUtensorMap& tm, cudaStream_t st) {
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, RAW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  gemm_tc_kernel<STAGES, MODE><<<grid, TC_THREADS, smem, st>>>(g, w, dbg);
+  gemm_tc_kernel<STAGES, RAW, MODE><<<grid, TC_THREADS, smem, st>>>(g, w, dbg, tm);
   return cudaGetLastError();
 }
 
@@ -479,12 +572,25 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
   const int total = m_tiles * w.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   TcDebugOpts dbg{swap_lbo_sbo, ablate};
-  const int stages = tc_smem_bytes(w.BN, 4) <= 226 * 1024 ? 4 : 3;
-  const size_t smem = tc_smem_bytes(w.BN, stages);
-#define OARD_TC_CASE(S, MD) \
-  if (stages == S && mode == MD) return launch_gemm_tc_inst<S, MD>(g, w, grid, smem, dbg, st);
-  OARD_TC_CASE(4, 0) OARD_TC_CASE(4, 1) OARD_TC_CASE(4, 2) OARD_TC_CASE(4, 3)
-  OARD_TC_CASE(3, 0) OARD_TC_CASE(3, 1) OARD_TC_CASE(3, 2) OARD_TC_CASE(3, 3)
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  const bool want_tma = !g.aidx && !(ablate & 16) && tc_make_a_map(&tm, g.A, g.M, g.K, g.lda);
+  const size_t lim = 227 * 1024;
+  int stages, raw;
+  if (want_tma) {
+    if (tc_smem_bytes(w.BN, 3, 3) <= lim) { stages = 3; raw = 3; }
+    else if (tc_smem_bytes(w.BN, 3, 2) <= lim) { stages = 3; raw = 2; }
+    else return cudaErrorInvalidValue;
+  } else {
+    raw = 0;
+    stages = tc_smem_bytes(w.BN, 4, 0) <= lim ? 4 : 3;
+  }
+  const size_t smem = tc_smem_bytes(w.BN, stages, raw);
+#define OARD_TC_CASE(S, R, MD) \
+  if (stages == S && raw == R && mode == MD) return launch_gemm_tc_inst<S, R, MD>(g, w, grid, smem, dbg, tm, st);
+#define OARD_TC_MODES(S, R) OARD_TC_CASE(S, R, 0) OARD_TC_CASE(S, R, 1) OARD_TC_CASE(S, R, 2) OARD_TC_CASE(S, R, 3)
+  OARD_TC_MODES(4, 0) OARD_TC_MODES(3, 0) OARD_TC_MODES(3, 3) OARD_TC_MODES(3, 2)
+#undef OARD_TC_MODES
 #undef OARD_TC_CASE
   return cudaErrorInvalidValue;
 }

@@ -411,7 +411,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"PQ", Nn * 2 * H * 4}, {"tN", Nn * H * 4}, {"X", Nn * 3 * H * 4}, {"vecA", Nn * 3 * H * 4},
       {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
       {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
-      {"ew", Ee * D * 4}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"ew", Ee * D * 4}, {"ew_act", Ee * D * 4}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
       {"d1", Ee * 3 * H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
   };
   for (auto& a : allocs) {
@@ -562,6 +562,7 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
         *vd = h->buf<float>("vd"), *XV = h->buf<float>("XV"), *O1 = h->buf<float>("O1"), *sn = h->buf<float>("sn"),
         *tu = h->buf<float>("tu");
   float *vec = h->buf<float>("vecA"), *vec2 = h->buf<float>("vecB");
+  float* ew_act = h->buf<float>("ew_act");
   float *ew = h->buf<float>("ew"), *hid1 = h->buf<float>("hid1"), *m2 = h->buf<float>("m2"),
         *rbf_act = h->buf<float>("rbf_act"), *f_act = h->buf<float>("f_act"), *d1 = h->buf<float>("d1"),
         *RB = h->buf<float>("RB"), *G = h->buf<float>("G");
@@ -703,6 +704,7 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     if (E) {
       g = mk(m2, H, w.eow, H, ew, D, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
+      g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = D;  // compact copy of the active rows: contiguous operand for dir_proj
       GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
@@ -715,8 +717,8 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
     g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
     GEMM_TC("gemm_xproj2", g, h->T[l].x2);
     if (E) {
-      g = mk(ew, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
-      g.aidx = act_idx; g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
+      g = mk(ew_act, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
+      g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
       GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
       g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
       g.m_dev = n_act;

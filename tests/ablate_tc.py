@@ -19,7 +19,7 @@ if __name__ == "__main__":
     E = 107790; EA = 34188
     shapes = [("edge1", E, 196, 684, 1, 1), ("edge2", E, 196, 196, 0, 1), ("edge_out", E, 684, 196, 3, 1),
               ("dir0", EA, 588, 684, 0, 1), ("dir2", EA, 588, 588, 2, 0), ("node", 2613, 196, 196, 0, 1)]
-    names = {0: "full", 1: "noAld", 2: "noEpi", 4: "noW", 8: "noMMA", 3: "noA+noEpi", 7: "onlyMMA", 15: "empty", 11: "onlyW", 14: "onlyA", 13: "onlyEpi"}
+    names = {0: "full", 16: "full_lsuA", 1: "noAld", 2: "noEpi", 3: "noA+noEpi", 7: "onlyMMA", 15: "empty", 14: "onlyA", 13: "onlyEpi"}
     for nm, M, N, K, mode, act in shapes:
         res = {names[a]: round(run(M, N, K, mode, act, a) * 1e3, 1) for a in names}
         ideal = 2.0 * M * (-(-N // 16) * 16) * (-(-K // 16) * 16) * 3 / 2.25e15 * 1e6
