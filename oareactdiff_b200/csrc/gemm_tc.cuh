@@ -21,6 +21,9 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"  // GemmArgs
 
@@ -37,6 +40,7 @@ constexpr int TC_SBO = (TC_KC / 8) * TC_CORE_BYTES;  // W operand: byte stride b
 constexpr int TC_A_LBO = 144;                        // A operand: K-adjacent core matrices 144 B apart (bank-conflict-free stores)
 constexpr int TC_A_SBO = (TC_KC / 8) * TC_A_LBO;     // 576
 constexpr int TC_A_PART = (TC_BM / 8) * TC_A_SBO;    // 9216 bytes per A part (hi or lo)
+constexpr int TC_IO_BYTES = 32 * 32 * 4;             // one 32x32 fp32 epilogue block (TMA box, 128B-swizzled)
 constexpr int TC_STG_LD = 36;                        // epilogue staging row pitch in floats (32 + 4 pad)
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_LD * 4;
 
@@ -45,6 +49,15 @@ struct TcWeight {
   const __nv_bfloat16* data;
   int N, K, BN, n_tiles, k_chunks;
 };
+
+// Output-column tile width: one tile (<= 256 columns, multiple of 16) when N fits, else equal tiles whose width is a multiple
+// of 32 so that the epilogue's 32-column TMA boxes of neighbouring tiles never overlap.
+inline int tc_choose_bn(int N) {
+  const int n_tiles = (N + 255) / 256;
+  const int per = (N + n_tiles - 1) / n_tiles;
+  const int q = n_tiles > 1 ? 32 : 16;
+  return (per + q - 1) / q * q;
+}
 
 __host__ __device__ inline size_t tc_weight_elems(int N, int K, int BN) {
   const int n_tiles = (N + BN - 1) / BN, k_chunks = (K + TC_KC - 1) / TC_KC;
@@ -119,6 +132,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// 2-D TMA tile store (SASS: UTMASTG): shared (dense box, optionally swizzled) -> global; out-of-bounds elements are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -201,16 +223,21 @@ struct TcDebugOpts {  // bring-up / ablation knobs (normally zero)
 //   2: * mul[m, n] (EquiMessage: rbf_proj gate)      3: + resid[m, n] (edge-state residual, may alias C)
 // RAW > 0: the A operand is contiguous (no row gather) and arrives by 2-D TMA into a RAW-deep ring of raw fp32 boxes;
 // RAW == 0: gathered / unaligned A through the LSU (coalesced float4 loads, register ring).
-template <int STAGES, int RAW, int MODE>
+// NIO > 0: the epilogue moves its blocks with TMA (residual / multiplier boxes in, output boxes out; NIO 4 KB buffers per
+// epilogue warp); NIO == 0: LSU epilogue with an smem transpose (fallback for unaligned outputs).
+template <int STAGES, int RAW, int MODE, int NIO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const __grid_constant__ CUtensorMap tmA) {
+gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const __grid_constant__ CUtensorMap tmA,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int BN = w.BN;
   const int W_PART = BN * TC_KC * 2;
   const int STAGE_BYTES = 2 * TC_A_PART + 2 * W_PART;
   uint8_t* raw_base = smem + (size_t)STAGES * STAGE_BYTES;
-  float* stg_all = reinterpret_cast<float*>(raw_base + (size_t)RAW * TC_RAW_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_all) + TC_STG_BYTES);
+  float* stg_all = reinterpret_cast<float*>(raw_base + (size_t)RAW * TC_RAW_BYTES);  // NIO == 0: transpose staging
+  uint8_t* io_all = raw_base + (size_t)RAW * TC_RAW_BYTES;                             // NIO > 0: TMA io blocks (1024-aligned)
+  constexpr int EPI_SMEM = NIO > 0 ? TC_EPI_WARPS * NIO * TC_IO_BYTES : TC_STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)RAW * TC_RAW_BYTES + EPI_SMEM);
   uint64_t* full_a = bars;
   uint64_t* full_w = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
@@ -218,7 +245,8 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   uint64_t* acc_empty = bars + 3 * STAGES + 2;
   uint64_t* raw_full = bars + 3 * STAGES + 4;
   uint64_t* raw_empty = raw_full + (RAW > 0 ? RAW : 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + (RAW > 0 ? RAW : 1));
+  uint64_t* aux_full = raw_empty + (RAW > 0 ? RAW : 1);  // [TC_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + TC_EPI_WARPS * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
@@ -237,6 +265,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
       ptx::mbar_init(&acc_full[b], 1);              // tcgen05.commit
       ptx::mbar_init(&acc_empty[b], TC_EPI_WARPS);  // one elected lane per epilogue warp
     }
+    for (int i = 0; i < TC_EPI_WARPS * 2; i++) ptx::mbar_init(&aux_full[i], 1);  // arrive.expect_tx by the warp's lane 0
     for (int r = 0; r < RAW; r++) {
       ptx::mbar_init(&raw_full[r], 1);               // arrive.expect_tx by the A loader lane
       ptx::mbar_init(&raw_empty[r], TC_PROD_WARPS);  // one elected lane per producer warp
@@ -318,6 +347,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float4*>(raw + roff[i]);
+        // cross-proxy WAR: these generic-proxy reads must be ordered before the TMA engine (async proxy) refills the box.
+        // Without this fence the refill can overtake the reads (seen on hardware: stale/corrupt rows in later tiles).
+        ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);  // box consumed (values are in registers)
         consume(c, v);
@@ -410,6 +442,108 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   } else {
     // ===================== epilogue warps 0-7 =====================
     // warp e reads TMEM lanes 32*(e%4).. (its row quarter) and takes the 32-column blocks with parity e/4.
+    if constexpr (NIO > 0) {
+      // ---- TMA epilogue: thread = output row.  A block is 32 rows x 32 columns (4 KB, 128-byte rows, 128B-swizzled so
+      // that both the row-per-thread accesses here and the TMA engine are bank-conflict free).  Residual / multiplier blocks
+      // are fetched by TMA one block ahead; results leave by TMA store.  No LSU traffic except bias and gathered rows.
+      const int rq = warp & 3, half = warp >> 2;
+      uint8_t* io = io_all + (size_t)warp * NIO * TC_IO_BYTES;
+      uint64_t* xbar = aux_full + warp * 2;
+      const int nblocks = (BN + 31) / 32;
+      const int sw = lane & 7;
+      constexpr bool HAS_AUX = (MODE == 2 || MODE == 3);
+      // block iterator over (tile, blk) in this warp's processing order (used to prefetch the next aux block)
+      int pf_tile = blockIdx.x, pf_blk = half;
+      auto pf_valid = [&]() { return pf_tile < total_tiles && pf_blk < nblocks; };
+      auto pf_next = [&]() {
+        pf_blk += 2;
+        if (pf_blk >= nblocks) { pf_blk = half; pf_tile += gridDim.x; }
+      };
+      uint32_t nb = 0;   // blocks processed by this warp
+      uint32_t npf = 0;  // aux blocks requested by this warp
+      auto issue_aux = [&]() {  // lane 0 only
+        if (!HAS_AUX) return;
+        while (pf_tile < total_tiles && pf_blk >= nblocks) pf_next();  // half == 1 with a single block
+        if (!pf_valid()) return;
+        const int b = npf % NIO;
+        ptx::mbar_arrive_expect_tx(&xbar[b], TC_IO_BYTES);
+        ptx::tma_load_2d(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
+                         (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b]);
+        npf++;
+        pf_next();
+      };
+      if (lane == 0) {
+        ptx::tma_prefetch_desc(&tmC);
+        if (HAS_AUX) { ptx::tma_prefetch_desc(&tmX); issue_aux(); }
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        const int m0r = (tile / w.n_tiles) * TC_BM + rq * 32;
+        const int m = m0r + lane;
+        const int n0 = (tile % w.n_tiles) * BN;
+        const bool ok = m < M;
+        const float* pr = nullptr;
+        const float* qr = nullptr;
+        if (MODE == 1 && ok) {
+          pr = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1;
+          qr = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2;
+        }
+        const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
+        const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
+        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        for (int blk = half; blk < nblocks; blk += 2, nb++) {
+          const int b = nb % NIO;
+          uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
+          float v[32];
+          ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+          if (HAS_AUX) {
+            // request the NEXT block's aux box (its buffer was last read by the store issued two blocks ago)
+            if (lane == 0 && NIO > 1) { ptx::bulk_wait_read0(); issue_aux(); }
+            ptx::mbar_wait(&xbar[b], (nb / NIO) & 1);
+          } else {
+            if (lane == 0) ptx::bulk_wait_read0();  // the previous store has finished reading this buffer
+            __syncwarp();
+          }
+          const int nblk = n0 + blk * 32;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int n = nblk + q * 4;
+            const bool nin = n < g.N && !(dbg.ablate & 2);
+            float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (g.bias && nin) { const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+            if (MODE == 1 && nin && ok) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(pr + n));
+              const float4 u = __ldg(reinterpret_cast<const float4*>(qr + n));
+              x.x += t.x + u.x; x.y += t.y + u.y; x.z += t.z + u.z; x.w += t.w + u.w;
+            }
+            if (g.act == 1) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
+            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+            float4* cell = reinterpret_cast<float4*>(iob + ((q ^ sw) << 4));
+            if (HAS_AUX) {
+              const float4 t = *cell;
+              if (MODE == 2) { x.x *= t.x; x.y *= t.y; x.z *= t.z; x.w *= t.w; }
+              else { x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+            }
+            *cell = x;
+            if (c2 >= 0 && nin) *reinterpret_cast<float4*>(g.C2 + (size_t)c2 * g.ldc2 + n) = x;
+          }
+          ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            if (!(dbg.ablate & 2)) ptx::tma_store_2d(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES);
+            ptx::bulk_commit();
+            if (HAS_AUX && NIO == 1) { ptx::bulk_wait_read0(); issue_aux(); }
+          }
+          __syncwarp();
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      }
+      if (lane == 0) ptx::bulk_wait_all();
+    } else {
     // thread = row after tcgen05.ld; a padded smem transpose turns that into 4 rows x 128 contiguous bytes per warp access.
     const int rq = warp & 3, half = warp >> 2;
     float* stg = stg_all + warp * 32 * TC_STG_LD;
@@ -500,6 +634,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
+      }
   }
 
   ptx::tc_fence_before();
@@ -510,12 +645,13 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   }
 }
 
-inline size_t tc_smem_bytes(int BN, int stages, int raw) {
-  return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + (size_t)raw * TC_RAW_BYTES + TC_STG_BYTES +
-         (3 * stages + 4 + 2 * (raw > 0 ? raw : 1)) * 8 + 16;
+inline size_t tc_smem_bytes(int BN, int stages, int raw, int nio) {
+  const size_t epi = nio > 0 ? (size_t)TC_EPI_WARPS * nio * TC_IO_BYTES : (size_t)TC_STG_BYTES;
+  return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + (size_t)raw * TC_RAW_BYTES + epi +
+         (3 * stages + 4 + 2 * (raw > 0 ? raw : 1) + 2 * TC_EPI_WARPS) * 8 + 16;
 }
 
-// cuTensorMapEncodeTiled through the runtime (no libcuda link): fp32 [rows, K] row-major, box {32, 128}, no swizzle
+// cuTensorMapEncodeTiled through the runtime (no libcuda link)
 typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -532,34 +668,39 @@ inline tc_encode_fn tc_get_encoder() {
   }
   return fn;
 }
-inline bool tc_make_a_map(CUtensorMap* tm, const float* A, int rows, int K, int lda) {
+// fp32 [rows, cols] row-major with leading dimension ld (floats); box {box_cols, box_rows}
+inline bool tc_make_map(CUtensorMap* tm, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
+                        bool swizzle128) {
   tc_encode_fn enc = tc_get_encoder();
-  if (!enc || (reinterpret_cast<uintptr_t>(A) & 15) || ((size_t)lda * 4) % 16) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+  if (!enc || !base || (reinterpret_cast<uintptr_t>(base) & 15) || ((size_t)ld * 4) % 16 || rows <= 0 || cols <= 0)
+    return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Requirements (checked): K % 4 == 0, lda % 4 == 0, N % 4 == 0, 16-byte aligned operands, BN % 16 == 0, BN <= 256,
 // at most one of {radd1+radd2, mul, resid}.
-template <int STAGES, int RAW, int MODE>
+template <int STAGES, int RAW, int MODE, int NIO>
 inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, TcDebugOpts dbg,
-                                       const CUtensorMap& tm, cudaStream_t st) {
+                                       const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmX,
+                                       cudaStream_t st) {
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, RAW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, RAW, MODE, NIO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  gemm_tc_kernel<STAGES, RAW, MODE><<<grid, TC_THREADS, smem, st>>>(g, w, dbg, tm);
+  gemm_tc_kernel<STAGES, RAW, MODE, NIO><<<grid, TC_THREADS, smem, st>>>(g, w, dbg, tmA, tmC, tmX);
   return cudaGetLastError();
 }
 
+// ablate bits 4/5 (16, 32) force the LSU paths for the A operand / the epilogue (for A/B comparisons)
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_sms, cudaStream_t st,
                                   int swap_lbo_sbo = 0, int ablate = 0) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
@@ -571,26 +712,42 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
   const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
   const int total = m_tiles * w.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  TcDebugOpts dbg{swap_lbo_sbo, ablate};
-  CUtensorMap tm;
-  memset(&tm, 0, sizeof tm);
-  const bool want_tma = !g.aidx && !(ablate & 16) && tc_make_a_map(&tm, g.A, g.M, g.K, g.lda);
-  const size_t lim = 227 * 1024;
-  int stages, raw;
-  if (want_tma) {
-    if (tc_smem_bytes(w.BN, 3, 3) <= lim) { stages = 3; raw = 3; }
-    else if (tc_smem_bytes(w.BN, 3, 2) <= lim) { stages = 3; raw = 2; }
-    else return cudaErrorInvalidValue;
-  } else {
-    raw = 0;
-    stages = tc_smem_bytes(w.BN, 4, 0) <= lim ? 4 : 3;
+  {  // OARD_TC_ABLATE=<bits> ORs ablation bits into every launch (16: LSU A operand, 32: LSU epilogue) for A/B debugging
+    static int env_bits = -1;
+    if (env_bits < 0) { const char* e = getenv("OARD_TC_ABLATE"); env_bits = e ? atoi(e) : 0; }
+    ablate |= env_bits;
   }
-  const size_t smem = tc_smem_bytes(w.BN, stages, raw);
-#define OARD_TC_CASE(S, R, MD) \
-  if (stages == S && raw == R && mode == MD) return launch_gemm_tc_inst<S, R, MD>(g, w, grid, smem, dbg, tm, st);
-#define OARD_TC_MODES(S, R) OARD_TC_CASE(S, R, 0) OARD_TC_CASE(S, R, 1) OARD_TC_CASE(S, R, 2) OARD_TC_CASE(S, R, 3)
-  OARD_TC_MODES(4, 0) OARD_TC_MODES(3, 0) OARD_TC_MODES(3, 3) OARD_TC_MODES(3, 2)
-#undef OARD_TC_MODES
+  TcDebugOpts dbg{swap_lbo_sbo, ablate};
+  CUtensorMap tmA, tmC, tmX;
+  memset(&tmA, 0, sizeof tmA); memset(&tmC, 0, sizeof tmC); memset(&tmX, 0, sizeof tmX);
+  const bool atma = !g.aidx && !(ablate & 16) && tc_make_map(&tmA, g.A, g.M, g.K, g.lda, TC_KC, TC_BM, false);
+  bool etma = !(ablate & 32) && tc_make_map(&tmC, g.C, g.M, g.N, g.ldc, 32, 32, true);
+  if (etma && mode == 2) etma = tc_make_map(&tmX, g.mul, g.M, g.N, g.ldmul, 32, 32, true);
+  if (etma && mode == 3) etma = tc_make_map(&tmX, g.resid, g.M, g.N, g.ldres, 32, 32, true);
+  const size_t lim = 227 * 1024;
+  // (stages, raw, nio) candidates in order of preference
+  int cand[4][3];
+  int nc = 0;
+  auto add = [&](int s_, int r_, int n_) { cand[nc][0] = s_; cand[nc][1] = r_; cand[nc][2] = n_; nc++; };
+  if (etma && mode >= 2) { if (atma) { add(3, 2, 2); add(2, 2, 2); } else { add(3, 0, 2); add(2, 0, 2); } }
+  else if (etma)         { if (atma) { add(3, 3, 1); add(3, 2, 1); add(2, 2, 1); } else { add(4, 0, 1); add(3, 0, 1); } }
+  else                   { if (atma) { add(3, 3, 0); add(3, 2, 0); } else { add(4, 0, 0); add(3, 0, 0); } }
+  int stages = 0, raw = 0, nio = 0;
+  for (int i = 0; i < nc; i++)
+    if (tc_smem_bytes(w.BN, cand[i][0], cand[i][1], cand[i][2]) <= lim) { stages = cand[i][0]; raw = cand[i][1]; nio = cand[i][2]; break; }
+  if (!stages) return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_bytes(w.BN, stages, raw, nio);
+#define OARD_TC_CASE(S, R, MD, NI) \
+  if (stages == S && raw == R && mode == MD && nio == NI) \
+    return launch_gemm_tc_inst<S, R, MD, NI>(g, w, grid, smem, dbg, tmA, tmC, tmX, st);
+#define OARD_TC_AUX(S, R, NI) OARD_TC_CASE(S, R, 2, NI) OARD_TC_CASE(S, R, 3, NI)
+#define OARD_TC_PLAIN(S, R, NI) OARD_TC_CASE(S, R, 0, NI) OARD_TC_CASE(S, R, 1, NI)
+  OARD_TC_AUX(3, 2, 2) OARD_TC_AUX(2, 2, 2) OARD_TC_AUX(3, 0, 2) OARD_TC_AUX(2, 0, 2)
+  OARD_TC_PLAIN(3, 3, 1) OARD_TC_PLAIN(3, 2, 1) OARD_TC_PLAIN(2, 2, 1) OARD_TC_PLAIN(4, 0, 1) OARD_TC_PLAIN(3, 0, 1)
+  OARD_TC_AUX(3, 3, 0) OARD_TC_AUX(3, 2, 0) OARD_TC_AUX(4, 0, 0) OARD_TC_AUX(3, 0, 0)
+  OARD_TC_PLAIN(3, 3, 0) OARD_TC_PLAIN(3, 2, 0) OARD_TC_PLAIN(4, 0, 0) OARD_TC_PLAIN(3, 0, 0)
+#undef OARD_TC_PLAIN
+#undef OARD_TC_AUX
 #undef OARD_TC_CASE
   return cudaErrorInvalidValue;
 }

@@ -278,8 +278,7 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     for (void* p : h->tc_bufs) cudaFree(p);
     h->tc_bufs.clear();
     auto pack = [&](const float* Wp, int ldw, int N, int K, TcWeight* out) -> int {
-      const int n_tiles = (N + 255) / 256;
-      const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+      const int BN = tc_choose_bn(N);
       const size_t elems = tc_weight_elems(N, K, BN);
       __nv_bfloat16* buf = nullptr;
       CU(cudaMalloc(&buf, elems * sizeof(__nv_bfloat16)));
@@ -799,8 +798,7 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
   __nv_bfloat16* buf = nullptr;
   if (use_tc) {
     if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
-    const int n_tiles = (N + 255) / 256;
-    const int BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+    const int BN = tc_choose_bn(N);
     CU(cudaMalloc(&buf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
     k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, buf);
     tw = TcWeight{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};

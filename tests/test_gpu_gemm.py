@@ -17,3 +17,15 @@ def test_gemm_tc_and_simt(M, N, K):
     for res, tol in ((tc, 3e-5), (tcs, 3e-5), (simt, 2e-6)):
         assert res.startswith("rel_err="), res
         assert float(res.split()[0].split("=")[1]) < tol and res.endswith("nan=0"), res
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 196, 684), (1000, 684, 196), (257, 588, 588), (5000, 588, 96), (40000, 196, 684),
+                                   (30000, 684, 196)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_gemm_tc_epilogue_modes(M, N, K, mode):
+    """Epilogue modes (two gathered adds / multiplier / in-place residual) incl. multi-tile-per-CTA sizes, on the TMA paths
+    and with the LSU fallbacks forced (ablate bits 16 / 32)."""
+    from tests.bringup_tc import run_mode
+    for ab in (0, 16, 32, 48):
+        res = run_mode(M, N, K, mode, ab)
+        assert res.startswith("rel_err=") and float(res.split()[0].split("=")[1]) < 3e-5 and res.endswith("nan=0"), (ab, res)
