@@ -140,7 +140,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -237,8 +236,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   uint8_t* raw_base = smem + (size_t)STAGES * STAGE_BYTES;
   float* stg_all = reinterpret_cast<float*>(raw_base + (size_t)RAW * TC_RAW_BYTES);  // NIO == 0: transpose staging
   uint8_t* io_all = raw_base + (size_t)RAW * TC_RAW_BYTES;                             // NIO > 0: TMA io blocks (1024-aligned)
-  constexpr int EW = NIO > 0 ? 4 : TC_EPI_WARPS;  // active epilogue warps (TMA epilogue: one per TMEM lane quarter)
-  constexpr int EPI_SMEM = NIO > 0 ? EW * NIO * TC_IO_BYTES : TC_STG_BYTES;
+  constexpr int EPI_SMEM = NIO > 0 ? TC_EPI_WARPS * NIO * TC_IO_BYTES : TC_STG_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)RAW * TC_RAW_BYTES + EPI_SMEM);
   uint64_t* full_a = bars;
   uint64_t* full_w = bars + STAGES;
@@ -247,8 +245,8 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   uint64_t* acc_empty = bars + 3 * STAGES + 2;
   uint64_t* raw_full = bars + 3 * STAGES + 4;
   uint64_t* raw_empty = raw_full + (RAW > 0 ? RAW : 1);
-  uint64_t* aux_full = raw_empty + (RAW > 0 ? RAW : 1);  // [4 warps][8]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 32);
+  uint64_t* aux_full = raw_empty + (RAW > 0 ? RAW : 1);  // [TC_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + TC_EPI_WARPS * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
@@ -265,9 +263,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
     }
     for (int b = 0; b < 2; b++) {
       ptx::mbar_init(&acc_full[b], 1);              // tcgen05.commit
-      ptx::mbar_init(&acc_empty[b], EW);  // one elected lane per active epilogue warp
+      ptx::mbar_init(&acc_empty[b], TC_EPI_WARPS);  // one elected lane per epilogue warp
     }
-    for (int i = 0; i < 32; i++) ptx::mbar_init(&aux_full[i], 1);  // arrive.expect_tx by the warp's lane 0
+    for (int i = 0; i < TC_EPI_WARPS * 2; i++) ptx::mbar_init(&aux_full[i], 1);  // arrive.expect_tx by the warp's lane 0
     for (int r = 0; r < RAW; r++) {
       ptx::mbar_init(&raw_full[r], 1);               // arrive.expect_tx by the A loader lane
       ptx::mbar_init(&raw_empty[r], TC_PROD_WARPS);  // one elected lane per producer warp
@@ -445,38 +443,39 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
     // ===================== epilogue warps 0-7 =====================
     // warp e reads TMEM lanes 32*(e%4).. (its row quarter) and takes the 32-column blocks with parity e/4.
     if constexpr (NIO > 0) {
-      // ---- TMA epilogue (4 warps, warp = TMEM lane quarter, thread = output row).  A block is 32 rows x 32 columns (4 KB,
-      // 128-byte rows, 128B-swizzled: the row-per-thread accesses here and the TMA engine are both bank-conflict free).
-      // Each warp owns a ring of NIO blocks: results leave by TMA store (two stores may be in flight); residual / multiplier
-      // blocks are requested NIO-2 blocks ahead by TMA load.  No LSU traffic except bias and gathered rows.
-      if (warp < EW) {
-      const int rq = warp;
+      // ---- TMA epilogue: thread = output row.  A block is 32 rows x 32 columns (4 KB, 128-byte rows, 128B-swizzled so
+      // that both the row-per-thread accesses here and the TMA engine are bank-conflict free).  Residual / multiplier blocks
+      // are fetched by TMA one block ahead; results leave by TMA store.  No LSU traffic except bias and gathered rows.
+      const int rq = warp & 3, half = warp >> 2;
       uint8_t* io = io_all + (size_t)warp * NIO * TC_IO_BYTES;
-      uint64_t* xbar = aux_full + warp * 8;
+      uint64_t* xbar = aux_full + warp * 2;
       const int nblocks = (BN + 31) / 32;
       const int sw = lane & 7;
       constexpr bool HAS_AUX = (MODE == 2 || MODE == 3);
-      constexpr int DIST = NIO - 2;  // aux prefetch distance in blocks (HAS_AUX requires NIO >= 3)
-      static_assert(!HAS_AUX || NIO >= 3, "aux modes need NIO >= 3");
-      int pf_tile = blockIdx.x, pf_blk = 0;  // (tile, blk) of the next aux block to request, in processing order
-      uint32_t npf = 0;
+      // block iterator over (tile, blk) in this warp's processing order (used to prefetch the next aux block)
+      int pf_tile = blockIdx.x, pf_blk = half;
+      auto pf_valid = [&]() { return pf_tile < total_tiles && pf_blk < nblocks; };
+      auto pf_next = [&]() {
+        pf_blk += 2;
+        if (pf_blk >= nblocks) { pf_blk = half; pf_tile += gridDim.x; }
+      };
+      uint32_t nb = 0;   // blocks processed by this warp
+      uint32_t npf = 0;  // aux blocks requested by this warp
       auto issue_aux = [&]() {  // lane 0 only
-        if (pf_tile >= total_tiles) return;
+        if (!HAS_AUX) return;
+        while (pf_tile < total_tiles && pf_blk >= nblocks) pf_next();  // half == 1 with a single block
+        if (!pf_valid()) return;
         const int b = npf % NIO;
         ptx::mbar_arrive_expect_tx(&xbar[b], TC_IO_BYTES);
         ptx::tma_load_2d(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
                          (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b]);
         npf++;
-        if (++pf_blk == nblocks) { pf_blk = 0; pf_tile += gridDim.x; }
+        pf_next();
       };
       if (lane == 0) {
         ptx::tma_prefetch_desc(&tmC);
-        if (HAS_AUX) {
-          ptx::tma_prefetch_desc(&tmX);
-          for (int d = 0; d < DIST; d++) issue_aux();
-        }
+        if (HAS_AUX) { ptx::tma_prefetch_desc(&tmX); issue_aux(); }
       }
-      uint32_t nb = 0;  // blocks processed by this warp
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
         const int buf = it & 1;
@@ -494,18 +493,19 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
         ptx::tc_fence_after();
-        for (int blk = 0; blk < nblocks; blk++, nb++) {
+        for (int blk = half; blk < nblocks; blk += 2, nb++) {
           const int b = nb % NIO;
           uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
           float v[32];
           ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
-          // the buffer that is (re)filled next was last read by the store issued two blocks ago: allow one store in flight
-          if (lane == 0) {
-            ptx::bulk_wait_read1();
-            if (HAS_AUX) issue_aux();
+          if (HAS_AUX) {
+            // request the NEXT block's aux box (its buffer was last read by the store issued two blocks ago)
+            if (lane == 0 && NIO > 1) { ptx::bulk_wait_read0(); issue_aux(); }
+            ptx::mbar_wait(&xbar[b], (nb / NIO) & 1);
+          } else {
+            if (lane == 0) ptx::bulk_wait_read0();  // the previous store has finished reading this buffer
+            __syncwarp();
           }
-          if (HAS_AUX) ptx::mbar_wait(&xbar[b], (nb / NIO) & 1);
-          else __syncwarp();
           const int nblk = n0 + blk * 32;
 #pragma unroll
           for (int q = 0; q < 8; q++) {
@@ -529,11 +529,12 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
             *cell = x;
             if (c2 >= 0 && nin) *reinterpret_cast<float4*>(g.C2 + (size_t)c2 * g.ldc2 + n) = x;
           }
-          ptx::fence_proxy_async();  // generic smem accesses -> ordered before the TMA engine's read / later refill
+          ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
             if (!(dbg.ablate & 2)) ptx::tma_store_2d(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES);
             ptx::bulk_commit();
+            if (HAS_AUX && NIO == 1) { ptx::bulk_wait_read0(); issue_aux(); }
           }
           __syncwarp();
         }
@@ -542,7 +543,6 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
       }
       if (lane == 0) ptx::bulk_wait_all();
-      }
     } else {
     // thread = row after tcgen05.ld; a padded smem transpose turns that into 4 rows x 128 contiguous bytes per warp access.
     const int rq = warp & 3, half = warp >> 2;
@@ -646,9 +646,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
 }
 
 inline size_t tc_smem_bytes(int BN, int stages, int raw, int nio) {
-  const size_t epi = nio > 0 ? (size_t)4 * nio * TC_IO_BYTES : (size_t)TC_STG_BYTES;
+  const size_t epi = nio > 0 ? (size_t)TC_EPI_WARPS * nio * TC_IO_BYTES : (size_t)TC_STG_BYTES;
   return (size_t)stages * (2 * TC_A_PART + 2 * BN * TC_KC * 2) + (size_t)raw * TC_RAW_BYTES + epi +
-         (3 * stages + 4 + 2 * (raw > 0 ? raw : 1) + 32) * 8 + 16;
+         (3 * stages + 4 + 2 * (raw > 0 ? raw : 1) + 2 * TC_EPI_WARPS) * 8 + 16;
 }
 
 // cuTensorMapEncodeTiled through the runtime (no libcuda link)
@@ -729,8 +729,8 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
   int cand[4][3];
   int nc = 0;
   auto add = [&](int s_, int r_, int n_) { cand[nc][0] = s_; cand[nc][1] = r_; cand[nc][2] = n_; nc++; };
-  if (etma && mode >= 2) { if (atma) { add(2, 2, 5); add(2, 2, 4); } else { add(3, 0, 5); add(2, 0, 5); } }
-  else if (etma)         { if (atma) { add(3, 3, 2); add(3, 2, 2); } else { add(4, 0, 2); add(3, 0, 2); } }
+  if (etma && mode >= 2) { if (atma) { add(3, 2, 2); add(2, 2, 2); } else { add(3, 0, 2); add(2, 0, 2); } }
+  else if (etma)         { if (atma) { add(3, 3, 1); add(3, 2, 1); add(2, 2, 1); } else { add(4, 0, 1); add(3, 0, 1); } }
   else                   { if (atma) { add(3, 3, 0); add(3, 2, 0); } else { add(4, 0, 0); add(3, 0, 0); } }
   int stages = 0, raw = 0, nio = 0;
   for (int i = 0; i < nc; i++)
@@ -742,8 +742,8 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
     return launch_gemm_tc_inst<S, R, MD, NI>(g, w, grid, smem, dbg, tmA, tmC, tmX, st);
 #define OARD_TC_AUX(S, R, NI) OARD_TC_CASE(S, R, 2, NI) OARD_TC_CASE(S, R, 3, NI)
 #define OARD_TC_PLAIN(S, R, NI) OARD_TC_CASE(S, R, 0, NI) OARD_TC_CASE(S, R, 1, NI)
-  OARD_TC_AUX(2, 2, 5) OARD_TC_AUX(2, 2, 4) OARD_TC_AUX(3, 0, 5) OARD_TC_AUX(2, 0, 5)
-  OARD_TC_PLAIN(3, 3, 2) OARD_TC_PLAIN(3, 2, 2) OARD_TC_PLAIN(4, 0, 2) OARD_TC_PLAIN(3, 0, 2)
+  OARD_TC_AUX(3, 2, 2) OARD_TC_AUX(2, 2, 2) OARD_TC_AUX(3, 0, 2) OARD_TC_AUX(2, 0, 2)
+  OARD_TC_PLAIN(3, 3, 1) OARD_TC_PLAIN(3, 2, 1) OARD_TC_PLAIN(2, 2, 1) OARD_TC_PLAIN(4, 0, 1) OARD_TC_PLAIN(3, 0, 1)
   OARD_TC_AUX(3, 3, 0) OARD_TC_AUX(3, 2, 0) OARD_TC_AUX(4, 0, 0) OARD_TC_AUX(3, 0, 0)
   OARD_TC_PLAIN(3, 3, 0) OARD_TC_PLAIN(3, 2, 0) OARD_TC_PLAIN(4, 0, 0) OARD_TC_PLAIN(3, 0, 0)
 #undef OARD_TC_PLAIN
