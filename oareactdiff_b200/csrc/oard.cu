@@ -78,6 +78,11 @@ struct oard_handle {
   int N = 0, E = 0, NC = 0;
   std::map<std::string, DevBuf> ws;  // named workspace buffers
   size_t ws_bytes = 0;
+  // CUDA graph of one forward (captured on an internal stream, replayed on the caller's stream)
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};  // [0]: subgraph_mask == NULL, [1]: with mask
+  int64_t graph_launches = 0;
   // profiling: CUDA-event timing per kernel class on sampled forwards
   int prof_every = 0;
   int64_t fwd_count = 0;
@@ -156,6 +161,11 @@ static void build_specs(oard_handle* h) {
   h->wset.assign(h->specs.size(), 0);
 }
 
+static void drop_graphs(oard_handle* h) {
+  for (auto& g : h->gexec)
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
+
 extern "C" int oard_abi_version(void) { return 1; }
 extern "C" const char* oard_last_error(void) { return g_err.c_str(); }
 
@@ -183,6 +193,8 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     const bool want_tc = !(env && strcmp(env, "simt") == 0);
     const bool dims_ok = cfg->hidden_channels % 4 == 0 && cfg->num_radial % 4 == 0;
     h->use_tc = want_tc && dims_ok && prop.major == 10;  // tcgen05 exists on sm_100 only
+    const char* eg = getenv("OARD_GRAPH");  // "0" disables CUDA-graph replay of the forward
+    h->use_graph = !(eg && strcmp(eg, "0") == 0);
   }
   for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
   *out = h;
@@ -201,6 +213,8 @@ extern "C" void oard_destroy(oard_handle* h) {
   for (float* p : h->wdev)
     if (p) cudaFree(p);
   for (void* p : h->tc_bufs) cudaFree(p);
+  drop_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_map(h->ws);
   free_map(h->snaps);
   delete h;
@@ -272,6 +286,7 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     w.l2w = W(u + "lin3.2.weight"); w.l2b = W(u + "lin3.2.bias");
     w.l4w = W(u + "lin3.4.weight"); w.l4b = W(u + "lin3.4.bias");
   }
+  drop_graphs(h);
   if (h->use_tc) {
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -394,6 +409,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
     comp_nodes[fill[c]++] = i;
   }
 
+  drop_graphs(h);
   free_map(h->ws);
   free_map(h->snaps);
   h->ws_bytes = 0;
@@ -410,7 +426,8 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"PQ", Nn * 2 * H * 4}, {"tN", Nn * H * 4}, {"X", Nn * 3 * H * 4}, {"vecA", Nn * 3 * H * 4},
       {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
       {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
-      {"ew", Ee * D * 4}, {"ew_act", Ee * D * 4}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"ew", Ee * D * 4}, {"ew_act", Ee * D * 4}, {"g_h_in", Nn * 32 * 4}, {"g_pos", Nn * 12}, {"g_sub", Ee * 8},
+      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
       {"d1", Ee * 3 * H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
   };
   for (auto& a : allocs) {
@@ -531,16 +548,9 @@ static GemmArgs mk(const float* A, int lda, const float* W, int ldw, float* C, i
   return g;
 }
 
-extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
-                            float* dpos, void* stream) {
-  if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
-  if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
-  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
-  CU(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+static int forward_impl(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
+                        float* dpos, cudaStream_t st) {
   h->launches = 0;
-  h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
-  h->fwd_count++;
   const oard_cfg& c = h->cfg;
   const int N = h->N, E = h->E, H = c.hidden_channels, R = c.num_radial, C = c.in_hidden_channels, D = 3 * H + R;
   const int HB = (H + 31) / 32 * 32, Hq = H / 4;
@@ -769,8 +779,55 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   PB("k_final", 0, N*H*4.0*5, 0);
   k_final<<<N, HB, 0, st>>>(H, C, tu, h->o_u2w, h->o_u2b, vec, h->o_v2w, s, h->eout_w, h->eout_b, dpos, h_out);
   KCHECK();
+  return OARD_OK;
+}
+
+extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
+                            float* dpos, void* stream) {
+  if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
+  if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
+  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
+  h->fwd_count++;
+  if (!h->cfg.object_aware) sub = nullptr;
+  const bool eager = !h->use_graph || h->debug || h->prof_now || h->fwd_count <= 1;  // first call warms up lazily-set attributes
+  if (eager) {
+    const int rc = forward_impl(h, h_in, pos, sub, h_out, dpos, st);
+    if (rc) return rc;
+    h->total_launches += h->launches;
+    return prof_harvest(h, st);
+  }
+  // ---- graph path: static I/O buffers, one cudaGraphLaunch per evaluation
+  const int N = h->N, E = h->E, C = h->cfg.in_hidden_channels;
+  const int gi = sub ? 1 : 0;
+  float *gh = h->buf<float>("g_h_in"), *gp = h->buf<float>("g_pos"), *gho = h->buf<float>("g_h_out"),
+        *gdp = h->buf<float>("g_dpos");
+  int64_t* gs = h->buf<int64_t>("g_sub");
+  if (!h->gexec[gi]) {
+    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CU(cudaStreamSynchronize(st));
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_impl(h, gh, gp, sub ? gs : nullptr, gho, gdp, h->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&h->gexec[gi], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+    h->graph_launches = h->launches;  // kernels recorded in the graph
+  }
+  CU(cudaMemcpyAsync(gh, h_in, (size_t)N * C * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(gp, pos, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
+  if (sub && E) CU(cudaMemcpyAsync(gs, sub, (size_t)E * 8, cudaMemcpyDeviceToDevice, st));
+  CU(cudaGraphLaunch(h->gexec[gi], st));
+  CU(cudaMemcpyAsync(h_out, gho, (size_t)N * C * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(dpos, gdp, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
+  h->launches = h->graph_launches;
   h->total_launches += h->launches;
-  return prof_harvest(h, st);
+  return OARD_OK;
 }
 
 extern "C" int oard_test_gemm_ex(int, int, int, int, const float*, const float*, const float*, float*, int, int, int, int,
