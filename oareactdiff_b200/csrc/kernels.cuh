@@ -446,6 +446,62 @@ __global__ void k_equi_reduce(int H, int reflect, const int* __restrict__ row_pt
   vec_out[o + 2 * H + h] = vec_in[o + 2 * H + h] + d2;
 }
 
+// float4 version of k_equi_reduce: one thread per 4 channels (H % 4 == 0), one block per target node.
+__global__ void __launch_bounds__(64) k_equi_reduce4(
+    int H, int reflect, const int* __restrict__ row_ptr, const int* __restrict__ ecol, const int* __restrict__ rev,
+    const int* __restrict__ act_pos, const float* __restrict__ G, const float* __restrict__ X,
+    const float4* __restrict__ geo, const float* __restrict__ pf, const float* __restrict__ vec_in,
+    float* __restrict__ vec_out, float* __restrict__ s) {
+  const int t = blockIdx.x, h = threadIdx.x * 4;
+  if (h >= H) return;
+  const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
+  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  const float* Xt = X + (size_t)t * 3 * H;
+  const float4 x0 = ld4(Xt + h), x1 = ld4(Xt + H + h), x2 = ld4(Xt + 2 * H + h);
+  float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
+  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  for (int e = r0; e < r1; e++) {
+    const int r = rev[e], p = act_pos[r];
+    if (p < 0) continue;  // masked edges contribute exactly 0
+    const int a = ecol[e];
+    const float* g = G + (size_t)p * 3 * H;
+    const float* Xa = X + (size_t)a * 3 * H;
+    const float* va = vec_in + (size_t)a * 3 * H;
+    const float4 g0 = ld4(g + h), g1 = ld4(g + H + h), g2 = ld4(g + 2 * H + h);
+    const float4 a0 = ld4(Xa + h), a1 = ld4(Xa + H + h), a2 = ld4(Xa + 2 * H + h);
+    const float4 v0 = ld4(va + h), v1 = ld4(va + H + h), v2 = ld4(va + 2 * H + h);
+    const float4 u = geo[r];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (!reflect) {
+      const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
+      const float bx = pf[t * 3], by = pf[t * 3 + 1], bz = pf[t * 3 + 2];
+      cx = ay * bz - az * by; cy = az * bx - ax * bz; cz = ax * by - ay * bx;
+      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
+      cx *= cinv; cy *= cinv; cz *= cinv;
+    }
+#define OARD_EQ(c)                                                                         \
+    {                                                                                      \
+      const float al = (a0.c + x0.c) * g0.c;                                               \
+      const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                                  \
+      const float ga = (a2.c + x2.c) * g2.c;                                               \
+      float m0 = fmaf(v0.c, be, ga * u.x), m1 = fmaf(v1.c, be, ga * u.y), m2 = fmaf(v2.c, be, ga * u.z); \
+      if (!reflect) { m0 = fmaf(al, cx, m0); m1 = fmaf(al, cy, m1); m2 = fmaf(al, cz, m2); }            \
+      dx.c += al;                                                                          \
+      d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+    }
+    OARD_EQ(x) OARD_EQ(y) OARD_EQ(z) OARD_EQ(w)
+#undef OARD_EQ
+  }
+  const size_t o = (size_t)t * 3 * H + h;
+  float4 sv = ld4(s + (size_t)t * H + h);
+  sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
+  *reinterpret_cast<float4*>(s + (size_t)t * H + h) = sv;
+  const float4 w0 = ld4(vec_in + o), w1 = ld4(vec_in + o + H), w2 = ld4(vec_in + o + 2 * H);
+  *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
+  *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
+  *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+}
+
 // EquiUpdate scalarisation on the node frame + lin3 (3->48->8->1) + vec_dot  (leftnet.py:326-336)
 __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, const float* __restrict__ nodeframe,
                              const float* __restrict__ s, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -467,18 +523,19 @@ __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, c
   float s1 = v10 * nf[1] + v11 * nf[4] + v12 * nf[7];
   const float s2 = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
   if (reflect) s1 = fabsf(s1);
-  float u[48];
+  // 3 -> 48 -> 8 -> 1 with the 8 second-layer accumulators kept independent (8-way ILP instead of 48-long chains)
+  float a[8];
 #pragma unroll
-  for (int k = 0; k < 48; k++)
-    u[k] = silu_fast(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
+  for (int q = 0; q < 8; q++) a[q] = B2[q];
+#pragma unroll 8
+  for (int k = 0; k < 48; k++) {
+    const float u = silu_fast(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = fmaf(W2[q * 48 + k], u, a[q]);
+  }
   float out = b4[0];
 #pragma unroll
-  for (int q = 0; q < 8; q++) {
-    float a = B2[q];
-#pragma unroll
-    for (int k = 0; k < 48; k++) a = fmaf(W2[q * 48 + k], u[k], a);
-    out = fmaf(W4[q], silu_fast(a), out);
-  }
+  for (int q = 0; q < 8; q++) out = fmaf(W4[q], silu_fast(a[q]), out);
   sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
   sx[(size_t)t * 2 * H + H + h] = out;
   vd[(size_t)t * H + h] = (v10 * v20 + v11 * v21 + v12 * v22) * rsqrtf((float)H);

@@ -50,6 +50,7 @@ struct LayerW {
   const float *e0w, *e0b, *e1w, *e1b, *n0w, *n0b, *n1w, *n1b, *eow, *eob, *attw, *attb, *glnw, *glnb;
   const float *d0w, *d0b, *d2w, *d2b, *x0w, *x2w, *rbfw, *mlnw, *mlnb;
   const float *vpw, *xv0w, *xv2w, *l0w, *l0b, *l2w, *l2b, *l4w, *l4b;
+  const float *pqw, *pqb;  // derived: [W_ai ; W_aj] stacked ([2H, H]) and [b_a ; 0]
 };
 
 }  // namespace
@@ -69,7 +70,7 @@ struct oard_handle {
   // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
   bool use_tc = false;
   int num_sms = 148;
-  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pi, pj, n0, n1, x0, x2, vp, xv0, xv2; };
+  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
   std::vector<LayerTc> T;
   TcWeight tc_rl0{}, tc_rl2{}, tc_s2v{}, tc_ov1{}, tc_ou0{};
   std::vector<void*> tc_bufs;
@@ -287,11 +288,28 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     w.l4w = W(u + "lin3.4.weight"); w.l4b = W(u + "lin3.4.bias");
   }
   drop_graphs(h);
-  if (h->use_tc) {
-    CU(cudaSetDevice(h->device));
+  CU(cudaSetDevice(h->device));
+  for (void* p : h->tc_bufs) cudaFree(p);
+  h->tc_bufs.clear();
+  {  // stacked P/Q weight of the GCL edge MLP's node part: one [N, H] x [H, 2H] GEMM instead of two
+    const int H = h->cfg.hidden_channels, R = h->cfg.num_radial, ld0 = 5 * H + R;
     cudaStream_t st = (cudaStream_t)stream;
-    for (void* p : h->tc_bufs) cudaFree(p);
-    h->tc_bufs.clear();
+    for (int l = 0; l < h->cfg.num_layers; l++) {
+      LayerW& w = h->L[l];
+      float *pqw = nullptr, *pqb = nullptr;
+      CU(cudaMalloc(&pqw, (size_t)2 * H * H * 4));
+      CU(cudaMalloc(&pqb, (size_t)2 * H * 4));
+      h->tc_bufs.push_back(pqw); h->tc_bufs.push_back(pqb);
+      CU(cudaMemcpy2DAsync(pqw, (size_t)H * 4, w.e0w, (size_t)ld0 * 4, (size_t)H * 4, H, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpy2DAsync(pqw + (size_t)H * H, (size_t)H * 4, w.e0w + H, (size_t)ld0 * 4, (size_t)H * 4, H,
+                           cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemsetAsync(pqb, 0, (size_t)2 * H * 4, st));
+      CU(cudaMemcpyAsync(pqb, w.e0b, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+      w.pqw = pqw; w.pqb = pqb;
+    }
+  }
+  if (h->use_tc) {
+    cudaStream_t st = (cudaStream_t)stream;
     auto pack = [&](const float* Wp, int ldw, int N, int K, TcWeight* out) -> int {
       const int BN = tc_choose_bn(N);
       const size_t elems = tc_weight_elems(N, K, BN);
@@ -320,8 +338,7 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.d0w, D, 3 * H, D, &t.d0))) return rc;
       if ((rc = pack(w.d2w, 3 * H, 3 * H, 3 * H, &t.d2))) return rc;
       if ((rc = pack(w.rbfw, R, 3 * H, R, &t.rbf))) return rc;
-      if ((rc = pack(w.e0w, 2 * H + D, H, H, &t.pi))) return rc;
-      if ((rc = pack(w.e0w + H, 2 * H + D, H, H, &t.pj))) return rc;
+      if ((rc = pack(w.pqw, H, 2 * H, H, &t.pq))) return rc;
       if ((rc = pack(w.n0w, 2 * H, H, 2 * H, &t.n0))) return rc;
       if ((rc = pack(w.n1w, H, H, H, &t.n1))) return rc;
       if ((rc = pack(w.x0w, H, H, H, &t.x0))) return rc;
@@ -686,11 +703,9 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     PB("k_layernorm", 0, N*H*8.0, 0);
     k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
     KCHECK();
-    GemmArgs g = mk(xa, 2 * H, w.e0w, ldw0, PQ, 2 * H, N, H, H);
-    g.bias = w.e0b;
-    GEMM_TC("gemm_gcl_P", g, h->T[l].pi);
-    g = mk(xa, 2 * H, w.e0w + H, ldw0, PQ + H, 2 * H, N, H, H);
-    GEMM_TC("gemm_gcl_Q", g, h->T[l].pj);
+    GemmArgs g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
+    g.bias = w.pqb;
+    GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
     if (E) {
       g = mk(ew, D, w.e0w + 2 * H, ldw0, hid1, H, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
@@ -737,7 +752,10 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
     PB("k_equi_reduce", 0, (double)E*(3.0*H*4+16), 1);
-    k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
+    if (H % 4 == 0 && H <= 256)
+      k_equi_reduce4<<<N, 64, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
+    else
+      k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
     KCHECK();
     std::swap(vec, vec2);
     if (h->debug) {
