@@ -279,12 +279,16 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(k):
             fn()
+        host_ms[fn.__name__] = (time.perf_counter() - t0) * 1e3 / k  # host enqueue time (no sync inside the loop)
         e1.record()
         barrier()
         return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -359,7 +363,7 @@ def run_b200(args, rank, world, local_rank):
                        "per-step collective)", "l2": "working set per evaluation (edge state 4*E*684 B = "
                        f"{workloads.edge_count(sizes) * 684 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
                        "weights": "torch.manual_seed(0) default init (checkpoint is a git-LFS pointer)"},
-            "clocks": clk, "gpu_launches": int(launches),
+            "clocks": clk, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps, "outputs_finite": finite},
             "active_edge_fraction": (af_lit["flops"] / max(af_lit["launches"], 1)) if af_lit else None,
