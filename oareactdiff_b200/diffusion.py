@@ -133,6 +133,76 @@ class EnVariationalDiffusion(nn.Module):
             zt[ii][:, :self.pos_dim] = remove_mean_batch(zt[ii][:, :self.pos_dim], masks[ii], self._B)
         return zt
 
+    # ---------------------------------------------------------------- fast reverse step (same arithmetic, fewer launches)
+    # sample()/inpaint() always call the reverse kernel with ONE (s, t) pair for the whole batch, so the schedule scalars
+    # of every step can be tabulated once (with the same float32 torch formulas as above, evaluated for all steps at
+    # once) and the per-fragment lists can live in one concatenated [N, nf] tensor.  ~20 launches per step instead of ~95.
+    def _fast_ok(self) -> bool:
+        own_noise = type(self).sample_combined_position_feature_noise is EnVariationalDiffusion.sample_combined_position_feature_noise
+        return len(set(self.node_nfs)) == 1 and not self.fixed_idx and not self.debug_asserts and own_noise
+
+    def _tables(self, timesteps: int, device):
+        key = (timesteps, str(device), self.schedule.gamma_module.gamma.data_ptr())
+        if getattr(self, "_tab_key", None) == key:
+            return self._tab
+        steps = torch.arange(timesteps + 1, device=device)
+        tt = (steps / timesteps).view(-1, 1)                       # t = k / T, float32 like (s_array + 1) / timesteps
+        gamma = self.schedule.gamma_module(tt)                     # [T+1, 1]
+        g_s, g_t = gamma[:-1], gamma[1:]
+        ref = torch.zeros(1, 1, device=device)
+        sigma2_ts, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(g_t, g_s, ref)
+        sigma_s, sigma_t = self.schedule.sigma(g_s, ref), self.schedule.sigma(g_t, ref)
+        tab = {
+            "tt": tt,                                               # device tensor, row k = t value of step k
+            "inv_alpha_ts": (1.0 / alpha_ts).flatten().tolist(),    # mu = z / alpha_ts - eps * coef  (z / a == z * (1/a) is NOT
+            "alpha_ts": alpha_ts.flatten().tolist(),                #   bit-identical, so the division is kept: see _fast_step)
+            "coef": (sigma2_ts / alpha_ts / sigma_t).flatten().tolist(),
+            "sigma": (sigma_ts * sigma_s / sigma_t).flatten().tolist(),
+            "alpha": self.schedule.alpha(gamma, ref).flatten().tolist(),
+            "sigma_abs": self.schedule.sigma(gamma, ref).flatten().tolist(),
+            "sigma_ts": sigma_ts.flatten().tolist(),
+        }
+        self._tab_key, self._tab = key, tab
+        return tab
+
+    def _seg_setup(self, masks):
+        """Per-(fragment, sample) segment ids of the concatenated node order and their inverse sizes."""
+        B = self._B
+        seg = torch.cat([m + f * B for f, m in enumerate(masks)])
+        cnt = torch.zeros(len(masks) * B, device=seg.device).index_add_(0, seg, torch.ones(seg.numel(), device=seg.device))
+        self._seg, self._seg_inv = seg, (1.0 / cnt.clamp(min=1))[:, None]
+        self._frag_off = [0]
+        for m in masks:
+            self._frag_off.append(self._frag_off[-1] + len(m))
+
+    def _remove_mean_cat(self, x: Tensor) -> Tensor:
+        mean = torch.zeros(self._seg_inv.size(0), x.size(1), device=x.device, dtype=x.dtype).index_add_(0, self._seg, x)
+        return x - (mean * self._seg_inv)[self._seg]
+
+    def _noise_cat(self, masks) -> Tensor:
+        """Concatenated CoM-free noise with the reference's draw order (per fragment: positions, then features)."""
+        xs, hs = [], []
+        for ii, mask in enumerate(masks):
+            xs.append(torch.randn((len(mask), self.pos_dim), device=mask.device))
+            hs.append(torch.randn((len(mask), self.node_nfs[ii] - self.pos_dim), device=mask.device))
+        x = self._remove_mean_cat(torch.cat(xs))
+        h = torch.cat(hs)
+        if self.pos_only:
+            h = torch.zeros_like(h)
+        return torch.cat([x, h], dim=1)
+
+    def _views(self, Z: Tensor):
+        o = self._frag_off
+        return [Z[o[f]:o[f + 1]] for f in range(len(o) - 1)]
+
+    def _fast_step(self, s_int: int, Z: Tensor, tab, edge_index, nfs, masks, conditions) -> Tensor:
+        """z_s ~ p(z_s | z_t) for t = s + 1 on the concatenated state (same formulas as sample_p_zs_given_zt)."""
+        eps = torch.cat(self._dyn(self._views(Z), edge_index, tab["tt"][s_int + 1].expand(self._B, 1), conditions, nfs, masks))
+        mu = Z / tab["alpha_ts"][s_int] - eps * tab["coef"][s_int]
+        Zs = mu + tab["sigma"][s_int] * self._noise_cat(masks)
+        Zs[:, :self.pos_dim] = self._remove_mean_cat(Zs[:, :self.pos_dim])
+        return Zs
+
     # ---------------------------------------------------------------- drivers
     def _setup(self, n_samples, fragments_nodes):
         masks = [get_mask_for_frag(n) for n in fragments_nodes]
@@ -163,16 +233,29 @@ class EnVariationalDiffusion(nn.Module):
         out_samples = [[torch.zeros((return_frames,) + zz.size(), device=zz.device) for zz in z]
                        for _ in range(return_frames)]
         dev = z[0].device
-        for s in reversed(range(0, timesteps)):
-            s_arr = torch.full((n_samples, 1), fill_value=s, device=dev)
-            t_arr = (s_arr + 1) / timesteps
-            s_arr = s_arr / timesteps
-            z = self.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z, edge_index=edge_index, n_frag_switch=nfs,
-                                          masks=masks, conditions=conditions, fix_noise=False)
-            if self.pos_only:
-                z = self._with_h0(z, h0)
-            if (s * return_frames) % timesteps == 0:
-                out_samples[(s * return_frames) // timesteps] = self.normalizer.unnormalize_z(z)
+        if self._fast_ok():
+            tab = self._tables(timesteps, dev)
+            self._seg_setup(masks)
+            Z = torch.cat(z).to(torch.float32)
+            H0 = torch.cat(h0).to(Z.dtype) if self.pos_only else None
+            for s in reversed(range(0, timesteps)):
+                Z = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
+                if self.pos_only:
+                    Z[:, self.pos_dim:] = H0
+                if (s * return_frames) % timesteps == 0:
+                    out_samples[(s * return_frames) // timesteps] = self.normalizer.unnormalize_z([v.clone() for v in self._views(Z)])
+            z = self._views(Z)
+        else:
+            for s in reversed(range(0, timesteps)):
+                s_arr = torch.full((n_samples, 1), fill_value=s, device=dev)
+                t_arr = (s_arr + 1) / timesteps
+                s_arr = s_arr / timesteps
+                z = self.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z, edge_index=edge_index, n_frag_switch=nfs,
+                                              masks=masks, conditions=conditions, fix_noise=False)
+                if self.pos_only:
+                    z = self._with_h0(z, h0)
+                if (s * return_frames) % timesteps == 0:
+                    out_samples[(s * return_frames) // timesteps] = self.normalizer.unnormalize_z(z)
         pos, cat, charge = self.sample_p_xh_given_z0(z, edge_index, nfs, masks, n_samples, conditions)
         if self.pos_only:
             cat = [_h0[:, :-1] for _h0 in h0]
@@ -204,6 +287,33 @@ class EnVariationalDiffusion(nn.Module):
         dev = z[0].device
         schedule = get_repaint_schedule(resamplings, jump_length, timesteps)
         s = timesteps - 1
+        if self._fast_ok():
+            tab = self._tables(timesteps, dev)
+            self._seg_setup(masks)
+            gamma_cpu = self.schedule.gamma_module.gamma.detach().float().cpu()
+            Z = torch.cat(z).to(torch.float32)
+            Xf = torch.cat(xh_fixed).to(torch.float32)
+            H0 = torch.cat(h0).to(Z.dtype)
+            known = torch.cat([torch.full((len(m), 1), ii in frag_fixed, dtype=torch.bool, device=dev)
+                               for ii, m in enumerate(masks)])
+            for i, n_denoise_steps in enumerate(schedule):
+                for j in range(n_denoise_steps):
+                    # known fragments: q(z_s | x) (noised_representation); unknown: reverse step from z_t
+                    Z_known = tab["alpha"][s] * Xf + tab["sigma_abs"][s] * self._noise_cat(masks)
+                    Z_unknown = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
+                    Z = torch.where(known, Z_known, Z_unknown)
+                    if self.pos_only:
+                        Z[:, p:] = H0
+                    if j == n_denoise_steps - 1 and i < len(schedule) - 1:  # jump back `jump_length` steps
+                        t = s + jump_length
+                        g_s, g_t = gamma_cpu[s].view(1, 1), gamma_cpu[t].view(1, 1)
+                        _, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(g_t, g_s, g_s)
+                        Z = float(alpha_ts) * Z + float(sigma_ts) * self._noise_cat(masks)
+                        Z[:, :p] = self._remove_mean_cat(Z[:, :p])
+                        s = t
+                    s = s - 1
+            z = self._views(Z)
+            schedule = []
         for i, n_denoise_steps in enumerate(schedule):
             for j in range(n_denoise_steps):
                 s_arr = torch.full((n_samples, 1), fill_value=s, device=dev)

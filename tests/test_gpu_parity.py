@@ -262,3 +262,35 @@ def test_c_abi_error_codes():
     h2 = C.c_void_p()
     assert lib.oard_create(C.byref(legacy_off), 0, C.byref(h2)) == -1
     lib.oard_destroy(h)
+
+
+def _sample_once(debug_asserts, seed, T=12, inpaint=False):
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2, cutoff=5.0)
+    sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 3, cfg, prefix_model="model.")
+    dyn = make_dynamics(cfg, sd)
+    sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True,
+                                     debug_asserts=debug_asserts).to(DEV)
+    sizes = [5, 9, 4]
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 1)
+    torch.manual_seed(seed)
+    if inpaint:
+        g = torch.Generator().manual_seed(5)
+        xh_fixed = [torch.cat([torch.randn(h.size(0), 3, generator=g), h], dim=1).to(DEV) for h in h0]
+        out, _ = ddpm.inpaint(len(sizes), [n.to(DEV) for n in nodes], cond.to(DEV), resamplings=2, jump_length=3,
+                              xh_fixed=xh_fixed, frag_fixed=[0, 2])
+    else:
+        out, _ = ddpm.sample(len(sizes), [n.to(DEV) for n in nodes], cond.to(DEV), h0=[h.to(DEV) for h in h0])
+    return [o.cpu() for o in out[0]], ddpm.n_evals
+
+
+@pytest.mark.parametrize("inpaint", [False, True])
+def test_fast_sampler_path_equals_reference_structured_path(inpaint):
+    """The tabulated / concatenated reverse loop (default) against the reference-structured per-fragment loop
+    (debug_asserts=True forces it) with the same CUDA RNG seed: same draws in the same order, same formulas."""
+    fast, n1 = _sample_once(False, 11, inpaint=inpaint)
+    slow, n2 = _sample_once(True, 11, inpaint=inpaint)
+    assert n1 == n2
+    for a, b in zip(fast, slow):
+        assert rel_err(a[:, :3], b[:, :3]) < 2e-4, rel_err(a[:, :3], b[:, :3])
+        assert torch.equal(a[:, 3:], b[:, 3:])
