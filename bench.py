@@ -246,30 +246,18 @@ def run_b200(args, rank, world, local_rank):
     def step_replay():
         torch.manual_seed(4321 + rank)
         masks, edge_index, nfs = ddpm._setup(B, nodes_d)
+        tab = ddpm._tables(T, dev)
+        ddpm._seg_setup(masks)
+        X = torch.cat(xh0_d)
+        H0 = torch.cat(h0_d)
         for s_int in reversed(range(T)):
-            s_arr = torch.full((B, 1), fill_value=s_int, device=dev)
-            t_arr = (s_arr + 1) / T
-            s_arr = s_arr / T
-            gamma_t = ddpm.schedule.inflate_batch_array(ddpm.schedule.gamma_module(t_arr), xh0_d[0])
-            z_t, _ = ddpm.noised_representation(xh0_d, masks, gamma_t)
-            z_t = ddpm._with_h0(z_t, h0_d)
-            ddpm.sample_p_zs_given_zt(s=s_arr, t=t_arr, zt_xh=z_t, edge_index=edge_index, n_frag_switch=nfs,
-                                      masks=masks, conditions=cond_d)
-        gamma_0 = ddpm.schedule.inflate_batch_array(ddpm.schedule.gamma_module(torch.zeros(B, 1, device=dev)), xh0_d[0])
-        z_0, _ = ddpm.noised_representation(xh0_d, masks, gamma_0)
-        return ddpm.sample_p_xh_given_z0(ddpm._with_h0(z_0, h0_d), edge_index, nfs, masks, B, cond_d)[0]
-
-    out_host = [torch.empty(h.size(0), 9).pin_memory() for h in h0_h]
-
-    def step_e2e():
-        torch.manual_seed(1234 + rank)
-        nd = [x.to(dev, non_blocking=True) for x in nodes_h]
-        hd = [x.to(dev, non_blocking=True) for x in h0_h]
-        cd = cond_h.to(dev, non_blocking=True)
-        out, _ = ddpm.sample(B, nd, cd, h0=hd)
-        for dst, src in zip(out_host, out[0]):
-            dst.copy_(src.to(torch.float32), non_blocking=True)
-        return out[0]
+            # state a trained model would see at t = s+1: q(z_t | x); then the usual reverse step (denoiser + posterior)
+            Z = tab["alpha"][s_int + 1] * X + tab["sigma_abs"][s_int + 1] * ddpm._noise_cat(masks)
+            Z[:, 3:] = H0
+            Z = ddpm._fast_step(s_int, Z, tab, edge_index, nfs, masks, cond_d)
+        Z0 = tab["alpha"][0] * X + tab["sigma_abs"][0] * ddpm._noise_cat(masks)
+        Z0[:, 3:] = H0
+        return ddpm.sample_p_xh_given_z0(ddpm._views(Z0), edge_index, nfs, masks, B, cond_d)[0]
 
     h2d = sum(x.numel() * x.element_size() for x in nodes_h + h0_h + [cond_h])
     d2h = sum(x.numel() * x.element_size() for x in out_host)
