@@ -259,7 +259,19 @@ def run_b200(args, rank, world, local_rank):
         Z0[:, 3:] = H0
         return ddpm.sample_p_xh_given_z0(ddpm._views(Z0), edge_index, nfs, masks, B, cond_d)[0]
 
-    h2d = sum(x.numel() * x.element_size() for x in nodes_h + h0_h + [cond_h])
+    out_host = [torch.empty(h.size(0), 9).pin_memory() for h in h0_h]
+
+    def step_e2e():
+        torch.manual_seed(1234 + rank)
+        nd = [x.to(dev, non_blocking=True) for x in nodes_h]
+        hd = [x.to(dev, non_blocking=True) for x in h0_h]
+        cd = cond_h.to(dev, non_blocking=True)
+        out, _ = ddpm.sample(B, nd, cd, h0=hd)
+        for dst, src in zip(out_host, out[0]):
+            dst.copy_(src.to(torch.float32), non_blocking=True)
+        return out[0]
+
+    h2d =sum(x.numel() * x.element_size() for x in nodes_h + h0_h + [cond_h])
     d2h = sum(x.numel() * x.element_size() for x in out_host)
 
     def barrier():
