@@ -105,6 +105,14 @@ int oard_test_gemm_ex(int device, int M, int N, int K, const float* A, const flo
                       int use_tc, int act, int swap_lbo_sbo, int mode, const float* aux, int ablate, int reps,
                       float* ms_out, void* stream);
 
+/* Unit-test / timing entry of the pair16 GEMM (csrc/gemm_p16.cuh: A operand and, optionally, the output stored in
+ * HBM as split-bf16 pairs in the tensor core's operand layout).  All tensors fp32 on the device; the entry converts.
+ * mode as above (3 updates C in place); c2_out != NULL also returns the compact copy of rows m % 3 == 0;
+ * ew: epilogue warps (0 = default, 8, 16). */
+int oard_test_gemm_p16(int device, int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
+                       int mode, const float* aux, int out_pair, int act, float* c2_out, int ew, int reps,
+                       float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,429 @@
+// tcgen05 GEMM whose A operand is already stored in HBM in the tensor core's own split-bf16 form ("pair16").
+//
+// pair16 layout of a row-major activation X[M, K] (row pitch ld floats, ld % 16 == 0, same bytes as fp32):
+//   every 16 consecutive values x[16g .. 16g+15] occupy 64 bytes:  [16 x bf16 hi | 16 x bf16 lo],  x ~= hi + lo
+//   (hi = bf16_rn(x), lo = bf16_rn(x - hi): 16 mantissa bits, exactly what the bf16x3 product consumes anyway).
+// A 2-D TMA box {32 floats = 128 B, 128 rows} with SWIZZLE_128B therefore lands a ready K-major UMMA operand for a
+// K chunk of 32: k-step j uses the sub-atom offsets  hi = 64 j,  lo = 64 j + 32  of every 128-byte row.  No producer
+// warps, no in-kernel fp32 -> bf16 conversion, no extra shared-memory copy (compare gemm_tc.cuh, whose per-chunk
+// convert/fence skeleton bounded it at 30-45 % tensor-pipe activity: profiles/r1_tc_notes.md).
+// The epilogue (thread = output row, 32x32 blocks, TMA in/out) can emit pair16 as well, so chains of edge GEMMs
+// (edge state -> GCL edge MLP -> edge state -> dir_proj) never touch fp32 in HBM.
+//
+//   C[m, n] = epi( sum_k A[m, k] * W[n, k] ),  three tcgen05.mma.kind::f16 per K step (a_hi w_hi + a_hi w_lo + a_lo w_hi)
+//
+// Warp roles (EW + 3 warps, 1 CTA/SM, persistent over tiles):
+//   warps 0..EW-1 epilogue (EW = 8 or 16; warp e owns TMEM lanes 32 (e % 4).. and column blocks e/4, e/4 + EW/4, ..)
+//   warp  EW      MMA issuer (one lane), owns TMEM alloc/dealloc, 2 accumulators
+//   warp  EW+1    A loader (one lane): 2-D TMA boxes into an SA-deep ring (the HBM stream: deep, 16 KB per slot)
+//   warp  EW+2    W loader (one lane): TMA bulk copies of the pre-tiled weight slabs into an SW-deep ring (L2-resident)
+// The two rings are separate because the A stream comes from HBM (needs ~64 KB in flight per SM to cover the latency)
+// while W comes from L2: with one shared ring the 26-32 KB W slab of every stage capped the A bytes in flight at 32 KB.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace oard {
+
+constexpr int P16_A_BYTES = TC_BM * 128;  // one A stage: 128 rows x 128 B
+
+// ---- pair16 encode / decode of 8 consecutive values (one 16-byte cell of hi and one of lo)
+__device__ __forceinline__ void p16_split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const float2 f = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void p16_join8(const uint4& hi, const uint4& lo, float* x) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    x[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+    x[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+  }
+}
+// byte offsets of value column c inside a pair16 row
+__host__ __device__ inline size_t p16_off_hi(int c) { return (size_t)(c >> 4) * 64 + (size_t)(c & 15) * 2; }
+__host__ __device__ inline int p16_ld(int K) { return (K + 15) / 16 * 16; }
+
+// fp32 [M, K] (ld_src) -> pair16 [M, p16_ld(K)] (ld_dst floats); pad columns are written as zeros.  One thread per 8 values.
+__global__ void k_p16_pack(const float* __restrict__ src, int ld_src, int M, int K, float* __restrict__ dst, int ld_dst) {
+  const int cells = ld_dst / 8;
+  const size_t total = (size_t)M * cells;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / cells), c8 = (int)(i % cells) * 8;
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = (c8 + k) < K ? src[(size_t)m * ld_src + c8 + k] : 0.f;
+    uint4 hi, lo;
+    p16_split8(x, hi, lo);
+    uint8_t* row = reinterpret_cast<uint8_t*>(dst + (size_t)m * ld_dst);
+    *reinterpret_cast<uint4*>(row + p16_off_hi(c8)) = hi;
+    *reinterpret_cast<uint4*>(row + p16_off_hi(c8) + 32) = lo;
+  }
+}
+// pair16 [M, ld_src] -> fp32 [M, K] (ld_dst)
+__global__ void k_p16_unpack(const float* __restrict__ src, int ld_src, int M, int K, float* __restrict__ dst, int ld_dst) {
+  const int cells = (K + 7) / 8;
+  const size_t total = (size_t)M * cells;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / cells), c8 = (int)(i % cells) * 8;
+    const uint8_t* row = reinterpret_cast<const uint8_t*>(src + (size_t)m * ld_src);
+    const uint4 hi = *reinterpret_cast<const uint4*>(row + p16_off_hi(c8));
+    const uint4 lo = *reinterpret_cast<const uint4*>(row + p16_off_hi(c8) + 32);
+    float x[8];
+    p16_join8(hi, lo, x);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c8 + k < K) dst[(size_t)m * ld_dst + c8 + k] = x[k];
+  }
+}
+
+// K-major SWIZZLE_128B shared-memory descriptor: LBO field 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B),
+// version 1 (bit 46), layout type 2 = SWIZZLE_128B (bits 61-63).  The start address may carry a 32/64/96-byte sub-atom
+// offset (K advance inside the swizzle atom); the stage base is 1024-byte aligned.
+__device__ __forceinline__ uint64_t p16_a_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// MODE: 0 plain (bias / SiLU / row scale), 1 + gathered row adds P[src] + Q[dst], 2 * mul[m, n] (fp32 aux),
+//       3 + resid[m, n] (aux in pair16 when OUT_PAIR, else fp32; may alias C).
+// OUT_PAIR: C (and the optional row-scattered copy C2) are written in pair16, else fp32.
+template <int SA, int SW, int MODE, bool OUT_PAIR, int EW, int NIO>
+__global__ void __launch_bounds__((EW + 3) * 32, 1)
+gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NCG = EW / 4;  // column groups of epilogue warps
+  const int BN = w.BN;
+  const int W_PART = BN * TC_KC * 2;
+  uint8_t* a_ring = smem;                                      // [SA][16 KB], 1024-aligned slots
+  uint8_t* w_ring = smem + (size_t)SA * P16_A_BYTES;           // [SW][hi BN x 64 B | lo BN x 64 B]
+  uint8_t* io_all = w_ring + (size_t)SW * 2 * W_PART;          // 1024-aligned (BN % 16 == 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(io_all + (size_t)EW * NIO * TC_IO_BYTES);
+  uint64_t* full_a = bars;                 // [SA] A box landed (complete_tx)
+  uint64_t* empty_a = full_a + SA;         // [SA] MMAs that read the slot retired (tcgen05.commit)
+  uint64_t* full_w = empty_a + SA;         // [SW]
+  uint64_t* empty_w = full_w + SW;         // [SW]
+  uint64_t* acc_full = empty_w + SW;       // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* aux_full = acc_empty + 2;      // [EW][NIO]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + EW * NIO);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
+  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int total_tiles = m_tiles * w.n_tiles;
+  const int k_chunks = w.k_chunks;
+  const int k16_total = (g.K + 15) / 16;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; s++) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < SW; s++) { ptx::mbar_init(&full_w[s], 1); ptx::mbar_init(&empty_w[s], 1); }
+    for (int b = 0; b < 2; b++) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], EW); }
+    for (int i = 0; i < EW * NIO; i++) ptx::mbar_init(&aux_full[i], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == EW) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == EW + 1) {
+    // ===================== A loader: 2-D TMA boxes {32 floats, 128 rows}, SWIZZLE_128B =====================
+    if (lane == 0) {
+      ptx::tma_prefetch_desc(&tmA);
+      uint32_t gchunk = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / w.n_tiles) * TC_BM;
+        for (int kc = 0; kc < k_chunks; kc++, gchunk++) {
+          const int s = gchunk % SA;
+          ptx::mbar_wait(&empty_a[s], ((gchunk / SA) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_a[s], P16_A_BYTES);
+          ptx::tma_load_2d(a_ring + (size_t)s * P16_A_BYTES, &tmA, kc * TC_KC, m0, &full_a[s]);
+        }
+      }
+    }
+  } else if (warp == EW + 2) {
+    // ===================== W loader: TMA bulk copies of pre-tiled slabs =====================
+    if (lane == 0) {
+      uint32_t gchunk = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % w.n_tiles;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w.data) + (size_t)nt * k_chunks * 2 * W_PART;
+        for (int kc = 0; kc < k_chunks; kc++, gchunk++) {
+          const int s = gchunk % SW;
+          ptx::mbar_wait(&empty_w[s], ((gchunk / SW) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W_PART);
+          ptx::bulk_g2s(w_ring + (size_t)s * 2 * W_PART, wsrc + (size_t)kc * 2 * W_PART, 2 * W_PART, &full_w[s]);
+        }
+      }
+    }
+  } else if (warp == EW) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc_idesc(TC_BM, BN);
+      uint32_t gchunk = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kc = 0; kc < k_chunks; kc++, gchunk++) {
+          const int sa = gchunk % SA, sw_ = gchunk % SW;
+          ptx::mbar_wait(&full_w[sw_], (gchunk / SW) & 1);
+          ptx::mbar_wait(&full_a[sa], (gchunk / SA) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(a_ring + (size_t)sa * P16_A_BYTES);
+          const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * 2 * W_PART), w_lo = w_hi + W_PART;
+          const int steps = min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
+          for (int j = 0; j < steps; j++) {
+            const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
+            const uint32_t kw = j * 2 * TC_CORE_BYTES;
+            const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+            ptx::umma_bf16(d_tmem, dah, dwh, idesc, (kc | j) != 0);
+            ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dal, dwh, idesc, 1);
+          }
+          ptx::umma_commit(&empty_a[sa]);  // both rings are released when these MMAs retire
+          ptx::umma_commit(&empty_w[sw_]);
+        }
+        ptx::umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread = output row, 32x32 blocks, TMA in / out =====================
+    const int rq = warp & 3, cg = warp >> 2;
+    uint8_t* io = io_all + (size_t)warp * NIO * TC_IO_BYTES;
+    uint64_t* xbar = aux_full + warp * NIO;
+    const int nblocks = (BN + 31) / 32;
+    const int sw = lane & 7;
+    constexpr bool HAS_AUX = (MODE == 2 || MODE == 3);
+    // Buffer ring per warp: block i uses buffer i % NIO from its aux load until its store has read it.  Aux loads run PF
+    // blocks ahead; the buffer of block nb + PF was last read by the store of block nb + PF - NIO, so at most
+    // PEND = NIO - 1 - PF newer stores may still be reading when it is refilled (NIO 2: PF 1, PEND 0; NIO 3: PF 1, PEND 1).
+    static_assert(NIO == 2 || NIO == 3, "NIO");
+    constexpr int PF = 1, PEND = NIO - 1 - PF;
+    int pf_tile = blockIdx.x, pf_blk = cg;
+    auto pf_next = [&]() {
+      pf_blk += NCG;
+      if (pf_blk >= nblocks) { pf_blk = cg; pf_tile += gridDim.x; }
+    };
+    uint32_t nb = 0, npf = 0;
+    auto issue_aux = [&]() {  // lane 0 only
+      if (!HAS_AUX) return;
+      while (pf_tile < total_tiles && pf_blk >= nblocks) pf_next();
+      if (pf_tile >= total_tiles) return;
+      const int b = npf % NIO;
+      ptx::mbar_arrive_expect_tx(&xbar[b], TC_IO_BYTES);
+      ptx::tma_load_2d(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
+                       (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b]);
+      npf++;
+      pf_next();
+    };
+    if (lane == 0) {
+      ptx::tma_prefetch_desc(&tmC);
+      if (HAS_AUX) {
+        ptx::tma_prefetch_desc(&tmX);
+        for (int i = 0; i < PF; i++) issue_aux();
+      }
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const int m0r = (tile / w.n_tiles) * TC_BM + rq * 32;
+      const int m = m0r + lane;
+      const int n0 = (tile % w.n_tiles) * BN;
+      const bool ok = m < M;
+      const float* pr = nullptr;
+      const float* qr = nullptr;
+      if (MODE == 1 && ok) {
+        pr = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1;
+        qr = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2;
+      }
+      const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
+      const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int blk = cg; blk < nblocks; blk += NCG, nb++) {
+        const int b = nb % NIO;
+        uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
+        float v[32];
+        ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+        if (HAS_AUX) {
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PEND) : "memory");
+            issue_aux();
+          }
+          ptx::mbar_wait(&xbar[b], (nb / NIO) & 1);
+        } else {
+          // buffer b was last read by the store of block nb - NIO: NIO - 1 newer stores may still be in flight
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NIO - 1) : "memory");
+          __syncwarp();
+        }
+        const int nblk = n0 + blk * 32;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int n = nblk + q * 4;
+          const bool nin = n < g.N;
+          float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (g.bias && nin) { const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+          if (MODE == 1 && nin && ok) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(pr + n));
+            const float4 u = __ldg(reinterpret_cast<const float4*>(qr + n));
+            x.x += t.x + u.x; x.y += t.y + u.y; x.z += t.z + u.z; x.w += t.w + u.w;
+          }
+          if (g.act == 1) { x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w); }
+          x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+          if (MODE == 2 || (MODE == 3 && !OUT_PAIR)) {  // fp32 aux block: cell q = columns 4q .. 4q+3
+            const float4 t = *reinterpret_cast<const float4*>(iob + ((q ^ sw) << 4));
+            if (MODE == 2) { x.x *= t.x; x.y *= t.y; x.z *= t.z; x.w *= t.w; }
+            else { x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+          }
+          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        if (OUT_PAIR) {
+          // row bytes: cells 0,1 = hi(v0..15), 2,3 = lo(v0..15), 4,5 = hi(v16..31), 6,7 = lo(v16..31)
+          uint4 cell[8];
+          if (MODE == 3) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) cell[q] = *reinterpret_cast<const uint4*>(iob + ((q ^ sw) << 4));
+            float e[8];
+            p16_join8(cell[0], cell[2], e);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += e[k];
+            p16_join8(cell[1], cell[3], e);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[8 + k] += e[k];
+            p16_join8(cell[4], cell[6], e);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[16 + k] += e[k];
+            p16_join8(cell[5], cell[7], e);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[24 + k] += e[k];
+          }
+          p16_split8(v, cell[0], cell[2]);
+          p16_split8(v + 8, cell[1], cell[3]);
+          p16_split8(v + 16, cell[4], cell[6]);
+          p16_split8(v + 24, cell[5], cell[7]);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            *reinterpret_cast<uint4*>(iob + ((q ^ sw) << 4)) = cell[q];
+            if (c2 >= 0 && (nblk + (q >> 2) * 16) < g.ldc2)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.C2 + (size_t)c2 * g.ldc2 + nblk) + q * 16) = cell[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *reinterpret_cast<float4*>(iob + ((q ^ sw) << 4)) = x;
+            if (c2 >= 0 && (nblk + q * 4) < g.N) *reinterpret_cast<float4*>(g.C2 + (size_t)c2 * g.ldc2 + nblk + q * 4) = x;
+          }
+        }
+        ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES);
+          ptx::bulk_commit();
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+    if (lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EW) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline size_t p16_smem_bytes(int BN, int sa, int sw, int ew, int nio) {
+  return (size_t)sa * P16_A_BYTES + (size_t)sw * 2 * BN * TC_KC * 2 + (size_t)ew * nio * TC_IO_BYTES +
+         (size_t)(2 * sa + 2 * sw + 4 + ew * nio) * 8 + 16;
+}
+
+template <int SA, int SW, int MODE, bool OUT_PAIR, int EW, int NIO>
+inline cudaError_t launch_gemm_p16_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, const CUtensorMap& tmA,
+                                        const CUtensorMap& tmC, const CUtensorMap& tmX, cudaStream_t st) {
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_p16_kernel<SA, SW, MODE, OUT_PAIR, EW, NIO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  gemm_p16_kernel<SA, SW, MODE, OUT_PAIR, EW, NIO><<<grid, (EW + 3) * 32, smem, st>>>(g, w, tmA, tmC, tmX);
+  return cudaGetLastError();
+}
+
+// A: pair16 [M, lda] with lda % 16 == 0 and lda >= K.  out_pair: C (ldc % 16 == 0, ldc >= N) and C2 in pair16, and the
+// residual (mode 3) is read as pair16; otherwise C / resid are fp32.  mul (mode 2) is always fp32.
+// ew_pref: 8 or 16 epilogue warps (16 only for aux modes); returns cudaErrorInvalidValue for unsupported shapes.
+inline cudaError_t launch_gemm_p16(const GemmArgs& g, const TcWeight& w, int num_sms, cudaStream_t st, bool out_pair,
+                                   int ew_pref = 0) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  if (g.K % 4 || g.lda % 16 || g.lda < g.K || g.N % 4 || g.ldc % 4 || w.BN % 16 || w.BN > 256 || w.BN < 16 ||
+      g.K != w.K || g.N != w.N || g.aidx)
+    return cudaErrorInvalidValue;
+  if (out_pair && (g.ldc % 16 || g.ldc < g.N || (g.C2 && g.ldc2 != g.ldc))) return cudaErrorInvalidValue;
+  const int nmode = (g.radd1 ? 1 : 0) + (g.mul ? 1 : 0) + (g.resid ? 1 : 0);
+  if (nmode > 1 || (g.radd1 && !g.radd2) || (!g.radd1 && g.radd2)) return cudaErrorInvalidValue;
+  const int mode = g.radd1 ? 1 : (g.mul ? 2 : (g.resid ? 3 : 0));
+  if (mode == 2 && out_pair) return cudaErrorInvalidValue;
+  if (mode == 3 && out_pair && g.ldres != g.ldc) return cudaErrorInvalidValue;
+  const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
+  const int total = m_tiles * w.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  static int env_ew = -1;
+  if (env_ew < 0) { const char* e = getenv("OARD_P16_EW"); env_ew = e ? atoi(e) : 0; }
+  // epilogue shape: the in-place residual update streams 2 x 4 KB per output block through the epilogue, so it gets 16
+  // warps (more blocks in flight per SM); the other modes 8 (measured: profiles/r1_p16_notes.md).  OARD_P16_EW overrides.
+  int ew = ew_pref ? ew_pref : (mode == 3 ? 16 : 8);
+  if (mode >= 2 && !ew_pref && (env_ew == 8 || env_ew == 16)) ew = env_ew;
+  if (mode < 2) ew = 8;
+  const int nio = 2;
+  CUtensorMap tmA, tmC, tmX;
+  memset(&tmA, 0, sizeof tmA); memset(&tmC, 0, sizeof tmC); memset(&tmX, 0, sizeof tmX);
+  if (!tc_make_map(&tmA, g.A, g.M, p16_ld(g.K), g.lda, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
+  if (!tc_make_map(&tmC, g.C, g.M, out_pair ? p16_ld(g.N) : g.N, g.ldc, 32, 32, true)) return cudaErrorInvalidValue;
+  if (mode == 2 && !tc_make_map(&tmX, g.mul, g.M, g.N, g.ldmul, 32, 32, true)) return cudaErrorInvalidValue;
+  if (mode == 3 && !tc_make_map(&tmX, g.resid, g.M, out_pair ? p16_ld(g.N) : g.N, g.ldres, 32, 32, true))
+    return cudaErrorInvalidValue;
+  const size_t lim = 227 * 1024;
+  // ring depths (A, W) in order of preference
+  static const int rings[3][2] = {{5, 3}, {4, 3}, {2, 2}};
+  int sa = 0, sw = 0;
+  auto pick = [&](int e_) {
+    for (auto& r : rings)
+      if (p16_smem_bytes(w.BN, r[0], r[1], e_, nio) <= lim) { sa = r[0]; sw = r[1]; return true; }
+    return false;
+  };
+  if (!pick(ew)) { ew = 8; if (!pick(ew)) return cudaErrorInvalidValue; }
+  const size_t smem = p16_smem_bytes(w.BN, sa, sw, ew, nio);
+#define OARD_P16_CASE(A_, W_, MD, OP, E)                                             \
+  if (sa == A_ && sw == W_ && mode == MD && out_pair == OP && ew == E)               \
+    return launch_gemm_p16_inst<A_, W_, MD, OP, E, 2>(g, w, grid, smem, tmA, tmC, tmX, st);
+#define OARD_P16_RINGS(MD, OP, E) OARD_P16_CASE(5, 3, MD, OP, E) OARD_P16_CASE(4, 3, MD, OP, E) OARD_P16_CASE(2, 2, MD, OP, E)
+  OARD_P16_RINGS(0, true, 8) OARD_P16_RINGS(0, false, 8) OARD_P16_RINGS(1, true, 8)
+  OARD_P16_RINGS(2, false, 8) OARD_P16_RINGS(2, false, 16)
+  OARD_P16_RINGS(3, true, 8) OARD_P16_RINGS(3, true, 16) OARD_P16_RINGS(3, false, 8)
+#undef OARD_P16_RINGS
+#undef OARD_P16_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace oard

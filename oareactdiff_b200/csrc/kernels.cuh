@@ -6,9 +6,22 @@
 // up to a warp multiple).  Aggregations at edge_index[1] (PyG 'target') are done as row sums over transposed edges,
 // so every reduction is a fixed-order segmented sum: no atomics, bitwise reproducible.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace oard {
+
+// Four SiLUs with ONE reciprocal (MUFU budget 5 instead of 8): 1/d_i from r = 1/(d0 d1 d2 d3).  The exponent is clamped
+// at 20 so the product stays below 6e34; for u < -20 the result is u * 2e-9 instead of ~0 (|error| < 1e-7 |u| / 50).
+__device__ __forceinline__ void silu4_shared_rcp(float& u0, float& u1, float& u2, float& u3) {
+  const float d0 = 1.0f + __expf(fminf(-u0, 20.f)), d1 = 1.0f + __expf(fminf(-u1, 20.f));
+  const float d2 = 1.0f + __expf(fminf(-u2, 20.f)), d3 = 1.0f + __expf(fminf(-u3, 20.f));
+  const float d01 = d0 * d1, d23 = d2 * d3;
+  const float r = __fdividef(1.0f, d01 * d23);
+  const float r01 = r * d23, r23 = r * d01;
+  u0 *= r01 * d1; u1 *= r01 * d0; u2 *= r23 * d3; u3 *= r23 * d2;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // (B) raw distance + cutoff/same-fragment edge mask.  leftnet.py:747-753
@@ -306,60 +319,6 @@ __global__ void k_s2v(int H, const int* __restrict__ row_ptr, const int* __restr
   o[h] = a0; o[H + h] = a1; o[2 * H + h] = a2;
 }
 
-// (I) initial edge state e0 = [ (sc3 | sc4) * rb | f | rbf ]  (leftnet.py:792-809).  One block per edge.
-// Masked edges carry the constant [c3 .. | f0 | 0].
-__global__ void k_edge_init(int H, int R, int Hq, int reflect, const int* __restrict__ esrc,
-                            const int* __restrict__ ecol, const int* __restrict__ act_pos,
-                            const float* __restrict__ pf, const float4* __restrict__ geo, const float* __restrict__ rb,
-                            const float* __restrict__ NE1, const float* __restrict__ f_act,
-                            const float* __restrict__ rbf_act, const float* __restrict__ f0,
-                            const float* __restrict__ c3, const float* __restrict__ l3_w0,
-                            const float* __restrict__ l3_b0, const float* __restrict__ l3_w2,
-                            const float* __restrict__ l3_b2, float* __restrict__ ew) {
-  extern __shared__ float sw[];  // w0[Hq*3], b0[Hq], w2[Hq]
-  const int e = blockIdx.x, h = threadIdx.x, D = 3 * H + R;
-  float* out = ew + (size_t)e * D;
-  const int p = act_pos[e];
-  if (p < 0) {
-    if (h < H) { const float c = *c3; out[h] = c; out[H + h] = c; out[2 * H + h] = f0[h]; }
-    for (int r = h; r < R; r += blockDim.x) out[3 * H + r] = 0.f;
-    return;
-  }
-  for (int k = h; k < Hq * 3; k += blockDim.x) sw[k] = l3_w0[k];
-  for (int k = h; k < Hq; k += blockDim.x) { sw[Hq * 3 + k] = l3_b0[k]; sw[Hq * 4 + k] = l3_w2[k]; }
-  __syncthreads();
-  for (int r = h; r < R; r += blockDim.x) out[3 * H + r] = rbf_act[(size_t)p * R + r];
-  if (h >= H) return;
-  const int i = esrc[e], j = ecol[e];
-  const float4 g = geo[e];
-  // edge frame columns: u (unit diff), c (unit cross of pos_frame_i x pos_frame_j), v = u x c   (:693-705)
-  const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2];
-  const float bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
-  float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-  const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
-  cx *= cinv; cy *= cinv; cz *= cinv;
-  const float vx = g.y * cz - g.z * cy, vy = g.z * cx - g.x * cz, vz = g.x * cy - g.y * cx;
-  const float rbe = rb[e], b2 = l3_b2[0];
-  const float* ni = NE1 + (size_t)i * 3 * H;
-  const float* nj = NE1 + (size_t)j * 3 * H;
-#pragma unroll
-  for (int side = 0; side < 2; side++) {
-    const float* n = side ? nj : ni;
-    const float n0 = n[h], n1 = n[H + h], n2 = n[2 * H + h];
-    const float s0 = n0 * g.x + n1 * g.y + n2 * g.z;
-    float s1 = n0 * cx + n1 * cy + n2 * cz;
-    const float s2 = n0 * vx + n1 * vy + n2 * vz;
-    if (reflect) s1 = fabsf(s1);
-    float acc = b2;
-    for (int k = 0; k < Hq; k++) {
-      const float u = fmaf(sw[k * 3], s0, fmaf(sw[k * 3 + 1], s1, fmaf(sw[k * 3 + 2], s2, sw[Hq * 3 + k])));
-      acc = fmaf(sw[Hq * 4 + k], silu_fast(u), acc);
-    }
-    out[side * H + h] = (acc + s0) * rbe;
-  }
-  out[2 * H + h] = f_act[(size_t)p * H + h];
-}
-
 // GCL attention gate + mean aggregation at the edge source (leftnet.py:169-183, util_funcs.py:27-45).
 // One block per node; warps take the row's edges round-robin.  m2 is scaled in place by its gate.
 __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restrict__ m2,
@@ -404,113 +363,113 @@ __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restr
   }
 }
 
-// EquiMessage message + aggregation at the edge target + residual (leftnet.py:263-284, 857-859).
-// One block per target node t; walks row t and uses the transposed edge r = (a -> t).
-__global__ void k_equi_reduce(int H, int reflect, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
-                              const int* __restrict__ rev, const int* __restrict__ act_pos,
-                              const float* __restrict__ G, const float* __restrict__ X,
-                              const float4* __restrict__ geo, const float* __restrict__ pf,
-                              const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
-  const int t = blockIdx.x, h = threadIdx.x;
-  if (h >= H) return;
-  const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
-  const float* Xt = X + (size_t)t * 3 * H;
-  const float x0 = Xt[h], x1 = Xt[H + h], x2 = Xt[2 * H + h];
-  float dx = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-  for (int e = row_ptr[t]; e < row_ptr[t + 1]; e++) {
-    const int r = rev[e], p = act_pos[r];
-    if (p < 0) continue;  // masked edges contribute exactly 0 (rbf_proj has no bias, rbf = 0)
-    const int a = ecol[e];
-    const float* g = G + (size_t)p * 3 * H;
-    const float* Xa = X + (size_t)a * 3 * H;
-    const float al = (Xa[h] + x0) * g[h];
-    const float be = (Xa[H + h] + x1) * g[H + h] * inv_sqrt_3;
-    const float ga = (Xa[2 * H + h] + x2) * g[2 * H + h];
-    const float4 u = geo[r];
-    const float* va = vec_in + (size_t)a * 3 * H;
-    float m0 = fmaf(va[h], be, ga * u.x), m1 = fmaf(va[H + h], be, ga * u.y), m2 = fmaf(va[2 * H + h], be, ga * u.z);
-    if (!reflect) {  // + x * edge_cross (leftnet.py:268-269); cross of pos_frame_a x pos_frame_t, unit
-      const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
-      const float bx = pf[t * 3], by = pf[t * 3 + 1], bz = pf[t * 3 + 2];
-      float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
-      m0 = fmaf(al, cx * cinv, m0); m1 = fmaf(al, cy * cinv, m1); m2 = fmaf(al, cz * cinv, m2);
-    }
-    dx += al;
-    d0 = fmaf(m0, inv_sqrt_h, d0); d1 = fmaf(m1, inv_sqrt_h, d1); d2 = fmaf(m2, inv_sqrt_h, d2);
-  }
-  const size_t o = (size_t)t * 3 * H;
-  s[(size_t)t * H + h] = (s[(size_t)t * H + h] + dx) * inv_sqrt_2;
-  vec_out[o + h] = vec_in[o + h] + d0;
-  vec_out[o + H + h] = vec_in[o + H + h] + d1;
-  vec_out[o + 2 * H + h] = vec_in[o + 2 * H + h] + d2;
+// Per-step lists over the compact active edges: for p = (t -> a), the compact position of the transposed edge (a -> t), the
+// neighbour a and the geometry of p (the transposed edge's unit vector is its exact negation).  They turn the
+// target-side aggregations into walks over contiguous index ranges [row_act_ptr[t], row_act_ptr[t+1]) with independent loads.
+__global__ void k_act_lists(const int* __restrict__ n_act, int cap, const int* __restrict__ act_idx,
+                            const int* __restrict__ act_pos, const int* __restrict__ rev, const int* __restrict__ ecol,
+                            const float4* __restrict__ geo, int* __restrict__ act_tr, int* __restrict__ act_col,
+                            float4* __restrict__ act_geo) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= min(*n_act, cap)) return;
+  const int e = act_idx[p];
+  act_tr[p] = act_pos[rev[e]];
+  act_col[p] = ecol[e];
+  act_geo[p] = geo[e];
 }
 
-// float4 version of k_equi_reduce: one thread per 4 channels (H % 4 == 0), one block per target node.
-__global__ void __launch_bounds__(64) k_equi_reduce4(
-    int H, int reflect, const int* __restrict__ row_ptr, const int* __restrict__ ecol, const int* __restrict__ rev,
-    const int* __restrict__ act_pos, const float* __restrict__ G, const float* __restrict__ X,
-    const float4* __restrict__ geo, const float* __restrict__ pf, const float* __restrict__ vec_in,
+// EquiMessage message + aggregation at the edge target + residual (leftnet.py:263-284, 857-859): the message-passing
+// kernel proper (HBM-bound: streams G[E_act, 3H] once).  One block per target node t; NG groups of 64 threads take the
+// node's active incoming edges round-robin (one thread = 4 channels, float4 loads, two edges in flight per group), the
+// NG partial sums are combined through shared memory in a fixed order (bitwise reproducible), then
+// s = (s + dx)/sqrt2, vec_out = vec_in + dvec.
+template <int NG>
+__global__ void __launch_bounds__(NG * 64) k_equi_reduce(
+    int H, int reflect, const int* __restrict__ row_act_ptr, const int* __restrict__ act_tr,
+    const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float* __restrict__ G,
+    const float* __restrict__ X, const float* __restrict__ pf, const float* __restrict__ vec_in,
     float* __restrict__ vec_out, float* __restrict__ s) {
-  const int t = blockIdx.x, h = threadIdx.x * 4;
-  if (h >= H) return;
+  extern __shared__ __align__(16) float4 eq_part[];  // [NG][4][H/4]
+  const int t = blockIdx.x, grp = threadIdx.x >> 6, h = (threadIdx.x & 63) * 4, H4 = H / 4;
+  const bool on = h < H;
   const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-  const float* Xt = X + (size_t)t * 3 * H;
-  const float4 x0 = ld4(Xt + h), x1 = ld4(Xt + H + h), x2 = ld4(Xt + 2 * H + h);
   float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
-  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
-  for (int e = r0; e < r1; e++) {
-    const int r = rev[e], p = act_pos[r];
-    if (p < 0) continue;  // masked edges contribute exactly 0
-    const int a = ecol[e];
-    const float* g = G + (size_t)p * 3 * H;
-    const float* Xa = X + (size_t)a * 3 * H;
-    const float* va = vec_in + (size_t)a * 3 * H;
-    const float4 g0 = ld4(g + h), g1 = ld4(g + H + h), g2 = ld4(g + 2 * H + h);
-    const float4 a0 = ld4(Xa + h), a1 = ld4(Xa + H + h), a2 = ld4(Xa + 2 * H + h);
-    const float4 v0 = ld4(va + h), v1 = ld4(va + H + h), v2 = ld4(va + 2 * H + h);
-    const float4 u = geo[r];
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    if (!reflect) {
-      const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
-      const float bx = pf[t * 3], by = pf[t * 3 + 1], bz = pf[t * 3 + 2];
-      cx = ay * bz - az * by; cy = az * bx - ax * bz; cz = ax * by - ay * bx;
-      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
-      cx *= cinv; cy *= cinv; cz *= cinv;
-    }
+  const int p0 = row_act_ptr[t], p1 = row_act_ptr[t + 1];
+  if (on) {
+    const float* Xt = X + (size_t)t * 3 * H;
+    const float4 x0 = ld4(Xt + h), x1 = ld4(Xt + H + h), x2 = ld4(Xt + 2 * H + h);
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (!reflect) { tx = pf[t * 3]; ty = pf[t * 3 + 1]; tz = pf[t * 3 + 2]; }
+    auto edge = [&](int p) {
+      const int pr = act_tr[p], a = act_col[p];
+      const float4 gm = act_geo[p];  // geometry of (t -> a); the message edge (a -> t) has the negated unit vector
+      const float ux = -gm.x, uy = -gm.y, uz = -gm.z;
+      const float* g = G + (size_t)pr * 3 * H;
+      const float* Xa = X + (size_t)a * 3 * H;
+      const float* va = vec_in + (size_t)a * 3 * H;
+      const float4 g0 = ld4(g + h), g1 = ld4(g + H + h), g2 = ld4(g + 2 * H + h);
+      const float4 a0 = ld4(Xa + h), a1 = ld4(Xa + H + h), a2 = ld4(Xa + 2 * H + h);
+      const float4 v0 = ld4(va + h), v1 = ld4(va + H + h), v2 = ld4(va + 2 * H + h);
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      if (!reflect) {  // + x * edge_cross (leftnet.py:268-269); cross of pos_frame_a x pos_frame_t, unit
+        const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
+        cx = ay * tz - az * ty; cy = az * tx - ax * tz; cz = ax * ty - ay * tx;
+        const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
+        cx *= cinv; cy *= cinv; cz *= cinv;
+      }
 #define OARD_EQ(c)                                                                         \
-    {                                                                                      \
-      const float al = (a0.c + x0.c) * g0.c;                                               \
-      const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                                  \
-      const float ga = (a2.c + x2.c) * g2.c;                                               \
-      float m0 = fmaf(v0.c, be, ga * u.x), m1 = fmaf(v1.c, be, ga * u.y), m2 = fmaf(v2.c, be, ga * u.z); \
-      if (!reflect) { m0 = fmaf(al, cx, m0); m1 = fmaf(al, cy, m1); m2 = fmaf(al, cz, m2); }            \
-      dx.c += al;                                                                          \
-      d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
-    }
-    OARD_EQ(x) OARD_EQ(y) OARD_EQ(z) OARD_EQ(w)
+      {                                                                                    \
+        const float al = (a0.c + x0.c) * g0.c;                                             \
+        const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                                \
+        const float ga = (a2.c + x2.c) * g2.c;                                             \
+        float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
+        if (!reflect) { m0 = fmaf(al, cx, m0); m1 = fmaf(al, cy, m1); m2 = fmaf(al, cz, m2); }          \
+        dx.c += al;                                                                        \
+        d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+      }
+      OARD_EQ(x) OARD_EQ(y) OARD_EQ(z) OARD_EQ(w)
 #undef OARD_EQ
+    };
+#pragma unroll 2
+    for (int p = p0 + grp; p < p1; p += NG) edge(p);
+    float4* mine = eq_part + (size_t)grp * 4 * H4 + (h >> 2);
+    mine[0] = dx; mine[H4] = d0; mine[2 * H4] = d1; mine[3 * H4] = d2;
   }
-  const size_t o = (size_t)t * 3 * H + h;
-  float4 sv = ld4(s + (size_t)t * H + h);
-  sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
-  *reinterpret_cast<float4*>(s + (size_t)t * H + h) = sv;
-  const float4 w0 = ld4(vec_in + o), w1 = ld4(vec_in + o + H), w2 = ld4(vec_in + o + 2 * H);
-  *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
-  *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
-  *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+  __syncthreads();
+  if (grp == 0 && on) {
+    auto add4 = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
+    for (int gq = 1; gq < NG; gq++) {
+      const float4* o = eq_part + (size_t)gq * 4 * H4 + (h >> 2);
+      add4(dx, o[0]); add4(d0, o[H4]); add4(d1, o[2 * H4]); add4(d2, o[3 * H4]);
+    }
+    const size_t o = (size_t)t * 3 * H + h;
+    float4 sv = ld4(s + (size_t)t * H + h);
+    sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
+    *reinterpret_cast<float4*>(s + (size_t)t * H + h) = sv;
+    const float4 w0 = ld4(vec_in + o), w1 = ld4(vec_in + o + H), w2 = ld4(vec_in + o + 2 * H);
+    *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
+    *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
+    *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+  }
 }
 
-// EquiUpdate scalarisation on the node frame + lin3 (3->48->8->1) + vec_dot  (leftnet.py:326-336)
+// EquiUpdate scalarisation on the node frame + lin3 (3->48->8->1) + vec_dot  (leftnet.py:326-336).
+// One thread per (node, channel).  The lin3 weights are broadcast from shared memory as float4 ((w0,w1,w2,b0) per hidden
+// unit, the 8 second-layer weights of a hidden unit as two float4): 3 LDS.128 per hidden unit instead of 12 LDS.32 (the
+// first version was bound by the shared-memory pipe), and four SiLUs share one reciprocal.
 __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, const float* __restrict__ nodeframe,
                              const float* __restrict__ s, const float* __restrict__ w0, const float* __restrict__ b0,
                              const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w4,
                              const float* __restrict__ b4, float* __restrict__ sx, float* __restrict__ vd) {
-  __shared__ float W0[48 * 3], B0[48], W2[8 * 48], B2[8], W4[8];
-  for (int k = threadIdx.x; k < 144; k += blockDim.x) W0[k] = w0[k];
-  for (int k = threadIdx.x; k < 48; k += blockDim.x) B0[k] = b0[k];
-  for (int k = threadIdx.x; k < 384; k += blockDim.x) W2[k] = w2[k];
+  __shared__ __align__(16) float4 Wq[48];
+  __shared__ __align__(16) float4 W2t[48][2];
+  __shared__ float B2[8], W4[8];
+  for (int k = threadIdx.x; k < 48; k += blockDim.x) {
+    Wq[k] = make_float4(w0[k * 3], w0[k * 3 + 1], w0[k * 3 + 2], b0[k]);
+    W2t[k][0] = make_float4(w2[k], w2[48 + k], w2[96 + k], w2[144 + k]);
+    W2t[k][1] = make_float4(w2[192 + k], w2[240 + k], w2[288 + k], w2[336 + k]);
+  }
   for (int k = threadIdx.x; k < 8; k += blockDim.x) { B2[k] = b2[k]; W4[k] = w4[k]; }
   __syncthreads();
   const int t = blockIdx.x, h = threadIdx.x;
@@ -523,19 +482,30 @@ __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, c
   float s1 = v10 * nf[1] + v11 * nf[4] + v12 * nf[7];
   const float s2 = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
   if (reflect) s1 = fabsf(s1);
-  // 3 -> 48 -> 8 -> 1 with the 8 second-layer accumulators kept independent (8-way ILP instead of 48-long chains)
   float a[8];
 #pragma unroll
   for (int q = 0; q < 8; q++) a[q] = B2[q];
-#pragma unroll 8
-  for (int k = 0; k < 48; k++) {
-    const float u = silu_fast(fmaf(W0[k * 3], s0, fmaf(W0[k * 3 + 1], s1, fmaf(W0[k * 3 + 2], s2, B0[k]))));
+#pragma unroll 2
+  for (int k = 0; k < 48; k += 4) {
+    float u[4];
 #pragma unroll
-    for (int q = 0; q < 8; q++) a[q] = fmaf(W2[q * 48 + k], u, a[q]);
+    for (int i = 0; i < 4; i++) {
+      const float4 q = Wq[k + i];
+      u[i] = fmaf(q.x, s0, fmaf(q.y, s1, fmaf(q.z, s2, q.w)));
+    }
+    silu4_shared_rcp(u[0], u[1], u[2], u[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float4 wa = W2t[k + i][0], wb = W2t[k + i][1];
+      a[0] = fmaf(wa.x, u[i], a[0]); a[1] = fmaf(wa.y, u[i], a[1]); a[2] = fmaf(wa.z, u[i], a[2]); a[3] = fmaf(wa.w, u[i], a[3]);
+      a[4] = fmaf(wb.x, u[i], a[4]); a[5] = fmaf(wb.y, u[i], a[5]); a[6] = fmaf(wb.z, u[i], a[6]); a[7] = fmaf(wb.w, u[i], a[7]);
+    }
   }
+  silu4_shared_rcp(a[0], a[1], a[2], a[3]);
+  silu4_shared_rcp(a[4], a[5], a[6], a[7]);
   float out = b4[0];
 #pragma unroll
-  for (int q = 0; q < 8; q++) out = fmaf(W4[q], silu_fast(a[q]), out);
+  for (int q = 0; q < 8; q++) out = fmaf(W4[q], a[q], out);
   sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
   sx[(size_t)t * 2 * H + H + h] = out;
   vd[(size_t)t * H + h] = (v10 * v20 + v11 * v21 + v12 * v22) * rsqrtf((float)H);
@@ -586,6 +556,206 @@ __global__ void k_final(int H, int C, const float* __restrict__ tu, const float*
   for (int c = 0; c < C; c++) {
     const float d = block_sum(ok ? sv * w_eout[c * H + h] : 0.f, sm);
     if (h == 0) h_out[(size_t)t * C + c] = d + b_eout[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pair16 storage (gemm_p16.cuh): every 16 consecutive values of a row are stored as 64 bytes [16 bf16 hi | 16 bf16 lo].
+__device__ __forceinline__ void pair16_store8(float* row_base, int c8, const float* x) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const float2 f = __bfloat1622float2(a);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+    hh[i] = *reinterpret_cast<const uint32_t*>(&a);
+    ll[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  uint8_t* p = reinterpret_cast<uint8_t*>(row_base) + (size_t)(c8 >> 4) * 64 + (size_t)(c8 & 15) * 2;
+  *reinterpret_cast<uint4*>(p) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  *reinterpret_cast<uint4*>(p + 32) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+__device__ __forceinline__ void pair16_load8(const float* row_base, int c8, float* x) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(row_base) + (size_t)(c8 >> 4) * 64 + (size_t)(c8 & 15) * 2;
+  const uint4 hi = *reinterpret_cast<const uint4*>(p), lo = *reinterpret_cast<const uint4*>(p + 32);
+  const uint32_t hh[4] = {hi.x, hi.y, hi.z, hi.w}, ll[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    x[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    x[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+  }
+}
+
+// Constant row of masked edges in the storage format of the edge state: [c3 x H | c3 x H | f0 | 0 x R | pad].  One block.
+template <bool PAIR>
+__global__ void k_const_row(int H, int R, int ld, const float* __restrict__ f0, const float* __restrict__ c3,
+                            float* __restrict__ crow) {
+  const float c = *c3;
+  for (int c8 = threadIdx.x * 8; c8 < ld; c8 += blockDim.x * 8) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int col = c8 + k;
+      x[k] = col < 2 * H ? c : (col < 3 * H ? f0[col - 2 * H] : 0.f);
+    }
+    if (PAIR) pair16_store8(crow, c8, x);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (c8 + k < ld) crow[c8 + k] = x[k];
+    }
+  }
+}
+
+// (I) initial edge state, masked edges: copy of the constant row.  One warp per edge, 16-byte copies (ld % 4 == 0).
+__global__ void k_edge_init_masked(int E, int ld, const int* __restrict__ act_pos, const float* __restrict__ crow,
+                                   float* __restrict__ ew) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= E || act_pos[e] >= 0) return;
+  const uint4* src = reinterpret_cast<const uint4*>(crow);
+  uint4* dst = reinterpret_cast<uint4*>(ew + (size_t)e * ld);
+  for (int k = lane; k < ld / 4; k += 32) dst[k] = src[k];
+}
+
+// (I) initial edge state of ACTIVE edges e0 = [ (sc3 | sc4) * rb | f | rbf ]  (leftnet.py:792-809).  Persistent blocks
+// stride over the compact active list; thread t < 2H evaluates lin3 (3 -> Hq -> 1, SiLU) for side t / H, channel t % H,
+// with the weights read as float4 (w0, w1, w2, b0) shared-memory broadcasts and four SiLUs per reciprocal.  The inputs
+// of the next edge are fetched before the current one is evaluated (the index -> geometry -> NE1 chain is three
+// dependent loads deep); the row is staged in shared memory and written once, in pair16 (PAIR) or fp32.
+struct EdgeInitIn { int e; float n0, n1, n2, gx, gy, gz, cx, cy, cz, rbe, fv, rv; };
+template <bool PAIR>
+__global__ void __launch_bounds__(448, 3) k_edge_init_act(
+    int H, int R, int Hq, int reflect, int ld, int cap, const int* __restrict__ n_act, const int* __restrict__ act_idx,
+    const int* __restrict__ esrc, const int* __restrict__ ecol, const float* __restrict__ pf,
+    const float4* __restrict__ geo, const float* __restrict__ rb, const float* __restrict__ NE1,
+    const float* __restrict__ f_act, const float* __restrict__ rbf_act, const float* __restrict__ l3_w0,
+    const float* __restrict__ l3_b0, const float* __restrict__ l3_w2, const float* __restrict__ l3_b2,
+    float* __restrict__ ew) {
+  extern __shared__ __align__(16) float sm_ei[];  // wq[Hq4] float4 | w2[Hq4] | row[ld]
+  const int na = min(*n_act, cap);
+  const int Hq4 = (Hq + 3) / 4 * 4;
+  float4* wq = reinterpret_cast<float4*>(sm_ei);
+  float* w2 = sm_ei + 4 * Hq4;
+  float* row = w2 + Hq4;
+  const int t = threadIdx.x;
+  for (int k = t; k < Hq4; k += blockDim.x) {
+    const bool in = k < Hq;  // padded entries: u = 0 -> silu = 0, weight 0
+    wq[k] = in ? make_float4(l3_w0[k * 3], l3_w0[k * 3 + 1], l3_w0[k * 3 + 2], l3_b0[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w2[k] = in ? l3_w2[k] : 0.f;
+  }
+  for (int k = 3 * H + R + t; k < ld; k += blockDim.x) row[k] = 0.f;
+  const int side = t >= H, h = t - side * H;
+  const float b2 = l3_b2[0];
+  auto load = [&](int p) {
+    EdgeInitIn in;
+    in.e = act_idx[p];
+    in.fv = t < H ? f_act[(size_t)p * H + t] : 0.f;
+    in.rv = t < R ? rbf_act[(size_t)p * R + t] : 0.f;
+    in.n0 = in.n1 = in.n2 = in.gx = in.gy = in.gz = in.cx = in.cy = in.cz = in.rbe = 0.f;
+    if (t < 2 * H) {
+      const int i = esrc[in.e], j = ecol[in.e];
+      const float4 g = geo[in.e];
+      in.gx = g.x; in.gy = g.y; in.gz = g.z;
+      in.rbe = rb[in.e];
+      // edge frame columns: u (unit diff), c (unit cross of pos_frame_i x pos_frame_j), v = u x c   (:693-705)
+      const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2];
+      const float bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
+      in.cx = ay * bz - az * by; in.cy = az * bx - ax * bz; in.cz = ax * by - ay * bx;
+      const float* n = NE1 + (size_t)(side ? j : i) * 3 * H;
+      in.n0 = n[h]; in.n1 = n[H + h]; in.n2 = n[2 * H + h];
+    }
+    return in;
+  };
+  int p = blockIdx.x;
+  EdgeInitIn cur{};
+  if (p < na) cur = load(p);
+  __syncthreads();
+  for (; p < na; p += gridDim.x) {
+    EdgeInitIn nxt{};
+    if (p + (int)gridDim.x < na) nxt = load(p + gridDim.x);
+    if (t < H) row[2 * H + t] = cur.fv;
+    if (t < R) row[3 * H + t] = cur.rv;
+    if (t < 2 * H) {
+      const float cinv = 1.0f / (sqrtf(cur.cx * cur.cx + cur.cy * cur.cy + cur.cz * cur.cz) + OARD_EPS);
+      const float cx = cur.cx * cinv, cy = cur.cy * cinv, cz = cur.cz * cinv;
+      const float vx = cur.gy * cz - cur.gz * cy, vy = cur.gz * cx - cur.gx * cz, vz = cur.gx * cy - cur.gy * cx;
+      const float s0 = cur.n0 * cur.gx + cur.n1 * cur.gy + cur.n2 * cur.gz;
+      float s1 = cur.n0 * cx + cur.n1 * cy + cur.n2 * cz;
+      const float s2 = cur.n0 * vx + cur.n1 * vy + cur.n2 * vz;
+      if (reflect) s1 = fabsf(s1);
+      float acc = b2;
+      for (int k = 0; k < Hq4; k += 4) {
+        const float4 q0 = wq[k], q1 = wq[k + 1], q2 = wq[k + 2], q3 = wq[k + 3];
+        const float4 ww = *reinterpret_cast<const float4*>(w2 + k);
+        float u0 = fmaf(q0.x, s0, fmaf(q0.y, s1, fmaf(q0.z, s2, q0.w)));
+        float u1 = fmaf(q1.x, s0, fmaf(q1.y, s1, fmaf(q1.z, s2, q1.w)));
+        float u2 = fmaf(q2.x, s0, fmaf(q2.y, s1, fmaf(q2.z, s2, q2.w)));
+        float u3 = fmaf(q3.x, s0, fmaf(q3.y, s1, fmaf(q3.z, s2, q3.w)));
+        silu4_shared_rcp(u0, u1, u2, u3);
+        acc = fmaf(ww.x, u0, fmaf(ww.y, u1, fmaf(ww.z, u2, fmaf(ww.w, u3, acc))));
+      }
+      row[t] = (acc + s0) * cur.rbe;
+    }
+    __syncthreads();
+    float* out = ew + (size_t)cur.e * ld;
+    if (PAIR) {
+      for (int c8 = t * 8; c8 < ld; c8 += blockDim.x * 8) pair16_store8(out, c8, row + c8);
+    } else {
+      for (int k = t; k < ld; k += blockDim.x) out[k] = row[k];
+    }
+    __syncthreads();
+    cur = nxt;
+  }
+}
+
+// GCL attention gate + mean aggregation at the edge source on a pair16 m2 (row pitch ld floats, H <= ld).
+// One block per node; warps take the row's edges round-robin; lane l < ld/8 owns 8 consecutive columns.
+__global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, float* __restrict__ m2,
+                              const float* __restrict__ w_att, const float* __restrict__ b_att, float* __restrict__ xa,
+                              int ldxa) {
+  extern __shared__ float part[];  // [nw][ld]
+  const int t = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  const int c8 = lane * 8;
+  const bool own = c8 < ld;
+  float wa[8], acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { acc[k] = 0.f; wa[k] = (own && c8 + k < H) ? w_att[c8 + k] : 0.f; }
+  const float ba = b_att[0];
+  for (int e = r0 + w; e < r1; e += 2 * nw) {  // two edges in flight per warp (independent loads), same summation order
+    const int e2 = e + nw;
+    const bool two = e2 < r1;
+    float* row = m2 + (size_t)e * ld;
+    float* row2 = m2 + (size_t)(two ? e2 : e) * ld;
+    float v[8], v2[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = 0.f; v2[k] = 0.f; }
+    if (own) { pair16_load8(row, c8, v); if (two) pair16_load8(row2, c8, v2); }
+    float d = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { d = fmaf(v[k], wa[k], d); d2 = fmaf(v2[k], wa[k], d2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+    const float att = silu(d + ba), att2 = silu(d2 + ba);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] *= att; acc[k] += v[k]; }
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { v2[k] *= att2; acc[k] += v2[k]; }
+    }
+    if (own) { pair16_store8(row, c8, v); if (two) pair16_store8(row2, c8, v2); }
+  }
+  if (own) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) part[w * ld + c8 + k] = acc[k];
+  }
+  __syncthreads();
+  const int h = threadIdx.x;
+  if (h < H) {
+    float s = 0.f;
+    for (int ww = 0; ww < nw; ww++) s += part[ww * ld + h];
+    const int cnt = r1 - r0;
+    xa[(size_t)t * ldxa + H + h] = s / (float)(cnt > 0 ? cnt : 1);
   }
 }
 

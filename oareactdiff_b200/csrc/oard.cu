@@ -17,6 +17,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_p16.cuh"
 #include "kernels.cuh"
 
 using namespace oard;
@@ -69,6 +70,8 @@ struct oard_handle {
   std::vector<LayerW> L;
   // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
   bool use_tc = false;
+  bool use_p16 = false;  // edge-level activations (edge state, GCL hidden, dir_proj hidden) stored as pair16 (gemm_p16.cuh)
+  int ldD = 0, ldH = 0, ld3H = 0;  // row pitches (floats) of the edge state / [E,H] / [E,3H] edge buffers
   int num_sms = 148;
   struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
   std::vector<LayerTc> T;
@@ -194,6 +197,12 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     const bool want_tc = !(env && strcmp(env, "simt") == 0);
     const bool dims_ok = cfg->hidden_channels % 4 == 0 && cfg->num_radial % 4 == 0;
     h->use_tc = want_tc && dims_ok && prop.major == 10;  // tcgen05 exists on sm_100 only
+    const char* ep = getenv("OARD_P16");  // "0": keep fp32 edge activations + the in-kernel-converting GEMM (gemm_tc.cuh)
+    h->use_p16 = h->use_tc && !(ep && strcmp(ep, "0") == 0);
+    const int H_ = cfg->hidden_channels, D_ = 3 * H_ + cfg->num_radial;
+    h->ldD = h->use_p16 ? p16_ld(D_) : D_;
+    h->ldH = h->use_p16 ? p16_ld(H_) : H_;
+    h->ld3H = h->use_p16 ? p16_ld(3 * H_) : 3 * H_;
     const char* eg = getenv("OARD_GRAPH");  // "0" disables CUDA-graph replay of the forward
     h->use_graph = !(eg && strcmp(eg, "0") == 0);
   }
@@ -310,8 +319,10 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
   }
   if (h->use_tc) {
     cudaStream_t st = (cudaStream_t)stream;
-    auto pack = [&](const float* Wp, int ldw, int N, int K, TcWeight* out) -> int {
-      const int BN = tc_choose_bn(N);
+    // bn > 0 overrides the output-tile width: node-level GEMMs (M = N_nodes, ~21 row tiles) use narrow tiles so that the
+    // grid covers most SMs and each CTA's epilogue is one or two 32-column blocks (they are latency-, not throughput-bound)
+    auto pack = [&](const float* Wp, int ldw, int N, int K, TcWeight* out, int bn = 0) -> int {
+      const int BN = bn > 0 ? bn : tc_choose_bn(N);
       const size_t elems = tc_weight_elems(N, K, BN);
       __nv_bfloat16* buf = nullptr;
       CU(cudaMalloc(&buf, elems * sizeof(__nv_bfloat16)));
@@ -325,9 +336,10 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     int rc;
     if ((rc = pack(h->rl0_w, R, H, R, &h->tc_rl0))) return rc;
     if ((rc = pack(h->rl2_w, H, H, H, &h->tc_rl2))) return rc;
-    if ((rc = pack(h->s2v_w, H, H, H, &h->tc_s2v))) return rc;
-    if ((rc = pack(h->o_v1w, H, H, H, &h->tc_ov1))) return rc;
-    if ((rc = pack(h->o_u0w, 2 * H, H, 2 * H, &h->tc_ou0))) return rc;
+    const int bnH = H > 32 ? 32 : 0, bn2H = 2 * H > 64 ? 64 : 0, bn3H = 3 * H > 96 ? 96 : 0;  // narrow tiles, multiples of 32
+    if ((rc = pack(h->s2v_w, H, H, H, &h->tc_s2v, bnH))) return rc;
+    if ((rc = pack(h->o_v1w, H, H, H, &h->tc_ov1, H > 128 ? 128 : 0))) return rc;
+    if ((rc = pack(h->o_u0w, 2 * H, H, 2 * H, &h->tc_ou0, bnH))) return rc;
     h->T.resize(h->cfg.num_layers);
     for (int l = 0; l < h->cfg.num_layers; l++) {
       const LayerW& w = h->L[l];
@@ -338,14 +350,14 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.d0w, D, 3 * H, D, &t.d0))) return rc;
       if ((rc = pack(w.d2w, 3 * H, 3 * H, 3 * H, &t.d2))) return rc;
       if ((rc = pack(w.rbfw, R, 3 * H, R, &t.rbf))) return rc;
-      if ((rc = pack(w.pqw, H, 2 * H, H, &t.pq))) return rc;
-      if ((rc = pack(w.n0w, 2 * H, H, 2 * H, &t.n0))) return rc;
-      if ((rc = pack(w.n1w, H, H, H, &t.n1))) return rc;
-      if ((rc = pack(w.x0w, H, H, H, &t.x0))) return rc;
-      if ((rc = pack(w.x2w, H, 3 * H, H, &t.x2))) return rc;
+      if ((rc = pack(w.pqw, H, 2 * H, H, &t.pq, bn2H))) return rc;
+      if ((rc = pack(w.n0w, 2 * H, H, 2 * H, &t.n0, bnH))) return rc;
+      if ((rc = pack(w.n1w, H, H, H, &t.n1, bnH))) return rc;
+      if ((rc = pack(w.x0w, H, H, H, &t.x0, bnH))) return rc;
+      if ((rc = pack(w.x2w, H, 3 * H, H, &t.x2, bn3H))) return rc;
       if ((rc = pack(w.vpw, H, 2 * H, H, &t.vp))) return rc;
-      if ((rc = pack(w.xv0w, 2 * H, H, 2 * H, &t.xv0))) return rc;
-      if ((rc = pack(w.xv2w, H, 3 * H, H, &t.xv2))) return rc;
+      if ((rc = pack(w.xv0w, 2 * H, H, 2 * H, &t.xv0, bnH))) return rc;
+      if ((rc = pack(w.xv2w, H, 3 * H, H, &t.xv2, bn3H))) return rc;
     }
   }
   h->committed = true;
@@ -435,7 +447,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   struct { const char* n; size_t b; } allocs[] = {
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
-      {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"row_cnt", Nn * 4},
+      {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
       {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
       {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
       {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
@@ -443,9 +455,9 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"PQ", Nn * 2 * H * 4}, {"tN", Nn * H * 4}, {"X", Nn * 3 * H * 4}, {"vecA", Nn * 3 * H * 4},
       {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
       {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
-      {"ew", Ee * D * 4}, {"ew_act", Ee * D * 4}, {"g_h_in", Nn * 32 * 4}, {"g_pos", Nn * 12}, {"g_sub", Ee * 8},
-      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * H * 4}, {"m2", Ee * H * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
-      {"d1", Ee * 3 * H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
+      {"ew", Ee * (size_t)h->ldD * 4}, {"ew_act", Ee * (size_t)h->ldD * 4}, {"crow", (size_t)h->ldD * 4}, {"g_h_in", Nn * 32 * 4}, {"g_pos", Nn * 12}, {"g_sub", Ee * 8},
+      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * (size_t)h->ldH * 4}, {"m2", Ee * (size_t)h->ldH * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"d1", Ee * (size_t)h->ld3H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
   };
   for (auto& a : allocs) {
     const int rc = ws_alloc(h, a.n, a.b);
@@ -552,6 +564,17 @@ static int snap(oard_handle* h, const std::string& name, const void* p, size_t b
     prof_end(h, st);                                                                                        \
   } while (0)
 #define PB(tag, flops, bytes, dyn) prof_begin(h, tag, (double)(flops), (double)(bytes), dyn, st)
+// edge state snapshot as fp32 [E, D] whatever the storage format (ew_act is free scratch at the snapshot points: it is
+// written by edge_out and consumed by dir_proj0 of the same layer)
+#define SNAP_EDGE(name)                                                                   \
+  do {                                                                                    \
+    if (h->debug && E) {                                                                  \
+      if (P) {                                                                            \
+        k_p16_unpack<<<1024, 256, 0, st>>>(ew, ldD, E, D, ew_act, D);                     \
+        SNAP(name, ew_act, (size_t)E * D * 4);                                            \
+      } else SNAP(name, ew, (size_t)E * D * 4);                                           \
+    }                                                                                     \
+  } while (0)
 #define SNAP(name, ptr, bytes)                                       \
   do {                                                               \
     const int rc_ = snap(h, name, ptr, bytes, st);                   \
@@ -613,6 +636,18 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     prof_end(h, st);                                                                                         \
   } while (0)
 
+#define GEMM_P16(tag, g, tw, outp)                                                                          \
+  do {                                                                                                       \
+    prof_begin(h, tag, 2.0 * (g).M * (g).N * (g).K, 4.0 * (g).M * ((g).K + (g).N + ((g).resid ? (g).N : 0)),   \
+               (g).m_dev != nullptr, st);                                                                    \
+    cudaError_t e_ = launch_gemm_p16(g, tw, h->num_sms, st, outp);                                           \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm_p16: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    h->launches++;                                                                                           \
+    prof_end(h, st);                                                                                         \
+  } while (0)
+  const bool P = h->use_p16;
+  const int ldD = h->ldD, ldH = h->ldH, ld3H = h->ld3H;
+
   // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
   if (E) { PB("k_edge_mask", 0, E*29.0, 0);
     k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
@@ -637,6 +672,12 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   PB("k_compact", 0, E*9.0, 0);
   k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
   KCHECK();
+  if (E) {
+    PB("k_act_lists", 0, E*40.0, 1);
+    k_act_lists<<<(E + 255) / 256, 256, 0, st>>>(n_act, E, act_idx, act_pos, rev, ecol, geo, h->buf<int>("act_tr"),
+                                                 h->buf<int>("act_col"), h->buf<float4>("act_geo"));
+    KCHECK();
+  }
   if (E) {
     const size_t tot = (size_t)E * R;
     PB("k_rbf", 0, (double)E*(R*4.0+20), 1);
@@ -673,10 +714,24 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   k_s2v<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, geo, q, NE1);
   KCHECK();
   if (E) {
+    // initial edge state (leftnet.py:792-809): masked edges get the constant row, active edges the scalarised lin3 terms
+    float* crow = h->buf<float>("crow");
+    const int Hq4 = (Hq + 3) / 4 * 4, ei_threads = (2 * H + 31) / 32 * 32;
+    const size_t ei_smem = (size_t)(5 * Hq4 + ldD) * sizeof(float);
     PB("k_edge_init", 0, (double)E*D*4.0, 0);
-    k_edge_init<<<E, HB, Hq * 5 * sizeof(float), st>>>(H, R, Hq, c.reflect_equiv, esrc, ecol, act_pos, pf, geo, rb, NE1,
-                                                       f_act, rbf_act, f0, c3, h->l3_w0, h->l3_b0, h->l3_w2, h->l3_b2,
-                                                       ew);
+    if (P) k_const_row<true><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
+    else k_const_row<false><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
+    k_edge_init_masked<<<(E + 7) / 8, 256, 0, st>>>(E, ldD, act_pos, crow, ew);
+    const int ei_grid = std::min(E, h->num_sms * 3);
+    if (P)
+      k_edge_init_act<true><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, Hq, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
+                                                                 pf, geo, rb, NE1, f_act, rbf_act, h->l3_w0, h->l3_b0, h->l3_w2,
+                                                                 h->l3_b2, ew);
+    else
+      k_edge_init_act<false><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, Hq, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
+                                                                  pf, geo, rb, NE1, f_act, rbf_act, h->l3_w0, h->l3_b0, h->l3_w2,
+                                                                  h->l3_b2, ew);
+    h->launches += 2;
     KCHECK();
   }
   {  // pos_expansion(pos_prjt): shared weights and a layer-independent input -> evaluated once (leftnet.py:840-841)
@@ -691,7 +746,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     SNAP("act_idx", act_idx, (size_t)E * 4); SNAP("n_act", n_act, 4); SNAP("pos_frame", pf, (size_t)N * 12);
     SNAP("geo", geo, (size_t)E * 16); SNAP("rb", rb, (size_t)E * 4); SNAP("f_act", f_act, (size_t)E * H * 4);
     SNAP("rbf_act", rbf_act, (size_t)E * R * 4); SNAP("s0", s, (size_t)N * H * 4);
-    SNAP("NE1", NE1, (size_t)N * 3 * H * 4); SNAP("e0", ew, (size_t)E * D * 4);
+    SNAP("NE1", NE1, (size_t)N * 3 * H * 4); SNAP_EDGE("e0");
     SNAP("nodeframe", nodeframe, (size_t)N * 36); SNAP("pos_prjt", pos_prjt, (size_t)N * 12);
   }
   CU(cudaMemsetAsync(vec, 0, (size_t)N * 3 * H * sizeof(float), st));
@@ -707,17 +762,18 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     g.bias = w.pqb;
     GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
     if (E) {
-      g = mk(ew, D, w.e0w + 2 * H, ldw0, hid1, H, E, H, D);
+      g = mk(ew, ldD, w.e0w + 2 * H, ldw0, hid1, ldH, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
-      GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
-      g = mk(hid1, H, w.e1w, H, m2, H, E, H, H);
+      if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
+      g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
       g.bias = w.e1b; g.act = 1;
-      GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
+      if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
     }
     PB("k_att_agg", 0, (double)E*H*8.0, 0);
-    k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
+    if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
+    else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
     KCHECK();
     g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
     g.bias = w.n0b; g.act = 1;
@@ -726,10 +782,10 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
     GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
     if (E) {
-      g = mk(m2, H, w.eow, H, ew, D, E, D, H);
-      g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = D;
-      g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = D;  // compact copy of the active rows: contiguous operand for dir_proj
-      GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
+      g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
+      g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
+      g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = ldD;  // compact copy of the active rows: contiguous operand for dir_proj
+      if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
     PB("k_layernorm", 0, N*H*8.0, 0);
@@ -741,27 +797,26 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
     GEMM_TC("gemm_xproj2", g, h->T[l].x2);
     if (E) {
-      g = mk(ew_act, D, w.d0w, D, d1, 3 * H, E, 3 * H, D);
+      g = mk(ew_act, ldD, w.d0w, D, d1, ld3H, E, 3 * H, D);
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
-      GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
+      if (P) GEMM_P16("gemm_dir_proj0", g, h->T[l].d0, true); else GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
       g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
       g.m_dev = n_act;
       GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
-      g = mk(d1, 3 * H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
+      g = mk(d1, ld3H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
-      GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
+      if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
-    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+16), 1);
-    if (H % 4 == 0 && H <= 256)
-      k_equi_reduce4<<<N, 64, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
-    else
-      k_equi_reduce<<<N, HB, 0, st>>>(H, c.reflect_equiv, row_ptr, ecol, rev, act_pos, G, X, geo, pf, vec, vec2, s);
+    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 traffic)
+    k_equi_reduce<4><<<N, 256, (size_t)4 * 4 * (H / 4) * sizeof(float4), st>>>(
+        H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"),
+        h->buf<float4>("act_geo"), G, X, pf, vec, vec2, s);
     KCHECK();
     std::swap(vec, vec2);
     if (h->debug) {
       const std::string ls = std::to_string(l), l1 = std::to_string(l + 1);
       SNAP("s_msg" + ls, s, (size_t)N * H * 4); SNAP("vec_msg" + ls, vec, (size_t)N * 3 * H * 4);
-      SNAP("e" + l1, ew, (size_t)E * D * 4);
+      SNAP_EDGE("e" + l1);
     }
     // ---- EquiUpdate (leftnet.py:325-346)
     if (c.update) {
@@ -894,6 +949,77 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
   if (buf) cudaFree(buf);
   if (e != cudaSuccess) return fail(OARD_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
   if (e2 != cudaSuccess) return fail(OARD_ECUDA, "gemm run: %s", cudaGetErrorString(e2));
+  return OARD_OK;
+}
+
+// Unit-test / timing entry of the pair16 GEMM (gemm_p16.cuh).  A[M,K], W[N,K], aux and C are fp32 DEVICE tensors; the
+// entry packs A (and, for mode 3 with out_pair, the residual) to pair16, runs the kernel and unpacks the result, so the
+// caller compares plain fp32.  mode: 0 plain, 1 gathered adds from aux[M,2N], 2 multiply by aux[M,N], 3 residual aux[M,N]
+// (in place, as the edge state is updated).  c2_out != NULL: rows m % 3 == 0 are also written to the compact copy
+// C2[m / 3] and returned there ([ceil(M/3), N] fp32).  ew: 0 default, 8 or 16 epilogue warps.
+extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
+                                  float* C, int mode, const float* aux, int out_pair, int act, float* c2_out, int ew,
+                                  int reps, float* ms_out, void* stream) {
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
+  const int Kp = p16_ld(K), Np = p16_ld(N), M3 = (M + 2) / 3;
+  float *Ap = nullptr, *Cp = nullptr, *C2p = nullptr;
+  int* idx = nullptr;
+  __nv_bfloat16* wbuf = nullptr;
+  CU(cudaMalloc(&Ap, (size_t)M * Kp * 4));
+  CU(cudaMalloc(&Cp, (size_t)M * Np * 4));
+  k_p16_pack<<<1024, 256, 0, st>>>(A, K, M, K, Ap, Kp);
+  const int BN = tc_choose_bn(N);
+  CU(cudaMalloc(&wbuf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
+  k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, wbuf);
+  TcWeight tw{wbuf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
+  const int ldc = out_pair ? Np : N;
+  GemmArgs g = mk(Ap, Kp, W, K, out_pair ? Cp : C, ldc, M, N, K);
+  g.bias = bias; g.act = act;
+  if (mode == 1) { g.radd1 = aux; g.ld1 = 2 * N; g.radd2 = aux + N; g.ld2 = 2 * N; }
+  if (mode == 2) { g.mul = aux; g.ldmul = N; }
+  if (mode == 3) {
+    if (out_pair) { g.resid = Cp; g.ldres = Np; }
+    else { CU(cudaMemcpyAsync(C, aux, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, st)); g.resid = C; g.ldres = N; }
+  }
+  if (c2_out) {
+    std::vector<int> hidx(M);
+    for (int m = 0; m < M; m++) hidx[m] = (m % 3 == 0) ? m / 3 : -1;
+    CU(cudaMalloc(&idx, (size_t)M * 4));
+    CU(cudaMemcpyAsync(idx, hidx.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMalloc(&C2p, (size_t)M3 * ldc * 4));
+    CU(cudaMemsetAsync(C2p, 0, (size_t)M3 * ldc * 4, st));
+    g.C2 = C2p; g.c2idx = idx; g.ldc2 = ldc;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaError_t e = cudaSuccess;
+  const int nrun = reps > 1 ? reps + 1 : 1;  // reps > 1: timing only (an in-place residual keeps accumulating)
+  if (mode == 3 && out_pair) k_p16_pack<<<1024, 256, 0, st>>>(aux, N, M, N, Cp, Np);
+  for (int r = 0; r < nrun && e == cudaSuccess; r++) {
+    if (r == nrun - (reps > 1 ? reps : 1)) cudaEventRecord(e0, st);
+    e = launch_gemm_p16(g, tw, prop.multiProcessorCount, st, out_pair != 0, ew);
+  }
+  cudaEventRecord(e1, st);
+  if (e == cudaSuccess && out_pair) k_p16_unpack<<<1024, 256, 0, st>>>(Cp, Np, M, N, C, N);
+  if (e == cudaSuccess && c2_out) {
+    if (out_pair) k_p16_unpack<<<1024, 256, 0, st>>>(C2p, Np, M3, N, c2_out, N);
+    else cudaMemcpyAsync(c2_out, C2p, (size_t)M3 * N * 4, cudaMemcpyDeviceToDevice, st);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / (reps > 1 ? reps : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(Ap); cudaFree(Cp); cudaFree(wbuf);
+  if (idx) cudaFree(idx);
+  if (C2p) cudaFree(C2p);
+  if (e != cudaSuccess) return fail(OARD_ECUDA, "gemm_p16 launch: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(OARD_ECUDA, "gemm_p16 run: %s", cudaGetErrorString(e2));
   return OARD_OK;
 }
 

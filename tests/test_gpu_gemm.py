@@ -29,3 +29,17 @@ def test_gemm_tc_epilogue_modes(M, N, K, mode):
     for ab in (0, 16, 32, 48):
         res = run_mode(M, N, K, mode, ab)
         assert res.startswith("rel_err=") and float(res.split()[0].split("=")[1]) < 3e-5 and res.endswith("nan=0"), (ab, res)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (300, 196, 684), (1000, 684, 196), (257, 588, 588), (5000, 588, 96),
+                                   (33, 32, 112), (20000, 196, 684), (30000, 684, 196)])
+@pytest.mark.parametrize("mode,out_pair", [(0, 1), (0, 0), (1, 1), (2, 0), (3, 1), (3, 0)])
+def test_gemm_p16(M, N, K, mode, out_pair):
+    """pair16 GEMM (A operand and optionally C / residual / compact copy stored as split-bf16 pairs in the UMMA operand
+    layout) against fp64: 3e-5 of max|ref| like the fp32-A kernel (the operands carry the same 16 mantissa bits; a
+    pair16 output adds one 2^-17 rounding)."""
+    from tests.bringup_p16 import run_p16
+    for ew in ((8, 16) if (mode >= 2 and (mode, out_pair) != (3, 0)) else (8,)):
+        res = run_p16(M, N, K, mode, out_pair, act=1, c2=(mode in (0, 3)), ew=ew)
+        assert "error" not in res, res
+        assert res["nan"] == 0 and res["rel_err"] < 3e-5 and res.get("rel_err_c2", 0.0) < 3e-5, (ew, res)
