@@ -10,8 +10,23 @@ namespace oard {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
-// ex2.approx / rcp.approx based SiLU (relative error ~1e-6): used where thousands of activations per thread dominate
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// MUFU wrappers with flush-to-zero: the non-ftz intrinsics (__expf, __fdividef) wrap every MUFU in range checks and
+// rescaling multiplies (3-4 extra instructions each), which dominated the activation-heavy kernels (ncu: r1o).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ex2.approx / rcp.approx based SiLU (relative error ~1e-6): used where thousands of activations per thread dominate.
+// x -> -inf gives x * 0 = -0; x -> +inf gives x * 1.
+__device__ __forceinline__ float silu_fast(float x) {
+  return x * fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -210,8 +210,8 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
     // Buffer ring per warp: block i uses buffer i % NIO from its aux load until its store has read it.  Aux loads run PF
     // blocks ahead; the buffer of block nb + PF was last read by the store of block nb + PF - NIO, so at most
     // PEND = NIO - 1 - PF newer stores may still be reading when it is refilled (NIO 2: PF 1, PEND 0; NIO 3: PF 1, PEND 1).
-    static_assert(NIO == 2 || NIO == 3, "NIO");
-    constexpr int PF = 1, PEND = NIO - 1 - PF;
+    static_assert(NIO >= 1 && NIO <= 3 && (NIO >= 2 || !HAS_AUX), "NIO");
+    constexpr int PF = 1, PEND = HAS_AUX ? NIO - 1 - PF : 0;
     int pf_tile = blockIdx.x, pf_blk = cg;
     auto pf_next = [&]() {
       pf_blk += NCG;
@@ -390,12 +390,14 @@ inline cudaError_t launch_gemm_p16(const GemmArgs& g, const TcWeight& w, int num
   const int grid = total < num_sms ? total : num_sms;
   static int env_ew = -1;
   if (env_ew < 0) { const char* e = getenv("OARD_P16_EW"); env_ew = e ? atoi(e) : 0; }
-  // epilogue shape: the in-place residual update streams 2 x 4 KB per output block through the epilogue, so it gets 16
-  // warps (more blocks in flight per SM); the other modes 8 (measured: profiles/r1_p16_notes.md).  OARD_P16_EW overrides.
-  int ew = ew_pref ? ew_pref : (mode == 3 ? 16 : 8);
-  if (mode >= 2 && !ew_pref && (env_ew == 8 || env_ew == 16)) ew = env_ew;
-  if (mode < 2) ew = 8;
-  const int nio = 2;
+  // Epilogue shape.  The epilogue is a per-warp latency chain (TMEM load -> activation -> split -> staging -> TMA store,
+  // ~700 instructions per 32x32 block at low ILP; ncu r1o), so the cure is more warps: 16 epilogue warps.  Plain modes
+  // (no streamed aux block) need one staging buffer per warp (NIO 1); the in-place residual update keeps two (the aux
+  // block of the next output block is in flight while the current one is processed).  The multiplier mode measured
+  // better with 8 warps and deeper operand rings.  OARD_P16_EW=8|16 overrides (A/B runs).
+  int ew = ew_pref ? ew_pref : (mode == 2 ? 8 : 16);
+  if (!ew_pref && (env_ew == 8 || env_ew == 16)) ew = env_ew;
+  int nio = (mode < 2 && ew == 16) ? 1 : 2;
   CUtensorMap tmA, tmC, tmX;
   memset(&tmA, 0, sizeof tmA); memset(&tmC, 0, sizeof tmC); memset(&tmX, 0, sizeof tmX);
   if (!tc_make_map(&tmA, g.A, g.M, p16_ld(g.K), g.lda, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
@@ -412,15 +414,17 @@ inline cudaError_t launch_gemm_p16(const GemmArgs& g, const TcWeight& w, int num
       if (p16_smem_bytes(w.BN, r[0], r[1], e_, nio) <= lim) { sa = r[0]; sw = r[1]; return true; }
     return false;
   };
-  if (!pick(ew)) { ew = 8; if (!pick(ew)) return cudaErrorInvalidValue; }
+  if (!pick(ew)) { ew = 8; nio = 2; if (!pick(ew)) return cudaErrorInvalidValue; }
   const size_t smem = p16_smem_bytes(w.BN, sa, sw, ew, nio);
-#define OARD_P16_CASE(A_, W_, MD, OP, E)                                             \
-  if (sa == A_ && sw == W_ && mode == MD && out_pair == OP && ew == E)               \
-    return launch_gemm_p16_inst<A_, W_, MD, OP, E, 2>(g, w, grid, smem, tmA, tmC, tmX, st);
-#define OARD_P16_RINGS(MD, OP, E) OARD_P16_CASE(5, 3, MD, OP, E) OARD_P16_CASE(4, 3, MD, OP, E) OARD_P16_CASE(2, 2, MD, OP, E)
-  OARD_P16_RINGS(0, true, 8) OARD_P16_RINGS(0, false, 8) OARD_P16_RINGS(1, true, 8)
-  OARD_P16_RINGS(2, false, 8) OARD_P16_RINGS(2, false, 16)
-  OARD_P16_RINGS(3, true, 8) OARD_P16_RINGS(3, true, 16) OARD_P16_RINGS(3, false, 8)
+#define OARD_P16_CASE(A_, W_, MD, OP, E, NI)                                         \
+  if (sa == A_ && sw == W_ && mode == MD && out_pair == OP && ew == E && nio == NI)  \
+    return launch_gemm_p16_inst<A_, W_, MD, OP, E, NI>(g, w, grid, smem, tmA, tmC, tmX, st);
+#define OARD_P16_RINGS(MD, OP, E, NI) \
+  OARD_P16_CASE(5, 3, MD, OP, E, NI) OARD_P16_CASE(4, 3, MD, OP, E, NI) OARD_P16_CASE(2, 2, MD, OP, E, NI)
+  OARD_P16_RINGS(0, true, 8, 2) OARD_P16_RINGS(0, false, 8, 2) OARD_P16_RINGS(1, true, 8, 2)
+  OARD_P16_RINGS(0, true, 16, 1) OARD_P16_RINGS(0, false, 16, 1) OARD_P16_RINGS(1, true, 16, 1)
+  OARD_P16_RINGS(2, false, 8, 2) OARD_P16_RINGS(2, false, 16, 2)
+  OARD_P16_RINGS(3, true, 8, 2) OARD_P16_RINGS(3, true, 16, 2) OARD_P16_RINGS(3, false, 8, 2)
 #undef OARD_P16_RINGS
 #undef OARD_P16_CASE
   return cudaErrorInvalidValue;

@@ -15,10 +15,11 @@ namespace oard {
 // Four SiLUs with ONE reciprocal (MUFU budget 5 instead of 8): 1/d_i from r = 1/(d0 d1 d2 d3).  The exponent is clamped
 // at 20 so the product stays below 6e34; for u < -20 the result is u * 2e-9 instead of ~0 (|error| < 1e-7 |u| / 50).
 __device__ __forceinline__ void silu4_shared_rcp(float& u0, float& u1, float& u2, float& u3) {
-  const float d0 = 1.0f + __expf(fminf(-u0, 20.f)), d1 = 1.0f + __expf(fminf(-u1, 20.f));
-  const float d2 = 1.0f + __expf(fminf(-u2, 20.f)), d3 = 1.0f + __expf(fminf(-u3, 20.f));
+  const float L = -1.4426950408889634f, C = 28.853900817779268f;  // -log2(e); 20 log2(e)
+  const float d0 = 1.0f + fast_ex2(fminf(L * u0, C)), d1 = 1.0f + fast_ex2(fminf(L * u1, C));
+  const float d2 = 1.0f + fast_ex2(fminf(L * u2, C)), d3 = 1.0f + fast_ex2(fminf(L * u3, C));
   const float d01 = d0 * d1, d23 = d2 * d3;
-  const float r = __fdividef(1.0f, d01 * d23);
+  const float r = fast_rcp(d01 * d23);
   const float r01 = r * d23, r23 = r * d01;
   u0 *= r01 * d1; u1 *= r01 * d0; u2 *= r23 * d3; u3 *= r23 * d2;
 }
@@ -384,7 +385,7 @@ __global__ void k_act_lists(const int* __restrict__ n_act, int cap, const int* _
 // NG partial sums are combined through shared memory in a fixed order (bitwise reproducible), then
 // s = (s + dx)/sqrt2, vec_out = vec_in + dvec.
 template <int NG>
-__global__ void __launch_bounds__(NG * 64) k_equi_reduce(
+__global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
     int H, int reflect, const int* __restrict__ row_act_ptr, const int* __restrict__ act_tr,
     const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float* __restrict__ G,
     const float* __restrict__ X, const float* __restrict__ pf, const float* __restrict__ vec_in,
@@ -431,7 +432,6 @@ __global__ void __launch_bounds__(NG * 64) k_equi_reduce(
       OARD_EQ(x) OARD_EQ(y) OARD_EQ(z) OARD_EQ(w)
 #undef OARD_EQ
     };
-#pragma unroll 2
     for (int p = p0 + grp; p < p1; p += NG) edge(p);
     float4* mine = eq_part + (size_t)grp * 4 * H4 + (h >> 2);
     mine[0] = dx; mine[H4] = d0; mine[2 * H4] = d1; mine[3 * H4] = d2;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NG * 64) k_equi_reduce(
 // One thread per (node, channel).  The lin3 weights are broadcast from shared memory as float4 ((w0,w1,w2,b0) per hidden
 // unit, the 8 second-layer weights of a hidden unit as two float4): 3 LDS.128 per hidden unit instead of 12 LDS.32 (the
 // first version was bound by the shared-memory pipe), and four SiLUs share one reciprocal.
-__global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, const float* __restrict__ nodeframe,
+__global__ void k_upd_scalar(int N, int H, int reflect, const float* __restrict__ VP, const float* __restrict__ nodeframe,
                              const float* __restrict__ s, const float* __restrict__ w0, const float* __restrict__ b0,
                              const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w4,
                              const float* __restrict__ b4, float* __restrict__ sx, float* __restrict__ vd) {
@@ -472,8 +472,10 @@ __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, c
   }
   for (int k = threadIdx.x; k < 8; k += blockDim.x) { B2[k] = b2[k]; W4[k] = w4[k]; }
   __syncthreads();
-  const int t = blockIdx.x, h = threadIdx.x;
+  const int h = threadIdx.x;
   if (h >= H) return;
+  const float bias4 = b4[0], inv_sqrt_h = rsqrtf((float)H);
+  for (int t = blockIdx.x; t < N; t += gridDim.x) {  // persistent: the weights are staged once per block
   const float* nf = nodeframe + (size_t)t * 9;
   const float* vp = VP + (size_t)t * 3 * 2 * H;
   const float v10 = vp[h], v11 = vp[2 * H + h], v12 = vp[4 * H + h];
@@ -503,12 +505,13 @@ __global__ void k_upd_scalar(int H, int reflect, const float* __restrict__ VP, c
   }
   silu4_shared_rcp(a[0], a[1], a[2], a[3]);
   silu4_shared_rcp(a[4], a[5], a[6], a[7]);
-  float out = b4[0];
+  float out = bias4;
 #pragma unroll
   for (int q = 0; q < 8; q++) out = fmaf(W4[q], a[q], out);
   sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
   sx[(size_t)t * 2 * H + H + h] = out;
-  vd[(size_t)t * H + h] = (v10 * v20 + v11 * v21 + v12 * v22) * rsqrtf((float)H);
+  vd[(size_t)t * H + h] = (v10 * v20 + v11 * v21 + v12 * v22) * inv_sqrt_h;
+  }
 }
 
 // EquiUpdate apply: s += (xv1 + xv2 + vec_dot)/sqrt2 ; vec += xv3 * vec2   (leftnet.py:338-346, 863-864)

@@ -808,7 +808,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
     PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 traffic)
-    k_equi_reduce<4><<<N, 256, (size_t)4 * 4 * (H / 4) * sizeof(float4), st>>>(
+    k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(
         H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"),
         h->buf<float4>("act_geo"), G, X, pf, vec, vec2, s);
     KCHECK();
@@ -823,7 +823,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
       GEMM_TC("gemm_vec_proj", g, h->T[l].vp);
       PB("k_upd_scalar", 0, N*H*4.0*9, 0);
-      k_upd_scalar<<<N, HB, 0, st>>>(H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
+      k_upd_scalar<<<std::min(N, h->num_sms * 8), HB, 0, st>>>(N, H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
                                      vd);
       KCHECK();
       g = mk(sx, 2 * H, w.xv0w, 2 * H, tN, H, N, H, 2 * H);

@@ -7,6 +7,7 @@ the reference's per-step `assert_mean_zero_with_mask` (4 `.item()` calls per ste
 start and end of a trajectory unless `debug_asserts=True`.  The RNG draw order of the reference is kept (per
 fragment: positions, then features).  Training `forward()` (loss terms) is a later row of SURVEY §8f.
 """
+import math
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -15,7 +16,7 @@ from torch import Tensor, nn
 
 from .dynamics import EGNNDynamics
 from .graph_tools import get_edges_index, get_mask_for_frag, get_n_frag_switch
-from .normalizer import Normalizer
+from .normalizer import FEATURE_MAPPING, Normalizer
 from .schedule import DiffSchedule, get_repaint_schedule
 
 
@@ -49,8 +50,132 @@ class EnVariationalDiffusion(nn.Module):
         self.debug_asserts = debug_asserts
         self.n_evals = 0  # denoiser evaluations of the last sample()/inpaint() call
 
-    def forward(self, representations, conditions, return_pred: bool = False):
-        raise NotImplementedError("training loss (en_diffusion.py:56-248) is outside round 1's hot path (SURVEY §8f)")
+    # ---------------------------------------------------------------- training / evaluation loss terms (forward only)
+    def _draw_t_int(self, num_sample: int, device) -> Tensor:
+        lowest_t = 0 if self.training else 1
+        return torch.randint(lowest_t, self.T + 1, size=(num_sample, 1), device=device).float()
+
+    @torch.no_grad()
+    def forward(self, representations: List[Dict], conditions: Tensor, return_pred: bool = False):
+        """Loss and NLL terms of one noised batch (en_diffusion.py:56-248), same keys and arithmetic as the reference.
+        The denoiser runs in the CUDA library, which has no backward yet: the terms are values (no autograd graph)."""
+        num_sample = representations[0]["size"].size(0)
+        n_nodes = torch.stack([rep["size"] for rep in representations], dim=0).sum(dim=0)
+        device = representations[0]["pos"].device
+        masks = [rep["mask"] for rep in representations]
+        self._combined, self._B = torch.cat(masks), num_sample
+        edge_index = get_edges_index(self._combined, remove_self_edge=True)
+        nfs = get_n_frag_switch([rep["size"] for rep in representations])
+        representations = self.normalizer.normalize(representations)
+        delta_log_px = self.delta_log_px(n_nodes.sum())
+        t_int = self._draw_t_int(num_sample, device)
+        s_int = t_int - 1
+        t_is_zero = (t_int == 0).float()
+        t_is_not_zero = 1 - t_is_zero
+        s, t = s_int / self.T, t_int / self.T
+        ref = representations[0]["pos"]
+        gamma_s = self.schedule.inflate_batch_array(self.schedule.gamma_module(s), ref)
+        gamma_t = self.schedule.inflate_batch_array(self.schedule.gamma_module(t), ref)
+        xh = [torch.cat([rep[k] for k in FEATURE_MAPPING], dim=1) for rep in representations]
+        z_t, eps_xh = self.noised_representation(xh, masks, gamma_t)
+        net_eps_xh = self._dyn(z_t, edge_index, t, conditions, nfs, masks)
+        if return_pred:
+            return eps_xh, net_eps_xh
+        p = self.pos_dim
+        if self.pos_only:
+            for ii in range(len(masks)):
+                net_eps_xh[ii][:, p:] = 0.0
+        error_t = [self._sum_except_batch((eps_xh[ii] - net_eps_xh[ii]) ** 2, masks[ii]) for ii in range(len(masks))]
+        SNR_weight = (1 - self.schedule.SNR(gamma_s - gamma_t)).squeeze(1)
+        neg_log_constants = -self.log_constants_p_x_given_z0(n_nodes, device)
+        kl_prior = torch.zeros_like(neg_log_constants)
+        if self.training:
+            log_p = self.log_pxh_given_z0_without_constants(representations, z_t, eps_xh, net_eps_xh, gamma_t, 1e-10)
+            tz = t_is_zero.squeeze()
+            loss_0_x, loss_0_cat, loss_0_charge = ([-lp * tz for lp in log_p[k]] for k in range(3))
+            error_t = [e * t_is_not_zero.squeeze() for e in error_t]
+        else:
+            t_zeros = torch.zeros_like(s)
+            gamma_0 = self.schedule.inflate_batch_array(self.schedule.gamma_module(t_zeros), ref)
+            z_0, eps_0 = self.noised_representation(xh, masks, gamma_0)
+            net_eps_0 = self._dyn(z_0, edge_index, t_zeros, conditions, nfs, masks)
+            log_p = self.log_pxh_given_z0_without_constants(representations, z_0, eps_0, net_eps_0, gamma_0, 1e-10)
+            loss_0_x, loss_0_cat, loss_0_charge = ([-lp for lp in log_p[k]] for k in range(3))
+        return {"delta_log_px": delta_log_px, "error_t": error_t, "SNR_weight": SNR_weight, "loss_0_x": loss_0_x,
+                "loss_0_cat": loss_0_cat, "loss_0_charge": loss_0_charge, "neg_log_constants": neg_log_constants,
+                "kl_prior": kl_prior, "log_pN": torch.zeros_like(kl_prior), "t_int": t_int.squeeze(),
+                "net_eps_xh": net_eps_xh, "eps_xh": eps_xh}
+
+    def _sum_except_batch(self, x: Tensor, indices: Tensor) -> Tensor:
+        """diffusion/_utils.py:34-35."""
+        return torch.zeros(self._B, device=x.device, dtype=x.dtype).index_add_(0, indices, x.sum(-1))
+
+    def delta_log_px(self, num_nodes):
+        return -self.subspace_dimensionality(num_nodes) * math.log(self.norm_values[0])  # en_diffusion.py:250-251
+
+    def subspace_dimensionality(self, input_size):
+        return (input_size - 1) * self.pos_dim  # en_diffusion.py:253-258
+
+    def log_constants_p_x_given_z0(self, n_nodes: Tensor, device) -> Tensor:
+        """en_diffusion.py:306-318."""
+        batch_size = len(n_nodes)
+        dof = self.subspace_dimensionality(n_nodes).to(device)
+        gamma_0 = self.schedule.gamma_module(torch.zeros((batch_size, 1), device=device))
+        log_sigma_x = 0.5 * gamma_0.view(batch_size)
+        return dof * (-log_sigma_x - 0.5 * math.log(2 * math.pi))
+
+    def log_pxh_given_z0_without_constants(self, representations, z_t, eps_xh, net_eps_xh, gamma_t, epsilon=1e-10):
+        """L0 terms: Gaussian position term, discretised-Gaussian atom-type and charge terms (en_diffusion.py:340-454)."""
+        p, n = self.pos_dim, len(representations)
+        cdf = lambda x: 0.5 * (1.0 + torch.erf(x / math.sqrt(2)))
+        masks = [rep["mask"] for rep in representations]
+        log_p_x = [-0.5 * self._sum_except_batch((eps_xh[ii][:, :p] - net_eps_xh[ii][:, :p]) ** 2, masks[ii]) for ii in range(n)]
+        z_t = [z[:, :3 + 5 + 1] for z in z_t]
+        for rep in representations:
+            rep["charge"] = rep["charge"][:, :1]
+        sigma_0 = self.schedule.sigma(gamma_t, target_tensor=z_t[0])
+        sigma_0_cat = sigma_0 * self.normalizer.norm_values[1]
+        atoms = [self.normalizer.unnormalize(rep["one_hot"], 1) for rep in representations]
+        centered_atoms = [self.normalizer.unnormalize(z[:, p:-1], 1) - 1 for z in z_t]
+        log_ph_cat = [torch.log(cdf((centered_atoms[ii] + 0.5) / sigma_0_cat[masks[ii]])
+                                - cdf((centered_atoms[ii] - 0.5) / sigma_0_cat[masks[ii]]) + epsilon) for ii in range(n)]
+        log_prob = [lp - torch.logsumexp(lp, dim=1, keepdim=True) for lp in log_ph_cat]
+        log_p_hcat = [self._sum_except_batch(log_prob[ii] * atoms[ii], masks[ii]) for ii in range(n)]
+        sigma_0_charge = sigma_0 * self.normalizer.norm_values[2]
+        charges = [self.normalizer.unnormalize(rep["charge"], 2) for rep in representations]
+        est_charges = [self.normalizer.unnormalize(z[:, -1:], 2).long() for z in z_t]
+        centered_charges = [charges[ii] - est_charges[ii] for ii in range(n)]
+        log_ph_charge = [torch.log(cdf((centered_charges[ii] + 0.5) / sigma_0_charge[masks[ii]])
+                                   - cdf((centered_charges[ii] - 0.5) / sigma_0_charge[masks[ii]]) + epsilon) for ii in range(n)]
+        log_p_hcharge = [self._sum_except_batch(log_ph_charge[ii], masks[ii]) for ii in range(n)]
+        return [log_p_x, log_p_hcat, log_p_hcharge]
+
+    def compute_loss(self, batch, scales=(1.0, 1.0, 1.0), training: Optional[bool] = None):
+        """The loss composition of `DDPMModule.compute_loss` (trainer/pl_trainer.py:208-282) on this module's terms:
+        returns (nll[B], info).  `scales` are the per-fragment weights (train_ts1x.py:111 uses [1, 2, 1])."""
+        representations, conditions = batch
+        training = self.training if training is None else training
+        sizes = [rep["size"] for rep in representations]
+        lt = self.forward(representations, conditions)
+        nfr = len(sizes)
+        denoms = [(self.pos_dim if self.pos_only else self.pos_dim + self.node_nfs[ii]) * sizes[ii] for ii in range(nfr)]
+        err_norm = [lt["error_t"][ii] / denoms[ii] * scales[ii] for ii in range(nfr)]
+        if self.loss_type == "l2" and training:
+            loss_t = torch.stack(err_norm, dim=0).sum(dim=0)
+            l0x = torch.stack([lt["loss_0_x"][ii] * scales[ii] / (self.pos_dim * sizes[ii]) for ii in range(nfr)], dim=0).sum(dim=0)
+            loss_0 = l0x + torch.stack(lt["loss_0_cat"], dim=0).sum(dim=0) + torch.stack(lt["loss_0_charge"], dim=0).sum(dim=0)
+        else:
+            loss_t = torch.stack([-self.T * 0.5 * lt["SNR_weight"] * e for e in lt["error_t"]], dim=0).sum(dim=0)
+            loss_0 = (torch.stack(lt["loss_0_x"], dim=0).sum(dim=0) + torch.stack(lt["loss_0_cat"], dim=0).sum(dim=0)
+                      + torch.stack(lt["loss_0_charge"], dim=0).sum(dim=0) + lt["neg_log_constants"])
+        nll = loss_t + loss_0 + lt["kl_prior"]
+        info = {}
+        for ii in range(nfr):
+            info[f"error_t_{ii}"] = err_norm[ii].mean() / (scales[ii] + 1e-4)
+            info[f"unorm_error_t_{ii}"] = lt["error_t"][ii].mean()
+        if not (self.loss_type == "l2" and training):
+            nll = nll - lt["delta_log_px"] - lt["log_pN"]
+        return nll, info
 
     # ---------------------------------------------------------------- noise
     def sample_combined_position_feature_noise(self, masks: List[Tensor]) -> List[Tensor]:

@@ -169,6 +169,48 @@ def case_inpaint(name, cfg, sizes, seed, T, resamplings, jump_length):
     print(name, "ok")
 
 
+def case_train_loss(name, cfg, sizes, seed, T, training):
+    """Loss terms of EnVariationalDiffusion.forward (en_diffusion.py:56-248) on one synthetic collate_fn-shaped batch
+    (dataset/base_dataset.py:54-88 keys: size, pos, one_hot, charge, mask).  The random draws of the reference call
+    (t_int and every noise sample) are recorded so that the CUDA path can be fed the same ones."""
+    ddpm, _ = build_ddpm(cfg, seed, T)
+    ddpm.train(training)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    reps = []
+    for f in range(3):
+        m = get_mask_for_frag(nodes[f])
+        pos = torch.randn(h0[f].size(0), 3, generator=g) * 1.5
+        cnt = torch.zeros(len(sizes)).index_add_(0, m, torch.ones(len(m)))
+        pos = pos - (torch.zeros(len(sizes), 3).index_add_(0, m, pos) / cnt[:, None])[m]  # centred per sample (base_dataset.py:215-218)
+        reps.append({"size": nodes[f].clone(), "pos": pos, "one_hot": h0[f][:, :5].clone(), "charge": h0[f][:, 5:].clone(), "mask": m})
+    draws = []
+    orig = ddpm.sample_combined_position_feature_noise
+
+    def rec(masks):
+        out = orig(masks)
+        draws.append([o.clone() for o in out])
+        return out
+    ddpm.sample_combined_position_feature_noise = rec
+    torch.manual_seed(seed)
+    inputs = {f"{k}{f}": r[k].numpy().copy() for f, r in enumerate(reps) for k in ("pos", "one_hot", "charge")}
+    with torch.no_grad():
+        lt = ddpm.forward([dict(r) for r in reps], cond)
+    out = dict(inputs)
+    for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "net_eps_xh", "eps_xh"):
+        for f in range(3):
+            out[f"{k}{f}"] = lt[k][f].numpy()
+    for k in ("SNR_weight", "neg_log_constants", "kl_prior", "t_int"):
+        out[k] = lt[k].numpy()
+    out["delta_log_px"] = np.float64(lt["delta_log_px"])
+    for d, dr in enumerate(draws):
+        for f in range(3):
+            out[f"noise{d}_{f}"] = dr[f].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), sizes=np.array(sizes), seed=np.int64(seed), T=np.int64(T),
+                        training=np.int64(training), n_draws=np.int64(len(draws)), cond=cond.numpy(), cfg=json.dumps(cfg), **out)
+    print(name, "ok t_int", lt["t_int"].tolist(), "error_t0", lt["error_t"][0].tolist())
+
+
 def t1x_histogram():
     path = "/root/reference/oa_reactdiff/data/transition1x/train.pkl"
     with open(path, "rb") as fh:
@@ -189,6 +231,11 @@ def t1x_histogram():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "train_loss":  # only the loss-term fixtures
+        case_train_loss("loss_small_train", SMALL_CFG, [5, 3, 4], seed=51, T=20, training=True)
+        case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
+        case_train_loss("loss_trained_train_b4", TRAINED_CFG, [4, 9, 14, 7], seed=53, T=100, training=True)
+        sys.exit(0)
     t1x_histogram()
     # raw LEFTNet.forward (reference tests/model style): full graph, and object-aware cut graph
     case_leftnet("leftnet_small_full", SMALL_CFG, 9, seed=11, pos_scale=3.0)
@@ -209,3 +256,6 @@ if __name__ == "__main__":
     case_sample("sample_small_T10", SMALL_CFG, [5, 3], seed=41, T=10)
     case_sample("sample_trained_cfg1_T10", TRAINED_CFG, [12], seed=42, T=10)
     case_inpaint("inpaint_small_T12_r2_j3", SMALL_CFG, [4, 6], seed=43, T=12, resamplings=2, jump_length=3)
+    case_train_loss("loss_small_train", SMALL_CFG, [5, 3, 4], seed=51, T=20, training=True)
+    case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
+    case_train_loss("loss_trained_train_b4", TRAINED_CFG, [4, 9, 14, 7], seed=53, T=100, training=True)

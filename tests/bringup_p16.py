@@ -70,7 +70,7 @@ def time_tc(M, N, K, mode, reps=10):
 if __name__ == "__main__":
     for (M, N, K) in [(128, 16, 32), (300, 196, 684), (1000, 684, 196), (257, 588, 588), (20000, 196, 684)]:
         for mode, op in [(0, 1), (0, 0), (1, 1), (2, 0), (3, 1)]:
-            for ew in ((8, 16) if mode >= 2 else (8,)):
+            for ew in (8, 16):
                 print(M, N, K, "mode", mode, "pair" if op else "fp32", "ew", ew, run_p16(M, N, K, mode, op, 1, c2=(mode == 3), ew=ew),
                       flush=True)
     E, Ea = 107790, 34188
@@ -78,6 +78,6 @@ if __name__ == "__main__":
               ("dir0", Ea, 588, 684, 0, 1), ("dir2", Ea, 588, 588, 2, 0)]
     for name, M, N, K, mode, op in shapes:
         row = {"tc_fp32A_us": round(1e3 * time_tc(M, N, K, mode), 1)}
-        for ew in ((8, 16) if mode >= 2 else (8,)):
+        for ew in (8, 16):
             row[f"p16_ew{ew}_us"] = round(1e3 * run_p16(M, N, K, mode, op, 1, c2=False, ew=ew, reps=10).get("ms", float("nan")), 1)
         print(name, M, N, K, row, flush=True)
