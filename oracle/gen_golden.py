@@ -171,10 +171,9 @@ def case_inpaint(name, cfg, sizes, seed, T, resamplings, jump_length):
 
 def case_train_loss(name, cfg, sizes, seed, T, training):
     """Loss terms of EnVariationalDiffusion.forward (en_diffusion.py:56-248) on one synthetic collate_fn-shaped batch
-    (dataset/base_dataset.py:54-88 keys: size, pos, one_hot, charge, mask).  The random draws of the reference call
-    (t_int and every noise sample) are recorded so that the CUDA path can be fed the same ones."""
-    ddpm, _ = build_ddpm(cfg, seed, T)
-    ddpm.train(training)
+    (dataset/base_dataset.py:54-88 keys: size, pos, one_hot, charge, mask), from the reference in fp64 (the parity target,
+    suffix-less keys) and in fp32 (keys *_f32: the reference's own precision gap).  The random draws of the reference call
+    (t_int and every noise sample; identical in both runs) are recorded so that the CUDA path can be fed the same ones."""
     nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, seed)
     g = torch.Generator().manual_seed(seed + 7)
     reps = []
@@ -184,31 +183,37 @@ def case_train_loss(name, cfg, sizes, seed, T, training):
         cnt = torch.zeros(len(sizes)).index_add_(0, m, torch.ones(len(m)))
         pos = pos - (torch.zeros(len(sizes), 3).index_add_(0, m, pos) / cnt[:, None])[m]  # centred per sample (base_dataset.py:215-218)
         reps.append({"size": nodes[f].clone(), "pos": pos, "one_hot": h0[f][:, :5].clone(), "charge": h0[f][:, 5:].clone(), "mask": m})
-    draws = []
-    orig = ddpm.sample_combined_position_feature_noise
+    out = {f"{k}{f}": r[k].numpy().copy() for f, r in enumerate(reps) for k in ("pos", "one_hot", "charge")}
+    all_draws = {}
+    for dt, tag in ((torch.float64, ""), (torch.float32, "_f32")):
+        ddpm, _ = build_ddpm(cfg, seed, T, dtype=dt)
+        ddpm.train(training)
+        draws = []
+        orig = ddpm.sample_combined_position_feature_noise
 
-    def rec(masks):
-        out = orig(masks)
-        draws.append([o.clone() for o in out])
-        return out
-    ddpm.sample_combined_position_feature_noise = rec
-    torch.manual_seed(seed)
-    inputs = {f"{k}{f}": r[k].numpy().copy() for f, r in enumerate(reps) for k in ("pos", "one_hot", "charge")}
-    with torch.no_grad():
-        lt = ddpm.forward([dict(r) for r in reps], cond)
-    out = dict(inputs)
-    for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "net_eps_xh", "eps_xh"):
+        def rec(masks, orig=orig, draws=draws):
+            o = orig(masks)
+            draws.append([x.clone() for x in o])
+            return o
+        ddpm.sample_combined_position_feature_noise = rec
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            lt = ddpm.forward([{k: (v.to(dt) if v.is_floating_point() else v.clone()) for k, v in r.items()} for r in reps], cond.to(dt))
+        for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "net_eps_xh", "eps_xh"):
+            for f in range(3):
+                out[f"{k}{f}{tag}"] = lt[k][f].numpy()
+        for k in ("SNR_weight", "neg_log_constants", "kl_prior", "t_int"):
+            out[f"{k}{tag}"] = lt[k].numpy()
+        out[f"delta_log_px{tag}"] = np.float64(lt["delta_log_px"])
+        all_draws[tag] = draws
+    for d, dr in enumerate(all_draws[""]):
         for f in range(3):
-            out[f"{k}{f}"] = lt[k][f].numpy()
-    for k in ("SNR_weight", "neg_log_constants", "kl_prior", "t_int"):
-        out[k] = lt[k].numpy()
-    out["delta_log_px"] = np.float64(lt["delta_log_px"])
-    for d, dr in enumerate(draws):
-        for f in range(3):
+            assert torch.equal(dr[f], all_draws["_f32"][d][f])
             out[f"noise{d}_{f}"] = dr[f].numpy()
+    assert np.array_equal(out["t_int"], out["t_int_f32"])
     np.savez_compressed(os.path.join(OUT, name + ".npz"), sizes=np.array(sizes), seed=np.int64(seed), T=np.int64(T),
-                        training=np.int64(training), n_draws=np.int64(len(draws)), cond=cond.numpy(), cfg=json.dumps(cfg), **out)
-    print(name, "ok t_int", lt["t_int"].tolist(), "error_t0", lt["error_t"][0].tolist())
+                        training=np.int64(training), n_draws=np.int64(len(all_draws[""])), cond=cond.numpy(), cfg=json.dumps(cfg), **out)
+    print(name, "ok t_int", out["t_int"].tolist(), "error_t0", out["error_t0"].tolist(), "f32", out["error_t0_f32"].tolist())
 
 
 def t1x_histogram():

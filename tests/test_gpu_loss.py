@@ -1,8 +1,8 @@
 """GPU parity of the training / evaluation loss terms (BASELINE config 5 forward part):
 `EnVariationalDiffusion.forward` and `compute_loss` through the CUDA denoiser against golden loss terms of the
 UNMODIFIED reference (oracle/gen_golden.py::case_train_loss), fed the reference's own random draws (t_int, noise).
-Tolerance: 2e-3 of max|ref| on every term (the reference ran in fp32 on the CPU: its own fp32-vs-fp64 gap on the
-network output is ~2e-4 and the squared errors double it)."""
+Target: the reference run in fp64; tolerance 1e-3 of max|ref| on every term (stated; the reference's own fp32 run is
+printed next to it — its gap to fp64 reaches 4e-3 on these fixtures because of the degenerate legacy node frame)."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +12,7 @@ from tests.test_gpu_parity import DEV, make_dynamics
 from tests.util import dyn_state_dict, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-3
+TOL = 1e-3
 
 
 class _ReplayDraws(ob.EnVariationalDiffusion):
@@ -53,7 +53,7 @@ def test_loss_terms_vs_reference_golden(name):
     g, ddpm, reps, cond = _setup(name)
     lt = ddpm.forward(reps, cond)
     assert np.array_equal(lt["t_int"].cpu().numpy(), g["t_int"])
-    worst = 0.0
+    worst, worst_ref = 0.0, 0.0
     for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "net_eps_xh", "eps_xh"):
         for f in range(3):
             ref = g[f"{k}{f}"]
@@ -61,12 +61,12 @@ def test_loss_terms_vs_reference_golden(name):
                 assert float(lt[k][f].abs().max()) == 0.0, (k, f)
                 continue
             e = rel_err(lt[k][f].cpu(), ref)
-            worst = max(worst, e)
+            worst, worst_ref = max(worst, e), max(worst_ref, rel_err(g[f"{k}{f}_f32"], ref))
             assert e < TOL, (k, f, e)
     for k in ("SNR_weight", "neg_log_constants", "kl_prior"):
         assert np.allclose(lt[k].cpu().numpy(), g[k], rtol=1e-5, atol=1e-6), k
     assert abs(float(lt["delta_log_px"]) - float(g["delta_log_px"])) < 1e-6
-    print(f"{name}: worst rel err of the loss terms vs the reference {worst:.2e}")
+    print(f"{name}: worst rel err of the loss terms vs the fp64 reference {worst:.2e} (reference fp32 vs fp64: {worst_ref:.2e})")
 
 
 @pytest.mark.parametrize("name", ["loss_small_train", "loss_small_eval"])

@@ -36,7 +36,7 @@ class _Replay(ob.EnVariationalDiffusion):
 def test_loss_terms_arithmetic_vs_reference_golden(name):
     g = load_golden(name)
     sizes = torch.tensor(g["sizes"])
-    dyn = _StubDynamics([[torch.from_numpy(g[f"net_eps_xh{f}"]) for f in range(3)]])
+    dyn = _StubDynamics([[torch.from_numpy(g[f"net_eps_xh{f}_f32"]) for f in range(3)]])
     sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", int(g["T"]), 1e-5), norm_values=(1.0, 1.0, 1.0))
     ddpm = _Replay(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True)
     ddpm.train(True)
@@ -47,7 +47,7 @@ def test_loss_terms_arithmetic_vs_reference_golden(name):
     lt = ddpm.forward(reps, torch.from_numpy(g["cond"]))
     for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "eps_xh"):
         for f in range(3):
-            assert np.allclose(lt[k][f].numpy(), g[f"{k}{f}"], rtol=2e-5, atol=1e-6), (k, f)
+            assert np.allclose(lt[k][f].numpy(), g[f"{k}{f}_f32"], rtol=2e-5, atol=1e-6), (k, f)
     for k in ("SNR_weight", "neg_log_constants", "kl_prior", "t_int"):
-        assert np.allclose(lt[k].numpy(), g[k], rtol=1e-6, atol=1e-7), k
-    assert abs(float(lt["delta_log_px"]) - float(g["delta_log_px"])) < 1e-9
+        assert np.allclose(lt[k].numpy(), g[k + "_f32"], rtol=1e-6, atol=1e-7), k
+    assert abs(float(lt["delta_log_px"]) - float(g["delta_log_px_f32"])) < 1e-9
