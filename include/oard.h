@@ -76,6 +76,37 @@ size_t oard_workspace_bytes(const oard_handle* h);
 int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* subgraph_mask, float* h_out,
                  float* dpos, void* stream);
 
+/* ---- Device-resident dynamics wrapper and reverse-diffusion step ----
+ *   oa_reactdiff/dynamics/egnn_dynamics.py:63-168   EGNNDynamics.forward        -> oard_dyn_forward
+ *   oa_reactdiff/dynamics/_base.py:82-132           encoders / decoders         -> oard_dyn_configure, oard_dyn_set_weight
+ *   oa_reactdiff/diffusion/en_diffusion.py:562-632  sample_p_zs_given_zt        -> oard_reverse_step
+ * The per-fragment encoder MLP, the time/condition channels, the NaN guard, the per-(fragment, sample) centre-of-mass
+ * removal, the decoder MLP and (for the step) the posterior mean, noise projection and h0 overwrite run as three small
+ * kernels around the LEFTNet forward; the whole call is replayed as ONE CUDA graph keyed by the caller's pointers
+ * (callers keep persistent buffers).  Weight names are the reference state-dict names below `dynamics.`:
+ * "encoders.{f}.mlp.{0,1}.linear.{weight,bias}", "decoders.{f}.mlp.{0,1}.linear.{weight,bias}". */
+int oard_dyn_configure(oard_handle* h, int n_frag, int node_nf, int condition_nf, int condition_time);
+int oard_dyn_num_weights(const oard_handle* h);
+const char* oard_dyn_weight_name(const oard_handle* h, int i);
+int64_t oard_dyn_weight_numel(const oard_handle* h, int i);
+int oard_dyn_set_weight(oard_handle* h, const char* name, const float* data, int64_t numel, int is_device, void* stream);
+/* After oard_plan: HOST arrays node_frag[N] (n_frag_switch, _graph_tools.py:62-81) and node_sample[N] (combined_mask,
+ * :84-96).  The nodes of every (fragment, sample) pair must be contiguous (they are in the reference's node order). */
+int oard_dyn_plan(oard_handle* h, const int64_t* node_frag_host, const int64_t* node_sample_host, int64_t n_samples);
+/* eps[N, node_nf] = EGNNDynamics.forward(xh[N, node_nf] (fragments concatenated), t[B], conditions[B, condition_nf]).
+ * Device pointers; t may be NULL when condition_time == 0, conditions when condition_nf == 0. */
+int oard_dyn_forward(oard_handle* h, const float* xh, const float* t, const float* conditions,
+                     const int64_t* subgraph_mask, float* eps, void* stream);
+/* One reverse step z_t -> z_s IN PLACE on z[N, node_nf] with one (s, t) pair for the whole batch:
+ *   eps = dynamics(z, t); mu = z / alpha_ts - eps * coef; z_s = mu + sigma * noise,
+ * noise_pos[N, 3] / noise_feat[N, node_nf - 3] = the caller's raw standard-normal draws (the position noise is projected
+ * on the zero-CoM subspace here, as are the new positions); noise_feat == NULL: zero feature noise (pos_only);
+ * h0[N, node_nf - 3] != NULL: features overwritten by h0 (pos_only, en_diffusion.py:524-527).
+ * t, alpha_ts, coef, sigma are the host-side schedule scalars of the step (diffusion/_schedule.py:132-203). */
+int oard_reverse_step(oard_handle* h, float* z, const float* noise_pos, const float* noise_feat, const float* h0,
+                      const float* conditions, const int64_t* subgraph_mask, float t, float alpha_ts, float coef,
+                      float sigma, void* stream);
+
 /* Parity instrumentation.  With debug on, oard_forward keeps snapshots of intermediates; oard_debug_read copies a
  * named snapshot to host (synchronises).  Names: mask(u8[E]) group(i32[N]) act_idx(i32[n_act]) n_act(i32[1])
  * pos_frame(f32[N,3]) geo(f32[E,4]) rb f_act rbf_act s0 NE1 e0 nodeframe pos_prjt s_msg{l} vec_msg{l} e{l} s{l} vec{l}. */

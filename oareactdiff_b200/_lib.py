@@ -51,6 +51,15 @@ SYMBOLS = {
     "oard_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "oard_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "oard_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oard_dyn_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "oard_dyn_num_weights": (C.c_int, [C.c_void_p]),
+    "oard_dyn_weight_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "oard_dyn_weight_numel": (C.c_int64, [C.c_void_p, C.c_int]),
+    "oard_dyn_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "oard_dyn_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "oard_dyn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oard_reverse_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                    C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "oard_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "oard_debug_bytes": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "oard_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),

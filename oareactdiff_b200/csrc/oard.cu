@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_p16.cuh"
 #include "kernels.cuh"
+#include "dynamics.cuh"
 
 using namespace oard;
 
@@ -103,6 +105,17 @@ struct oard_handle {
   bool debug = false;
   std::map<std::string, DevBuf> snaps;
   int64_t launches = 0;
+  // device-resident dynamics wrapper + reverse step (dynamics.cuh)
+  bool dyn_cfg = false, dyn_committed = false, dyn_planned = false;
+  int dyn_nfrag = 0, dyn_nf = 0, dyn_d = 0, dyn_emb = 0, dyn_cnd = 0, dyn_ctime = 0, dyn_S = 0, dyn_B = 0;
+  std::vector<WeightSpec> dspecs;
+  std::unordered_map<std::string, int> dspec_idx;
+  std::vector<float*> ddev;
+  std::vector<char> dset;
+  DynCodec codec{};
+  int nan_counter = 0;
+  struct GraphSlot { int kind; std::array<const void*, 6> key; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<GraphSlot> gslots;  // whole-call graphs of oard_dyn_forward (kind 0) / oard_reverse_step (kind 1), keyed by pointers
 
   template <typename T>
   T* buf(const char* name) { return reinterpret_cast<T*>(ws.at(name).p); }
@@ -168,6 +181,9 @@ static void build_specs(oard_handle* h) {
 static void drop_graphs(oard_handle* h) {
   for (auto& g : h->gexec)
     if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  for (auto& s : h->gslots)
+    if (s.exec) cudaGraphExecDestroy(s.exec);
+  h->gslots.clear();
 }
 
 extern "C" int oard_abi_version(void) { return 1; }
@@ -223,6 +239,8 @@ extern "C" void oard_destroy(oard_handle* h) {
   for (float* p : h->wdev)
     if (p) cudaFree(p);
   for (void* p : h->tc_bufs) cudaFree(p);
+  for (float* p : h->ddev)
+    if (p) cudaFree(p);
   drop_graphs(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_map(h->ws);
@@ -443,6 +461,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   free_map(h->snaps);
   h->ws_bytes = 0;
   h->planned = false;
+  h->dyn_planned = false;
   const size_t H = h->cfg.hidden_channels, R = h->cfg.num_radial, D = 3 * H + R, Nn = N, Ee = E > 0 ? E : 1;
   struct { const char* n; size_t b; } allocs[] = {
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
@@ -855,6 +874,27 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   return OARD_OK;
 }
 
+// Capture (once per mask variant) the forward on the static I/O buffers g_h_in / g_pos / g_sub -> g_h_out / g_dpos.
+static int ensure_fwd_graph(oard_handle* h, int gi, cudaStream_t st) {
+  if (h->gexec[gi]) return OARD_OK;
+  float *gh = h->buf<float>("g_h_in"), *gp = h->buf<float>("g_pos"), *gho = h->buf<float>("g_h_out"),
+        *gdp = h->buf<float>("g_dpos");
+  int64_t* gs = h->buf<int64_t>("g_sub");
+  if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  CU(cudaStreamSynchronize(st));
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = forward_impl(h, gh, gp, gi ? gs : nullptr, gho, gdp, h->cap_stream);
+  cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+  ce = cudaGraphInstantiate(&h->gexec[gi], graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+  h->graph_launches = h->launches;  // kernels recorded in the graph
+  return OARD_OK;
+}
+
 extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
                             float* dpos, void* stream) {
   if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
@@ -878,19 +918,9 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   float *gh = h->buf<float>("g_h_in"), *gp = h->buf<float>("g_pos"), *gho = h->buf<float>("g_h_out"),
         *gdp = h->buf<float>("g_dpos");
   int64_t* gs = h->buf<int64_t>("g_sub");
-  if (!h->gexec[gi]) {
-    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
-    CU(cudaStreamSynchronize(st));
-    cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = forward_impl(h, gh, gp, sub ? gs : nullptr, gho, gdp, h->cap_stream);
-    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&h->gexec[gi], graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
-    h->graph_launches = h->launches;  // kernels recorded in the graph
+  {
+    const int rc = ensure_fwd_graph(h, gi, st);
+    if (rc) return rc;
   }
   CU(cudaMemcpyAsync(gh, h_in, (size_t)N * C * 4, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(gp, pos, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
@@ -901,6 +931,250 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   h->launches = h->graph_launches;
   h->total_launches += h->launches;
   return OARD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dynamics + reverse step
+// Device-resident EGNNDynamics.forward (egnn_dynamics.py:63-168) and one reverse-diffusion step
+// (en_diffusion.py:562-632) around the LEFTNet forward: SURVEY §8f row 1.
+extern "C" int oard_dyn_configure(oard_handle* h, int n_frag, int node_nf, int condition_nf, int condition_time) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  const int C = h->cfg.in_hidden_channels, d = node_nf - 3, emb = C - (condition_time ? 1 : 0) - std::max(condition_nf, 0);
+  if (n_frag <= 0 || n_frag > DYN_MAX_FRAG) return fail(OARD_EINVAL, "n_frag must be in [1,%d]", DYN_MAX_FRAG);
+  if (d <= 0 || d > DYN_MAX_D) return fail(OARD_EINVAL, "node_nf - 3 must be in [1,%d], got %d", DYN_MAX_D, d);
+  if (emb <= 0 || emb > DYN_MAX_D) return fail(OARD_EINVAL, "embed width %d (= in_hidden_channels - time - conditions) out of range", emb);
+  if (condition_nf < 0) return fail(OARD_EINVAL, "condition_nf < 0");
+  CU(cudaSetDevice(h->device));
+  for (float* p : h->ddev)
+    if (p) cudaFree(p);
+  h->dspecs.clear(); h->dspec_idx.clear(); h->ddev.clear(); h->dset.clear();
+  auto add = [&](const std::string& n, int64_t numel) {
+    h->dspec_idx[n] = (int)h->dspecs.size();
+    h->dspecs.push_back({n, numel});
+  };
+  for (int f = 0; f < n_frag; f++) {  // dynamics/_base.py:91-109: MLP(d -> 2d -> emb) / MLP(emb -> 2d -> d)
+    const std::string e = "encoders." + std::to_string(f) + ".mlp.", dd = "decoders." + std::to_string(f) + ".mlp.";
+    add(e + "0.linear.weight", 2 * d * d); add(e + "0.linear.bias", 2 * d);
+    add(e + "1.linear.weight", emb * 2 * d); add(e + "1.linear.bias", emb);
+    add(dd + "0.linear.weight", 2 * d * emb); add(dd + "0.linear.bias", 2 * d);
+    add(dd + "1.linear.weight", d * 2 * d); add(dd + "1.linear.bias", d);
+  }
+  h->ddev.assign(h->dspecs.size(), nullptr);
+  h->dset.assign(h->dspecs.size(), 0);
+  for (size_t i = 0; i < h->dspecs.size(); i++) CU(cudaMalloc(&h->ddev[i], h->dspecs[i].numel * sizeof(float)));
+  h->dyn_nfrag = n_frag; h->dyn_nf = node_nf; h->dyn_d = d; h->dyn_emb = emb; h->dyn_cnd = condition_nf;
+  h->dyn_ctime = condition_time ? 1 : 0;
+  h->dyn_cfg = true; h->dyn_committed = false; h->dyn_planned = false;
+  drop_graphs(h);
+  return OARD_OK;
+}
+
+extern "C" int oard_dyn_num_weights(const oard_handle* h) { return h ? (int)h->dspecs.size() : 0; }
+extern "C" const char* oard_dyn_weight_name(const oard_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->dspecs.size()) ? h->dspecs[i].name.c_str() : nullptr;
+}
+extern "C" int64_t oard_dyn_weight_numel(const oard_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->dspecs.size()) ? h->dspecs[i].numel : -1;
+}
+
+extern "C" int oard_dyn_set_weight(oard_handle* h, const char* name, const float* data, int64_t numel, int is_device,
+                                   void* stream) {
+  if (!h || !name || !data) return fail(OARD_EINVAL, "null argument");
+  if (!h->dyn_cfg) return fail(OARD_ESTATE, "oard_dyn_configure has not been called");
+  auto it = h->dspec_idx.find(name);
+  if (it == h->dspec_idx.end()) return fail(OARD_EINVAL, "unknown dynamics weight '%s'", name);
+  const WeightSpec& s = h->dspecs[it->second];
+  if (numel != s.numel) return fail(OARD_EINVAL, "weight '%s': expected %lld elements, got %lld", name,
+                                    (long long)s.numel, (long long)numel);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->ddev[it->second], data, numel * sizeof(float),
+                     is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  h->dset[it->second] = 1;
+  bool all = true;
+  for (char c : h->dset) all = all && c;
+  if (all) {
+    auto W = [&](const std::string& n) -> const float* { return h->ddev[h->dspec_idx.at(n)]; };
+    for (int f = 0; f < h->dyn_nfrag; f++) {
+      const std::string e = "encoders." + std::to_string(f) + ".mlp.", dd = "decoders." + std::to_string(f) + ".mlp.";
+      h->codec.ew0[f] = W(e + "0.linear.weight"); h->codec.eb0[f] = W(e + "0.linear.bias");
+      h->codec.ew1[f] = W(e + "1.linear.weight"); h->codec.eb1[f] = W(e + "1.linear.bias");
+      h->codec.dw0[f] = W(dd + "0.linear.weight"); h->codec.db0[f] = W(dd + "0.linear.bias");
+      h->codec.dw1[f] = W(dd + "1.linear.weight"); h->codec.db1[f] = W(dd + "1.linear.bias");
+    }
+    h->dyn_committed = true;
+  }
+  return OARD_OK;
+}
+
+extern "C" int oard_dyn_plan(oard_handle* h, const int64_t* node_frag, const int64_t* node_sample, int64_t n_samples) {
+  if (!h || !node_frag || !node_sample) return fail(OARD_EINVAL, "null argument");
+  if (!h->dyn_cfg) return fail(OARD_ESTATE, "oard_dyn_configure has not been called");
+  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
+  if (n_samples <= 0) return fail(OARD_EINVAL, "n_samples must be > 0");
+  CU(cudaSetDevice(h->device));
+  const int N = h->N;
+  std::vector<int> nfrag(N), nsamp(N), seg_ptr, seg_frag;
+  std::unordered_map<uint64_t, int> seen;
+  for (int n = 0; n < N; n++) {
+    if (node_frag[n] < 0 || node_frag[n] >= h->dyn_nfrag) return fail(OARD_EGRAPH, "node %d: fragment id %lld out of range", n, (long long)node_frag[n]);
+    if (node_sample[n] < 0 || node_sample[n] >= n_samples) return fail(OARD_EGRAPH, "node %d: sample id %lld out of range", n, (long long)node_sample[n]);
+    nfrag[n] = (int)node_frag[n]; nsamp[n] = (int)node_sample[n];
+    if (n == 0 || nfrag[n] != nfrag[n - 1] || nsamp[n] != nsamp[n - 1]) {
+      const uint64_t key = ((uint64_t)nfrag[n] << 32) | (uint32_t)nsamp[n];
+      if (!seen.emplace(key, 1).second)
+        return fail(OARD_EGRAPH, "nodes of (fragment %d, sample %d) are not contiguous", nfrag[n], nsamp[n]);
+      seg_ptr.push_back(n);
+      seg_frag.push_back(nfrag[n]);
+    }
+  }
+  seg_ptr.push_back(N);
+  const int S = (int)seg_frag.size();
+  for (const char* nm : {"dyn_node_frag", "dyn_node_sample", "dyn_seg_ptr", "dyn_seg_frag", "dyn_vel", "dyn_prm", "dyn_flag"}) {
+    auto it = h->ws.find(nm);
+    if (it != h->ws.end()) { cudaFree(it->second.p); h->ws_bytes -= it->second.bytes; h->ws.erase(it); }
+  }
+  int rc;
+  if ((rc = ws_alloc(h, "dyn_node_frag", (size_t)N * 4)) || (rc = ws_alloc(h, "dyn_node_sample", (size_t)N * 4)) ||
+      (rc = ws_alloc(h, "dyn_seg_ptr", (size_t)(S + 1) * 4)) || (rc = ws_alloc(h, "dyn_seg_frag", (size_t)S * 4)) ||
+      (rc = ws_alloc(h, "dyn_vel", (size_t)N * 12)) || (rc = ws_alloc(h, "dyn_prm", 64)) || (rc = ws_alloc(h, "dyn_flag", 16)))
+    return rc;
+  CU(cudaMemcpy(h->buf<int>("dyn_node_frag"), nfrag.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->buf<int>("dyn_node_sample"), nsamp.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->buf<int>("dyn_seg_ptr"), seg_ptr.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->buf<int>("dyn_seg_frag"), seg_frag.data(), (size_t)S * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemset(h->buf<float>("dyn_prm"), 0, 64));
+  h->dyn_S = S; h->dyn_B = (int)n_samples;
+  h->dyn_planned = true;
+  for (auto& s : h->gslots)
+    if (s.exec) cudaGraphExecDestroy(s.exec);
+  h->gslots.clear();
+  return OARD_OK;
+}
+
+// prologue -> LEFTNet forward -> epilogue (mode 0: eps out; mode 1: in-place reverse step) on stream st
+static int dyn_impl(oard_handle* h, int mode, const float* xh, const float* t_dev, const float* cond, const int64_t* sub,
+                    float* eps, float* z, const float* noise, const float* noise_h, const float* h0, cudaStream_t st,
+                    bool fwd_graph = false) {
+  const int N = h->N, C = h->cfg.in_hidden_channels, nf = h->dyn_nf, d = h->dyn_d, emb = h->dyn_emb;
+  float *gh = h->buf<float>("g_h_in"), *gp = h->buf<float>("g_pos"), *gho = h->buf<float>("g_h_out"),
+        *gdp = h->buf<float>("g_dpos"), *vel = h->buf<float>("dyn_vel"), *prm = h->buf<float>("dyn_prm");
+  int* flag = h->buf<int>("dyn_flag");
+  const bool prof = h->prof_now;
+  if (prof) prof_begin(h, "k_dyn_pre", 0, (double)N * (nf + C + 3) * 4.0, false, st);
+  k_dyn_pre<<<(N + 127) / 128, 128, 0, st>>>(N, nf, d, emb, C, h->dyn_cnd, h->dyn_ctime, mode == 0 ? xh : z,
+                                             h->buf<int>("dyn_node_frag"), h->buf<int>("dyn_node_sample"), h->codec, t_dev,
+                                             prm, cond, gp, gh, flag);
+  {
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "k_dyn_pre launch: %s", cudaGetErrorString(e_));
+    prof_end(h, st);
+  }
+  if (fwd_graph) {  // the forward as the cached graph on the static buffers (the wrapper kernels already use them)
+    const int gi = sub ? 1 : 0;
+    const int rc = ensure_fwd_graph(h, gi, st);
+    if (rc) return rc;
+    if (sub && h->E) CU(cudaMemcpyAsync(h->buf<int64_t>("g_sub"), sub, (size_t)h->E * 8, cudaMemcpyDeviceToDevice, st));
+    CU(cudaGraphLaunch(h->gexec[gi], st));
+    h->launches = h->graph_launches;
+  } else {
+    const int rc = forward_impl(h, gh, gp, sub, gho, gdp, st);
+    if (rc) return rc;
+  }
+  if (prof) prof_begin(h, "k_dyn_vel", 0, (double)N * 36.0, false, st);
+  k_dyn_vel<<<(N * 3 + 255) / 256, 256, 0, st>>>(N * 3, gp, gdp, vel, flag);
+  KCHECK();
+  if (prof) prof_begin(h, "k_dyn_post", 0, (double)N * (3.0 * nf + C + 3) * 4.0, false, st);
+  const int S = h->dyn_S, grid = (S * 32 + 127) / 128;
+  if (mode == 0)
+    k_dyn_post<0><<<grid, 128, 0, st>>>(S, nf, d, emb, C, h->buf<int>("dyn_seg_ptr"), h->buf<int>("dyn_seg_frag"), h->codec,
+                                        vel, gho, flag, prm, eps, nullptr, nullptr, nullptr, nullptr);
+  else
+    k_dyn_post<1><<<grid, 128, 0, st>>>(S, nf, d, emb, C, h->buf<int>("dyn_seg_ptr"), h->buf<int>("dyn_seg_frag"), h->codec,
+                                        vel, gho, flag, prm, nullptr, z, noise, noise_h, h0);
+  KCHECK();
+  h->launches += 1;  // k_dyn_pre (issued before forward_impl reset the counter)
+  return OARD_OK;
+}
+
+static int dyn_run(oard_handle* h, int mode, const float* xh, const float* t_dev, const float* cond, const int64_t* sub,
+                   float* eps, float* z, const float* noise, const float* noise_h, const float* h0, cudaStream_t st) {
+  h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
+  h->fwd_count++;
+  if (!h->cfg.object_aware) sub = nullptr;
+  const bool eager = !h->use_graph || h->debug || h->prof_now || h->fwd_count <= 1;
+  if (eager || mode == 0) {
+    // mode 0 (dyn_forward) is called with fresh tensors (loss terms, final decode): its wrapper kernels are issued
+    // directly around the cached forward graph; the whole-call graph below is for the reverse step's persistent buffers
+    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, st, !eager);
+    if (rc) return rc;
+    h->total_launches += h->launches;
+    return prof_harvest(h, st);
+  }
+  const std::array<const void*, 6> key = {mode == 0 ? (const void*)xh : (const void*)z, mode == 0 ? (const void*)eps : (const void*)noise,
+                                          mode == 0 ? (const void*)t_dev : (const void*)noise_h, (const void*)cond, (const void*)sub,
+                                          (const void*)h0};
+  oard_handle::GraphSlot* slot = nullptr;
+  for (auto& s : h->gslots)
+    if (s.kind == mode && s.key == key) { slot = &s; break; }
+  if (!slot) {
+    if (h->gslots.size() >= 8) {  // callers keep persistent buffers; a churn of pointers just recaptures
+      if (h->gslots.front().exec) cudaGraphExecDestroy(h->gslots.front().exec);
+      h->gslots.erase(h->gslots.begin());
+    }
+    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CU(cudaStreamSynchronize(st));
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, h->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t ex = nullptr;
+    ce = cudaGraphInstantiate(&ex, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+    h->gslots.push_back({mode, key, ex, h->launches});
+    slot = &h->gslots.back();
+  }
+  CU(cudaGraphLaunch(slot->exec, st));
+  h->launches = slot->launches;
+  h->total_launches += h->launches;
+  return OARD_OK;
+}
+
+static int dyn_ready(oard_handle* h) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
+  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
+  if (!h->dyn_cfg || !h->dyn_committed) return fail(OARD_ESTATE, "dynamics weights are not all set (oard_dyn_configure / oard_dyn_set_weight)");
+  if (!h->dyn_planned) return fail(OARD_ESTATE, "oard_dyn_plan has not been called (after oard_plan)");
+  return OARD_OK;
+}
+
+extern "C" int oard_dyn_forward(oard_handle* h, const float* xh, const float* t, const float* cond, const int64_t* sub,
+                                float* eps, void* stream) {
+  int rc = dyn_ready(h);
+  if (rc) return rc;
+  if (!xh || !eps) return fail(OARD_EINVAL, "null argument");
+  if (h->dyn_ctime && !t) return fail(OARD_EINVAL, "condition_time is set: t[B] is required");
+  if (h->dyn_cnd > 0 && !cond) return fail(OARD_EINVAL, "condition_nf > 0: conditions[B, condition_nf] is required");
+  CU(cudaSetDevice(h->device));
+  return dyn_run(h, 0, xh, t, cond, sub, eps, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int oard_reverse_step(oard_handle* h, float* z, const float* noise, const float* noise_h, const float* h0,
+                                 const float* cond, const int64_t* sub, float t, float alpha_ts, float coef, float sigma,
+                                 void* stream) {
+  int rc = dyn_ready(h);
+  if (rc) return rc;
+  if (!z || !noise) return fail(OARD_EINVAL, "null argument");
+  if (h->dyn_cnd > 0 && !cond) return fail(OARD_EINVAL, "condition_nf > 0: conditions[B, condition_nf] is required");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  k_set_params<<<1, 1, 0, st>>>(h->buf<float>("dyn_prm"), t, alpha_ts, coef, sigma, h->nan_counter++);
+  CU(cudaGetLastError());
+  rc = dyn_run(h, 1, nullptr, nullptr, cond, sub, nullptr, z, noise, noise_h, h0, st);
+  h->total_launches += 1;
+  return rc;
 }
 
 extern "C" int oard_test_gemm_ex(int, int, int, int, const float*, const float*, const float*, float*, int, int, int, int,

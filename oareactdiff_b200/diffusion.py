@@ -279,6 +279,7 @@ class EnVariationalDiffusion(nn.Module):
         sigma_s, sigma_t = self.schedule.sigma(g_s, ref), self.schedule.sigma(g_t, ref)
         tab = {
             "tt": tt,                                               # device tensor, row k = t value of step k
+            "t": tt.flatten().tolist(),
             "inv_alpha_ts": (1.0 / alpha_ts).flatten().tolist(),    # mu = z / alpha_ts - eps * coef  (z / a == z * (1/a) is NOT
             "alpha_ts": alpha_ts.flatten().tolist(),                #   bit-identical, so the division is kept: see _fast_step)
             "coef": (sigma2_ts / alpha_ts / sigma_t).flatten().tolist(),
@@ -328,6 +329,39 @@ class EnVariationalDiffusion(nn.Module):
         Zs[:, :self.pos_dim] = self._remove_mean_cat(Zs[:, :self.pos_dim])
         return Zs
 
+    # ---------------------------------------------------------------- device-resident reverse step
+    # One reverse step = the caller's six standard-normal draws (reference order, torch generator) + ONE C call that
+    # replays the whole step (dynamics prologue, LEFTNet, epilogue, posterior update, CoM projections, h0 overwrite) as a
+    # CUDA graph on persistent buffers: oard_reverse_step (include/oard.h).
+    def _device_ok(self, device) -> bool:
+        return self._fast_ok() and self.pos_dim == 3 and getattr(self.dynamics, "fused_ok", lambda d: False)(device)
+
+    def _device_setup(self, Z: Tensor, masks, edge_index, nfs, conditions, H0: Optional[Tensor]):
+        dyn = self.dynamics
+        eng, g = dyn.fused_engine(Z.device, edge_index, nfs, self._combined)
+        N, p, d = Z.size(0), self.pos_dim, self.node_nfs[0] - self.pos_dim
+        nx, nh = torch.empty(N, p, device=Z.device), torch.empty(N, d, device=Z.device)
+        o = self._frag_off
+        views = []
+        for f in range(len(masks)):  # draw order of sample_combined_position_feature_noise: positions, then features
+            views += [nx[o[f]:o[f + 1]], nh[o[f]:o[f + 1]]]
+        cond = None
+        if dyn.condition_nf > 0:
+            cond = conditions.to(torch.float32).reshape(self._B, -1).contiguous()
+        self._dev = dict(eng=eng, nx=nx, nh=nh, views=views, cond=cond, sub=g["sub_flat"] if dyn.model.object_aware else None,
+                         H0=None if H0 is None else H0.to(torch.float32).contiguous())
+
+    def _device_step(self, s_int: int, Z: Tensor, tab) -> Tensor:
+        """In place on Z (fp32, contiguous, persistent across the trajectory)."""
+        dv = self._dev
+        for v in dv["views"]:
+            v.normal_()
+        self.n_evals += 1
+        dv["eng"].reverse_step(Z, dv["nx"], None if self.pos_only else dv["nh"], dv["H0"] if self.pos_only else None,
+                               dv["cond"], dv["sub"], tab["t"][s_int + 1], tab["alpha_ts"][s_int], tab["coef"][s_int],
+                               tab["sigma"][s_int])
+        return Z
+
     # ---------------------------------------------------------------- drivers
     def _setup(self, n_samples, fragments_nodes):
         masks = [get_mask_for_frag(n) for n in fragments_nodes]
@@ -361,12 +395,18 @@ class EnVariationalDiffusion(nn.Module):
         if self._fast_ok():
             tab = self._tables(timesteps, dev)
             self._seg_setup(masks)
-            Z = torch.cat(z).to(torch.float32)
+            Z = torch.cat(z).to(torch.float32).contiguous()
             H0 = torch.cat(h0).to(Z.dtype) if self.pos_only else None
+            on_device = self._device_ok(dev)
+            if on_device:
+                self._device_setup(Z, masks, edge_index, nfs, conditions, H0)
             for s in reversed(range(0, timesteps)):
-                Z = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
-                if self.pos_only:
-                    Z[:, self.pos_dim:] = H0
+                if on_device:
+                    self._device_step(s, Z, tab)
+                else:
+                    Z = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
+                    if self.pos_only:
+                        Z[:, self.pos_dim:] = H0
                 if (s * return_frames) % timesteps == 0:
                     out_samples[(s * return_frames) // timesteps] = self.normalizer.unnormalize_z([v.clone() for v in self._views(Z)])
             z = self._views(Z)
@@ -416,25 +456,33 @@ class EnVariationalDiffusion(nn.Module):
             tab = self._tables(timesteps, dev)
             self._seg_setup(masks)
             gamma_cpu = self.schedule.gamma_module.gamma.detach().float().cpu()
-            Z = torch.cat(z).to(torch.float32)
+            Z = torch.cat(z).to(torch.float32).contiguous()
             Xf = torch.cat(xh_fixed).to(torch.float32)
             H0 = torch.cat(h0).to(Z.dtype)
             known = torch.cat([torch.full((len(m), 1), ii in frag_fixed, dtype=torch.bool, device=dev)
                                for ii, m in enumerate(masks)])
+            on_device = self._device_ok(dev)
+            if on_device:
+                self._device_setup(Z, masks, edge_index, nfs, conditions, H0 if self.pos_only else None)
             for i, n_denoise_steps in enumerate(schedule):
                 for j in range(n_denoise_steps):
                     # known fragments: q(z_s | x) (noised_representation); unknown: reverse step from z_t
                     Z_known = tab["alpha"][s] * Xf + tab["sigma_abs"][s] * self._noise_cat(masks)
-                    Z_unknown = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
-                    Z = torch.where(known, Z_known, Z_unknown)
+                    if on_device:
+                        self._device_step(s, Z, tab)
+                        torch.where(known, Z_known, Z, out=Z)
+                    else:
+                        Z_unknown = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
+                        Z = torch.where(known, Z_known, Z_unknown)
                     if self.pos_only:
                         Z[:, p:] = H0
                     if j == n_denoise_steps - 1 and i < len(schedule) - 1:  # jump back `jump_length` steps
                         t = s + jump_length
                         g_s, g_t = gamma_cpu[s].view(1, 1), gamma_cpu[t].view(1, 1)
                         _, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(g_t, g_s, g_s)
-                        Z = float(alpha_ts) * Z + float(sigma_ts) * self._noise_cat(masks)
-                        Z[:, :p] = self._remove_mean_cat(Z[:, :p])
+                        Zj = float(alpha_ts) * Z + float(sigma_ts) * self._noise_cat(masks)
+                        Zj[:, :p] = self._remove_mean_cat(Zj[:, :p])
+                        Z = Z.copy_(Zj) if on_device else Zj  # the device step replays a graph on Z's storage
                         s = t
                     s = s - 1
             z = self._views(Z)

@@ -78,14 +78,49 @@ class EGNNDynamics(BaseDynamics):
             seg = n_frag_switch * n_samples + combined_mask
             n_seg = len(self.fragment_names) * n_samples
             cnt = torch.zeros(max(n_seg, 1), device=seg.device).index_add_(0, seg, torch.ones_like(seg, dtype=torch.float32))
-            self._graph = dict(sub=sub[:, None], frag_index=frag_index, seg=seg, n_seg=max(n_seg, 1),
-                               inv_cnt=(1.0 / cnt.clamp(min=1))[:, None])
+            self._graph = dict(sub=sub[:, None], sub_flat=sub.to(torch.int64).contiguous(), frag_index=frag_index, seg=seg,
+                               n_seg=max(n_seg, 1), n_samples=n_samples, inv_cnt=(1.0 / cnt.clamp(min=1))[:, None])
             self._graph_key = key
         return self._graph
+
+    # ---- device-resident path: prologue, LEFTNet and epilogue behind the C ABI (oard_dyn_forward / oard_reverse_step)
+    def fused_ok(self, device) -> bool:
+        return (isinstance(self.model, LEFTNetB200) and torch.device(device).type == "cuda" and self.pos_dim == 3
+                and len(set(self.node_nfs)) == 1 and self.node_nfs[0] - 3 <= 16 and self.update_pocket_coords
+                and len(self.fragment_names) <= 8 and getattr(self, "use_fused", True))
+
+    def fused_engine(self, device, edge_index: Tensor, n_frag_switch: Tensor, combined_mask: Tensor):
+        """The model's engine with weights, plan and dynamics plan current for this graph; returns (engine, graph cache)."""
+        g = self._graph_cache(edge_index, n_frag_switch, combined_mask)
+        eng = self.model.engine(device)
+        if not (self.model.assume_static_weights and eng.weights_key is not None):
+            eng.sync_weights(self.model)
+        eng.plan(edge_index, combined_mask.numel())
+        if not (self.model.assume_static_weights and getattr(eng, "dyn_weights_key", None) is not None):
+            eng.dyn_sync(self, len(self.fragment_names), self.node_nfs[0], self.condition_nf, self.condition_time)
+        eng.dyn_plan(n_frag_switch, combined_mask, g["n_samples"])
+        return eng, g
+
+    @torch.no_grad()
+    def _forward_fused(self, xh, edge_index, t, conditions, n_frag_switch, combined_mask):
+        dev = xh[0].device
+        eng, g = self.fused_engine(dev, edge_index, n_frag_switch, combined_mask)
+        B = g["n_samples"]
+        Z = torch.cat(xh).to(torch.float32).contiguous()
+        tb = None
+        if self.condition_time:
+            tb = (t.reshape(1).expand(B) if t.numel() == 1 else t.reshape(-1)).to(torch.float32).contiguous()
+        cond = conditions.to(torch.float32).reshape(B, -1).contiguous() if self.condition_nf > 0 else None
+        sub = g["sub_flat"] if self.model.object_aware else None
+        eps = eng.dyn_forward(Z, tb, cond, sub, torch.empty_like(Z))
+        fi = g["frag_index"]
+        return [eps[fi[ii]:fi[ii + 1]] for ii in range(len(self.fragment_names))], None
 
     def forward(self, xh: List[Tensor], edge_index: Tensor, t: Tensor, conditions: Tensor, n_frag_switch: Tensor,
                 combined_mask: Tensor, edge_attr: Optional[Tensor] = None) -> Tuple[List[Tensor], Tensor]:
         """Predict eps for every fragment (egnn_dynamics.py:63-168).  Returns (list of [N_f, node_nf], None)."""
+        if edge_attr is None and self.fused_ok(xh[0].device):
+            return self._forward_fused(xh, edge_index, t, conditions, n_frag_switch, combined_mask)
         g = self._graph_cache(edge_index, n_frag_switch, combined_mask)
         p = self.pos_dim
         pos = torch.cat([_xh[:, :p] for _xh in xh], dim=0)

@@ -164,6 +164,7 @@ class _Engine:
         ei = edge_index.detach().to("cpu", torch.int64).contiguous()
         _lib.check(self.lib.oard_plan(self.h, n_nodes, ei.size(1), C.c_void_p(ei.data_ptr())))
         self.plan_key, self.N, self.E = key, n_nodes, ei.size(1)
+        self.dyn_plan_key = None
 
     def forward(self, h: Tensor, pos: Tensor, sub: Optional[Tensor]):
         h = h.detach().to(torch.float32).contiguous()
@@ -180,6 +181,57 @@ class _Engine:
                                          C.c_void_p(h_out.data_ptr()), C.c_void_p(dpos.data_ptr()),
                                          self._stream(self.device)))
         return h_out, dpos
+
+    # ---- device-resident dynamics wrapper + reverse step (include/oard.h)
+    def dyn_sync(self, dynamics: nn.Module, n_frag: int, node_nf: int, condition_nf: int, condition_time: bool):
+        """Push the encoder / decoder MLPs of an EGNNDynamics (dynamics/_base.py:91-109) into the handle."""
+        cfg_key = (n_frag, node_nf, condition_nf, bool(condition_time))
+        if getattr(self, "dyn_cfg_key", None) != cfg_key:
+            _lib.check(self.lib.oard_dyn_configure(self.h, n_frag, node_nf, max(condition_nf, 0), int(condition_time)))
+            self.dyn_names = [self.lib.oard_dyn_weight_name(self.h, i).decode()
+                              for i in range(self.lib.oard_dyn_num_weights(self.h))]
+            self.dyn_cfg_key, self.dyn_weights_key, self.dyn_plan_key = cfg_key, None, None
+        sd = {**{"encoders." + k: v for k, v in dynamics.encoders.state_dict(keep_vars=True).items()},
+              **{"decoders." + k: v for k, v in dynamics.decoders.state_dict(keep_vars=True).items()}}
+        key = tuple((sd[n].data_ptr(), sd[n]._version) for n in self.dyn_names)
+        if key == self.dyn_weights_key:
+            return
+        st = self._stream(self.device)
+        for name in self.dyn_names:
+            t = sd[name]
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            _lib.check(self.lib.oard_dyn_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), 1, st))
+        self.dyn_weights_key = key
+
+    def dyn_plan(self, n_frag_switch: Tensor, combined_mask: Tensor, n_samples: int):
+        key = (self.plan_key, n_frag_switch.data_ptr(), n_frag_switch._version, combined_mask.data_ptr(),
+               combined_mask._version, n_samples)
+        if key == getattr(self, "dyn_plan_key", None):
+            return
+        nf = n_frag_switch.detach().to("cpu", torch.int64).contiguous()
+        cm = combined_mask.detach().to("cpu", torch.int64).contiguous()
+        if nf.numel() != self.N or cm.numel() != self.N:
+            raise ValueError(f"n_frag_switch / combined_mask must have {self.N} entries")
+        _lib.check(self.lib.oard_dyn_plan(self.h, C.c_void_p(nf.data_ptr()), C.c_void_p(cm.data_ptr()), n_samples))
+        self.dyn_plan_key = key
+
+    @staticmethod
+    def _ptr(t: Optional[Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def dyn_forward(self, xh: Tensor, t: Optional[Tensor], cond: Optional[Tensor], sub: Optional[Tensor], out: Tensor):
+        """eps = EGNNDynamics.forward on the concatenated fragments; all tensors fp32 / int64, contiguous, on the device."""
+        _lib.check(self.lib.oard_dyn_forward(self.h, self._ptr(xh), self._ptr(t), self._ptr(cond), self._ptr(sub),
+                                             self._ptr(out), self._stream(self.device)))
+        return out
+
+    def reverse_step(self, z: Tensor, noise_x: Tensor, noise_h: Optional[Tensor], h0: Optional[Tensor],
+                     cond: Optional[Tensor], sub: Optional[Tensor], t: float, alpha_ts: float, coef: float, sigma: float):
+        """z_t -> z_s in place (one CUDA-graph launch)."""
+        _lib.check(self.lib.oard_reverse_step(self.h, self._ptr(z), self._ptr(noise_x), self._ptr(noise_h), self._ptr(h0),
+                                              self._ptr(cond), self._ptr(sub), t, alpha_ts, coef, sigma,
+                                              self._stream(self.device)))
 
     # ---- parity instrumentation
     def set_debug(self, on: bool):

@@ -56,7 +56,17 @@ def main():
     eng = dyn.model.engine(dev)
     out = {}
 
-    # (c) full reverse step (what sample() runs per step)
+    # (c) full reverse step (what sample() runs per step): device-resident step (one CUDA graph) and the host-composed one
+    Zd = Z.clone().contiguous()
+    ddpm._device_setup(Zd, masks, edge_index, nfs, cond, H0)
+
+    def dstep():
+        Zd.copy_(Z)
+        ddpm._device_step(500, Zd, tab)
+    out["device_step_ms"], out["device_step_host_ms"] = timed(dstep, reps)
+    _, out["device_step_host_unthrottled_ms"] = timed(dstep, 6, warm=0)
+    dyn.use_fused = False
+
     def step():
         z = ddpm._fast_step(500, Z, tab, edge_index, nfs, masks, cond)
         z[:, 3:] = H0
@@ -70,6 +80,8 @@ def main():
     def dyn_fwd():
         dyn(xh=ddpm._views(Z), edge_index=edge_index, t=tt, conditions=cond, n_frag_switch=nfs, combined_mask=ddpm._combined)
     out["dynamics_ms"], out["dynamics_host_ms"] = timed(dyn_fwd, reps)
+    dyn.use_fused = True
+    out["dynamics_fused_ms"], out["dynamics_fused_host_ms"] = timed(dyn_fwd, reps)
 
     # (a) LEFTNet evaluation alone through the C ABI
     N = Z.size(0)

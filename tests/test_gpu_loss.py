@@ -13,6 +13,7 @@ from tests.util import dyn_state_dict, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+ZERO = 1e-6  # |term| below this is treated as zero (absolute)
 
 
 class _ReplayDraws(ob.EnVariationalDiffusion):
@@ -57,8 +58,10 @@ def test_loss_terms_vs_reference_golden(name):
     for k in ("error_t", "loss_0_x", "loss_0_cat", "loss_0_charge", "net_eps_xh", "eps_xh"):
         for f in range(3):
             ref = g[f"{k}{f}"]
-            if np.abs(ref).max() == 0:
-                assert float(lt[k][f].abs().max()) == 0.0, (k, f)
+            if np.abs(ref).max() < ZERO:
+                # terms that are zero up to the 1e-10 epsilon inside log(cdf - cdf + eps) (en_diffusion.py:420-446): the fp64
+                # reference keeps ~1e-9 there, any fp32 evaluation (the reference's own included) gives exactly 0
+                assert float(lt[k][f].abs().max()) < ZERO, (k, f)
                 continue
             e = rel_err(lt[k][f].cpu(), ref)
             worst, worst_ref = max(worst, e), max(worst_ref, rel_err(g[f"{k}{f}_f32"], ref))

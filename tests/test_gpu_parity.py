@@ -264,10 +264,11 @@ def test_c_abi_error_codes():
     lib.oard_destroy(h)
 
 
-def _sample_once(debug_asserts, seed, T=12, inpaint=False):
+def _sample_once(debug_asserts, seed, T=12, inpaint=False, use_fused=True):
     cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2, cutoff=5.0)
     sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 3, cfg, prefix_model="model.")
     dyn = make_dynamics(cfg, sd)
+    dyn.use_fused = use_fused
     sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
     ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True,
                                      debug_asserts=debug_asserts).to(DEV)
@@ -293,4 +294,55 @@ def test_fast_sampler_path_equals_reference_structured_path(inpaint):
     assert n1 == n2
     for a, b in zip(fast, slow):
         assert rel_err(a[:, :3], b[:, :3]) < 2e-4, rel_err(a[:, :3], b[:, :3])
+        assert torch.equal(a[:, 3:], b[:, 3:])
+
+
+def _dyn_inputs(name):
+    g = load_golden(name)
+    nfs_list = [int(x) for x in g["node_nfs"]]
+    dyn = make_dynamics(g["cfg"], dyn_state_dict(g), nfs_list, int(g["condition_nf"]))
+    xh = [torch.from_numpy(g[f"xh{f}"]).float().to(DEV) for f in range(len(nfs_list))]
+    args = (xh, torch.from_numpy(g["edge_index"]).to(DEV), torch.from_numpy(g["t"]).float().to(DEV),
+            torch.from_numpy(g["cond"]).float().to(DEV), torch.from_numpy(g["n_frag_switch"]).to(DEV),
+            torch.from_numpy(g["combined_mask"]).to(DEV))
+    return g, dyn, args
+
+
+@pytest.mark.parametrize("name", ["dyn_trained_cfg1", "dyn_trained_b4", "dyn_trained_b3_far"])
+def test_device_dynamics_equals_host_composed_dynamics(name):
+    """oard_dyn_forward (encoders, time/condition channels, NaN guard, CoM removal, decoders as CUDA kernels around the
+    LEFTNet graph) against the torch-composed wrapper around the same LEFTNet kernels, and against the reference golden."""
+    g, dyn, args = _dyn_inputs(name)
+    assert dyn.fused_ok(DEV)
+    for _ in range(3):  # eager first call, then the cached forward graph
+        fused, _ = dyn(*args)
+    dyn.use_fused = False
+    host, _ = dyn(*args)
+    for f in range(len(fused)):
+        e = rel_err(fused[f].cpu(), host[f].cpu())
+        e64 = rel_err(fused[f].cpu(), g[f"out{f}_f64"])
+        print(f"{name} frag{f}: fused vs host-composed {e:.2e}; vs fp64 reference {e64:.2e}")
+        assert e < 1e-4 and e64 < REL_TOL  # encoder/decoder MLPs: in-kernel fma chains vs cuBLAS
+
+
+def test_device_nan_guard_replaces_output_with_noise():
+    """egnn_dynamics.py:138-143: a NaN anywhere in the velocity replaces the whole velocity by noise (then CoM-free)."""
+    g, dyn, args = _dyn_inputs("dyn_trained_b4")
+    xh = [x.clone() for x in args[0]]
+    xh[1][0, 0] = float("nan")
+    out, _ = dyn(xh, *args[1:])
+    vel = torch.cat([o[:, :3] for o in out])
+    assert bool(torch.isfinite(vel).all()) and 0.5 < float(vel.std()) < 1.5
+
+
+@pytest.mark.parametrize("inpaint", [False, True])
+def test_device_reverse_step_equals_host_fast_step(inpaint):
+    """oard_reverse_step (one CUDA graph per step) against the host-composed `_fast_step` with the same CUDA RNG seed."""
+    devp, n1 = _sample_once(False, 11, inpaint=inpaint)
+    hostp, n2 = _sample_once(False, 11, inpaint=inpaint, use_fused=False)
+    assert n1 == n2
+    for a, b in zip(devp, hostp):
+        e = rel_err(a[:, :3], b[:, :3])
+        print(f"device step vs host step (inpaint={inpaint}): {e:.2e}")
+        assert e < 2e-4, e
         assert torch.equal(a[:, 3:], b[:, 3:])
