@@ -28,9 +28,10 @@ __device__ __forceinline__ void silu4_shared_rcp(float& u0, float& u1, float& u2
 // (B) raw distance + cutoff/same-fragment edge mask.  leftnet.py:747-753
 __global__ void k_edge_mask(int E, const int* __restrict__ esrc, const int* __restrict__ ecol,
                             const float* __restrict__ pos, const int64_t* __restrict__ sub, float cutoff,
-                            uint8_t* __restrict__ mask) {
+                            uint8_t* __restrict__ mask, uint8_t* __restrict__ sub8) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  sub8[e] = (sub == nullptr || sub[e] > 0);  // same-fragment relation (an equivalence): groups of k_equi_frag
   const int i = esrc[e], j = ecol[e];
   const float dx = pos[i * 3 + 0] - pos[j * 3 + 0], dy = pos[i * 3 + 1] - pos[j * 3 + 1],
               dz = pos[i * 3 + 2] - pos[j * 3 + 2];
@@ -142,13 +143,19 @@ __global__ void k_group_ids(int N, const int* __restrict__ owner, const uint8_t*
 // (E) edge geometry on pos_frame, masked (leftnet.py:693-705,764-771,785): geo[e] = (u_x,u_y,u_z,dist), rb[e];
 // also counts the row's active edges.  One warp per CSR row.
 __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
-                            const uint8_t* __restrict__ mask, const float* __restrict__ pf, float cutoff,
-                            float4* __restrict__ geo, float* __restrict__ rb, int* __restrict__ row_cnt) {
+                            const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sub8,
+                            const float* __restrict__ pf, float cutoff, float4* __restrict__ geo, float* __restrict__ rb,
+                            int* __restrict__ row_cnt, int* __restrict__ leader, int* __restrict__ glocal) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= N) return;
   const float ax = pf[t * 3 + 0], ay = pf[t * 3 + 1], az = pf[t * 3 + 2];
-  int cnt = 0;
+  int cnt = 0, lead = t, below = 0;
   for (int e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) {
+    if (sub8[e]) {  // same-group neighbour: the group's leader is its smallest node id, glocal = rank inside the group
+      const int j = ecol[e];
+      lead = min(lead, j);
+      below += j < t;
+    }
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     float r = 1.0f;  // 0.5*(cos(0)+1)
     if (mask[e]) {
@@ -164,12 +171,16 @@ __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* _
     rb[e] = r;
   }
   cnt = (int)warp_sum((float)cnt);
-  if (lane == 0) row_cnt[t] = cnt;
+  below = (int)warp_sum((float)below);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
+  if (lane == 0) { row_cnt[t] = cnt; leader[t] = lead; glocal[t] = below; }
 }
 
 // exclusive scan of row_cnt -> row_act_ptr[N+1], n_act = total.  Single block.
 __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restrict__ row_act_ptr,
-                            int* __restrict__ n_act) {
+                            int* __restrict__ n_act, const int* __restrict__ leader, int* __restrict__ lead_list,
+                            int* __restrict__ n_lead, int* __restrict__ work_ctr, int n_ctr) {
   __shared__ int sm[1025];
   const int T = blockDim.x, tid = threadIdx.x, per = (N + T - 1) / T;
   const int b = min(N, tid * per), e = min(N, b + per);
@@ -184,6 +195,20 @@ __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restr
   int run = sm[tid];
   for (int i = b; i < e; i++) { row_act_ptr[i] = run; run += row_cnt[i]; }
   if (tid == T - 1) { row_act_ptr[N] = sm[T]; *n_act = sm[T]; }
+  // ordered compaction of the group leaders (leader[t] == t) and reset of the per-layer work counters of k_equi_frag
+  __syncthreads();
+  s = 0;
+  for (int i = b; i < e; i++) s += leader[i] == i;
+  sm[tid + 1] = s;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= T; i++) sm[i] += sm[i - 1];
+  __syncthreads();
+  run = sm[tid];
+  for (int i = b; i < e; i++)
+    if (leader[i] == i) lead_list[run++] = i;
+  if (tid == T - 1) *n_lead = sm[T];
+  if (tid < n_ctr) work_ctr[tid] = 0;
 }
 
 // ordered compaction of active edges: act_idx[p] = e, act_pos[e] = p or -1.  One warp per row.
@@ -451,6 +476,127 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
     *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
     *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
     *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+  }
+}
+
+// EquiMessage message + aggregation, group-staged form of k_equi_reduce (reflect_equiv only; same arithmetic).  A "group"
+// is a class of the same-fragment relation (sub8): every active source of a target lies in the target's group, so the
+// X and vec rows a group needs (the L2 gather traffic that bounded k_equi_reduce: 2 x 3H floats per edge) are staged ONCE
+// in shared memory and the kernel streams only G[E_act, 3H] from HBM.  Work item = (group, channel slice of CH channels);
+// items are handed out through an atomic counter (dynamic balance; results do not depend on the assignment).  Inside an
+// item each warp takes the group's targets round-robin; lane = (q, e4): float4 column q of the slice, edge slot e4 of 4
+// edges in flight (x2 unrolled); the four partial sums are combined by a fixed shuffle tree (bitwise reproducible).
+template <int CH>
+__global__ void __launch_bounds__(256) k_equi_frag(
+    int H, int NS, int gmax, const int* __restrict__ n_lead, const int* __restrict__ lead_list, int* __restrict__ work_ctr,
+    const int* __restrict__ row_ptr, const int* __restrict__ ecol, const uint8_t* __restrict__ sub8,
+    const int* __restrict__ glocal, const int* __restrict__ row_act_ptr, const int* __restrict__ act_tr,
+    const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float* __restrict__ G,
+    const float* __restrict__ X, const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
+  constexpr int Q = CH / 4;  // float4 columns per slice
+  extern __shared__ __align__(16) float4 ef_sm[];
+  float4* Xs = ef_sm;                       // [gmax][3][Q]
+  float4* Vs = ef_sm + (size_t)gmax * 3 * Q;  // [gmax][3][Q]
+  int* members = reinterpret_cast<int*>(Vs + (size_t)gmax * 3 * Q);  // [gmax]
+  __shared__ int w_sh, gs_sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int q = lane >> 2, e4 = lane & 3;
+  const bool on = q < Q;
+  const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
+  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  const int total = *n_lead * NS;
+  for (;;) {
+    __syncthreads();  // previous item fully consumed (smem reuse, w_sh)
+    if (tid == 0) w_sh = atomicAdd(work_ctr, 1);
+    __syncthreads();
+    const int w = w_sh;
+    if (w >= total) break;
+    const int b = lead_list[w / NS], h0 = (w % NS) * CH;
+    if (warp == 0) {  // ordered member list: the leader, then its same-group neighbours (ascending, CSR order)
+      int cnt = 1;
+      if (lane == 0) members[0] = b;
+      const int r0 = row_ptr[b], r1 = row_ptr[b + 1];
+      for (int e0 = r0; e0 < r1; e0 += 32) {
+        const int e = e0 + lane;
+        const bool a = e < r1 && sub8[e];
+        const unsigned bal = __ballot_sync(0xffffffffu, a);
+        if (a) members[cnt + __popc(bal & ((1u << lane) - 1u))] = ecol[e];
+        cnt += __popc(bal);
+      }
+      if (lane == 0) gs_sh = cnt;
+    }
+    __syncthreads();
+    const int gs = gs_sh;
+    for (int i = tid; i < gs * 3 * Q; i += blockDim.x) {
+      const int m = i / (3 * Q), r = i - m * 3 * Q, c = r / Q, qq = r - c * Q;
+      const size_t off = (size_t)members[m] * 3 * H + (size_t)c * H + h0 + 4 * qq;
+      Xs[i] = ld4(X + off);
+      Vs[i] = ld4(vec_in + off);
+    }
+    __syncthreads();
+    for (int tl = warp; tl < gs; tl += nw) {
+      const int t = members[tl];
+      const int p0 = row_act_ptr[t], p1 = row_act_ptr[t + 1];
+      float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
+      float4 x0 = dx, x1 = dx, x2 = dx;
+      if (on) { x0 = Xs[(tl * 3 + 0) * Q + q]; x1 = Xs[(tl * 3 + 1) * Q + q]; x2 = Xs[(tl * 3 + 2) * Q + q]; }
+      auto edge = [&](int pr, int al, const float4 gm, const float4 g0, const float4 g1, const float4 g2) {
+        const float ux = -gm.x, uy = -gm.y, uz = -gm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
+        const float4 a0 = Xs[(al * 3 + 0) * Q + q], a1 = Xs[(al * 3 + 1) * Q + q], a2 = Xs[(al * 3 + 2) * Q + q];
+        const float4 v0 = Vs[(al * 3 + 0) * Q + q], v1 = Vs[(al * 3 + 1) * Q + q], v2 = Vs[(al * 3 + 2) * Q + q];
+#define OARD_EQF(c)                                                                          \
+        {                                                                                    \
+          const float al_ = (a0.c + x0.c) * g0.c;                                            \
+          const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                                \
+          const float ga = (a2.c + x2.c) * g2.c;                                             \
+          const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
+          dx.c += al_;                                                                       \
+          d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+        }
+        OARD_EQF(x) OARD_EQF(y) OARD_EQF(z) OARD_EQF(w)
+#undef OARD_EQF
+        (void)pr;
+      };
+      if (on) {
+        int p = p0 + e4;
+        for (; p + 4 < p1; p += 8) {  // two edges per slot in flight
+          const int prA = act_tr[p], prB = act_tr[p + 4];
+          const int aA = glocal[act_col[p]], aB = glocal[act_col[p + 4]];
+          const float4 gmA = act_geo[p], gmB = act_geo[p + 4];
+          const float* gA = G + (size_t)prA * 3 * H + h0 + 4 * q;
+          const float* gB = G + (size_t)prB * 3 * H + h0 + 4 * q;
+          const float4 A0 = ld4(gA), A1 = ld4(gA + H), A2 = ld4(gA + 2 * H);
+          const float4 B0 = ld4(gB), B1 = ld4(gB + H), B2 = ld4(gB + 2 * H);
+          edge(prA, aA, gmA, A0, A1, A2);
+          edge(prB, aB, gmB, B0, B1, B2);
+        }
+        if (p < p1) {
+          const int prA = act_tr[p], aA = glocal[act_col[p]];
+          const float4 gmA = act_geo[p];
+          const float* gA = G + (size_t)prA * 3 * H + h0 + 4 * q;
+          edge(prA, aA, gmA, ld4(gA), ld4(gA + H), ld4(gA + 2 * H));
+        }
+      }
+      // fixed-order combination of the four edge slots
+#define OARD_RED4(v)                                                                                    \
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);         \
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, 1); v.w += __shfl_xor_sync(0xffffffffu, v.w, 1);         \
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);         \
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, 2); v.w += __shfl_xor_sync(0xffffffffu, v.w, 2);
+      OARD_RED4(dx) OARD_RED4(d0) OARD_RED4(d1) OARD_RED4(d2)
+#undef OARD_RED4
+      if (on && e4 == 0) {
+        const size_t o = (size_t)t * 3 * H + h0 + 4 * q;
+        float* sp = s + (size_t)t * H + h0 + 4 * q;
+        float4 sv = ld4(sp);
+        sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
+        *reinterpret_cast<float4*>(sp) = sv;
+        const float4 w0 = Vs[(tl * 3 + 0) * Q + q], w1 = Vs[(tl * 3 + 1) * Q + q], w2 = Vs[(tl * 3 + 2) * Q + q];
+        *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
+        *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
+        *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+      }
+    }
   }
 }
 

@@ -1,0 +1,428 @@
+// Node-level GEMMs of one LEFTNet layer (sm_100a): a lean, latency-oriented small-M kernel.  Reference:
+// oa_reactdiff/model/leftnet.py: GCL node MLP (:172-181), x_layernorm + x_proj (:244-247), EquiUpdate (:325-346, 860-864),
+// GCL x_layernorm + the node part [P | Q] of the edge MLP (:840-841, :160).
+//
+// Why: with N ~ 2.6 k node rows the ~15 node-level launches per layer are latency-bound: ~14 us each on the persistent
+// tcgen05 kernel (TMEM allocation, tensor-map fetch, a 7-deep TMA->convert->MMA pipeline for ONE tile per CTA), ~190 us
+// per layer for 1.6 % of the FLOPs.  Here a CTA stages its A tile (16*MT rows x K, split to bf16 hi/lo) in shared
+// memory with ONE round of loads, each warp streams the B fragments of its n-tiles straight from L2 into registers and
+// runs warp-level mma.sync (m16n8k16, fp32 accumulate) with the same bf16x3 split as the tcgen05 path (a_hi w_hi +
+// a_hi w_lo + a_lo w_hi).  Row-local neighbours are fused: LayerNorm (+ pos_expansion add) into the A staging, the
+// EquiUpdate scalarisation / lin3 / vec_dot into vec_proj's epilogue, the EquiUpdate apply into xvec_proj.2's epilogue.
+// A measured dead end (profiles/r1_node_chain_notes.md): carrying a 16/32-row tile through the WHOLE chain in one fat CTA
+// needs every CTA to stream the layer's 1.2-1.5 MB of weights from L2 with 13 warps per SM: 62 / 150 us per launch.
+//
+// Weights are pre-packed at oard_commit_weights in B-fragment order: for n-tile jt (8 output columns) and k-step ks
+// (16 inputs) lane l holds {hi(b0), hi(b1), lo(b0), lo(b1)} as one uint4, b0 = W[n][k0..k0+1], b1 = W[n][k0+8..k0+9],
+// n = jt*8 + l/4, k0 = ks*16 + (l%4)*2  ->  one coalesced 512-byte load per warp per (tile, k-step).  `nsplit` > 1
+// interleaves the output column blocks of a fused projection (tile jt -> part jt % nsplit, channel tile jt / nsplit) so
+// that one thread holds v1/v2 (vec_proj) or a/b/c (xvec_proj.2) of the SAME channel in its accumulators.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace oard {
+
+struct MsWeight {
+  const uint4* data;
+  int N, K, nsplit, part;  // part = N / nsplit channels per part
+  int NT8, K16;            // n-tiles (over the interleaved, padded column space) and k-steps
+};
+
+__host__ __device__ inline int ms_nt8(int N, int nsplit) { return nsplit * ((N / nsplit + 7) / 8); }
+__host__ __device__ inline int ms_k16(int K) { return (K + 15) / 16; }
+inline size_t ms_weight_elems(int N, int K, int nsplit) { return (size_t)ms_nt8(N, nsplit) * ms_k16(K) * 32; }  // uint4
+
+__global__ void k_ms_pack(const float* __restrict__ W, int ldw, int N, int K, int nsplit, uint4* __restrict__ out) {
+  const int part = N / nsplit, NT8 = nsplit * ((part + 7) / 8), K16 = (K + 15) / 16;
+  const size_t total = (size_t)NT8 * K16 * 32;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int lane = (int)(i & 31), ks = (int)((i >> 5) % K16), jt = (int)((i >> 5) / K16);
+    const int p = jt % nsplit, ch = (jt / nsplit) * 8 + (lane >> 2);
+    const int k0 = ks * 16 + (lane & 3) * 2;
+    uint32_t r[4];
+    for (int half = 0; half < 2; half++) {
+      float w[2];
+      for (int j = 0; j < 2; j++) {
+        const int k = k0 + half * 8 + j;
+        w[j] = (ch < part && k < K) ? W[(size_t)(p * part + ch) * ldw + k] : 0.f;
+      }
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(w[0], w[1]);
+      const float2 hf = __bfloat1622float2(hi);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(w[0] - hf.x, w[1] - hf.y);
+      r[half] = *reinterpret_cast<const uint32_t*>(&hi);
+      r[2 + half] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+    out[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+__device__ __forceinline__ void ms_ldmatrix4(uint32_t (&a)[4], const __nv_bfloat16* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ms_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[i][mt][r] = sum_k A[mt*16 + row(r)][k] * W[tile jt0+i][col(r)][k] over K16 k-steps.  A: bf16 hi / lo row-major in
+// shared memory, row pitch lda elements ((lda * 2) % 32 == 16: conflict-free ldmatrix), zero-padded to K16*16 columns.
+template <int MT, int NTW>
+__device__ __forceinline__ void ms_gemm_group(float (&acc)[NTW][MT][4], const __nv_bfloat16* Ahi, const __nv_bfloat16* Alo,
+                                              int lda, const MsWeight& w, int jt0, int lane) {
+#pragma unroll
+  for (int i = 0; i < NTW; i++)
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) acc[i][m][r] = 0.f;
+  const int K16 = w.K16;
+  const uint4* wp[NTW];
+#pragma unroll
+  for (int i = 0; i < NTW; i++) wp[i] = w.data + ((size_t)min(jt0 + i, w.NT8 - 1) * K16) * 32 + lane;
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+  const __nv_bfloat16* ah = Ahi + (size_t)arow * lda + acol;
+  const __nv_bfloat16* al = Alo + (size_t)arow * lda + acol;
+  constexpr int PF = 4;  // k-steps of B fragments in flight (L2 latency)
+  uint4 bq[PF][NTW];
+#pragma unroll
+  for (int u = 0; u < PF; u++)
+#pragma unroll
+    for (int i = 0; i < NTW; i++) bq[u][i] = (u < K16) ? __ldg(wp[i] + (size_t)u * 32) : make_uint4(0, 0, 0, 0);
+  for (int ks0 = 0; ks0 < K16; ks0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int ks = ks0 + u;
+      if (ks < K16) {
+        uint4 b[NTW];
+#pragma unroll
+        for (int i = 0; i < NTW; i++) {
+          b[i] = bq[u][i];
+          if (ks + PF < K16) bq[u][i] = __ldg(wp[i] + (size_t)(ks + PF) * 32);
+        }
+        // the three products of one accumulator are dependent MMAs: issue them product-major over the NTW x MT independent
+        // accumulators so that consecutive instructions never wait on each other
+        uint32_t fh[MT][4], fl[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          ms_ldmatrix4(fh[m], ah + (size_t)m * 16 * lda + ks * 16);
+          ms_ldmatrix4(fl[m], al + (size_t)m * 16 * lda + ks * 16);
+        }
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int i = 0; i < NTW; i++) ms_mma(acc[i][m], fh[m], b[i].x, b[i].y);
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int i = 0; i < NTW; i++) ms_mma(acc[i][m], fh[m], b[i].z, b[i].w);
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int i = 0; i < NTW; i++) ms_mma(acc[i][m], fl[m], b[i].x, b[i].y);
+      }
+    }
+  }
+}
+
+// store one fp32 value as bf16 hi / lo into an A-operand tile
+__device__ __forceinline__ void ms_put(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[off] = h;
+  lo[off] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void ms_put2(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float v0, float v1) {  // off even
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  const float2 hf = __bfloat1622float2(h);
+  *reinterpret_cast<__nv_bfloat162*>(hi + off) = h;
+  *reinterpret_cast<__nv_bfloat162*>(lo + off) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+}
+
+__host__ __device__ inline int ms_lda(int K) { return ms_k16(K) * 16 + 8; }  // bf16 elements; (lda*2) % 32 == 16
+
+// MODE 0: C = act(A' W^T + bias) (+ resid), A' = A or LayerNorm(A (+ add)) * gamma + beta (row-wise, fused into staging)
+// MODE 1: vec_proj (W packed with nsplit 2: v1 | v2) on A = vec[Nn, 3, H], tile = 16 nodes (rows component-major), with
+//         the EquiUpdate scalarisation on the node frame, lin3 (3 -> 48 -> 8 -> 1, SiLU) and vec_dot in the epilogue
+//         (leftnet.py:326-336):  sx = [s | lin3(scalars)], vd = <v1, v2>/sqrt(H), v2 kept for the apply step
+// MODE 2: xvec_proj.2 (W packed with nsplit 3: a | b | c) with the EquiUpdate apply in the epilogue (:338-346, 863-864):
+//         s += (a + b + vd)/sqrt2 ; vec += c * v2
+struct MsGemmArgs {
+  int M, K;
+  const float* A; int lda;
+  MsWeight w;
+  int ln; const float* add; const float* gamma; const float* beta; float* ln_out; int ld_ln_out;
+  const float* bias; int act; const float* resid; int ldres; float* C; int ldc;
+  int H, reflect;
+  const float* nodeframe; const float *l0w, *l0b, *l2w, *l2b, *l4w, *l4b;
+  const float* s_in; float* sx; float* vd; float* v2;
+  float* s; float* vec;
+};
+
+template <int MT, int NTW, int MODE, int NW>
+__global__ void __launch_bounds__(NW * 32) k_ms_gemm(const MsGemmArgs a) {
+  extern __shared__ __align__(16) uint8_t msg_sm[];
+  constexpr int R = 16 * MT;
+  const int K = a.K, lds = ms_lda(K), M = a.M;
+  __nv_bfloat16* Ah = reinterpret_cast<__nv_bfloat16*>(msg_sm);
+  __nv_bfloat16* Al = Ah + (size_t)R * lds;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  const int row0 = blockIdx.x * (MODE == 1 ? 16 : R);  // MODE 1: first node of the tile
+  const __nv_bfloat16 z16 = __float2bfloat16_rn(0.f);
+  // lin3 weights (MODE 1) as float4 broadcasts, node frames of the tile
+  float4* Wq = reinterpret_cast<float4*>(Al + (size_t)R * lds);  // [48] (w0, w1, w2, b0)
+  float4* W2t = Wq + 48;                                         // [48][2]
+  float* B2 = reinterpret_cast<float*>(W2t + 96);                // [8]
+  float* W4 = B2 + 8;                                            // [8]
+  float* NF = W4 + 8;                                            // [16][9]
+  if (MODE == 1) {
+    for (int k = tid; k < 48; k += NW * 32) {
+      Wq[k] = make_float4(a.l0w[k * 3], a.l0w[k * 3 + 1], a.l0w[k * 3 + 2], a.l0b[k]);
+      W2t[k * 2] = make_float4(a.l2w[k], a.l2w[48 + k], a.l2w[96 + k], a.l2w[144 + k]);
+      W2t[k * 2 + 1] = make_float4(a.l2w[192 + k], a.l2w[240 + k], a.l2w[288 + k], a.l2w[336 + k]);
+    }
+    for (int k = tid; k < 8; k += NW * 32) { B2[k] = a.l2b[k]; W4[k] = a.l4w[k]; }
+    for (int i = tid; i < 16 * 9; i += NW * 32) NF[i] = (row0 + i / 9 < M) ? a.nodeframe[(size_t)row0 * 9 + i] : 0.f;
+  }
+  // ---- stage the A tile (bf16 hi / lo), zero the K padding
+  if (MODE != 1 && a.ln) {
+    // LayerNorm rows: a warp takes rows warp, warp + NW, ...; four rows of loads in flight (K <= 256)
+    for (int rb = warp; rb < R; rb += 4 * NW) {
+      float v[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = rb + j * NW, row = row0 + r;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int c = lane + 32 * q;
+          float x = 0.f;
+          if (r < R && row < M && c < K) {
+            x = a.A[(size_t)row * a.lda + c];
+            if (a.add) x += a.add[(size_t)row * K + c];
+          }
+          v[j][q] = x;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = rb + j * NW, row = row0 + r;
+        if (r >= R) continue;  // warp-uniform
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) sum += v[j][q];
+        const float mean = warp_sum(sum) / (float)K;
+        float var = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const float d = (lane + 32 * q < K) ? v[j][q] - mean : 0.f; var += d * d; }
+        const float rstd = rsqrtf(warp_sum(var) / (float)K + 1e-5f);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int c = lane + 32 * q;
+          if (c < K) {
+            const float y = (v[j][q] - mean) * rstd * a.gamma[c] + a.beta[c];
+            ms_put(Ah, Al, (size_t)r * lds + c, row < M ? y : 0.f);
+            if (a.ln_out && blockIdx.y == 0 && row < M) a.ln_out[(size_t)row * a.ld_ln_out + c] = y;
+          }
+        }
+      }
+    }
+  } else {
+    // thread = (float4 column tid % 64, row group tid / 64): 8 rows of loads in flight per thread, no index division
+    const int c4n = K / 4;
+    constexpr int NRG = NW * 32 / 64;
+    for (int c4 = tid & 63; c4 < c4n; c4 += 64) {
+      const int c = c4 * 4;
+      for (int rb = (tid >> 6) * 8; rb < R; rb += 8 * NRG) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int r = rb + j;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (MODE == 1) {
+            const int comp = r >> 4, nl = r & 15;  // tile row = component * 16 + node
+            if (row0 + nl < M) v[j] = *reinterpret_cast<const float4*>(a.A + ((size_t)(row0 + nl) * 3 + comp) * a.lda + c);
+          } else if (row0 + r < M) {
+            v[j] = *reinterpret_cast<const float4*>(a.A + (size_t)(row0 + r) * a.lda + c);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          ms_put2(Ah, Al, (size_t)(rb + j) * lds + c, v[j].x, v[j].y);
+          ms_put2(Ah, Al, (size_t)(rb + j) * lds + c + 2, v[j].z, v[j].w);
+        }
+      }
+    }
+  }
+  for (int i = tid; i < R * (lds - K); i += NW * 32) {
+    const int r = i / (lds - K), c = K + (i - r * (lds - K));
+    Ah[(size_t)r * lds + c] = z16; Al[(size_t)r * lds + c] = z16;
+  }
+  __syncthreads();
+
+  const int groups = (a.w.NT8 + NTW - 1) / NTW;  // grid.y = ceil(groups / NW): one group per warp
+  const int g_begin = blockIdx.y * NW, g_end = min(groups, g_begin + NW);
+  float acc[NTW][MT][4];
+  for (int grp = g_begin + warp; grp < g_end; grp += NW) {
+    const int jt0 = grp * NTW;
+    ms_gemm_group<MT, NTW>(acc, Ah, Al, lds, a.w, jt0, lane);
+    if (MODE == 0) {
+      // residual / bias values are fetched for the whole group first (C may alias resid, so the compiler cannot hoist the
+      // loads over the stores by itself: 16 serialised L2 round trips otherwise)
+      float2 rr[NTW][MT][2], bb[NTW];
+#pragma unroll
+      for (int i = 0; i < NTW; i++) {
+        const int col = (jt0 + i) * 8 + t2;
+        const bool cv = jt0 + i < a.w.NT8 && col < a.w.N;
+        bb[i] = (a.bias && cv) ? *reinterpret_cast<const float2*>(a.bias + col) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int row = row0 + m * 16 + g + hh * 8;
+            rr[i][m][hh] = (a.resid && cv && row < M) ? *reinterpret_cast<const float2*>(a.resid + (size_t)row * a.ldres + col)
+                                                     : make_float2(0.f, 0.f);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < NTW; i++) {
+        const int col = (jt0 + i) * 8 + t2;
+        if (jt0 + i < a.w.NT8 && col < a.w.N) {
+#pragma unroll
+          for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+              const int row = row0 + m * 16 + g + hh * 8;
+              if (row < M) {
+                float v0 = acc[i][m][2 * hh] + bb[i].x, v1 = acc[i][m][2 * hh + 1] + bb[i].y;
+                if (a.act) { v0 = silu(v0); v1 = silu(v1); }
+                v0 += rr[i][m][hh].x; v1 += rr[i][m][hh].y;
+                *reinterpret_cast<float2*>(a.C + (size_t)row * a.ldc + col) = make_float2(v0, v1);
+              }
+            }
+        }
+      }
+    } else if (MODE == 1) {
+      // acc[0] = v1 tile, acc[1] = v2 tile of channel tile jt0 / 2; m = component; thread holds nodes g, g + 8, channels ch0, ch0 + 1
+      const int H = a.H, ch0 = (jt0 >> 1) * 8 + t2;
+      const float inv_sqrt_h = rsqrtf((float)H);
+      if (ch0 < H) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int nl = g + hh * 8, node = row0 + nl;
+          const float* nf = NF + nl * 9;
+          float sig[2], vdv[2];
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int r = 2 * hh + j;
+            const float v10 = acc[0][0][r], v11 = acc[0][1][r], v12 = acc[0][2][r];
+            const float s0 = v10 * nf[0] + v11 * nf[3] + v12 * nf[6];
+            float s1 = v10 * nf[1] + v11 * nf[4] + v12 * nf[7];
+            const float s2 = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
+            if (a.reflect) s1 = fabsf(s1);
+            float q[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = B2[k];
+#pragma unroll 2
+            for (int k = 0; k < 48; k += 4) {
+              float u[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const float4 w = Wq[k + i];
+                u[i] = fmaf(w.x, s0, fmaf(w.y, s1, fmaf(w.z, s2, w.w)));
+              }
+              silu4_shared_rcp(u[0], u[1], u[2], u[3]);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const float4 wa = W2t[(k + i) * 2], wb = W2t[(k + i) * 2 + 1];
+                q[0] = fmaf(wa.x, u[i], q[0]); q[1] = fmaf(wa.y, u[i], q[1]); q[2] = fmaf(wa.z, u[i], q[2]); q[3] = fmaf(wa.w, u[i], q[3]);
+                q[4] = fmaf(wb.x, u[i], q[4]); q[5] = fmaf(wb.y, u[i], q[5]); q[6] = fmaf(wb.z, u[i], q[6]); q[7] = fmaf(wb.w, u[i], q[7]);
+              }
+            }
+            silu4_shared_rcp(q[0], q[1], q[2], q[3]);
+            silu4_shared_rcp(q[4], q[5], q[6], q[7]);
+            float out = a.l4b[0];
+#pragma unroll
+            for (int k = 0; k < 8; k++) out = fmaf(W4[k], q[k], out);
+            sig[j] = out;
+            vdv[j] = (v10 * acc[1][0][r] + v11 * acc[1][1][r] + v12 * acc[1][2][r]) * inv_sqrt_h;
+          }
+          if (node < M) {
+            *reinterpret_cast<float2*>(a.sx + (size_t)node * 2 * H + ch0) =
+                *reinterpret_cast<const float2*>(a.s_in + (size_t)node * H + ch0);
+            *reinterpret_cast<float2*>(a.sx + (size_t)node * 2 * H + H + ch0) = make_float2(sig[0], sig[1]);
+            *reinterpret_cast<float2*>(a.vd + (size_t)node * H + ch0) = make_float2(vdv[0], vdv[1]);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+              *reinterpret_cast<float2*>(a.v2 + ((size_t)node * 3 + c) * H + ch0) = make_float2(acc[1][c][2 * hh], acc[1][c][2 * hh + 1]);
+          }
+        }
+      }
+    } else {
+      // acc[0..2] = a | b | c tiles of channel tile jt0 / 3; rows = nodes
+      const int H = a.H, ch0 = (jt0 / 3) * 8 + t2;
+      const float inv_sqrt_2 = 0.70710678118654752f;
+      if (ch0 < H) {
+        float2 sv[MT][2], vdv[MT][2], vv[MT][2][3], w2[MT][2][3];  // all loads first (see MODE 0)
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int node = min(row0 + m * 16 + g + hh * 8, M - 1);
+            sv[m][hh] = *reinterpret_cast<const float2*>(a.s + (size_t)node * H + ch0);
+            vdv[m][hh] = *reinterpret_cast<const float2*>(a.vd + (size_t)node * H + ch0);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              vv[m][hh][c] = *reinterpret_cast<const float2*>(a.vec + ((size_t)node * 3 + c) * H + ch0);
+              w2[m][hh][c] = *reinterpret_cast<const float2*>(a.v2 + ((size_t)node * 3 + c) * H + ch0);
+            }
+          }
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int node = row0 + m * 16 + g + hh * 8;
+            if (node < M) {
+              float2 o = sv[m][hh];
+              o.x += (acc[0][m][2 * hh] + acc[1][m][2 * hh] + vdv[m][hh].x) * inv_sqrt_2;
+              o.y += (acc[0][m][2 * hh + 1] + acc[1][m][2 * hh + 1] + vdv[m][hh].y) * inv_sqrt_2;
+              *reinterpret_cast<float2*>(a.s + (size_t)node * H + ch0) = o;
+              const float x0 = acc[2][m][2 * hh], x1 = acc[2][m][2 * hh + 1];
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                float2 q = vv[m][hh][c];
+                q.x = fmaf(x0, w2[m][hh][c].x, q.x); q.y = fmaf(x1, w2[m][hh][c].y, q.y);
+                *reinterpret_cast<float2*>(a.vec + ((size_t)node * 3 + c) * H + ch0) = q;
+              }
+            }
+          }
+      }
+    }
+  }
+}
+
+template <int MT, int MODE>
+inline size_t ms_gemm_smem(int K) {
+  return (size_t)16 * MT * ms_lda(K) * 2 * 2 + (MODE == 1 ? (48 + 96) * 16 + 16 * 4 + 16 * 9 * 4 + 32 : 0);
+}
+
+template <int MT, int NTW, int MODE, int NW>
+inline cudaError_t launch_ms_gemm(const MsGemmArgs& a, cudaStream_t st) {
+  const size_t smem = ms_gemm_smem<MT, MODE>(a.K);
+  static size_t attr_smem = 0;  // per instantiation
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_ms_gemm<MT, NTW, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  if (a.K % 4 || a.K > 256 * (a.ln ? 1 : 4) || a.w.K != a.K || a.lda % 4 || a.w.NT8 % (MODE == 0 ? 1 : NTW)) return cudaErrorInvalidValue;
+  const int groups = (a.w.NT8 + NTW - 1) / NTW;
+  dim3 grid((a.M + (MODE == 1 ? 16 : 16 * MT) - 1) / (MODE == 1 ? 16 : 16 * MT), (groups + NW - 1) / NW);
+  k_ms_gemm<MT, NTW, MODE, NW><<<grid, NW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace oard

@@ -21,6 +21,7 @@
 #include "gemm_p16.cuh"
 #include "kernels.cuh"
 #include "dynamics.cuh"
+#include "node_chain.cuh"
 
 using namespace oard;
 
@@ -76,12 +77,15 @@ struct oard_handle {
   int ldD = 0, ldH = 0, ld3H = 0;  // row pitches (floats) of the edge state / [E,H] / [E,3H] edge buffers
   int num_sms = 148;
   struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
+  struct LayerMs { MsWeight n0, n1, x0, x2, vp, xv0, xv2, pq; };  // node_chain.cuh (mma.sync fragment order)
+  std::vector<LayerMs> Ms;
+  bool use_chain = false;  // node-level GEMMs on the lean mma.sync kernel with fused LayerNorm / EquiUpdate (node_chain.cuh)
   std::vector<LayerTc> T;
   TcWeight tc_rl0{}, tc_rl2{}, tc_s2v{}, tc_ov1{}, tc_ou0{};
   std::vector<void*> tc_bufs;
   // plan
   bool planned = false;
-  int N = 0, E = 0, NC = 0;
+  int N = 0, E = 0, NC = 0, max_comp = 1;
   std::map<std::string, DevBuf> ws;  // named workspace buffers
   size_t ws_bytes = 0;
   // CUDA graph of one forward (captured on an internal stream, replayed on the caller's stream)
@@ -219,6 +223,12 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     h->ldD = h->use_p16 ? p16_ld(D_) : D_;
     h->ldH = h->use_p16 ? p16_ld(H_) : H_;
     h->ld3H = h->use_p16 ? p16_ld(3 * H_) : 3 * H_;
+    // OARD_CHAIN=1: node-level GEMMs on the mma.sync kernel with fused LayerNorm / EquiUpdate (node_chain.cuh).  Parity-green
+    // but measured SLOWER than the tcgen05 launches (legacy mma.sync issues at ~1/20 of the tcgen05 rate on sm_100:
+    // profiles/r1_node_chain_notes.md), so it is off by default.
+    const char* ec = getenv("OARD_CHAIN");
+    h->use_chain = h->use_tc && cfg->update && cfg->hidden_channels % 4 == 0 && (ec && strcmp(ec, "1") == 0) &&
+                   cfg->hidden_channels <= 256 && ms_gemm_smem<4, 0>(2 * cfg->hidden_channels) <= 227 * 1024;
     const char* eg = getenv("OARD_GRAPH");  // "0" disables CUDA-graph replay of the forward
     h->use_graph = !(eg && strcmp(eg, "0") == 0);
   }
@@ -378,6 +388,33 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.xv2w, H, 3 * H, H, &t.xv2, bn3H))) return rc;
     }
   }
+  if (h->use_chain) {
+    cudaStream_t st = (cudaStream_t)stream;
+    auto packms = [&](const float* Wp, int ldw, int N, int K, int nsplit, MsWeight* out) -> int {
+      uint4* buf = nullptr;
+      CU(cudaMalloc(&buf, ms_weight_elems(N, K, nsplit) * sizeof(uint4)));
+      h->tc_bufs.push_back(buf);
+      k_ms_pack<<<128, 256, 0, st>>>(Wp, ldw, N, K, nsplit, buf);
+      CU(cudaGetLastError());
+      *out = MsWeight{buf, N, K, nsplit, N / nsplit, ms_nt8(N, nsplit), ms_k16(K)};
+      return OARD_OK;
+    };
+    const int H = h->cfg.hidden_channels;
+    h->Ms.resize(h->cfg.num_layers);
+    int rc;
+    for (int l = 0; l < h->cfg.num_layers; l++) {
+      const LayerW& w = h->L[l];
+      auto& m = h->Ms[l];
+      if ((rc = packms(w.n0w, 2 * H, H, 2 * H, 1, &m.n0))) return rc;
+      if ((rc = packms(w.n1w, H, H, H, 1, &m.n1))) return rc;
+      if ((rc = packms(w.x0w, H, H, H, 1, &m.x0))) return rc;
+      if ((rc = packms(w.x2w, H, 3 * H, H, 1, &m.x2))) return rc;
+      if ((rc = packms(w.vpw, H, 2 * H, H, 2, &m.vp))) return rc;
+      if ((rc = packms(w.xv0w, 2 * H, H, 2 * H, 1, &m.xv0))) return rc;
+      if ((rc = packms(w.xv2w, H, 3 * H, H, 3, &m.xv2))) return rc;
+      if ((rc = packms(w.pqw, H, 2 * H, H, 1, &m.pq))) return rc;
+    }
+  }
   h->committed = true;
   return OARD_OK;
 }
@@ -467,7 +504,8 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
       {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
-      {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
+      {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"lead_list", Nn * 4},
+      {"n_lead", 16}, {"work_ctr", 64 * 4}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
       {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
       {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
       {"NE1", Nn * 3 * H * 4}, {"pe_t", Nn * (H / 2) * 4}, {"pe", Nn * H * 4}, {"xa", Nn * 2 * H * 4},
@@ -492,6 +530,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   CU(cudaMemcpy(h->buf<int>("comp_nodes"), comp_nodes.data(), Nn * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->buf<int>("node_local"), node_local.data(), Nn * 4, cudaMemcpyHostToDevice));
   h->N = N; h->E = E; h->NC = NC;
+  h->max_comp = count.empty() ? 1 : *std::max_element(count.begin(), count.end());
   h->planned = true;
   return OARD_OK;
 }
@@ -664,12 +703,26 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     h->launches++;                                                                                           \
     prof_end(h, st);                                                                                         \
   } while (0)
+#define GEMM_MS(tag, m, MT_, NTW_, MODE_, NW_)                                                                \
+  do {                                                                                                       \
+    prof_begin(h, tag, 2.0 * (m).M * (m).w.N * (m).K * ((MODE_) == 1 ? 3 : 1), 4.0 * (m).M * ((m).K + (m).w.N), false, st); \
+    cudaError_t e_ = launch_ms_gemm<MT_, NTW_, MODE_, NW_>(m, st);                                           \
+    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm_ms: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    h->launches++;                                                                                           \
+    prof_end(h, st);                                                                                         \
+  } while (0)
+  auto msa = [&](const float* A, int lda, int K, const MsWeight& w_, float* C, int ldc) {
+    MsGemmArgs m;
+    memset(&m, 0, sizeof m);
+    m.M = N; m.K = K; m.A = A; m.lda = lda; m.w = w_; m.C = C; m.ldc = ldc; m.H = H; m.reflect = c.reflect_equiv;
+    return m;
+  };
   const bool P = h->use_p16;
   const int ldD = h->ldD, ldH = h->ldH, ld3H = h->ld3H;
 
   // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
   if (E) { PB("k_edge_mask", 0, E*29.0, 0);
-    k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask); KCHECK(); }
+    k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask, h->buf<uint8_t>("sub8")); KCHECK(); }
   PB("k_group_frame", 0, N*64.0, 0);
   k_group_frame<256><<<h->NC, 128, 0, st>>>(h->buf<int>("comp_ptr"), h->buf<int>("comp_nodes"),
                                             h->buf<int>("node_local"), row_ptr, ecol, mask, pos, pf, nodeframe, pos_prjt,
@@ -682,11 +735,12 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     KCHECK();
   }
   PB("k_edge_geom", 0, E*25.0, 0);
-  k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, pf, c.cutoff, geo, rb,
-                                                    h->buf<int>("row_cnt"));
+  k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, h->buf<uint8_t>("sub8"), pf, c.cutoff, geo, rb,
+                                                    h->buf<int>("row_cnt"), h->buf<int>("leader"), h->buf<int>("glocal"));
   KCHECK();
   PB("k_scan_rows", 0, N*8.0, 0);
-  k_scan_rows<<<1, 1024, 0, st>>>(N, h->buf<int>("row_cnt"), h->buf<int>("row_act_ptr"), n_act);
+  k_scan_rows<<<1, 1024, 0, st>>>(N, h->buf<int>("row_cnt"), h->buf<int>("row_act_ptr"), n_act, h->buf<int>("leader"),
+                                  h->buf<int>("lead_list"), h->buf<int>("n_lead"), h->buf<int>("work_ctr"), 64);
   KCHECK();
   PB("k_compact", 0, E*9.0, 0);
   k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
@@ -774,12 +828,20 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     const LayerW& w = h->L[l];
     const int ldw0 = 2 * H + D;
     // ---- GCLMessage (leftnet.py:157-183).  W_a = [W_ai | W_aj | W_ae]: the x_i / x_j parts are per-node GEMMs.
-    PB("k_layernorm", 0, N*H*8.0, 0);
-    k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
-    KCHECK();
-    GemmArgs g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
-    g.bias = w.pqb;
-    GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
+    const bool chain = h->use_chain;
+    GemmArgs g;
+    if (chain) {  // x = LN(s + pos_expansion) fused into the staging of the [P | Q] GEMM
+      MsGemmArgs m = msa(s, H, H, h->Ms[l].pq, PQ, 2 * H);
+      m.ln = 1; m.add = pe; m.gamma = w.glnw; m.beta = w.glnb; m.ln_out = xa; m.ld_ln_out = 2 * H; m.bias = w.pqb;
+      GEMM_MS("gemm_gcl_PQ", m, 4, 2, 0, 4);
+    } else {
+      PB("k_layernorm", 0, N*H*8.0, 0);
+      k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
+      KCHECK();
+      g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
+      g.bias = w.pqb;
+      GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
+    }
     if (E) {
       g = mk(ew, ldD, w.e0w + 2 * H, ldw0, hid1, ldH, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
@@ -794,12 +856,21 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
     else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
     KCHECK();
-    g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
-    g.bias = w.n0b; g.act = 1;
-    GEMM_TC("gemm_gcl_node0", g, h->T[l].n0);
-    g = mk(tN, H, w.n1w, H, s, H, N, H, H);
-    g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
-    GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
+    if (chain) {
+      MsGemmArgs m = msa(xa, 2 * H, 2 * H, h->Ms[l].n0, tN, H);
+      m.bias = w.n0b; m.act = 1;
+      GEMM_MS("gemm_gcl_node0", m, 4, 2, 0, 4);
+      m = msa(tN, H, H, h->Ms[l].n1, s, H);
+      m.bias = w.n1b; m.act = c.legacy ? 0 : 1; m.resid = xa; m.ldres = 2 * H;
+      GEMM_MS("gemm_gcl_node1", m, 4, 2, 0, 4);
+    } else {
+      g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
+      g.bias = w.n0b; g.act = 1;
+      GEMM_TC("gemm_gcl_node0", g, h->T[l].n0);
+      g = mk(tN, H, w.n1w, H, s, H, N, H, H);
+      g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
+      GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
+    }
     if (E) {
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
@@ -807,14 +878,22 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
-    PB("k_layernorm", 0, N*H*8.0, 0);
-    k_layernorm<<<N, HB, 0, st>>>(H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
-    KCHECK();
-    g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
-    g.act = 1;
-    GEMM_TC("gemm_xproj0", g, h->T[l].x0);
-    g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
-    GEMM_TC("gemm_xproj2", g, h->T[l].x2);
+    if (chain) {  // message x_layernorm fused into the staging of x_proj.0
+      MsGemmArgs m = msa(s, H, H, h->Ms[l].x0, tmpH, H);
+      m.ln = 1; m.gamma = w.mlnw; m.beta = w.mlnb; m.act = 1;
+      GEMM_MS("gemm_xproj0", m, 4, 2, 0, 4);
+      m = msa(tmpH, H, H, h->Ms[l].x2, X, 3 * H);
+      GEMM_MS("gemm_xproj2", m, 4, 2, 0, 4);
+    } else {
+      PB("k_layernorm", 0, N*H*8.0, 0);
+      k_layernorm<<<N, HB, 0, st>>>(H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
+      KCHECK();
+      g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
+      g.act = 1;
+      GEMM_TC("gemm_xproj0", g, h->T[l].x0);
+      g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
+      GEMM_TC("gemm_xproj2", g, h->T[l].x2);
+    }
     if (E) {
       g = mk(ew_act, ldD, w.d0w, D, d1, ld3H, E, 3 * H, D);
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
@@ -826,10 +905,36 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
-    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 traffic)
-    k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(
-        H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"),
-        h->buf<float4>("act_geo"), G, X, pf, vec, vec2, s);
+    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
+    {
+      // group-staged kernel (k_equi_frag): channel slice CH = largest multiple of 4 that divides H and is <= 32
+      int CH = 0;
+      for (int cch = 32; cch >= 4; cch -= 4)
+        if (H % cch == 0) { CH = cch; break; }
+      const size_t ef_smem = (size_t)h->max_comp * (2 * 3 * CH * 4 + 4);
+      static int env_frag = -1;
+      if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
+      const bool frag_ok = env_frag && c.reflect_equiv && l < 64 && ef_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
+      if (frag_ok && E) {
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (ef_smem + 1024)));
+        const int grid = h->num_sms * per_sm;
+#define OARD_EF(CHV)                                                                                                   \
+        {                                                                                                              \
+          static bool attr = false;                                                                                    \
+          if (!attr) { CU(cudaFuncSetAttribute(k_equi_frag<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+          k_equi_frag<CHV><<<grid, 256, ef_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int>("lead_list"), \
+              h->buf<int>("work_ctr") + l, row_ptr, ecol, h->buf<uint8_t>("sub8"), h->buf<int>("glocal"),              \
+              h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"), h->buf<float4>("act_geo"), G, X, \
+              vec, vec2, s);                                                                                           \
+        }
+        if (CH == 28) OARD_EF(28) else if (CH == 32) OARD_EF(32) else OARD_EF(16)
+#undef OARD_EF
+      } else {
+        k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(
+            H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"),
+            h->buf<float4>("act_geo"), G, X, pf, vec, vec2, s);
+      }
+    }
     KCHECK();
     std::swap(vec, vec2);
     if (h->debug) {
@@ -838,7 +943,18 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       SNAP_EDGE("e" + l1);
     }
     // ---- EquiUpdate (leftnet.py:325-346)
-    if (c.update) {
+    if (chain) {  // EquiUpdate: scalarisation / lin3 / vec_dot in vec_proj's epilogue, the apply step in xvec_proj.2's
+      MsGemmArgs m = msa(vec, H, H, h->Ms[l].vp, nullptr, 0);
+      m.nodeframe = nodeframe; m.l0w = w.l0w; m.l0b = w.l0b; m.l2w = w.l2w; m.l2b = w.l2b; m.l4w = w.l4w; m.l4b = w.l4b;
+      m.s_in = s; m.sx = sx; m.vd = vd; m.v2 = VP;
+      GEMM_MS("gemm_vec_proj", m, 3, 2, 1, 8);
+      m = msa(sx, 2 * H, 2 * H, h->Ms[l].xv0, tN, H);
+      m.act = 1;
+      GEMM_MS("gemm_xvec0", m, 4, 2, 0, 4);
+      m = msa(tN, H, H, h->Ms[l].xv2, nullptr, 0);
+      m.s = s; m.vec = vec; m.vd = vd; m.v2 = VP;
+      GEMM_MS("gemm_xvec2", m, 4, 3, 2, 4);
+    } else if (c.update) {
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
       GEMM_TC("gemm_vec_proj", g, h->T[l].vp);
       PB("k_upd_scalar", 0, N*H*4.0*9, 0);
