@@ -348,7 +348,8 @@ def run_b200(args, rank, world, local_rank):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if dom and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        t_ = json.load(open(tpath)).get(dom)
+        traffic = t_.get("dram_bytes_per_launch") if isinstance(t_, dict) else t_  # ncu dram read+write bytes of one launch
     roof = None
     ridge = pk["tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)  # FLOP per byte where the two roofs meet (bf16 tensor vs HBM)
     if dom:
