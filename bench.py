@@ -19,6 +19,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO prints it on stdout) is silenced
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "reactions/sec full 1000-step reverse diffusion, Transition1x-shaped batch"
 UNIT = "reactions/s"

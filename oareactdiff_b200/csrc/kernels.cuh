@@ -145,16 +145,18 @@ __global__ void k_group_ids(int N, const int* __restrict__ owner, const uint8_t*
 __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
                             const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sub8,
                             const float* __restrict__ pf, float cutoff, float4* __restrict__ geo, float* __restrict__ rb,
-                            int* __restrict__ row_cnt, int* __restrict__ leader, int* __restrict__ glocal) {
+                            int* __restrict__ row_cnt, int* __restrict__ leader, int* __restrict__ glocal,
+                            int* __restrict__ gsize) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= N) return;
   const float ax = pf[t * 3 + 0], ay = pf[t * 3 + 1], az = pf[t * 3 + 2];
-  int cnt = 0, lead = t, below = 0;
+  int cnt = 0, lead = t, below = 0, gsz = 0;
   for (int e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) {
     if (sub8[e]) {  // same-group neighbour: the group's leader is its smallest node id, glocal = rank inside the group
       const int j = ecol[e];
       lead = min(lead, j);
       below += j < t;
+      gsz++;
     }
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     float r = 1.0f;  // 0.5*(cos(0)+1)
@@ -172,15 +174,17 @@ __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* _
   }
   cnt = (int)warp_sum((float)cnt);
   below = (int)warp_sum((float)below);
+  gsz = (int)warp_sum((float)gsz);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
-  if (lane == 0) { row_cnt[t] = cnt; leader[t] = lead; glocal[t] = below; }
+  if (lane == 0) { row_cnt[t] = cnt; leader[t] = lead; glocal[t] = below; gsize[t] = gsz + 1; }
 }
 
 // exclusive scan of row_cnt -> row_act_ptr[N+1], n_act = total.  Single block.
 __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restrict__ row_act_ptr,
-                            int* __restrict__ n_act, const int* __restrict__ leader, int* __restrict__ lead_list,
-                            int* __restrict__ n_lead, int* __restrict__ work_ctr, int n_ctr) {
+                            int* __restrict__ n_act, const int* __restrict__ leader, const int* __restrict__ gsize,
+                            int* __restrict__ lead_list, int2* __restrict__ lead_info, int* __restrict__ n_lead,
+                            int* __restrict__ work_ctr, int n_ctr) {
   __shared__ int sm[1025];
   const int T = blockDim.x, tid = threadIdx.x, per = (N + T - 1) / T;
   const int b = min(N, tid * per), e = min(N, b + per);
@@ -209,6 +213,21 @@ __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restr
     if (leader[i] == i) lead_list[run++] = i;
   if (tid == T - 1) *n_lead = sm[T];
   if (tid < n_ctr) work_ctr[tid] = 0;
+  // offsets of the groups' member lists (exclusive scan of the group sizes in leader order)
+  __syncthreads();
+  s = 0;
+  for (int i = b; i < e; i++) s += leader[i] == i ? gsize[i] : 0;
+  const int first = sm[tid];  // index of this thread's first leader in lead_list
+  __syncthreads();
+  sm[tid + 1] = s;
+  if (tid == 0) sm[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= T; i++) sm[i] += sm[i - 1];
+  __syncthreads();
+  int off = sm[tid], li = first;
+  for (int i = b; i < e; i++)
+    if (leader[i] == i) { lead_info[li++] = make_int2(off, gsize[i]); off += gsize[i]; }  // (member-list offset, size)
 }
 
 // ordered compaction of active edges: act_idx[p] = e, act_pos[e] = p or -1.  One warp per row.
@@ -394,14 +413,41 @@ __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restr
 // target-side aggregations into walks over contiguous index ranges [row_act_ptr[t], row_act_ptr[t+1]) with independent loads.
 __global__ void k_act_lists(const int* __restrict__ n_act, int cap, const int* __restrict__ act_idx,
                             const int* __restrict__ act_pos, const int* __restrict__ rev, const int* __restrict__ ecol,
-                            const float4* __restrict__ geo, int* __restrict__ act_tr, int* __restrict__ act_col,
-                            float4* __restrict__ act_geo) {
+                            const float4* __restrict__ geo, const int* __restrict__ glocal, int* __restrict__ act_tr,
+                            int* __restrict__ act_col, float4* __restrict__ act_geo, int2* __restrict__ act_rec) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= min(*n_act, cap)) return;
   const int e = act_idx[p];
-  act_tr[p] = act_pos[rev[e]];
-  act_col[p] = ecol[e];
+  const int tr = act_pos[rev[e]], a = ecol[e];
+  act_tr[p] = tr;
+  act_col[p] = a;
   act_geo[p] = geo[e];
+  act_rec[p] = make_int2(tr, glocal[a]);  // k_equi_frag: G row of the message edge, source's rank inside its group
+}
+
+// Member lists of the groups, once per forward: gm_node[off + i] = i-th member (ascending), gm_rap[off + i] = its range of
+// compact active edges.  One warp per group.
+__global__ void k_group_members(const int* __restrict__ n_lead, const int* __restrict__ lead_list,
+                                const int2* __restrict__ lead_info, const int* __restrict__ row_ptr,
+                                const int* __restrict__ ecol, const uint8_t* __restrict__ sub8,
+                                const int* __restrict__ row_act_ptr, int* __restrict__ gm_node, int2* __restrict__ gm_rap) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gi >= *n_lead) return;
+  const int b = lead_list[gi], off = lead_info[gi].x;
+  if (lane == 0) { gm_node[off] = b; gm_rap[off] = make_int2(row_act_ptr[b], row_act_ptr[b + 1]); }
+  int cnt = 1;
+  const int r0 = row_ptr[b], r1 = row_ptr[b + 1];
+  for (int e0 = r0; e0 < r1; e0 += 32) {
+    const int e = e0 + lane;
+    const bool a = e < r1 && sub8[e];
+    const unsigned bal = __ballot_sync(0xffffffffu, a);
+    if (a) {
+      const int j = ecol[e], o = off + cnt + __popc(bal & ((1u << lane) - 1u));
+      gm_node[o] = j;
+      gm_rap[o] = make_int2(row_act_ptr[j], row_act_ptr[j + 1]);
+    }
+    cnt += __popc(bal);
+  }
 }
 
 // EquiMessage message + aggregation at the edge target + residual (leftnet.py:263-284, 857-859): the message-passing
@@ -483,120 +529,222 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
 // is a class of the same-fragment relation (sub8): every active source of a target lies in the target's group, so the
 // X and vec rows a group needs (the L2 gather traffic that bounded k_equi_reduce: 2 x 3H floats per edge) are staged ONCE
 // in shared memory and the kernel streams only G[E_act, 3H] from HBM.  Work item = (group, channel slice of CH channels);
-// items are handed out through an atomic counter (dynamic balance; results do not depend on the assignment).  Inside an
-// item each warp takes the group's targets round-robin; lane = (q, e4): float4 column q of the slice, edge slot e4 of 4
-// edges in flight (x2 unrolled); the four partial sums are combined by a fixed shuffle tree (bitwise reproducible).
+// items are handed out through an atomic counter whose next value is fetched while the current item runs (dynamic
+// balance; results do not depend on the assignment).  Per item the dependent memory round trips are: member list + edge
+// ranges (k_group_members, once per forward) -> {X / vec rows, edge records} -> G rows.  Each warp takes the group's
+// targets round-robin; lane = (q, e4): float4 column q of the slice, edge slot e4 of 4 edges in flight (x2 unrolled); the
+// four partial sums are combined by a fixed shuffle tree (bitwise reproducible).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int EF_CE = 8;  // edges per chunk (one cp.async group)
+template <int CH>
+__host__ __device__ constexpr int ef_stage_f4() { return EF_CE * 3 * (CH / 4) + EF_CE + 2; }  // G rows | geometry | source ranks
+template <int CH>
+inline size_t ef_smem_bytes(int gmax) {
+  return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * 2 * (4 + 8) + (size_t)8 * 2 * ef_stage_f4<CH>() * 16;
+}
+
+// Messages are STAGED THROUGH SHARED MEMORY: a warp walks the chunks (<= 8 edges) of its targets; the G rows of chunk k+1
+// are in flight as one cp.async group (and the edge records of chunk k+2 as plain loads) while chunk k is evaluated, so
+// the only exposed latency per item is the first chunk's.
 template <int CH>
 __global__ void __launch_bounds__(256) k_equi_frag(
-    int H, int NS, int gmax, const int* __restrict__ n_lead, const int* __restrict__ lead_list, int* __restrict__ work_ctr,
-    const int* __restrict__ row_ptr, const int* __restrict__ ecol, const uint8_t* __restrict__ sub8,
-    const int* __restrict__ glocal, const int* __restrict__ row_act_ptr, const int* __restrict__ act_tr,
-    const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float* __restrict__ G,
-    const float* __restrict__ X, const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
+    int H, int NS, int gmax, const int* __restrict__ n_lead, const int2* __restrict__ lead_info,
+    int* __restrict__ work_ctr, const int* __restrict__ gm_node,
+    const int2* __restrict__ gm_rap, const int2* __restrict__ act_rec, const float4* __restrict__ act_geo,
+    const float* __restrict__ G, const float* __restrict__ X, const float* __restrict__ vec_in,
+    float* __restrict__ vec_out, float* __restrict__ s) {
   constexpr int Q = CH / 4;  // float4 columns per slice
+  constexpr int STG = ef_stage_f4<CH>();
   extern __shared__ __align__(16) float4 ef_sm[];
-  float4* Xs = ef_sm;                       // [gmax][3][Q]
+  float4* Xs = ef_sm;                         // [gmax][3][Q]
   float4* Vs = ef_sm + (size_t)gmax * 3 * Q;  // [gmax][3][Q]
-  int* members = reinterpret_cast<int*>(Vs + (size_t)gmax * 3 * Q);  // [gmax]
-  __shared__ int w_sh, gs_sh;
+  const int gpad = (gmax + 3) & ~3;
+  int* mem_node_all = reinterpret_cast<int*>(Vs + (size_t)gmax * 3 * Q);     // [2][gpad]   (double-buffered descriptors)
+  int2* mem_rap_all = reinterpret_cast<int2*>(mem_node_all + 2 * gpad);      // [2][gpad]
+  float4* wb_all = reinterpret_cast<float4*>(mem_rap_all + 2 * gpad);        // [8 warps][2 stages][STG]
+  __shared__ int w_sm[2];
+  __shared__ int2 info_sm[2];  // (group size, number of active edges inside the group)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int q = lane >> 2, e4 = lane & 3;
   const bool on = q < Q;
+  float4* wb = wb_all + (size_t)warp * 2 * STG;
   const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
   const int total = *n_lead * NS;
-  for (;;) {
-    __syncthreads();  // previous item fully consumed (smem reuse, w_sh)
-    if (tid == 0) w_sh = atomicAdd(work_ctr, 1);
-    __syncthreads();
-    const int w = w_sh;
-    if (w >= total) break;
-    const int b = lead_list[w / NS], h0 = (w % NS) * CH;
-    if (warp == 0) {  // ordered member list: the leader, then its same-group neighbours (ascending, CSR order)
-      int cnt = 1;
-      if (lane == 0) members[0] = b;
-      const int r0 = row_ptr[b], r1 = row_ptr[b + 1];
-      for (int e0 = r0; e0 < r1; e0 += 32) {
-        const int e = e0 + lane;
-        const bool a = e < r1 && sub8[e];
-        const unsigned bal = __ballot_sync(0xffffffffu, a);
-        if (a) members[cnt + __popc(bal & ((1u << lane) - 1u))] = ecol[e];
-        cnt += __popc(bal);
+  const int nwk = nw - 1;  // worker warps; the last warp fetches the NEXT item's descriptor while the workers run
+  // next work item -> (w, member-list offset/size, member list + edge ranges) in descriptor buffer b: three dependent
+  // global round trips that never sit on the workers' critical path
+  auto fetch_desc = [&](int b) {
+    int w2 = 0;
+    if (lane == 0) w2 = atomicAdd(work_ctr, 1);
+    w2 = __shfl_sync(0xffffffffu, w2, 0);
+    int2 inf = make_int2(0, 0);
+    int ne = 0;
+    if (w2 < total) {
+      inf = lead_info[w2 / NS];
+      for (int i = lane; i < inf.y; i += 32) {
+        const int2 rap = gm_rap[inf.x + i];
+        mem_node_all[b * gpad + i] = gm_node[inf.x + i];
+        mem_rap_all[b * gpad + i] = rap;
+        ne += rap.y - rap.x;
       }
-      if (lane == 0) gs_sh = cnt;
     }
-    __syncthreads();
-    const int gs = gs_sh;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ne += __shfl_xor_sync(0xffffffffu, ne, o);
+    if (lane == 0) { w_sm[b] = w2; info_sm[b] = make_int2(inf.y, ne); }
+  };
+  int cur = 0;
+  if (warp == nw - 1) fetch_desc(0);
+  __syncthreads();
+  for (;; cur ^= 1) {
+    const int w = w_sm[cur];
+    if (w >= total) break;
+    const int gi = w / NS, h0 = (w - gi * NS) * CH;
+    const int gs = info_sm[cur].x;
+    const int* mem_node = mem_node_all + cur * gpad;
+    const int2* mem_rap = mem_rap_all + cur * gpad;
+    if (info_sm[cur].y == 0) {
+      // no active edge inside the group (cutoff emptied): s <- s / sqrt2, vec_out <- vec_in, no staging (block-uniform branch)
+      __syncthreads();  // everyone has read the descriptor
+      if (warp == nw - 1) fetch_desc(cur ^ 1);
+      for (int i = tid; i < gs * 4 * Q; i += blockDim.x) {
+        const int m = i / (4 * Q), r = i - m * 4 * Q, c = r / Q, qq = r - c * Q;
+        const int t = mem_node[m];
+        if (c == 0) {
+          float* sp = s + (size_t)t * H + h0 + 4 * qq;
+          float4 v = ld4(sp);
+          v.x *= inv_sqrt_2; v.y *= inv_sqrt_2; v.z *= inv_sqrt_2; v.w *= inv_sqrt_2;
+          *reinterpret_cast<float4*>(sp) = v;
+        } else {
+          const size_t o = (size_t)t * 3 * H + (size_t)(c - 1) * H + h0 + 4 * qq;
+          *reinterpret_cast<float4*>(vec_out + o) = ld4(vec_in + o);
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     for (int i = tid; i < gs * 3 * Q; i += blockDim.x) {
       const int m = i / (3 * Q), r = i - m * 3 * Q, c = r / Q, qq = r - c * Q;
-      const size_t off = (size_t)members[m] * 3 * H + (size_t)c * H + h0 + 4 * qq;
-      Xs[i] = ld4(X + off);
-      Vs[i] = ld4(vec_in + off);
+      const size_t o = (size_t)mem_node[m] * 3 * H + (size_t)c * H + h0 + 4 * qq;
+      Xs[i] = ld4(X + o);
+      Vs[i] = ld4(vec_in + o);
     }
-    __syncthreads();
-    for (int tl = warp; tl < gs; tl += nw) {
-      const int t = members[tl];
-      const int p0 = row_act_ptr[t], p1 = row_act_ptr[t + 1];
-      float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
-      float4 x0 = dx, x1 = dx, x2 = dx;
-      if (on) { x0 = Xs[(tl * 3 + 0) * Q + q]; x1 = Xs[(tl * 3 + 1) * Q + q]; x2 = Xs[(tl * 3 + 2) * Q + q]; }
-      auto edge = [&](int pr, int al, const float4 gm, const float4 g0, const float4 g1, const float4 g2) {
-        const float ux = -gm.x, uy = -gm.y, uz = -gm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
-        const float4 a0 = Xs[(al * 3 + 0) * Q + q], a1 = Xs[(al * 3 + 1) * Q + q], a2 = Xs[(al * 3 + 2) * Q + q];
-        const float4 v0 = Vs[(al * 3 + 0) * Q + q], v1 = Vs[(al * 3 + 1) * Q + q], v2 = Vs[(al * 3 + 2) * Q + q];
-#define OARD_EQF(c)                                                                          \
-        {                                                                                    \
-          const float al_ = (a0.c + x0.c) * g0.c;                                            \
-          const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                                \
-          const float ga = (a2.c + x2.c) * g2.c;                                             \
-          const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
-          dx.c += al_;                                                                       \
-          d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
-        }
-        OARD_EQF(x) OARD_EQF(y) OARD_EQF(z) OARD_EQF(w)
-#undef OARD_EQF
-        (void)pr;
-      };
+    // ---- this warp's chunk walk (all control flow below is warp-uniform)
+    struct Chunk { int tl, p, pend, n; bool valid; };
+    auto mk_chunk = [&](int tl, int p, int pend) {
+      Chunk c;
+      c.tl = tl; c.p = p; c.pend = pend; c.valid = tl < gs; c.n = c.valid ? min(EF_CE, max(pend - p, 0)) : 0;
+      return c;
+    };
+    auto first_of = [&](int tl) {
+      if (tl >= gs) return mk_chunk(tl, 0, 0);
+      const int2 rap = mem_rap[tl];
+      return mk_chunk(tl, rap.x, rap.y);
+    };
+    auto advance = [&](const Chunk& c) {
+      if (!c.valid) return c;
+      if (c.p + EF_CE < c.pend) return mk_chunk(c.tl, c.p + EF_CE, c.pend);
+      return first_of(c.tl + nwk);
+    };
+    auto load_rec = [&](const Chunk& c, int2& r, float4& gm) {
+      r = make_int2(0, 0); gm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < c.n) { r = act_rec[c.p + lane]; gm = act_geo[c.p + lane]; }
+    };
+    auto issue_g = [&](const Chunk& c, const int2 r, const float4 gm, int stage) {
+      float4* gb = wb + (size_t)stage * STG;
+      if (lane < EF_CE) {
+        gb[EF_CE * 3 * Q + lane] = gm;
+        reinterpret_cast<int*>(gb + EF_CE * 3 * Q + EF_CE)[lane] = r.y;
+      }
+      const int tot = c.n * 3 * Q;
+      for (int i0 = 0; i0 < tot; i0 += 32) {
+        const int i = i0 + lane, e = min(i / (3 * Q), EF_CE - 1), rr = i - e * 3 * Q, cc = rr / Q, qq = rr - cc * Q;
+        const int tr = __shfl_sync(0xffffffffu, r.x, e);
+        if (i < tot) cp_async16(gb + i, G + (size_t)tr * 3 * H + (size_t)cc * H + h0 + 4 * qq);
+      }
+      cp_async_commit();
+    };
+    Chunk c0 = first_of(warp < nwk ? warp : gs), c1 = advance(c0);
+    int2 r0, r1;
+    float4 gm0, gm1;
+    load_rec(c0, r0, gm0);
+    load_rec(c1, r1, gm1);
+    __syncthreads();  // tiles staged
+    if (warp == nw - 1) fetch_desc(cur ^ 1);
+    if (c0.valid) issue_g(c0, r0, gm0, 0);
+    int stage = 0;
+    float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx, x0 = dx, x1 = dx, x2 = dx, sv = dx;
+    while (c0.valid) {
+      const Chunk c2 = advance(c1);
+      int2 r2;
+      float4 gm2;
+      load_rec(c2, r2, gm2);
+      if (c1.valid) { issue_g(c1, r1, gm1, stage ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+      const int tl = c0.tl;
+      if (c0.p == mem_rap[tl].x) {  // first chunk of the target
+        dx = make_float4(0.f, 0.f, 0.f, 0.f); d0 = dx; d1 = dx; d2 = dx;
+        if (on) { x0 = Xs[(tl * 3 + 0) * Q + q]; x1 = Xs[(tl * 3 + 1) * Q + q]; x2 = Xs[(tl * 3 + 2) * Q + q]; }
+        if (on && e4 == 0) sv = ld4(s + (size_t)mem_node[tl] * H + h0 + 4 * q);  // consumed when the target's last chunk is done
+      }
+      const float4* gb = wb + (size_t)stage * STG;
       if (on) {
-        int p = p0 + e4;
-        for (; p + 4 < p1; p += 8) {  // two edges per slot in flight
-          const int prA = act_tr[p], prB = act_tr[p + 4];
-          const int aA = glocal[act_col[p]], aB = glocal[act_col[p + 4]];
-          const float4 gmA = act_geo[p], gmB = act_geo[p + 4];
-          const float* gA = G + (size_t)prA * 3 * H + h0 + 4 * q;
-          const float* gB = G + (size_t)prB * 3 * H + h0 + 4 * q;
-          const float4 A0 = ld4(gA), A1 = ld4(gA + H), A2 = ld4(gA + 2 * H);
-          const float4 B0 = ld4(gB), B1 = ld4(gB + H), B2 = ld4(gB + 2 * H);
-          edge(prA, aA, gmA, A0, A1, A2);
-          edge(prB, aB, gmB, B0, B1, B2);
-        }
-        if (p < p1) {
-          const int prA = act_tr[p], aA = glocal[act_col[p]];
-          const float4 gmA = act_geo[p];
-          const float* gA = G + (size_t)prA * 3 * H + h0 + 4 * q;
-          edge(prA, aA, gmA, ld4(gA), ld4(gA + H), ld4(gA + 2 * H));
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = e4 + 4 * jj;
+          if (j < c0.n) {
+            const float4 gm = gb[EF_CE * 3 * Q + j];
+            const int al = reinterpret_cast<const int*>(gb + EF_CE * 3 * Q + EF_CE)[j];
+            const float4 g0 = gb[(j * 3 + 0) * Q + q], g1 = gb[(j * 3 + 1) * Q + q], g2 = gb[(j * 3 + 2) * Q + q];
+            const float ux = -gm.x, uy = -gm.y, uz = -gm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
+            const float4 a0 = Xs[(al * 3 + 0) * Q + q], a1 = Xs[(al * 3 + 1) * Q + q], a2 = Xs[(al * 3 + 2) * Q + q];
+            const float4 v0 = Vs[(al * 3 + 0) * Q + q], v1 = Vs[(al * 3 + 1) * Q + q], v2 = Vs[(al * 3 + 2) * Q + q];
+#define OARD_EQF(c)                                                                          \
+            {                                                                                \
+              const float al_ = (a0.c + x0.c) * g0.c;                                        \
+              const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                            \
+              const float ga = (a2.c + x2.c) * g2.c;                                         \
+              const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
+              dx.c += al_;                                                                   \
+              d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+            }
+            OARD_EQF(x) OARD_EQF(y) OARD_EQF(z) OARD_EQF(w)
+#undef OARD_EQF
+          }
         }
       }
-      // fixed-order combination of the four edge slots
+      if (c0.p + EF_CE >= c0.pend) {  // last chunk of the target: fixed-order combination of the four edge slots, write
+        const int t = mem_node[tl];
 #define OARD_RED4(v)                                                                                    \
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);         \
-      v.z += __shfl_xor_sync(0xffffffffu, v.z, 1); v.w += __shfl_xor_sync(0xffffffffu, v.w, 1);         \
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);         \
-      v.z += __shfl_xor_sync(0xffffffffu, v.z, 2); v.w += __shfl_xor_sync(0xffffffffu, v.w, 2);
-      OARD_RED4(dx) OARD_RED4(d0) OARD_RED4(d1) OARD_RED4(d2)
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);       \
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, 1); v.w += __shfl_xor_sync(0xffffffffu, v.w, 1);       \
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);       \
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, 2); v.w += __shfl_xor_sync(0xffffffffu, v.w, 2);
+        OARD_RED4(dx) OARD_RED4(d0) OARD_RED4(d1) OARD_RED4(d2)
 #undef OARD_RED4
-      if (on && e4 == 0) {
-        const size_t o = (size_t)t * 3 * H + h0 + 4 * q;
-        float* sp = s + (size_t)t * H + h0 + 4 * q;
-        float4 sv = ld4(sp);
-        sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
-        *reinterpret_cast<float4*>(sp) = sv;
-        const float4 w0 = Vs[(tl * 3 + 0) * Q + q], w1 = Vs[(tl * 3 + 1) * Q + q], w2 = Vs[(tl * 3 + 2) * Q + q];
-        *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
-        *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
-        *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+        if (on && e4 == 0) {
+          const size_t o = (size_t)t * 3 * H + h0 + 4 * q;
+          float* sp = s + (size_t)t * H + h0 + 4 * q;
+          sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
+          *reinterpret_cast<float4*>(sp) = sv;
+          const float4 w0 = Vs[(tl * 3 + 0) * Q + q], w1 = Vs[(tl * 3 + 1) * Q + q], w2 = Vs[(tl * 3 + 2) * Q + q];
+          *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
+          *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
+          *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+        }
       }
+      __syncwarp();  // the stage is free for the chunk after next
+      c0 = c1; c1 = c2; r1 = r2; gm1 = gm2; stage ^= 1;
     }
+    __syncthreads();  // tiles dead, next descriptor published
   }
 }
 

@@ -504,7 +504,8 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
       {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
-      {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"lead_list", Nn * 4},
+      {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"gsize", Nn * 4}, {"lead_list", Nn * 4}, {"lead_info", Nn * 8},
+      {"gm_node", Nn * 4}, {"gm_rap", Nn * 8}, {"act_rec", Ee * 8},
       {"n_lead", 16}, {"work_ctr", 64 * 4}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
       {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
       {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
@@ -736,19 +737,26 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   }
   PB("k_edge_geom", 0, E*25.0, 0);
   k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, h->buf<uint8_t>("sub8"), pf, c.cutoff, geo, rb,
-                                                    h->buf<int>("row_cnt"), h->buf<int>("leader"), h->buf<int>("glocal"));
+                                                    h->buf<int>("row_cnt"), h->buf<int>("leader"), h->buf<int>("glocal"), h->buf<int>("gsize"));
   KCHECK();
   PB("k_scan_rows", 0, N*8.0, 0);
   k_scan_rows<<<1, 1024, 0, st>>>(N, h->buf<int>("row_cnt"), h->buf<int>("row_act_ptr"), n_act, h->buf<int>("leader"),
-                                  h->buf<int>("lead_list"), h->buf<int>("n_lead"), h->buf<int>("work_ctr"), 64);
+                                  h->buf<int>("gsize"), h->buf<int>("lead_list"), h->buf<int2>("lead_info"), h->buf<int>("n_lead"),
+                                  h->buf<int>("work_ctr"), 64);
   KCHECK();
   PB("k_compact", 0, E*9.0, 0);
   k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
   KCHECK();
   if (E) {
     PB("k_act_lists", 0, E*40.0, 1);
-    k_act_lists<<<(E + 255) / 256, 256, 0, st>>>(n_act, E, act_idx, act_pos, rev, ecol, geo, h->buf<int>("act_tr"),
-                                                 h->buf<int>("act_col"), h->buf<float4>("act_geo"));
+    k_act_lists<<<(E + 255) / 256, 256, 0, st>>>(n_act, E, act_idx, act_pos, rev, ecol, geo, h->buf<int>("glocal"),
+                                                 h->buf<int>("act_tr"), h->buf<int>("act_col"), h->buf<float4>("act_geo"),
+                                                 h->buf<int2>("act_rec"));
+    KCHECK();
+    PB("k_group_members", 0, N*24.0, 0);
+    k_group_members<<<(N * 32 + 255) / 256, 256, 0, st>>>(h->buf<int>("n_lead"), h->buf<int>("lead_list"), h->buf<int2>("lead_info"),
+                                                        row_ptr, ecol, h->buf<uint8_t>("sub8"), h->buf<int>("row_act_ptr"),
+                                                        h->buf<int>("gm_node"), h->buf<int2>("gm_rap"));
     KCHECK();
   }
   if (E) {
@@ -911,7 +919,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       int CH = 0;
       for (int cch = 32; cch >= 4; cch -= 4)
         if (H % cch == 0) { CH = cch; break; }
-      const size_t ef_smem = (size_t)h->max_comp * (2 * 3 * CH * 4 + 4);
+      const size_t ef_smem = CH == 28 ? ef_smem_bytes<28>(h->max_comp) : (CH == 32 ? ef_smem_bytes<32>(h->max_comp) : ef_smem_bytes<16>(h->max_comp));
       static int env_frag = -1;
       if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
       const bool frag_ok = env_frag && c.reflect_equiv && l < 64 && ef_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
@@ -922,10 +930,9 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
         {                                                                                                              \
           static bool attr = false;                                                                                    \
           if (!attr) { CU(cudaFuncSetAttribute(k_equi_frag<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-          k_equi_frag<CHV><<<grid, 256, ef_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int>("lead_list"), \
-              h->buf<int>("work_ctr") + l, row_ptr, ecol, h->buf<uint8_t>("sub8"), h->buf<int>("glocal"),              \
-              h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"), h->buf<float4>("act_geo"), G, X, \
-              vec, vec2, s);                                                                                           \
+          k_equi_frag<CHV><<<grid, 256, ef_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
+              h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),     \
+              h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                          \
         }
         if (CH == 28) OARD_EF(28) else if (CH == 32) OARD_EF(32) else OARD_EF(16)
 #undef OARD_EF
