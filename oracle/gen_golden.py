@@ -216,6 +216,70 @@ def case_train_loss(name, cfg, sizes, seed, T, training):
     print(name, "ok t_int", out["t_int"].tolist(), "error_t0", out["error_t0"].tolist(), "f32", out["error_t0_f32"].tolist())
 
 
+def synthetic_raw_dataset(seed=7, n=9):
+    """A raw Transition1x-style dict (the schema transition1x.py:46-85 reads) with ragged sizes, an excluded multi-fragment
+    reaction and a `use_ind` subset."""
+    rng = np.random.RandomState(seed)
+    sizes = [int(x) for x in rng.randint(3, 9, size=n)]
+    raw = {"single_fragment": [1, 1, 0, 1, 1, 1, 1, 0, 1][:n], "use_ind": [0, 1, 3, 5, 6, 8]}
+    for k in ("reactant", "transition_state", "product"):
+        raw[k] = {"num_atoms": list(sizes), "charges": [], "positions": [], "wB97x_6-31G(d).energy": [float(x) for x in rng.randn(n)]}
+    for i, m in enumerate(sizes):
+        z = rng.choice([1, 6, 7, 8, 9], size=m).tolist()
+        for k in ("reactant", "transition_state", "product"):
+            raw[k]["charges"].append(list(z))
+            raw[k]["positions"].append((rng.randn(m, 3) * 1.3 + rng.randn(1, 3)).tolist())
+    return raw
+
+
+def case_dataset(name="dataset_small"):
+    """ProcessedTS1x + BaseDataset.collate_fn + sampling_tools of the unmodified reference on a synthetic raw dataset
+    (dataset/transition1x.py:21-150, base_dataset.py:54-88, utils/sampling_tools.py:64-149)."""
+    import copy
+    import tempfile
+    from oa_reactdiff.dataset.transition1x import ProcessedTS1x
+    from oa_reactdiff.utils.sampling_tools import assemble_sample_inputs, write_tmp_xyz
+    raw = synthetic_raw_dataset()
+    out = {"raw": json.dumps(raw)}
+    variants = {"plain": dict(single_frag_only=True, use_by_ind=False, swapping_react_prod=False),
+                "swap_useind": dict(single_frag_only=True, use_by_ind=True, swapping_react_prod=True),
+                "all_zero": dict(single_frag_only=False, use_by_ind=False, swapping_react_prod=False, zero_charge=True, center=False)}
+    out["variants"] = json.dumps(variants)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "raw.pkl")
+        for vn, kw in variants.items():
+            pickle.dump(copy.deepcopy(raw), open(path, "wb"))
+            ds = ProcessedTS1x(path, **kw)
+            idxs = [len(ds) - 1, 0, 2] if len(ds) > 2 else list(range(len(ds)))
+            reps, cond = ProcessedTS1x.collate_fn([ds[i] for i in idxs])
+            out[f"{vn}/len"] = np.int64(len(ds))
+            out[f"{vn}/idxs"] = np.array(idxs)
+            out[f"{vn}/cond"] = cond.numpy()
+            for f, r in enumerate(reps):
+                for k, v in r.items():
+                    out[f"{vn}/{k}{f}"] = v.numpy()
+            one = ds[1]
+            for k, v in one.items():
+                out[f"{vn}/item1/{k}"] = v.numpy()
+        atoms = ["C", "H", "H", "O", "N", "F"]
+        for ft in (False, True):
+            h0 = assemble_sample_inputs(atoms, device=torch.device("cpu"), n_samples=2, frag_type=ft)
+            for f in range(3):
+                out[f"h0_ft{int(ft)}_{f}"] = h0[f].numpy()
+        g = torch.Generator().manual_seed(3)
+        nodes = [torch.tensor([2, 4])] * 3
+        samples = [torch.cat([torch.randn(6, 3, generator=g), torch.zeros(6, 5), torch.tensor([[1.], [6.], [7.], [8.], [9.], [1.]])], dim=1)
+                   for _ in range(3)]
+        write_tmp_xyz(nodes, samples, idx=[0, 1, 2], prefix="gen", localpath=td, ex_ind=3)
+        for fn in sorted(os.listdir(td)):
+            if fn.endswith(".xyz"):
+                out["xyz/" + fn] = open(os.path.join(td, fn)).read()
+        for f in range(3):
+            out[f"xyz_in{f}"] = samples[f].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps({}), **out)
+    print(name, "ok", [k for k in out if k.endswith("/len")], [int(out[k]) for k in out if k.endswith("/len")])
+
+
 def t1x_histogram():
     path = "/root/reference/oa_reactdiff/data/transition1x/train.pkl"
     with open(path, "rb") as fh:
@@ -236,6 +300,9 @@ def t1x_histogram():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "dataset":  # only the dataset / sampling-tools fixture
+        case_dataset()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train_loss":  # only the loss-term fixtures
         case_train_loss("loss_small_train", SMALL_CFG, [5, 3, 4], seed=51, T=20, training=True)
         case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
@@ -264,3 +331,4 @@ if __name__ == "__main__":
     case_train_loss("loss_small_train", SMALL_CFG, [5, 3, 4], seed=51, T=20, training=True)
     case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
     case_train_loss("loss_trained_train_b4", TRAINED_CFG, [4, 9, 14, 7], seed=53, T=100, training=True)
+    case_dataset()

@@ -95,3 +95,26 @@ def test_compute_loss_composition(name):
     e = rel_err(nll.cpu(), ref)
     print(f"{name}: nll rel err {e:.2e}", nll.tolist())
     assert e < TOL and all(torch.isfinite(v) for v in info.values())
+
+
+def test_packed_batch_producer_feeds_compute_loss():
+    """data.ProcessedTS1x.batch() (pinned staging, one H2D per tensor) -> compute_loss on the CUDA path: same nll as the
+    batch collated per sample with the reference's collate_fn semantics."""
+    import copy
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_small.npz"))
+    raw = json.loads(str(z["raw"]))
+    ds = ob.ProcessedTS1x(copy.deepcopy(raw))
+    g, ddpm, _, _ = _setup("loss_small_train")
+    idxs = [4, 0, 2, 5]
+    out = []
+    for producer in (lambda: ds.batch(idxs, device=DEV),
+                     lambda: ob.ProcessedTS1x.collate_fn([{k: v.to(DEV) for k, v in ds[i].items()} for i in idxs])):
+        reps, cond = producer()
+        reps = [{k: (v.float() if k in ("pos", "one_hot", "charge") else v) for k, v in r.items()} for r in reps]
+        torch.manual_seed(5)
+        ddpm.__class__ = ob.EnVariationalDiffusion  # the plain module: its own t_int / noise draws
+        nll, info = ddpm.compute_loss((reps, cond.float()), scales=(1.0, 2.0, 1.0), training=True)
+        out.append(nll.cpu())
+    assert torch.isfinite(out[0]).all() and torch.equal(out[0], out[1])
