@@ -250,6 +250,7 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
         qr = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2;
       }
       const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
+      const float ps = (ok && g.prescale) ? g.prescale[m] : 1.f;
       const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
       ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
@@ -258,6 +259,10 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
         uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
         float v[32];
         ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+        if (g.prescale) {
+#pragma unroll
+          for (int k = 0; k < 32; k++) v[k] *= ps;
+        }
         if (HAS_AUX) {
           if (lane == 0) {
             asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PEND) : "memory");

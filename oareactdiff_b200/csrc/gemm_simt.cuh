@@ -15,6 +15,7 @@ struct GemmArgs {
   int M, N, K;
   const int* m_dev;  // optional: actual M lives in device memory (dynamic active-edge count); M is then the cap
   // epilogue, applied in this order
+  const float* prescale;                             // * prescale[m]  (row scale of the raw product, before bias)
   const float* bias;                                 // + bias[n]
   const float* radd1; const int* ridx1; int ld1;     // + radd1[ridx1[m], n]
   const float* radd2; const int* ridx2; int ld2;     // + radd2[ridx2[m], n]
@@ -127,11 +128,12 @@ __global__ void __launch_bounds__(GTHREADS) gemm_simt_kernel(const GemmArgs g) {
     const float* r1 = g.radd1 ? g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1 : nullptr;
     const float* r2 = g.radd2 ? g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2 : nullptr;
     const float rs = g.rowscale ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
+    const float ps = g.prescale ? g.prescale[m] : 1.f;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
-      float v = acc[i][j];
+      float v = acc[i][j] * ps;
       if (g.bias) v += g.bias[n];
       if (r1) v += r1[n];
       if (r2) v += r2[n];

@@ -490,6 +490,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           qr = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2;
         }
         const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
+        const float ps = (ok && g.prescale) ? g.prescale[m] : 1.f;
         const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
         ptx::tc_fence_after();
@@ -498,6 +499,10 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
           float v[32];
           ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+          if (g.prescale) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] *= ps;
+          }
           if (HAS_AUX) {
             // request the NEXT block's aux box (its buffer was last read by the store issued two blocks ago)
             if (lane == 0 && NIO > 1) { ptx::bulk_wait_read0(); issue_aux(); }
@@ -591,6 +596,12 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         {
           float v[32];
           ptx::tmem_ld32(tmem_base + buf * 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
+          if (g.prescale) {  // here thread = accumulator row (TMEM lane)
+            const int mrow = m_base + lane;
+            const float ps = mrow < M ? g.prescale[mrow] : 1.f;
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] *= ps;
+          }
 #pragma unroll
           for (int q = 0; q < 8; q++)
             *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);

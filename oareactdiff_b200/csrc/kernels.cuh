@@ -346,6 +346,42 @@ __global__ void k_layernorm(int H, const float* __restrict__ x, int ldx, const f
   }
 }
 
+// Warp-per-row LayerNorm (H <= 256): no block barriers, 8 rows per 256-thread block.  Same arithmetic as k_layernorm.
+__global__ void __launch_bounds__(256) k_layernorm_w(int rows, int H, const float* __restrict__ x, int ldx,
+                                                      const float* __restrict__ add, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int act_silu,
+                                                      float* __restrict__ out, int ldo) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= rows) return;
+  float v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int h = lane + 32 * q;
+    v[q] = 0.f;
+    if (h < H) {
+      v[q] = x[(size_t)t * ldx + h];
+      if (add) v[q] += add[(size_t)t * H + h];
+    }
+    sum += v[q];
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const float d = (lane + 32 * q < H) ? v[q] - mean : 0.f; var += d * d; }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + 1e-5f);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int h = lane + 32 * q;
+    if (h < H) {
+      float y = (v[q] - mean) * rstd;
+      if (gamma) y = y * gamma[h] + beta[h];
+      if (act_silu) y = silu(y);
+      out[(size_t)t * ldo + h] = y;
+    }
+  }
+}
+
 // (H) CFConvS2V aggregation: NE1_t[c,:] = sum_{e: tgt = t, active} f_e * u_e[c] * q[src]   (leftnet.py:116-125)
 __global__ void k_s2v(int H, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
                       const int* __restrict__ rev, const int* __restrict__ act_pos, const float* __restrict__ f_act,
@@ -365,10 +401,12 @@ __global__ void k_s2v(int H, const int* __restrict__ row_ptr, const int* __restr
 }
 
 // GCL attention gate + mean aggregation at the edge source (leftnet.py:169-183, util_funcs.py:27-45).
-// One block per node; warps take the row's edges round-robin.  m2 is scaled in place by its gate.
-__global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restrict__ m2,
-                          const float* __restrict__ w_att, const float* __restrict__ b_att, float* __restrict__ xa,
-                          int ldxa) {
+// One block per node; warps take the row's edges round-robin.  m2 is NOT rewritten: the gate is a per-edge scalar, so
+// edge_out_trans applies it to its accumulator rows (W (att m) = att (W m): GemmArgs::prescale) and this kernel only
+// stores att[e] — half the HBM traffic of the in-place version.
+__global__ void k_att_agg(int H, const int* __restrict__ row_ptr, const float* __restrict__ m2,
+                          const float* __restrict__ w_att, const float* __restrict__ b_att, float* __restrict__ att_out,
+                          float* __restrict__ xa, int ldxa) {
   extern __shared__ float part[];  // [nw][H]
   const int t = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
@@ -377,7 +415,7 @@ __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restr
   for (int k = 0; k < 8; k++) acc[k] = 0.f;
   const float ba = b_att[0];
   for (int e = r0 + w; e < r1; e += nw) {
-    float* row = m2 + (size_t)e * H;
+    const float* row = m2 + (size_t)e * H;
     float v[8], d = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -387,10 +425,11 @@ __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, float* __restr
     }
     d = warp_sum(d);
     const float att = silu(d + ba);
+    if (lane == 0) att_out[e] = att;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int h = lane + 32 * k;
-      if (h < H) { const float m = v[k] * att; row[h] = m; acc[k] += m; }
+      if (h < H) acc[k] += v[k] * att;
     }
   }
 #pragma unroll
@@ -748,6 +787,74 @@ __global__ void __launch_bounds__(256) k_equi_frag(
   }
 }
 
+// lin3 weights of the EquiUpdate (3 -> 48 -> 8 -> 1, leftnet.py:305-312) / of the edge scalarisation (3 -> H/4 -> 1, :626-630)
+// passed BY VALUE: kernel parameters live in the constant bank, so with fully unrolled loops every weight is an immediate
+// constant operand of its FFMA — no load instruction and no shared-memory traffic.  (The shared-memory float4-broadcast
+// versions were bound by the LDS return bandwidth: 3 LDS.128 = 1.5 KB per warp per hidden unit, 0.37-0.45 IPC.)
+struct Lin3U { float w0[48 * 3], b0[48], w2[8 * 48], b2[8], w4[8], b4; };
+struct Lin3E { float w0[64 * 3], b0[64], w2[64], b2; int hq; };
+
+constexpr int US_NT = 2;  // nodes per thread: the four evaluations share every weight operand
+__global__ void __launch_bounds__(256) k_upd_scalar_c(int N, int H, int reflect, const float* __restrict__ VP,
+                                                       const float* __restrict__ nodeframe, const float* __restrict__ s,
+                                                       const __grid_constant__ Lin3U W, float* __restrict__ sx,
+                                                       float* __restrict__ vd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tg = idx / H, h = idx - tg * H;
+  if (tg * US_NT >= N) return;
+  const float inv_sqrt_h = rsqrtf((float)H);
+  float s0[US_NT], s1[US_NT], s2[US_NT], vdv[US_NT], a[US_NT][8];
+#pragma unroll
+  for (int j = 0; j < US_NT; j++) {
+    const int t = min(tg * US_NT + j, N - 1);
+    const float* nf = nodeframe + (size_t)t * 9;
+    const float* vp = VP + (size_t)t * 3 * 2 * H;
+    const float v10 = vp[h], v11 = vp[2 * H + h], v12 = vp[4 * H + h];
+    const float v20 = vp[H + h], v21 = vp[3 * H + h], v22 = vp[5 * H + h];
+    s0[j] = v10 * nf[0] + v11 * nf[3] + v12 * nf[6];
+    s1[j] = v10 * nf[1] + v11 * nf[4] + v12 * nf[7];
+    s2[j] = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
+    if (reflect) s1[j] = fabsf(s1[j]);
+    vdv[j] = (v10 * v20 + v11 * v21 + v12 * v22) * inv_sqrt_h;
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[j][q] = W.b2[q];
+  }
+#pragma unroll
+  for (int k = 0; k < 48; k += 4) {
+    float u[US_NT][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float w0 = W.w0[(k + i) * 3], w1 = W.w0[(k + i) * 3 + 1], w2 = W.w0[(k + i) * 3 + 2], bb = W.b0[k + i];
+#pragma unroll
+      for (int j = 0; j < US_NT; j++) u[j][i] = fmaf(w0, s0[j], fmaf(w1, s1[j], fmaf(w2, s2[j], bb)));
+    }
+#pragma unroll
+    for (int j = 0; j < US_NT; j++) silu4_shared_rcp(u[j][0], u[j][1], u[j][2], u[j][3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const float w = W.w2[q * 48 + k + i];
+#pragma unroll
+        for (int j = 0; j < US_NT; j++) a[j][q] = fmaf(w, u[j][i], a[j][q]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < US_NT; j++) {
+    const int t = tg * US_NT + j;
+    silu4_shared_rcp(a[j][0], a[j][1], a[j][2], a[j][3]);
+    silu4_shared_rcp(a[j][4], a[j][5], a[j][6], a[j][7]);
+    float out = W.b4;
+#pragma unroll
+    for (int q = 0; q < 8; q++) out = fmaf(W.w4[q], a[j][q], out);
+    if (t < N) {
+      sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
+      sx[(size_t)t * 2 * H + H + h] = out;
+      vd[(size_t)t * H + h] = vdv[j];
+    }
+  }
+}
+
 // EquiUpdate scalarisation on the node frame + lin3 (3->48->8->1) + vec_dot  (leftnet.py:326-336).
 // One thread per (node, channel).  The lin3 weights are broadcast from shared memory as float4 ((w0,w1,w2,b0) per hidden
 // unit, the 8 second-layer weights of a hidden unit as two float4): 3 LDS.128 per hidden unit instead of 12 LDS.32 (the
@@ -919,37 +1026,28 @@ __global__ void k_edge_init_masked(int E, int ld, const int* __restrict__ act_po
 // with the weights read as float4 (w0, w1, w2, b0) shared-memory broadcasts and four SiLUs per reciprocal.  The inputs
 // of the next edge are fetched before the current one is evaluated (the index -> geometry -> NE1 chain is three
 // dependent loads deep); the row is staged in shared memory and written once, in pair16 (PAIR) or fp32.
-struct EdgeInitIn { int e; float n0, n1, n2, gx, gy, gz, cx, cy, cz, rbe, fv, rv; };
+struct EdgeInitIn { int e; float a0, a1, a2, b0, b1, b2, gx, gy, gz, cx, cy, cz, rbe, fv, rv; };
+// Thread h < H evaluates lin3 for BOTH sides (NE1 of the source and of the target) of channel h: the two evaluations share
+// every weight operand, which halves the constant-bank traffic that bounds this kernel.
 template <bool PAIR>
-__global__ void __launch_bounds__(448, 3) k_edge_init_act(
-    int H, int R, int Hq, int reflect, int ld, int cap, const int* __restrict__ n_act, const int* __restrict__ act_idx,
+__global__ void __launch_bounds__(256, 4) k_edge_init_act(
+    int H, int R, int reflect, int ld, int cap, const int* __restrict__ n_act, const int* __restrict__ act_idx,
     const int* __restrict__ esrc, const int* __restrict__ ecol, const float* __restrict__ pf,
     const float4* __restrict__ geo, const float* __restrict__ rb, const float* __restrict__ NE1,
-    const float* __restrict__ f_act, const float* __restrict__ rbf_act, const float* __restrict__ l3_w0,
-    const float* __restrict__ l3_b0, const float* __restrict__ l3_w2, const float* __restrict__ l3_b2,
+    const float* __restrict__ f_act, const float* __restrict__ rbf_act, const __grid_constant__ Lin3E W,
     float* __restrict__ ew) {
-  extern __shared__ __align__(16) float sm_ei[];  // wq[Hq4] float4 | w2[Hq4] | row[ld]
+  extern __shared__ __align__(16) float sm_ei[];  // row[ld]
   const int na = min(*n_act, cap);
-  const int Hq4 = (Hq + 3) / 4 * 4;
-  float4* wq = reinterpret_cast<float4*>(sm_ei);
-  float* w2 = sm_ei + 4 * Hq4;
-  float* row = w2 + Hq4;
+  float* row = sm_ei;
   const int t = threadIdx.x;
-  for (int k = t; k < Hq4; k += blockDim.x) {
-    const bool in = k < Hq;  // padded entries: u = 0 -> silu = 0, weight 0
-    wq[k] = in ? make_float4(l3_w0[k * 3], l3_w0[k * 3 + 1], l3_w0[k * 3 + 2], l3_b0[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    w2[k] = in ? l3_w2[k] : 0.f;
-  }
   for (int k = 3 * H + R + t; k < ld; k += blockDim.x) row[k] = 0.f;
-  const int side = t >= H, h = t - side * H;
-  const float b2 = l3_b2[0];
   auto load = [&](int p) {
     EdgeInitIn in;
     in.e = act_idx[p];
     in.fv = t < H ? f_act[(size_t)p * H + t] : 0.f;
     in.rv = t < R ? rbf_act[(size_t)p * R + t] : 0.f;
-    in.n0 = in.n1 = in.n2 = in.gx = in.gy = in.gz = in.cx = in.cy = in.cz = in.rbe = 0.f;
-    if (t < 2 * H) {
+    in.a0 = in.a1 = in.a2 = in.b0 = in.b1 = in.b2 = in.gx = in.gy = in.gz = in.cx = in.cy = in.cz = in.rbe = 0.f;
+    if (t < H) {
       const int i = esrc[in.e], j = ecol[in.e];
       const float4 g = geo[in.e];
       in.gx = g.x; in.gy = g.y; in.gz = g.z;
@@ -958,8 +1056,10 @@ __global__ void __launch_bounds__(448, 3) k_edge_init_act(
       const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2];
       const float bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
       in.cx = ay * bz - az * by; in.cy = az * bx - ax * bz; in.cz = ax * by - ay * bx;
-      const float* n = NE1 + (size_t)(side ? j : i) * 3 * H;
-      in.n0 = n[h]; in.n1 = n[H + h]; in.n2 = n[2 * H + h];
+      const float* ni = NE1 + (size_t)i * 3 * H;
+      const float* nj = NE1 + (size_t)j * 3 * H;
+      in.a0 = ni[t]; in.a1 = ni[H + t]; in.a2 = ni[2 * H + t];
+      in.b0 = nj[t]; in.b1 = nj[H + t]; in.b2 = nj[2 * H + t];
     }
     return in;
   };
@@ -972,26 +1072,36 @@ __global__ void __launch_bounds__(448, 3) k_edge_init_act(
     if (p + (int)gridDim.x < na) nxt = load(p + gridDim.x);
     if (t < H) row[2 * H + t] = cur.fv;
     if (t < R) row[3 * H + t] = cur.rv;
-    if (t < 2 * H) {
+    if (t < H) {
       const float cinv = 1.0f / (sqrtf(cur.cx * cur.cx + cur.cy * cur.cy + cur.cz * cur.cz) + OARD_EPS);
       const float cx = cur.cx * cinv, cy = cur.cy * cinv, cz = cur.cz * cinv;
       const float vx = cur.gy * cz - cur.gz * cy, vy = cur.gz * cx - cur.gx * cz, vz = cur.gx * cy - cur.gy * cx;
-      const float s0 = cur.n0 * cur.gx + cur.n1 * cur.gy + cur.n2 * cur.gz;
-      float s1 = cur.n0 * cx + cur.n1 * cy + cur.n2 * cz;
-      const float s2 = cur.n0 * vx + cur.n1 * vy + cur.n2 * vz;
-      if (reflect) s1 = fabsf(s1);
-      float acc = b2;
-      for (int k = 0; k < Hq4; k += 4) {
-        const float4 q0 = wq[k], q1 = wq[k + 1], q2 = wq[k + 2], q3 = wq[k + 3];
-        const float4 ww = *reinterpret_cast<const float4*>(w2 + k);
-        float u0 = fmaf(q0.x, s0, fmaf(q0.y, s1, fmaf(q0.z, s2, q0.w)));
-        float u1 = fmaf(q1.x, s0, fmaf(q1.y, s1, fmaf(q1.z, s2, q1.w)));
-        float u2 = fmaf(q2.x, s0, fmaf(q2.y, s1, fmaf(q2.z, s2, q2.w)));
-        float u3 = fmaf(q3.x, s0, fmaf(q3.y, s1, fmaf(q3.z, s2, q3.w)));
-        silu4_shared_rcp(u0, u1, u2, u3);
-        acc = fmaf(ww.x, u0, fmaf(ww.y, u1, fmaf(ww.z, u2, fmaf(ww.w, u3, acc))));
+      const float s0 = cur.a0 * cur.gx + cur.a1 * cur.gy + cur.a2 * cur.gz;
+      float s1 = cur.a0 * cx + cur.a1 * cy + cur.a2 * cz;
+      const float s2 = cur.a0 * vx + cur.a1 * vy + cur.a2 * vz;
+      const float r0 = cur.b0 * cur.gx + cur.b1 * cur.gy + cur.b2 * cur.gz;
+      float r1 = cur.b0 * cx + cur.b1 * cy + cur.b2 * cz;
+      const float r2 = cur.b0 * vx + cur.b1 * vy + cur.b2 * vz;
+      if (reflect) { s1 = fabsf(s1); r1 = fabsf(r1); }
+      float acc = W.b2, bcc = W.b2;
+#pragma unroll
+      for (int k = 0; k < 64; k += 4) {
+        if (k < W.hq) {  // uniform; entries hq .. hq4 are zero-filled on the host
+          float u[4], v[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float w0 = W.w0[(k + i) * 3], w1 = W.w0[(k + i) * 3 + 1], w2 = W.w0[(k + i) * 3 + 2], bb = W.b0[k + i];
+            u[i] = fmaf(w0, s0, fmaf(w1, s1, fmaf(w2, s2, bb)));
+            v[i] = fmaf(w0, r0, fmaf(w1, r1, fmaf(w2, r2, bb)));
+          }
+          silu4_shared_rcp(u[0], u[1], u[2], u[3]);
+          silu4_shared_rcp(v[0], v[1], v[2], v[3]);
+          acc = fmaf(W.w2[k], u[0], fmaf(W.w2[k + 1], u[1], fmaf(W.w2[k + 2], u[2], fmaf(W.w2[k + 3], u[3], acc))));
+          bcc = fmaf(W.w2[k], v[0], fmaf(W.w2[k + 1], v[1], fmaf(W.w2[k + 2], v[2], fmaf(W.w2[k + 3], v[3], bcc))));
+        }
       }
       row[t] = (acc + s0) * cur.rbe;
+      row[H + t] = (bcc + r0) * cur.rbe;
     }
     __syncthreads();
     float* out = ew + (size_t)cur.e * ld;
@@ -1007,9 +1117,9 @@ __global__ void __launch_bounds__(448, 3) k_edge_init_act(
 
 // GCL attention gate + mean aggregation at the edge source on a pair16 m2 (row pitch ld floats, H <= ld).
 // One block per node; warps take the row's edges round-robin; lane l < ld/8 owns 8 consecutive columns.
-__global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, float* __restrict__ m2,
-                              const float* __restrict__ w_att, const float* __restrict__ b_att, float* __restrict__ xa,
-                              int ldxa) {
+__global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, const float* __restrict__ m2,
+                              const float* __restrict__ w_att, const float* __restrict__ b_att,
+                              float* __restrict__ att_out, float* __restrict__ xa, int ldxa) {
   extern __shared__ float part[];  // [nw][ld]
   const int t = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
@@ -1022,8 +1132,8 @@ __global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, fl
   for (int e = r0 + w; e < r1; e += 2 * nw) {  // two edges in flight per warp (independent loads), same summation order
     const int e2 = e + nw;
     const bool two = e2 < r1;
-    float* row = m2 + (size_t)e * ld;
-    float* row2 = m2 + (size_t)(two ? e2 : e) * ld;
+    const float* row = m2 + (size_t)e * ld;
+    const float* row2 = m2 + (size_t)(two ? e2 : e) * ld;
     float v[8], v2[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { v[k] = 0.f; v2[k] = 0.f; }
@@ -1034,13 +1144,13 @@ __global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, fl
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
     const float att = silu(d + ba), att2 = silu(d2 + ba);
+    if (lane == 0) { att_out[e] = att; if (two) att_out[e2] = att2; }
 #pragma unroll
-    for (int k = 0; k < 8; k++) { v[k] *= att; acc[k] += v[k]; }
+    for (int k = 0; k < 8; k++) acc[k] += v[k] * att;
     if (two) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) { v2[k] *= att2; acc[k] += v2[k]; }
+      for (int k = 0; k < 8; k++) acc[k] += v2[k] * att2;
     }
-    if (own) { pair16_store8(row, c8, v); if (two) pair16_store8(row2, c8, v2); }
   }
   if (own) {
 #pragma unroll

@@ -79,6 +79,9 @@ struct oard_handle {
   struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
   struct LayerMs { MsWeight n0, n1, x0, x2, vp, xv0, xv2, pq; };  // node_chain.cuh (mma.sync fragment order)
   std::vector<LayerMs> Ms;
+  std::vector<Lin3U> lin3u;  // per layer, host copies passed by value (constant bank)
+  Lin3E lin3e{};
+  bool use_lin3c = false;
   bool use_chain = false;  // node-level GEMMs on the lean mma.sync kernel with fused LayerNorm / EquiUpdate (node_chain.cuh)
   std::vector<LayerTc> T;
   TcWeight tc_rl0{}, tc_rl2{}, tc_s2v{}, tc_ov1{}, tc_ou0{};
@@ -388,6 +391,32 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.xv2w, H, 3 * H, H, &t.xv2, bn3H))) return rc;
     }
   }
+  {  // lin3 weights as by-value kernel parameters (kernels.cuh Lin3U / Lin3E)
+    const int Hq = h->cfg.hidden_channels / 4;
+    const char* el = getenv("OARD_LIN3");  // "smem": the shared-memory broadcast kernels
+    h->use_lin3c = !(el && strcmp(el, "smem") == 0);
+    if (Hq > 64) return fail(OARD_EINVAL, "hidden_channels / 4 must be <= 64");
+    {
+      CU(cudaStreamSynchronize((cudaStream_t)stream));
+      memset(&h->lin3e, 0, sizeof h->lin3e);
+      h->lin3e.hq = Hq;
+      CU(cudaMemcpy(h->lin3e.w0, h->l3_w0, (size_t)Hq * 3 * 4, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(h->lin3e.b0, h->l3_b0, (size_t)Hq * 4, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(h->lin3e.w2, h->l3_w2, (size_t)Hq * 4, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(&h->lin3e.b2, h->l3_b2, 4, cudaMemcpyDeviceToHost));
+      h->lin3u.resize(h->cfg.num_layers);
+      for (int l = 0; l < h->cfg.num_layers; l++) {
+        Lin3U& u = h->lin3u[l];
+        const LayerW& w = h->L[l];
+        CU(cudaMemcpy(u.w0, w.l0w, sizeof u.w0, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(u.b0, w.l0b, sizeof u.b0, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(u.w2, w.l2w, sizeof u.w2, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(u.b2, w.l2b, sizeof u.b2, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(u.w4, w.l4w, sizeof u.w4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&u.b4, w.l4b, 4, cudaMemcpyDeviceToHost));
+      }
+    }
+  }
   if (h->use_chain) {
     cudaStream_t st = (cudaStream_t)stream;
     auto packms = [&](const float* Wp, int ldw, int N, int K, int nsplit, MsWeight* out) -> int {
@@ -503,7 +532,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   struct { const char* n; size_t b; } allocs[] = {
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
-      {"mask", Ee}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
+      {"mask", Ee}, {"att", Ee * 4}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
       {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"gsize", Nn * 4}, {"lead_list", Nn * 4}, {"lead_info", Nn * 8},
       {"gm_node", Nn * 4}, {"gm_rap", Nn * 8}, {"act_rec", Ee * 8},
       {"n_lead", 16}, {"work_ctr", 64 * 4}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
@@ -789,7 +818,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     GEMM_TC("gemm_s2v_lin", g, h->tc_s2v);
   }
   PB("k_layernorm", 0, N*H*8.0, 0);
-  k_layernorm<<<N, HB, 0, st>>>(H, tmpH, H, nullptr, nullptr, nullptr, 1, q, H);
+  k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, tmpH, H, nullptr, nullptr, nullptr, 1, q, H);
   KCHECK();
   PB("k_s2v", 0, (double)E*(H*8.0+28), 1);
   k_s2v<<<N, HB, 0, st>>>(H, row_ptr, ecol, rev, act_pos, f_act, geo, q, NE1);
@@ -797,21 +826,19 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   if (E) {
     // initial edge state (leftnet.py:792-809): masked edges get the constant row, active edges the scalarised lin3 terms
     float* crow = h->buf<float>("crow");
-    const int Hq4 = (Hq + 3) / 4 * 4, ei_threads = (2 * H + 31) / 32 * 32;
-    const size_t ei_smem = (size_t)(5 * Hq4 + ldD) * sizeof(float);
+    const int ei_threads = HB;  // one thread per channel, both sides
+    const size_t ei_smem = (size_t)ldD * sizeof(float);
     PB("k_edge_init", 0, (double)E*D*4.0, 0);
     if (P) k_const_row<true><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
     else k_const_row<false><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
     k_edge_init_masked<<<(E + 7) / 8, 256, 0, st>>>(E, ldD, act_pos, crow, ew);
-    const int ei_grid = std::min(E, h->num_sms * 3);
+    const int ei_grid = std::min(E, h->num_sms * 4);  // = resident blocks (launch bounds 256 x 4)
     if (P)
-      k_edge_init_act<true><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, Hq, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                 pf, geo, rb, NE1, f_act, rbf_act, h->l3_w0, h->l3_b0, h->l3_w2,
-                                                                 h->l3_b2, ew);
+      k_edge_init_act<true><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
+                                                                 pf, geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
     else
-      k_edge_init_act<false><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, Hq, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                  pf, geo, rb, NE1, f_act, rbf_act, h->l3_w0, h->l3_b0, h->l3_w2,
-                                                                  h->l3_b2, ew);
+      k_edge_init_act<false><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
+                                                                  pf, geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
     h->launches += 2;
     KCHECK();
   }
@@ -844,7 +871,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       GEMM_MS("gemm_gcl_PQ", m, 4, 2, 0, 4);
     } else {
       PB("k_layernorm", 0, N*H*8.0, 0);
-      k_layernorm<<<N, HB, 0, st>>>(H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
+      k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
       KCHECK();
       g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
       g.bias = w.pqb;
@@ -860,9 +887,9 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.bias = w.e1b; g.act = 1;
       if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
     }
-    PB("k_att_agg", 0, (double)E*H*8.0, 0);
-    if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
-    else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, xa, 2 * H);
+    PB("k_att_agg", 0, (double)E*(H*4.0+4), 0);
+    if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
+    else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
     KCHECK();
     if (chain) {
       MsGemmArgs m = msa(xa, 2 * H, 2 * H, h->Ms[l].n0, tN, H);
@@ -882,6 +909,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     if (E) {
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
+      g.prescale = h->buf<float>("att");  // attention gate of the edge (k_att_agg): W (att m) = att (W m)
       g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = ldD;  // compact copy of the active rows: contiguous operand for dir_proj
       if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
     }
@@ -894,7 +922,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       GEMM_MS("gemm_xproj2", m, 4, 2, 0, 4);
     } else {
       PB("k_layernorm", 0, N*H*8.0, 0);
-      k_layernorm<<<N, HB, 0, st>>>(H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
+      k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
       KCHECK();
       g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
       g.act = 1;
@@ -965,7 +993,10 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
       GEMM_TC("gemm_vec_proj", g, h->T[l].vp);
       PB("k_upd_scalar", 0, N*H*4.0*9, 0);
-      k_upd_scalar<<<std::min(N, h->num_sms * 8), HB, 0, st>>>(N, H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
+      if (h->use_lin3c)
+        k_upd_scalar_c<<<(((N + US_NT - 1) / US_NT) * H + 255) / 256, 256, 0, st>>>(N, H, c.reflect_equiv, VP, nodeframe, s, h->lin3u[l], sx, vd);
+      else
+        k_upd_scalar<<<std::min(N, h->num_sms * 8), HB, 0, st>>>(N, H, c.reflect_equiv, VP, nodeframe, s, w.l0w, w.l0b, w.l2w, w.l2b, w.l4w, w.l4b, sx,
                                      vd);
       KCHECK();
       g = mk(sx, 2 * H, w.xv0w, 2 * H, tN, H, N, H, 2 * H);

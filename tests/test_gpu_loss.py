@@ -117,4 +117,4 @@ def test_packed_batch_producer_feeds_compute_loss():
         ddpm.__class__ = ob.EnVariationalDiffusion  # the plain module: its own t_int / noise draws
         nll, info = ddpm.compute_loss((reps, cond.float()), scales=(1.0, 2.0, 1.0), training=True)
         out.append(nll.cpu())
-    assert torch.isfinite(out[0]).all() and torch.equal(out[0], out[1])
+    assert torch.isfinite(out[0]).all() and torch.allclose(out[0], out[1], rtol=1e-5)  # index_add_ order differs run to run
