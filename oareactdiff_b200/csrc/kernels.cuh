@@ -24,6 +24,33 @@ __device__ __forceinline__ void silu4_shared_rcp(float& u0, float& u1, float& u2
   u0 *= r01 * d1; u1 *= r01 * d0; u2 *= r23 * d3; u3 *= r23 * d2;
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issued instruction).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 ld2(const float2& w) { return *reinterpret_cast<const f32x2*>(&w); }
+// silu4_shared_rcp on pairs: the same formulas element-wise (ex2 / rcp / min stay scalar: MUFU and FMNMX have no pair form)
+__device__ __forceinline__ void silu4_shared_rcp2(f32x2& u0, f32x2& u1, f32x2& u2, f32x2& u3) {
+  const f32x2 L = pk2(-1.4426950408889634f, -1.4426950408889634f), one = pk2(1.0f, 1.0f);
+  const float C = 28.853900817779268f;
+  auto den = [&](f32x2 u) {
+    float a, b;
+    upk2(mul2(L, u), a, b);
+    return add2(one, pk2(fast_ex2(fminf(a, C)), fast_ex2(fminf(b, C))));
+  };
+  const f32x2 d0 = den(u0), d1 = den(u1), d2 = den(u2), d3 = den(u3);
+  const f32x2 d01 = mul2(d0, d1), d23 = mul2(d2, d3);
+  float pa, pb;
+  upk2(mul2(d01, d23), pa, pb);
+  const f32x2 r = pk2(fast_rcp(pa), fast_rcp(pb));
+  const f32x2 r01 = mul2(r, d23), r23 = mul2(r, d01);
+  u0 = mul2(u0, mul2(r01, d1)); u1 = mul2(u1, mul2(r01, d0));
+  u2 = mul2(u2, mul2(r23, d3)); u3 = mul2(u3, mul2(r23, d2));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // (B) raw distance + cutoff/same-fragment edge mask.  leftnet.py:747-753
 __global__ void k_edge_mask(int E, const int* __restrict__ esrc, const int* __restrict__ ecol,
@@ -791,10 +818,11 @@ __global__ void __launch_bounds__(256) k_equi_frag(
 // passed BY VALUE: kernel parameters live in the constant bank, so with fully unrolled loops every weight is an immediate
 // constant operand of its FFMA — no load instruction and no shared-memory traffic.  (The shared-memory float4-broadcast
 // versions were bound by the LDS return bandwidth: 3 LDS.128 = 1.5 KB per warp per hidden unit, 0.37-0.45 IPC.)
-struct Lin3U { float w0[48 * 3], b0[48], w2[8 * 48], b2[8], w4[8], b4; };
-struct Lin3E { float w0[64 * 3], b0[64], w2[64], b2; int hq; };
+// Every weight is stored as the pair (w, w): one 64-bit constant operand of an FFMA2 that evaluates two items at once.
+struct Lin3U { float2 w0[48 * 3], b0[48], w2[8 * 48], b2[8]; float w4[8], b4; };
+struct Lin3E { float2 w0[64 * 3], b0[64], w2[64]; float b2; int hq; };
 
-constexpr int US_NT = 2;  // nodes per thread: the four evaluations share every weight operand
+constexpr int US_NT = 2;  // nodes per thread = the two halves of every packed operation
 __global__ void __launch_bounds__(256) k_upd_scalar_c(int N, int H, int reflect, const float* __restrict__ VP,
                                                        const float* __restrict__ nodeframe, const float* __restrict__ s,
                                                        const __grid_constant__ Lin3U W, float* __restrict__ sx,
@@ -803,10 +831,10 @@ __global__ void __launch_bounds__(256) k_upd_scalar_c(int N, int H, int reflect,
   const int tg = idx / H, h = idx - tg * H;
   if (tg * US_NT >= N) return;
   const float inv_sqrt_h = rsqrtf((float)H);
-  float s0[US_NT], s1[US_NT], s2[US_NT], vdv[US_NT], a[US_NT][8];
+  float s0[2], s1[2], s2[2], vdv[2];
 #pragma unroll
-  for (int j = 0; j < US_NT; j++) {
-    const int t = min(tg * US_NT + j, N - 1);
+  for (int j = 0; j < 2; j++) {
+    const int t = min(tg * 2 + j, N - 1);
     const float* nf = nodeframe + (size_t)t * 9;
     const float* vp = VP + (size_t)t * 3 * 2 * H;
     const float v10 = vp[h], v11 = vp[2 * H + h], v12 = vp[4 * H + h];
@@ -816,40 +844,38 @@ __global__ void __launch_bounds__(256) k_upd_scalar_c(int N, int H, int reflect,
     s2[j] = v10 * nf[2] + v11 * nf[5] + v12 * nf[8];
     if (reflect) s1[j] = fabsf(s1[j]);
     vdv[j] = (v10 * v20 + v11 * v21 + v12 * v22) * inv_sqrt_h;
-#pragma unroll
-    for (int q = 0; q < 8; q++) a[j][q] = W.b2[q];
   }
+  const f32x2 p0 = pk2(s0[0], s0[1]), p1 = pk2(s1[0], s1[1]), p2 = pk2(s2[0], s2[1]);
+  f32x2 a[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) a[q] = ld2(W.b2[q]);
 #pragma unroll
   for (int k = 0; k < 48; k += 4) {
-    float u[US_NT][4];
+    f32x2 u[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float w0 = W.w0[(k + i) * 3], w1 = W.w0[(k + i) * 3 + 1], w2 = W.w0[(k + i) * 3 + 2], bb = W.b0[k + i];
-#pragma unroll
-      for (int j = 0; j < US_NT; j++) u[j][i] = fmaf(w0, s0[j], fmaf(w1, s1[j], fmaf(w2, s2[j], bb)));
-    }
-#pragma unroll
-    for (int j = 0; j < US_NT; j++) silu4_shared_rcp(u[j][0], u[j][1], u[j][2], u[j][3]);
+    for (int i = 0; i < 4; i++)
+      u[i] = fma2(ld2(W.w0[(k + i) * 3]), p0, fma2(ld2(W.w0[(k + i) * 3 + 1]), p1, fma2(ld2(W.w0[(k + i) * 3 + 2]), p2, ld2(W.b0[k + i]))));
+    silu4_shared_rcp2(u[0], u[1], u[2], u[3]);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const float w = W.w2[q * 48 + k + i];
+      for (int q = 0; q < 8; q++) a[q] = fma2(ld2(W.w2[q * 48 + k + i]), u[i], a[q]);
+  }
+  silu4_shared_rcp2(a[0], a[1], a[2], a[3]);
+  silu4_shared_rcp2(a[4], a[5], a[6], a[7]);
+  float o0 = W.b4, o1 = W.b4;
 #pragma unroll
-        for (int j = 0; j < US_NT; j++) a[j][q] = fmaf(w, u[j][i], a[j][q]);
-      }
+  for (int q = 0; q < 8; q++) {
+    float x, y;
+    upk2(a[q], x, y);
+    o0 = fmaf(W.w4[q], x, o0); o1 = fmaf(W.w4[q], y, o1);
   }
 #pragma unroll
-  for (int j = 0; j < US_NT; j++) {
-    const int t = tg * US_NT + j;
-    silu4_shared_rcp(a[j][0], a[j][1], a[j][2], a[j][3]);
-    silu4_shared_rcp(a[j][4], a[j][5], a[j][6], a[j][7]);
-    float out = W.b4;
-#pragma unroll
-    for (int q = 0; q < 8; q++) out = fmaf(W.w4[q], a[j][q], out);
+  for (int j = 0; j < 2; j++) {
+    const int t = tg * 2 + j;
     if (t < N) {
       sx[(size_t)t * 2 * H + h] = s[(size_t)t * H + h];
-      sx[(size_t)t * 2 * H + H + h] = out;
+      sx[(size_t)t * 2 * H + H + h] = j ? o1 : o0;
       vd[(size_t)t * H + h] = vdv[j];
     }
   }
@@ -1083,23 +1109,22 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
       float r1 = cur.b0 * cx + cur.b1 * cy + cur.b2 * cz;
       const float r2 = cur.b0 * vx + cur.b1 * vy + cur.b2 * vz;
       if (reflect) { s1 = fabsf(s1); r1 = fabsf(r1); }
-      float acc = W.b2, bcc = W.b2;
+      // the two sides are the two halves of every packed operation
+      const f32x2 p0 = pk2(s0, r0), p1 = pk2(s1, r1), p2 = pk2(s2, r2);
+      f32x2 acc2 = pk2(W.b2, W.b2);
 #pragma unroll
       for (int k = 0; k < 64; k += 4) {
         if (k < W.hq) {  // uniform; entries hq .. hq4 are zero-filled on the host
-          float u[4], v[4];
+          f32x2 u[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float w0 = W.w0[(k + i) * 3], w1 = W.w0[(k + i) * 3 + 1], w2 = W.w0[(k + i) * 3 + 2], bb = W.b0[k + i];
-            u[i] = fmaf(w0, s0, fmaf(w1, s1, fmaf(w2, s2, bb)));
-            v[i] = fmaf(w0, r0, fmaf(w1, r1, fmaf(w2, r2, bb)));
-          }
-          silu4_shared_rcp(u[0], u[1], u[2], u[3]);
-          silu4_shared_rcp(v[0], v[1], v[2], v[3]);
-          acc = fmaf(W.w2[k], u[0], fmaf(W.w2[k + 1], u[1], fmaf(W.w2[k + 2], u[2], fmaf(W.w2[k + 3], u[3], acc))));
-          bcc = fmaf(W.w2[k], v[0], fmaf(W.w2[k + 1], v[1], fmaf(W.w2[k + 2], v[2], fmaf(W.w2[k + 3], v[3], bcc))));
+          for (int i = 0; i < 4; i++)
+            u[i] = fma2(ld2(W.w0[(k + i) * 3]), p0, fma2(ld2(W.w0[(k + i) * 3 + 1]), p1, fma2(ld2(W.w0[(k + i) * 3 + 2]), p2, ld2(W.b0[k + i]))));
+          silu4_shared_rcp2(u[0], u[1], u[2], u[3]);
+          acc2 = fma2(ld2(W.w2[k]), u[0], fma2(ld2(W.w2[k + 1]), u[1], fma2(ld2(W.w2[k + 2]), u[2], fma2(ld2(W.w2[k + 3]), u[3], acc2))));
         }
       }
+      float acc, bcc;
+      upk2(acc2, acc, bcc);
       row[t] = (acc + s0) * cur.rbe;
       row[H + t] = (bcc + r0) * cur.rbe;
     }

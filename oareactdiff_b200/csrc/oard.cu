@@ -400,18 +400,25 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       CU(cudaStreamSynchronize((cudaStream_t)stream));
       memset(&h->lin3e, 0, sizeof h->lin3e);
       h->lin3e.hq = Hq;
-      CU(cudaMemcpy(h->lin3e.w0, h->l3_w0, (size_t)Hq * 3 * 4, cudaMemcpyDeviceToHost));
-      CU(cudaMemcpy(h->lin3e.b0, h->l3_b0, (size_t)Hq * 4, cudaMemcpyDeviceToHost));
-      CU(cudaMemcpy(h->lin3e.w2, h->l3_w2, (size_t)Hq * 4, cudaMemcpyDeviceToHost));
+      std::vector<float> tmp(8 * 48 + 64 * 3);
+      auto fetch = [&](const float* dev, size_t n) -> int {
+        CU(cudaMemcpy(tmp.data(), dev, n * 4, cudaMemcpyDeviceToHost));
+        return OARD_OK;
+      };
+      auto dup = [&](float2* dst, size_t n) { for (size_t i = 0; i < n; i++) dst[i] = make_float2(tmp[i], tmp[i]); };
+      int rc;
+      if ((rc = fetch(h->l3_w0, (size_t)Hq * 3))) return rc; dup(h->lin3e.w0, (size_t)Hq * 3);
+      if ((rc = fetch(h->l3_b0, Hq))) return rc; dup(h->lin3e.b0, Hq);
+      if ((rc = fetch(h->l3_w2, Hq))) return rc; dup(h->lin3e.w2, Hq);
       CU(cudaMemcpy(&h->lin3e.b2, h->l3_b2, 4, cudaMemcpyDeviceToHost));
       h->lin3u.resize(h->cfg.num_layers);
       for (int l = 0; l < h->cfg.num_layers; l++) {
         Lin3U& u = h->lin3u[l];
         const LayerW& w = h->L[l];
-        CU(cudaMemcpy(u.w0, w.l0w, sizeof u.w0, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(u.b0, w.l0b, sizeof u.b0, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(u.w2, w.l2w, sizeof u.w2, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(u.b2, w.l2b, sizeof u.b2, cudaMemcpyDeviceToHost));
+        if ((rc = fetch(w.l0w, 48 * 3))) return rc; dup(u.w0, 48 * 3);
+        if ((rc = fetch(w.l0b, 48))) return rc; dup(u.b0, 48);
+        if ((rc = fetch(w.l2w, 8 * 48))) return rc; dup(u.w2, 8 * 48);
+        if ((rc = fetch(w.l2b, 8))) return rc; dup(u.b2, 8);
         CU(cudaMemcpy(u.w4, w.l4w, sizeof u.w4, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&u.b4, w.l4b, 4, cudaMemcpyDeviceToHost));
       }
