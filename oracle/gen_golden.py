@@ -216,6 +216,68 @@ def case_train_loss(name, cfg, sizes, seed, T, training):
     print(name, "ok t_int", out["t_int"].tolist(), "error_t0", out["error_t0"].tolist(), "f32", out["error_t0_f32"].tolist())
 
 
+def case_train_grad(name, cfg, sizes, seed, T, store_full):
+    """Gradients of the l2 training objective (DDPMModule.compute_loss with loss_type "l2", trainer/pl_trainer.py:208-282,
+    scales [1, 2, 1] of train_ts1x.py:111, mean over the batch) w.r.t. every parameter of the dynamics, from the
+    UNMODIFIED reference's autograd in fp64 (and fp32: the reference's own gap).  Inputs and random draws as in
+    case_train_loss.  store_full: the gradients themselves; otherwise (large configs) per-parameter L2 norms and the
+    projection on a seeded random direction (a checksum that a wrong backward cannot reproduce by accident)."""
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    reps = []
+    for f in range(3):
+        m = get_mask_for_frag(nodes[f])
+        pos = torch.randn(h0[f].size(0), 3, generator=g) * 1.5
+        cnt = torch.zeros(len(sizes)).index_add_(0, m, torch.ones(len(m)))
+        pos = pos - (torch.zeros(len(sizes), 3).index_add_(0, m, pos) / cnt[:, None])[m]
+        reps.append({"size": nodes[f].clone(), "pos": pos, "one_hot": h0[f][:, :5].clone(), "charge": h0[f][:, 5:].clone(), "mask": m})
+    out = {f"{k}{f}": r[k].numpy().copy() for f, r in enumerate(reps) for k in ("pos", "one_hot", "charge")}
+    scales = (1.0, 2.0, 1.0)
+    all_draws = {}
+    for dt, tag in ((torch.float64, ""), (torch.float32, "_f32")):
+        ddpm, _ = build_ddpm(cfg, seed, T, dtype=dt)
+        ddpm.train(True)
+        draws = []
+        orig = ddpm.sample_combined_position_feature_noise
+
+        def rec(masks, orig=orig, draws=draws):
+            o = orig(masks)
+            draws.append([x.clone() for x in o])
+            return o
+        ddpm.sample_combined_position_feature_noise = rec
+        torch.manual_seed(seed)
+        lt = ddpm.forward([{k: (v.to(dt) if v.is_floating_point() else v.clone()) for k, v in r.items()} for r in reps], cond.to(dt))
+        sz = [r["size"].to(dt) for r in reps]
+        loss_t = sum(lt["error_t"][f] / (3 * sz[f]) * scales[f] for f in range(3))
+        loss_0 = (sum(lt["loss_0_x"][f] * scales[f] / (3 * sz[f]) for f in range(3)) + sum(lt["loss_0_cat"][f] for f in range(3))
+                  + sum(lt["loss_0_charge"][f] for f in range(3)))
+        loss = (loss_t + loss_0 + lt["kl_prior"]).mean()
+        ddpm.zero_grad()
+        loss.backward()
+        out[f"loss{tag}"] = np.float64(loss.detach())
+        out[f"t_int{tag}"] = lt["t_int"].detach().numpy()
+        gen = torch.Generator().manual_seed(seed + 99)
+        names = []
+        for pn, prm in ddpm.dynamics.named_parameters():
+            gr = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+            names.append(pn)
+            direction = torch.randn(prm.shape, generator=gen, dtype=torch.float64)
+            out[f"gnorm{tag}/{pn}"] = np.float64(gr.double().norm())
+            out[f"gproj{tag}/{pn}"] = np.float64((gr.double() * direction).sum())
+            if store_full:
+                out[f"grad{tag}/{pn}"] = gr.detach().numpy()
+        all_draws[tag] = draws
+    for d, dr in enumerate(all_draws[""]):
+        for f in range(3):
+            assert torch.equal(dr[f], all_draws["_f32"][d][f])
+            out[f"noise{d}_{f}"] = dr[f].numpy()
+    assert np.array_equal(out["t_int"], out["t_int_f32"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), sizes=np.array(sizes), seed=np.int64(seed), T=np.int64(T),
+                        n_draws=np.int64(len(all_draws[""])), cond=cond.numpy(), cfg=json.dumps(cfg), scales=np.array(scales),
+                        param_names=json.dumps(names), store_full=np.int64(store_full), **out)
+    print(name, "ok loss", float(out["loss"]), "f32", float(out["loss_f32"]), "params", len(names))
+
+
 def synthetic_raw_dataset(seed=7, n=9):
     """A raw Transition1x-style dict (the schema transition1x.py:46-85 reads) with ragged sizes, an excluded multi-fragment
     reaction and a `use_ind` subset."""
@@ -300,6 +362,10 @@ def t1x_histogram():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "train_grad":  # only the gradient fixtures
+        case_train_grad("grad_small_train", SMALL_CFG, [5, 3, 4], seed=61, T=20, store_full=True)
+        case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":  # only the dataset / sampling-tools fixture
         case_dataset()
         sys.exit(0)
@@ -332,3 +398,5 @@ if __name__ == "__main__":
     case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
     case_train_loss("loss_trained_train_b4", TRAINED_CFG, [4, 9, 14, 7], seed=53, T=100, training=True)
     case_dataset()
+    case_train_grad("grad_small_train", SMALL_CFG, [5, 3, 4], seed=61, T=20, store_full=True)
+    case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)

@@ -302,8 +302,9 @@ def leftnet_forward(sd: Dict[str, Tensor], cfg: Dict, h: Tensor, pos: Tensor, ed
     S1 = torch.sum(NE1[i].unsqueeze(2) * frame.unsqueeze(-1), dim=1)  # :792 [E,3(k),H]
     S2 = torch.sum(NE1[j].unsqueeze(2) * frame.unsqueeze(-1), dim=1)  # :793
     if reflect:
-        S1[:, 1, :] = S1[:, 1, :].abs()
-        S2[:, 1, :] = S2[:, 1, :].abs()  # :794-796
+        # out of place (same values): the reference clones before the in-place write so that autograd works (:794-796)
+        S1 = torch.cat([S1[:, :1], S1[:, 1:2].abs(), S1[:, 2:]], dim=1)
+        S2 = torch.cat([S2[:, :1], S2[:, 1:2].abs(), S2[:, 2:]], dim=1)
 
     def lin3(x):
         return _lin(p, "lin3.2", F.silu(_lin(p, "lin3.0", x)))
@@ -366,7 +367,7 @@ def leftnet_forward(sd: Dict[str, Tensor], cfg: Dict, h: Tensor, pos: Tensor, ed
             v1, v2 = torch.split(vp, H, dim=-1)
             Sc = torch.sum(v1.unsqueeze(2) * nodeframe.unsqueeze(-1), dim=1)  # [N,3(k),H]
             if reflect:
-                Sc[:, 1, :] = Sc[:, 1, :].abs()
+                Sc = torch.cat([Sc[:, :1], Sc[:, 1:2].abs(), Sc[:, 2:]], dim=1)
             t = Sc.permute(0, 2, 1)
             t = F.silu(_lin(p, u + "lin3.0", t))
             t = F.silu(_lin(p, u + "lin3.2", t))
@@ -421,6 +422,33 @@ def dynamics_forward(sd: Dict[str, Tensor], cfg: Dict, xh: List[Tensor], edge_in
         out.append(torch.cat([remove_mean_batch(vel[sl], combined_mask[sl]),
                               _mlp(sd, f"decoders.{f}", h_final[sl], 2, last_no_act=True)], dim=-1))  # :147-160
     return out
+
+
+def train_loss_l2(sd: Dict[str, Tensor], cfg: Dict, gamma: Tensor, xh: List[Tensor], masks: List[Tensor], sizes: Tensor,
+                  cond: Tensor, t_int: Tensor, eps: List[Tensor], scales=(1.0, 2.0, 1.0), pos_dim: int = 3,
+                  condition_nf: int = 1) -> Tensor:
+    """The l2 training objective for t_int > 0 with pos_only=True and the identity Normalizer: en_diffusion.py:56-248
+    (z_t = alpha_t x + sigma_t eps, error_t = sum (eps - net_eps)^2 per sample with the feature channels of net_eps zeroed)
+    composed as trainer/pl_trainer.py:208-282 (loss_type "l2": error_t / (3 n) * scale per fragment, mean over the batch).
+    Differentiable w.r.t. sd (torch autograd): the checker for the CUDA backward."""
+    assert bool((t_int > 0).all()), "t = 0 samples use the L0 terms (en_diffusion.py:340-454), not restated here"
+    T = gamma.numel() - 1
+    dt = xh[0].dtype
+    t = (t_int / T).view(-1, 1).to(dt)
+    g_t = gamma[torch.round(t * T).long().view(-1)].to(dt).view(-1, 1)
+    alpha, sigma = torch.sqrt(torch.sigmoid(-g_t)), torch.sqrt(torch.sigmoid(g_t))
+    z = [alpha[masks[f]] * xh[f] + sigma[masks[f]] * eps[f] for f in range(len(xh))]
+    cm = torch.cat(masks)
+    nfs = torch.cat([torch.full((len(m),), f, dtype=torch.long) for f, m in enumerate(masks)])
+    ei = get_edges_index(cm, remove_self_edge=True)
+    net = dynamics_forward(sd, cfg, z, ei, t, cond.to(dt), nfs, cm, pos_dim, condition_nf)
+    B = sizes.numel()
+    loss = torch.zeros(B, dtype=dt)
+    for f in range(len(xh)):
+        d = eps[f] - torch.cat([net[f][:, :pos_dim], torch.zeros_like(net[f][:, pos_dim:])], dim=1)
+        err = torch.zeros(B, dtype=dt).index_add_(0, masks[f], (d ** 2).sum(-1))
+        loss = loss + err / (pos_dim * sizes.to(dt)) * scales[f]
+    return loss.mean()
 
 
 # --------------------------------------------------------------------------- noise schedule
