@@ -1154,27 +1154,35 @@ __global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, co
 #pragma unroll
   for (int k = 0; k < 8; k++) { acc[k] = 0.f; wa[k] = (own && c8 + k < H) ? w_att[c8 + k] : 0.f; }
   const float ba = b_att[0];
-  for (int e = r0 + w; e < r1; e += 2 * nw) {  // two edges in flight per warp (independent loads), same summation order
-    const int e2 = e + nw;
-    const bool two = e2 < r1;
-    const float* row = m2 + (size_t)e * ld;
-    const float* row2 = m2 + (size_t)(two ? e2 : e) * ld;
-    float v[8], v2[8];
+  constexpr int NE = 2;  // edges in flight per warp (NE = 4 measured slower: 47 vs 40 us, fewer busy warps per row), same summation order
+  for (int e0 = r0 + w; e0 < r1; e0 += NE * nw) {
+    float v[NE][8], d[NE];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { v[k] = 0.f; v2[k] = 0.f; }
-    if (own) { pair16_load8(row, c8, v); if (two) pair16_load8(row2, c8, v2); }
-    float d = 0.f, d2 = 0.f;
+    for (int j = 0; j < NE; j++) {
+      const int e = e0 + j * nw;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { d = fmaf(v[k], wa[k], d); d2 = fmaf(v2[k], wa[k], d2); }
+      for (int k = 0; k < 8; k++) v[j][k] = 0.f;
+      if (own && e < r1) pair16_load8(m2 + (size_t)e * ld, c8, v[j]);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
-    const float att = silu(d + ba), att2 = silu(d2 + ba);
-    if (lane == 0) { att_out[e] = att; if (two) att_out[e2] = att2; }
+    for (int j = 0; j < NE; j++) {
+      d[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] += v[k] * att;
-    if (two) {
+      for (int k = 0; k < 8; k++) d[j] = fmaf(v[j][k], wa[k], d[j]);
+    }
 #pragma unroll
-      for (int k = 0; k < 8; k++) acc[k] += v2[k] * att2;
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < NE; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+      const int e = e0 + j * nw;
+      if (e < r1) {  // warp-uniform
+        const float att = silu(d[j] + ba);
+        if (lane == 0) att_out[e] = att;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += v[j][k] * att;
+      }
     }
   }
   if (own) {
