@@ -889,10 +889,30 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
-      if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
-      g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
-      g.bias = w.e1b; g.act = 1;
-      if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
+      static int env_mlp2 = -1;
+      // OARD_MLP2=1: both layers of the edge MLP in one kernel (gemm_p16_mlp2_kernel).  Parity-green, but measured slower
+      // (160 vs 97 + 43 us per layer): with 512 TMEM columns and 227 KB of shared memory there is room for ONE accumulator
+      // per layer and ONE hidden tile, so MMA1 of the next tile cannot overlap the epilogues and the A stream (3 x 16 KB
+      // ring) starves; see profiles/r1_tc_notes.md.  Off by default.
+      if (env_mlp2 < 0) { const char* e = getenv("OARD_MLP2"); env_mlp2 = (e && strcmp(e, "1") == 0) ? 1 : 0; }
+      bool fused = false;
+      if (P && env_mlp2) {  // both layers of the edge MLP in one kernel: the hidden activation stays in shared memory
+        GemmArgs g2 = g;
+        g2.C = m2; g2.ldc = ldH;
+        prof_begin(h, "gemm_gcl_edge12", 2.0 * E * H * (D + H), 4.0 * E * (D + H), false, st);
+        cudaError_t e_ = launch_gemm_p16_mlp2(g2, h->T[l].e0, h->T[l].e1, w.e1b, h->num_sms, st);
+        if (e_ == cudaSuccess) { fused = true; h->launches++; prof_end(h, st); }
+        else if (e_ == cudaErrorInvalidValue) {  // shape does not fit the fused kernel: drop the profile record, two launches
+          cudaGetLastError();
+          if (h->prof_now) { h->prof_recs.pop_back(); h->ev_used -= 2; }
+        } else return fail(OARD_ECUDA, "%s:%d gemm_p16_mlp2: %s", __FILE__, __LINE__, cudaGetErrorString(e_));
+      }
+      if (!fused) {
+        if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
+        g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
+        g.bias = w.e1b; g.act = 1;
+        if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
+      }
     }
     PB("k_att_agg", 0, (double)E*(H*4.0+4), 0);
     if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
@@ -1363,7 +1383,8 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
   __nv_bfloat16* buf = nullptr;
   if (use_tc) {
     if (prop.major != 10) return fail(OARD_EINVAL, "tcgen05 path needs an sm_100 device");
-    const int BN = tc_choose_bn(N);
+    const char* ebn = getenv("OARD_TEST_BN");  // tile width override (the forward uses narrow tiles for node-level GEMMs)
+    const int BN = ebn ? atoi(ebn) : tc_choose_bn(N);
     CU(cudaMalloc(&buf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
     k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, buf);
     tw = TcWeight{buf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
@@ -1407,7 +1428,8 @@ extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* 
   CU(cudaMalloc(&Ap, (size_t)M * Kp * 4));
   CU(cudaMalloc(&Cp, (size_t)M * Np * 4));
   k_p16_pack<<<1024, 256, 0, st>>>(A, K, M, K, Ap, Kp);
-  const int BN = tc_choose_bn(N);
+  const char* ebn = getenv("OARD_TEST_BN");
+  const int BN = ebn ? atoi(ebn) : tc_choose_bn(N);
   CU(cudaMalloc(&wbuf, tc_weight_elems(N, K, BN) * sizeof(__nv_bfloat16)));
   k_tc_pack_weight<<<256, 256, 0, st>>>(W, K, N, K, BN, wbuf);
   TcWeight tw{wbuf, N, K, BN, (N + BN - 1) / BN, (K + TC_KC - 1) / TC_KC};
