@@ -165,7 +165,7 @@ def run_reference(args, rank, world):
                              "sample": f"{args.steps} reverse steps (1 denoiser evaluation each, {per_eval:.2f} s/eval) on the "
                                        f"full batch, extrapolated x{T + 1}; torch {torch.__version__} CPU fp32"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
@@ -409,16 +409,35 @@ def run_b200(args, rank, world, local_rank):
                         for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share"])[:12]}}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, T)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything libraries print on fd 1 while the benchmark runs (NCCL's version
+    # banner at communicator creation, for one) is sent to stderr; emit() writes the result to the saved descriptor
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
