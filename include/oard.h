@@ -107,6 +107,19 @@ int oard_reverse_step(oard_handle* h, float* z, const float* noise_pos, const fl
                       const float* conditions, const int64_t* subgraph_mask, float t, float alpha_ts, float coef,
                       float sigma, void* stream);
 
+/* ---- Training: differentiable forward + backward (BASELINE config 5) ----
+ *   oa_reactdiff/model/leftnet.py:724-891 under torch autograd  -> oard_forward_train + oard_backward
+ * oard_forward_train = LEFTNet.forward in exact fp32 with every activation the backward needs kept in the handle
+ * (csrc/train_core.h; the graph artefacts and geometry come from the inference kernels: no parameter lies upstream of
+ * the positions, so they carry no gradient).  oard_backward consumes dL/dh_out [N,C] and dL/ddpos [N,3] (device),
+ * writes dL/dh_in [N,C] and ACCUMULATES dL/dparameter into per-weight gradient buffers (reference state-dict names),
+ * read with oard_get_grad (device destination) and cleared with oard_zero_grads.  First, un-tuned version. */
+int oard_forward_train(oard_handle* h, const float* h_in, const float* pos, const int64_t* subgraph_mask, float* h_out,
+                       float* dpos, void* stream);
+int oard_backward(oard_handle* h, const float* g_h_out, const float* g_dpos, float* g_h_in, void* stream);
+int oard_zero_grads(oard_handle* h, void* stream);
+int oard_get_grad(oard_handle* h, const char* name, float* dst_device, int64_t numel, void* stream);
+
 /* Parity instrumentation.  With debug on, oard_forward keeps snapshots of intermediates; oard_debug_read copies a
  * named snapshot to host (synchronises).  Names: mask(u8[E]) group(i32[N]) act_idx(i32[n_act]) n_act(i32[1])
  * pos_frame(f32[N,3]) geo(f32[E,4]) rb f_act rbf_act s0 NE1 e0 nodeframe pos_prjt s_msg{l} vec_msg{l} e{l} s{l} vec{l}. */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liboard_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "oard.cu")]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "oard.h")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-shared", "-Xcompiler", "-fPIC"]
 
 
@@ -60,6 +60,10 @@ SYMBOLS = {
     "oard_dyn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oard_reverse_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "oard_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oard_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oard_zero_grads": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "oard_get_grad": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "oard_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "oard_debug_bytes": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "oard_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),

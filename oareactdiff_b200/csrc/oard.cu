@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "dynamics.cuh"
 #include "node_chain.cuh"
+#include "train_core.h"
 
 using namespace oard;
 
@@ -112,6 +113,9 @@ struct oard_handle {
   bool debug = false;
   std::map<std::string, DevBuf> snaps;
   int64_t launches = 0;
+  // training: differentiable core (train_core.h) + dense geometry adapter buffers
+  oard_train::Ctx tctx;
+  bool train_ready = false, train_fwd_done = false;
   // device-resident dynamics wrapper + reverse step (dynamics.cuh)
   bool dyn_cfg = false, dyn_committed = false, dyn_planned = false;
   int dyn_nfrag = 0, dyn_nf = 0, dyn_d = 0, dyn_emb = 0, dyn_cnd = 0, dyn_ctime = 0, dyn_S = 0, dyn_B = 0;
@@ -255,6 +259,7 @@ extern "C" void oard_destroy(oard_handle* h) {
   for (float* p : h->ddev)
     if (p) cudaFree(p);
   drop_graphs(h);
+  h->tctx.release();
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_map(h->ws);
   free_map(h->snaps);
@@ -535,6 +540,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   h->ws_bytes = 0;
   h->planned = false;
   h->dyn_planned = false;
+  h->train_fwd_done = false;
   const size_t H = h->cfg.hidden_channels, R = h->cfg.num_radial, D = 3 * H + R, Nn = N, Ee = E > 0 ? E : 1;
   struct { const char* n; size_t b; } allocs[] = {
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
@@ -1111,6 +1117,121 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   CU(cudaMemcpyAsync(dpos, gdp, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
   h->launches = h->graph_launches;
   h->total_launches += h->launches;
+  return OARD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ training
+// Dense geometry for the differentiable core from the artefacts of the inference kernels (all masked like the reference:
+// leftnet.py:764-782): frame[e] = (coord_diff, coord_cross, coord_vertical) rows, rbf rows scattered from the compact list.
+static void train_adapter(oard_handle* h, float* frame, float* rbf_dense, float* inv_deg, cudaStream_t st) {
+  const int N = h->N, E = h->E, R = h->cfg.num_radial;
+  const int *esrc = h->buf<int>("esrc"), *ecol = h->buf<int>("ecol"), *row_ptr = h->buf<int>("row_ptr"), *act_pos = h->buf<int>("act_pos");
+  const uint8_t* mask = h->buf<uint8_t>("mask");
+  const float4* geo = h->buf<float4>("geo");
+  const float *pf = h->buf<float>("pf"), *rbf_act = h->buf<float>("rbf_act");
+  oard_train::par_for(st, (size_t)E, [=] __host__ __device__(size_t e) {
+    float* f = frame + e * 9;
+    for (int k = 0; k < 9; k++) f[k] = 0.f;
+    if (mask[e]) {
+      const int i = esrc[e], j = ecol[e];
+      const float4 g = geo[e];
+      const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2], bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
+      float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
+      cx *= cinv; cy *= cinv; cz *= cinv;
+      f[0] = g.x; f[1] = g.y; f[2] = g.z;
+      f[3] = cx; f[4] = cy; f[5] = cz;
+      f[6] = g.y * cz - g.z * cy; f[7] = g.z * cx - g.x * cz; f[8] = g.x * cy - g.y * cx;
+    }
+  });
+  oard_train::par_for(st, (size_t)E * R, [=] __host__ __device__(size_t i) {
+    const size_t e = i / R, r = i % R;
+    const int p = act_pos[e];
+    rbf_dense[i] = p >= 0 ? rbf_act[(size_t)p * R + r] : 0.f;
+  });
+  oard_train::par_for(st, (size_t)N, [=] __host__ __device__(size_t t) {
+    const int d = row_ptr[t + 1] - row_ptr[t];
+    inv_deg[t] = 1.0f / (float)(d > 0 ? d : 1);
+  });
+}
+
+static int train_setup(oard_handle* h) {
+  if (h->train_ready) return OARD_OK;
+  oard_train::Ctx& c = h->tctx;
+  c.H = h->cfg.hidden_channels; c.R = h->cfg.num_radial; c.C = h->cfg.in_hidden_channels; c.L = h->cfg.num_layers;
+  c.reflect = h->cfg.reflect_equiv; c.legacy = h->cfg.legacy;
+  for (size_t i = 0; i < h->specs.size(); i++) {
+    const std::string& n = h->specs[i].name;
+    c.W[n] = h->wdev[i];
+    c.wn[n] = (size_t)h->specs[i].numel;
+    c.dW[n] = oard_train::dev_alloc((size_t)h->specs[i].numel);
+    if (!c.dW[n]) return fail(OARD_ECUDA, "cudaMalloc of the gradient buffer of '%s' failed", n.c_str());
+  }
+  h->train_ready = true;
+  return OARD_OK;
+}
+
+extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float* pos, const int64_t* sub, float* h_out,
+                                  float* dpos, void* stream) {
+  if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
+  if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
+  if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
+  if (!h->cfg.update || !h->cfg.legacy) return fail(OARD_EINVAL, "training path implements update=1, legacy=1 only");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = train_setup(h);
+  if (rc) return rc;
+  // graph artefacts + geometry: the inference kernels (their outputs of this call are scratch)
+  rc = forward_impl(h, h_in, pos, h->cfg.object_aware ? sub : nullptr, h->buf<float>("g_h_out"), h->buf<float>("g_dpos"), st);
+  if (rc) return rc;
+  oard_train::Ctx& c = h->tctx;
+  c.N = h->N; c.E = h->E; c.stream = st;
+  float* frame = c.A("geo_frame", (size_t)h->E * 9);
+  float* rbf_dense = c.A("geo_rbf", (size_t)h->E * h->cfg.num_radial);
+  float* inv_deg = c.A("geo_inv_deg", (size_t)h->N);
+  if (!frame || !rbf_dense || !inv_deg) return fail(OARD_ECUDA, "cudaMalloc failed (training geometry)");
+  train_adapter(h, frame, rbf_dense, inv_deg, st);
+  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), frame, h->buf<float>("rb"), rbf_dense, inv_deg,
+                         h->buf<float>("nodeframe"), h->buf<float>("pos_prjt")};
+  float* h_saved = c.A("h_in_saved", (size_t)h->N * h->cfg.in_hidden_channels);
+  if (!h_saved) return fail(OARD_ECUDA, "cudaMalloc failed (training input copy)");
+  CU(cudaMemcpyAsync(h_saved, h_in, (size_t)h->N * h->cfg.in_hidden_channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  oard_train::forward(c, G, h_saved, h_out, dpos);
+  CU(cudaGetLastError());
+  h->train_fwd_done = true;
+  return OARD_OK;
+}
+
+extern "C" int oard_backward(oard_handle* h, const float* g_h_out, const float* g_dpos, float* g_h_in, void* stream) {
+  if (!h || !g_h_out || !g_dpos || !g_h_in) return fail(OARD_EINVAL, "null argument");
+  if (!h->train_fwd_done) return fail(OARD_ESTATE, "oard_forward_train has not been called for the current plan");
+  CU(cudaSetDevice(h->device));
+  oard_train::Ctx& c = h->tctx;
+  c.stream = stream;
+  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), c.act.at("geo_frame"), h->buf<float>("rb"), c.act.at("geo_rbf"),
+                         c.act.at("geo_inv_deg"), h->buf<float>("nodeframe"), h->buf<float>("pos_prjt")};
+  // the saved node-feature input: z_emb / ne_pre were computed from it; the caller's h_in may be gone, so keep a copy
+  oard_train::backward(c, G, c.act.at("h_in_saved"), g_h_out, g_dpos, g_h_in);
+  CU(cudaGetLastError());
+  return OARD_OK;
+}
+
+extern "C" int oard_zero_grads(oard_handle* h, void* stream) {
+  if (!h) return fail(OARD_EINVAL, "null handle");
+  CU(cudaSetDevice(h->device));
+  int rc = train_setup(h);
+  if (rc) return rc;
+  for (auto& kv : h->tctx.dW) CU(cudaMemsetAsync(kv.second, 0, h->tctx.wn[kv.first] * sizeof(float), (cudaStream_t)stream));
+  return OARD_OK;
+}
+
+extern "C" int oard_get_grad(oard_handle* h, const char* name, float* dst, int64_t numel, void* stream) {
+  if (!h || !name || !dst) return fail(OARD_EINVAL, "null argument");
+  auto it = h->tctx.dW.find(name);
+  if (it == h->tctx.dW.end()) return fail(OARD_EINVAL, "no gradient buffer '%s' (call oard_forward_train first)", name);
+  if ((size_t)numel != h->tctx.wn[name]) return fail(OARD_EINVAL, "gradient '%s': expected %zu elements, got %lld", name, h->tctx.wn[name], (long long)numel);
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(dst, it->second, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return OARD_OK;
 }
 

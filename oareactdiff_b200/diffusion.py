@@ -55,10 +55,15 @@ class EnVariationalDiffusion(nn.Module):
         lowest_t = 0 if self.training else 1
         return torch.randint(lowest_t, self.T + 1, size=(num_sample, 1), device=device).float()
 
-    @torch.no_grad()
     def forward(self, representations: List[Dict], conditions: Tensor, return_pred: bool = False):
         """Loss and NLL terms of one noised batch (en_diffusion.py:56-248), same keys and arithmetic as the reference.
-        The denoiser runs in the CUDA library, which has no backward yet: the terms are values (no autograd graph)."""
+        Values only (no autograd graph) unless the model's `enable_training_path` is set and grad mode is on, in which case
+        the terms carry gradients to every parameter of the dynamics (oard_forward_train / oard_backward)."""
+        with_grad = torch.is_grad_enabled() and getattr(getattr(self.dynamics, "model", None), "enable_training_path", False)
+        with torch.set_grad_enabled(with_grad):
+            return self._forward_terms(representations, conditions, return_pred)
+
+    def _forward_terms(self, representations: List[Dict], conditions: Tensor, return_pred: bool = False):
         num_sample = representations[0]["size"].size(0)
         n_nodes = torch.stack([rep["size"] for rep in representations], dim=0).sum(dim=0)
         device = representations[0]["pos"].device

@@ -85,6 +85,8 @@ class EGNNDynamics(BaseDynamics):
 
     # ---- device-resident path: prologue, LEFTNet and epilogue behind the C ABI (oard_dyn_forward / oard_reverse_step)
     def fused_ok(self, device) -> bool:
+        if torch.is_grad_enabled() and getattr(self.model, "enable_training_path", False):
+            return False  # training: the torch-composed wrapper below carries autograd through encoders / decoders
         return (isinstance(self.model, LEFTNetB200) and torch.device(device).type == "cuda" and self.pos_dim == 3
                 and len(set(self.node_nfs)) == 1 and self.node_nfs[0] - 3 <= 16 and self.update_pocket_coords
                 and len(self.fragment_names) <= 8 and getattr(self, "use_fused", True))

@@ -5,7 +5,8 @@ Same constructor kwargs, same parameter/buffer names (SURVEY.md App. B — check
 `EGNNDynamics(model=LEFTNetB200, model_config=...)` (dynamics/_base.py:62-64).
 
 The torch modules below only HOLD parameters; all arithmetic of `forward` runs in hand-written CUDA kernels
-(csrc/) behind the C ABI of include/oard.h.  Inference only: outputs are detached (no autograd through the kernels).
+(csrc/) behind the C ABI of include/oard.h.  Default: inference (outputs detached).  With `enable_training_path = True`
+and grad mode on, `forward` is an autograd node whose forward / backward are `oard_forward_train` / `oard_backward`.
 """
 import ctypes as C
 import math
@@ -233,6 +234,34 @@ class _Engine:
                                               self._ptr(cond), self._ptr(sub), t, alpha_ts, coef, sigma,
                                               self._stream(self.device)))
 
+    # ---- training: differentiable forward + backward behind the C ABI (include/oard.h, csrc/train_core.h)
+    def forward_train(self, h: Tensor, pos: Tensor, sub: Optional[Tensor]):
+        h = h.detach().to(torch.float32).contiguous()
+        pos = pos.detach().to(torch.float32).contiguous()
+        h_out, dpos = torch.empty_like(h), torch.empty_like(pos)
+        sp = None
+        if sub is not None:
+            sub = sub.detach().reshape(-1).to(torch.int64).contiguous()
+            if sub.numel() != self.E:
+                raise ValueError(f"subgraph_mask has {sub.numel()} entries, edge_index has {self.E} edges")
+            sp = C.c_void_p(sub.data_ptr())
+        st = self._stream(self.device)
+        _lib.check(self.lib.oard_zero_grads(self.h, st))
+        _lib.check(self.lib.oard_forward_train(self.h, self._ptr(h), self._ptr(pos), sp, self._ptr(h_out), self._ptr(dpos), st))
+        return h_out, dpos
+
+    def backward(self, g_h: Tensor, g_dpos: Tensor) -> Tensor:
+        g_h = g_h.detach().to(torch.float32).contiguous()
+        g_dpos = g_dpos.detach().to(torch.float32).contiguous()
+        g_in = torch.empty_like(g_h)
+        _lib.check(self.lib.oard_backward(self.h, self._ptr(g_h), self._ptr(g_dpos), self._ptr(g_in), self._stream(self.device)))
+        return g_in
+
+    def get_grad(self, name: str, like: Tensor) -> Tensor:
+        out = torch.empty(like.shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.oard_get_grad(self.h, name.encode(), self._ptr(out), out.numel(), self._stream(self.device)))
+        return out
+
     # ---- parity instrumentation
     def set_debug(self, on: bool):
         _lib.check(self.lib.oard_set_debug(self.h, int(on)))
@@ -263,6 +292,29 @@ class _Engine:
             _lib.check(self.lib.oard_profile_get(self.h, i, C.byref(tag), C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)))
             out[tag.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
         return out
+
+
+class _LeftnetTrainFn(torch.autograd.Function):
+    """LEFTNet.forward with gradients: forward = oard_forward_train (exact fp32, activations kept in the handle), backward =
+    oard_backward (hand-derived, csrc/train_core.h).  One forward/backward pair in flight per engine.  No gradient flows to
+    the positions (no parameter lies upstream of them in the dynamics)."""
+
+    @staticmethod
+    def forward(ctx, eng, names, h, pos, sub, *tensors):
+        h_out, dpos = eng.forward_train(h, pos, sub)
+        ctx.eng, ctx.names = eng, names
+        ctx.meta = [(t.shape, t.dtype, t.requires_grad) for t in tensors]
+        ctx.h_dtype = h.dtype
+        return h_out.to(h.dtype), dpos.to(pos.dtype)
+
+    @staticmethod
+    def backward(ctx, g_h, g_dpos):
+        eng = ctx.eng
+        g_in = eng.backward(g_h, g_dpos).to(ctx.h_dtype)
+        grads = []
+        for name, (shape, dtype, req) in zip(ctx.names, ctx.meta):
+            grads.append(eng.get_grad(name, torch.empty(shape, device="meta")).to(dtype) if req else None)
+        return (None, None, g_in, None, None, *grads)
 
 
 class LEFTNetB200(nn.Module):
@@ -305,6 +357,10 @@ class LEFTNetB200(nn.Module):
         self.inv_sqrt_2 = 1 / math.sqrt(2.0)
         self._engines: Dict[torch.device, _Engine] = {}
         self.assume_static_weights = False  # set True to skip the per-call weight-version check
+        # True: under torch.enable_grad() forward() builds an autograd node (oard_forward_train / oard_backward).  Off by
+        # default: the training kernels are validated in their host-emulation build (tests/test_train_emu.py) but have not
+        # run on hardware yet (tests/test_gpu_train.py, OARD_TRAIN_GPU=1).
+        self.enable_training_path = False
 
     # tensors the C library needs, keyed by reference state-dict name
     def _oard_tensors(self) -> Dict[str, Tensor]:
@@ -321,10 +377,31 @@ class LEFTNetB200(nn.Module):
             eng = self._engines[device] = _Engine(self.cfg, device)
         return eng
 
-    @torch.no_grad()
     def forward(self, h: Tensor, pos: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None,
                 node_mask: Optional[Tensor] = None, edge_mask: Optional[Tensor] = None,
                 update_coords_mask: Optional[Tensor] = None, subgraph_mask: Optional[Tensor] = None):
+        if self.enable_training_path and torch.is_grad_enabled():
+            return self._forward_train(h, pos, edge_index, node_mask, update_coords_mask, subgraph_mask)
+        return self._forward_infer(h, pos, edge_index, edge_attr, node_mask, edge_mask, update_coords_mask, subgraph_mask)
+
+    def _forward_train(self, h, pos, edge_index, node_mask, update_coords_mask, subgraph_mask):
+        eng = self.engine(pos.device)
+        eng.sync_weights(self)
+        eng.plan(edge_index, pos.size(0))
+        sd = self._oard_tensors()
+        tensors = [sd[n] for n in eng.names]
+        h_out, dpos = _LeftnetTrainFn.apply(eng, list(eng.names), h, pos, subgraph_mask if self.object_aware else None, *tensors)
+        if update_coords_mask is not None:
+            dpos = update_coords_mask * dpos
+        pos_out = pos + dpos
+        if node_mask is not None:
+            h_out = h_out * node_mask
+        return h_out, pos_out, None
+
+    @torch.no_grad()
+    def _forward_infer(self, h: Tensor, pos: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None,
+                       node_mask: Optional[Tensor] = None, edge_mask: Optional[Tensor] = None,
+                       update_coords_mask: Optional[Tensor] = None, subgraph_mask: Optional[Tensor] = None):
         eng = self.engine(pos.device)
         if not (self.assume_static_weights and eng.weights_key is not None):
             eng.sync_weights(self)
