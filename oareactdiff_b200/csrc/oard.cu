@@ -1182,6 +1182,7 @@ extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float
   int rc = train_setup(h);
   if (rc) return rc;
   // graph artefacts + geometry: the inference kernels (their outputs of this call are scratch)
+  h->prof_now = false;
   rc = forward_impl(h, h_in, pos, h->cfg.object_aware ? sub : nullptr, h->buf<float>("g_h_out"), h->buf<float>("g_dpos"), st);
   if (rc) return rc;
   oard_train::Ctx& c = h->tctx;
@@ -1189,10 +1190,16 @@ extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float
   float* frame = c.A("geo_frame", (size_t)h->E * 9);
   float* rbf_dense = c.A("geo_rbf", (size_t)h->E * h->cfg.num_radial);
   float* inv_deg = c.A("geo_inv_deg", (size_t)h->N);
-  if (!frame || !rbf_dense || !inv_deg) return fail(OARD_ECUDA, "cudaMalloc failed (training geometry)");
+  // private copies of the per-step constants the backward reads: a later inference call may overwrite the workspace
+  float* rb_c = c.A("geo_rb", (size_t)h->E);
+  float* nf_c = c.A("geo_nodeframe", (size_t)h->N * 9);
+  float* pp_c = c.A("geo_pos_prjt", (size_t)h->N * 3);
+  if (!frame || !rbf_dense || !inv_deg || !rb_c || !nf_c || !pp_c) return fail(OARD_ECUDA, "cudaMalloc failed (training geometry)");
   train_adapter(h, frame, rbf_dense, inv_deg, st);
-  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), frame, h->buf<float>("rb"), rbf_dense, inv_deg,
-                         h->buf<float>("nodeframe"), h->buf<float>("pos_prjt")};
+  CU(cudaMemcpyAsync(rb_c, h->buf<float>("rb"), (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(nf_c, h->buf<float>("nodeframe"), (size_t)h->N * 36, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(pp_c, h->buf<float>("pos_prjt"), (size_t)h->N * 12, cudaMemcpyDeviceToDevice, st));
+  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), frame, rb_c, rbf_dense, inv_deg, nf_c, pp_c};
   float* h_saved = c.A("h_in_saved", (size_t)h->N * h->cfg.in_hidden_channels);
   if (!h_saved) return fail(OARD_ECUDA, "cudaMalloc failed (training input copy)");
   CU(cudaMemcpyAsync(h_saved, h_in, (size_t)h->N * h->cfg.in_hidden_channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1208,8 +1215,8 @@ extern "C" int oard_backward(oard_handle* h, const float* g_h_out, const float* 
   CU(cudaSetDevice(h->device));
   oard_train::Ctx& c = h->tctx;
   c.stream = stream;
-  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), c.act.at("geo_frame"), h->buf<float>("rb"), c.act.at("geo_rbf"),
-                         c.act.at("geo_inv_deg"), h->buf<float>("nodeframe"), h->buf<float>("pos_prjt")};
+  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), c.act.at("geo_frame"), c.act.at("geo_rb"), c.act.at("geo_rbf"),
+                         c.act.at("geo_inv_deg"), c.act.at("geo_nodeframe"), c.act.at("geo_pos_prjt")};
   // the saved node-feature input: z_emb / ne_pre were computed from it; the caller's h_in may be gone, so keep a copy
   oard_train::backward(c, G, c.act.at("h_in_saved"), g_h_out, g_dpos, g_h_in);
   CU(cudaGetLastError());

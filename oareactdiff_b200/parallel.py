@@ -44,6 +44,45 @@ def broadcast_module_(module: nn.Module, src: int = 0) -> int:
     return flat.numel() * 4
 
 
+@torch.no_grad()
+def allreduce_gradients_(module: nn.Module, bucket_bytes: int = 64 << 20) -> int:
+    """Data-parallel training (the reference trains under Lightning DDP, trainer/train_ts1x.py:214-232): average the
+    parameter gradients over the ranks in flat buckets (one collective per ~64 MB instead of one per tensor: on NVSwitch the
+    cost is launch latency, not link count).  Parameters without a gradient on this rank contribute zeros, so every rank
+    issues the same collectives.  Returns the bytes reduced."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    params = [p for p in module.parameters() if p.requires_grad]
+    total, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal bucket, size, total
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= world
+        o = 0
+        for p in bucket:
+            g = flat[o:o + p.numel()].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            o += p.numel()
+        total += flat.numel() * 4
+        bucket, size = [], 0
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return total
+
+
 def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([float(value)], device=device)
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -1,4 +1,5 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: reaction sharding, weight broadcast, max-over-ranks."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: reaction sharding, weight broadcast, max-over-ranks,
+bucketed gradient averaging."""
 import os
 
 import torch
@@ -30,8 +31,13 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     mx = parallel.max_over_ranks(10.0 + rank, "cpu")
+    # gradient averaging: rank r has grad = (r + 1) on the first Linear's weight only; tiny buckets force several collectives
+    m[0].weight.grad = torch.full_like(m[0].weight, float(rank + 1))
+    nred = parallel.allreduce_gradients_(m, bucket_bytes=64)
+    ok_grad = bool(torch.allclose(m[0].weight.grad, torch.full_like(m[0].weight, (1 + world) / 2.0))) and \
+        all(float(p.grad.abs().max()) == 0.0 for n, p in m.named_parameters() if n != "0.weight")
     if rank == 0:
-        out.put((nbytes, bool(all(torch.equal(g, gathered[0]) for g in gathered)), mx))
+        out.put((nbytes, bool(all(torch.equal(g, gathered[0]) for g in gathered)), mx, nred, ok_grad))
     dist.destroy_process_group()
 
 
@@ -45,5 +51,6 @@ def test_broadcast_and_max_over_ranks_gloo_world2():
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    nbytes, equal, mx = q.get()
+    nbytes, equal, mx, nred, ok_grad = q.get()
     assert nbytes == (7 * 5 + 5 + 5 + 5) * 4 and equal and mx == 11.0
+    assert nred == (7 * 5 + 5 + 5 + 5) * 4 and ok_grad
