@@ -116,6 +116,7 @@ struct oard_handle {
   // training: differentiable core (train_core.h) + dense geometry adapter buffers
   oard_train::Ctx tctx;
   bool train_ready = false, train_fwd_done = false;
+  int train_n_act = 0;
   // device-resident dynamics wrapper + reverse step (dynamics.cuh)
   bool dyn_cfg = false, dyn_committed = false, dyn_planned = false;
   int dyn_nfrag = 0, dyn_nf = 0, dyn_d = 0, dyn_emb = 0, dyn_cnd = 0, dyn_ctime = 0, dyn_S = 0, dyn_B = 0;
@@ -1199,7 +1200,16 @@ extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float
   CU(cudaMemcpyAsync(rb_c, h->buf<float>("rb"), (size_t)h->E * 4, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(nf_c, h->buf<float>("nodeframe"), (size_t)h->N * 36, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(pp_c, h->buf<float>("pos_prjt"), (size_t)h->N * 12, cudaMemcpyDeviceToDevice, st));
-  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), frame, rb_c, rbf_dense, inv_deg, nf_c, pp_c};
+  // compact list of active edges: the count is read back (one host sync per training step)
+  int n_act = 0;
+  CU(cudaMemcpyAsync(&n_act, h->buf<int>("n_act"), 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  n_act = std::min(n_act, h->E);
+  int* act_c = reinterpret_cast<int*>(c.A("geo_act_idx", (size_t)std::max(h->E, 1)));
+  if (!act_c) return fail(OARD_ECUDA, "cudaMalloc failed (training geometry)");
+  CU(cudaMemcpyAsync(act_c, h->buf<int>("act_idx"), (size_t)n_act * 4, cudaMemcpyDeviceToDevice, st));
+  h->train_n_act = n_act;
+  oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), frame, rb_c, rbf_dense, inv_deg, nf_c, pp_c, act_c, n_act};
   float* h_saved = c.A("h_in_saved", (size_t)h->N * h->cfg.in_hidden_channels);
   if (!h_saved) return fail(OARD_ECUDA, "cudaMalloc failed (training input copy)");
   CU(cudaMemcpyAsync(h_saved, h_in, (size_t)h->N * h->cfg.in_hidden_channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1216,7 +1226,8 @@ extern "C" int oard_backward(oard_handle* h, const float* g_h_out, const float* 
   oard_train::Ctx& c = h->tctx;
   c.stream = stream;
   oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), c.act.at("geo_frame"), c.act.at("geo_rb"), c.act.at("geo_rbf"),
-                         c.act.at("geo_inv_deg"), c.act.at("geo_nodeframe"), c.act.at("geo_pos_prjt")};
+                         c.act.at("geo_inv_deg"), c.act.at("geo_nodeframe"), c.act.at("geo_pos_prjt"),
+                         reinterpret_cast<const int*>(c.act.at("geo_act_idx")), h->train_n_act};
   // the saved node-feature input: z_emb / ne_pre were computed from it; the caller's h_in may be gone, so keep a copy
   oard_train::backward(c, G, c.act.at("h_in_saved"), g_h_out, g_dpos, g_h_in);
   CU(cudaGetLastError());

@@ -141,6 +141,8 @@ struct Geometry {            // dense per-edge / per-node constants of one forwa
   const float* inv_deg_i;    // [N] 1 / max(1, #edges with ei == t)  (GCL mean aggregation at edge_index[0])
   const float* nodeframe;    // [N, 3(xyz), 3(k)]
   const float* pos_prjt;     // [N, 3]
+  const int* act_idx;        // [n_act] edges with mask = 1, ascending: EquiMessage (dir_proj / rbf_proj / messages) runs on
+  int n_act;                 //   these only — on masked edges rbf = 0, so its forward AND backward contributions vanish
 };
 
 struct Ctx {
@@ -430,21 +432,26 @@ inline void forward(Ctx& c, const Geometry& G, const float* h_in, float* h_out, 
     lin_fwd(c, N, H, H, y, H, c.w(ml + "x_proj.0.weight"), H, nullptr, xh_pre, H);
     silu_fwd(c, (size_t)N * H, xh_pre, xh);
     lin_fwd(c, N, 3 * H, H, xh, H, c.w(ml + "x_proj.2.weight"), H, nullptr, X, 3 * H);
-    float* d_pre = c.A("d_pre_" + sl, (size_t)E * 3 * H); float* d1 = c.A("d1_" + sl, (size_t)E * 3 * H);
-    float* D2 = c.A("D2_" + sl, (size_t)E * 3 * H); float* RB = c.A("RB_" + sl, (size_t)E * 3 * H);
-    lin_fwd(c, E, 3 * H, D, e_new, D, c.w(ml + "dir_proj.0.weight"), D, c.w(ml + "dir_proj.0.bias"), d_pre, 3 * H);
-    silu_fwd(c, (size_t)E * 3 * H, d_pre, d1);
-    lin_fwd(c, E, 3 * H, 3 * H, d1, 3 * H, c.w(ml + "dir_proj.2.weight"), 3 * H, c.w(ml + "dir_proj.2.bias"), D2, 3 * H);
-    lin_fwd(c, E, 3 * H, R, rbf, R, c.w(ml + "rbf_proj.weight"), R, nullptr, RB, 3 * H);
+    // active edges only (compact rows p = 0 .. n_act-1 of edge act_idx[p])
+    const int nA = G.n_act; const int* aidx = G.act_idx;
+    float* ea = c.A("ea_" + sl, (size_t)nA * D); float* rbfa = c.A("rbfa", (size_t)nA * R);
+    par_for(c.stream, (size_t)nA * D, OARD_LAMBDA(size_t i) { ea[i] = e_new[(size_t)aidx[i / D] * D + (i % D)]; });
+    if (l == 0) par_for(c.stream, (size_t)nA * R, OARD_LAMBDA(size_t i) { rbfa[i] = rbf[(size_t)aidx[i / R] * R + (i % R)]; });
+    float* d_pre = c.A("d_pre_" + sl, (size_t)nA * 3 * H); float* d1 = c.A("d1_" + sl, (size_t)nA * 3 * H);
+    float* D2 = c.A("D2_" + sl, (size_t)nA * 3 * H); float* RB = c.A("RB_" + sl, (size_t)nA * 3 * H);
+    lin_fwd(c, nA, 3 * H, D, ea, D, c.w(ml + "dir_proj.0.weight"), D, c.w(ml + "dir_proj.0.bias"), d_pre, 3 * H);
+    silu_fwd(c, (size_t)nA * 3 * H, d_pre, d1);
+    lin_fwd(c, nA, 3 * H, 3 * H, d1, 3 * H, c.w(ml + "dir_proj.2.weight"), 3 * H, c.w(ml + "dir_proj.2.bias"), D2, 3 * H);
+    lin_fwd(c, nA, 3 * H, R, rbfa, R, c.w(ml + "rbf_proj.weight"), R, nullptr, RB, 3 * H);
     float* s2 = c.A("s2_" + sl, (size_t)N * H); float* vec1 = c.A("vec1_" + sl, (size_t)N * 3 * H);
     par_for(c.stream, (size_t)N * H, OARD_LAMBDA(size_t i) { s2[i] = s1[i]; });  // accumulates dx, scaled below
     par_for(c.stream, (size_t)N * 3 * H, OARD_LAMBDA(size_t i) { vec1[i] = vec[i]; });
-    par_for(c.stream, (size_t)E * H, OARD_LAMBDA(size_t i) {
-      const size_t ee = i / H, h = i % H;
+    par_for(c.stream, (size_t)nA * H, OARD_LAMBDA(size_t i) {
+      const size_t p = i / H, h = i % H, ee = aidx[p];
       const size_t a = ei[ee], t = ej[ee];
-      const float al = (X[a * 3 * H + h] + X[t * 3 * H + h]) * RB[ee * 3 * H + h] * D2[ee * 3 * H + h];
-      const float be = (X[a * 3 * H + H + h] + X[t * 3 * H + H + h]) * RB[ee * 3 * H + H + h] * D2[ee * 3 * H + H + h] * inv_sqrt_3;
-      const float ga = (X[a * 3 * H + 2 * H + h] + X[t * 3 * H + 2 * H + h]) * RB[ee * 3 * H + 2 * H + h] * D2[ee * 3 * H + 2 * H + h];
+      const float al = (X[a * 3 * H + h] + X[t * 3 * H + h]) * RB[p * 3 * H + h] * D2[p * 3 * H + h];
+      const float be = (X[a * 3 * H + H + h] + X[t * 3 * H + H + h]) * RB[p * 3 * H + H + h] * D2[p * 3 * H + H + h] * inv_sqrt_3;
+      const float ga = (X[a * 3 * H + 2 * H + h] + X[t * 3 * H + 2 * H + h]) * RB[p * 3 * H + 2 * H + h] * D2[p * 3 * H + 2 * H + h];
       t_atomic_add(&s2[t * H + h], al);
       for (int cc = 0; cc < 3; cc++) {
         float v = vec[(a * 3 + cc) * H + h] * be + ga * frame[ee * 9 + cc];
@@ -584,7 +591,7 @@ inline void backward(Ctx& c, const Geometry& G, const float* h_in, const float* 
     float* x = act("x_" + sl); float* xa = act("xa_" + sl); float* s1 = act("s1_" + sl); float* s2 = act("s2_" + sl);
     float* vec1 = act("vec1_" + sl); float* VP = act("VP_" + sl); float* XV = act("XV_" + sl); float* X = act("X_" + sl);
     float* D2 = act("D2_" + sl); float* RB = act("RB_" + sl); float* m = act("m_" + sl); float* mg = act("mg_" + sl);
-    (void)s2; (void)xa;
+    (void)s2; (void)xa; (void)e_new;
     // ---- EquiUpdate (apply)
     float* g_XV = c.A("g_XV", (size_t)N * 3 * H); float* g_VP = c.Z("g_VP", (size_t)N * 3 * 2 * H); float* g_vd = c.A("g_vd", (size_t)N * H);
     par_for(c.stream, (size_t)N * H, OARD_LAMBDA(size_t i) {
@@ -627,16 +634,17 @@ inline void backward(Ctx& c, const Geometry& G, const float* h_in, const float* 
     }
     lin_bwd(c, 3 * N, 2 * H, H, vec1, H, c.w(u + "vec_proj.weight"), H, g_VP, 2 * H, gvec, H, 1.f, c.g(u + "vec_proj.weight"), nullptr);
     // ---- EquiMessage: s2 = (s1 + dx)/sqrt2, vec1 = vec_l + dvec
-    float* g_X = c.Z("g_X", (size_t)N * 3 * H); float* g_RB = c.A("g_RB", (size_t)E * 3 * H); float* g_D2 = c.A("g_D2", (size_t)E * 3 * H);
+    const int nA = G.n_act; const int* aidx = G.act_idx;
+    float* g_X = c.Z("g_X", (size_t)N * 3 * H); float* g_RB = c.A("g_RB", (size_t)nA * 3 * H); float* g_D2 = c.A("g_D2", (size_t)nA * 3 * H);
     float* g_vecl = c.A("g_vecl", (size_t)N * 3 * H);
     par_for(c.stream, (size_t)N * 3 * H, OARD_LAMBDA(size_t i) { g_vecl[i] = gvec[i]; });
-    par_for(c.stream, (size_t)E * H, OARD_LAMBDA(size_t i) {
-      const size_t ee = i / H, h = i % H;
+    par_for(c.stream, (size_t)nA * H, OARD_LAMBDA(size_t i) {
+      const size_t p = i / H, h = i % H, ee = aidx[p];
       const size_t a = ei[ee], t = ej[ee];
       float xs[3], gm[3];
       for (int k = 0; k < 3; k++) {
         xs[k] = X[a * 3 * H + k * H + h] + X[t * 3 * H + k * H + h];
-        gm[k] = RB[ee * 3 * H + k * H + h] * D2[ee * 3 * H + k * H + h];
+        gm[k] = RB[p * 3 * H + k * H + h] * D2[p * 3 * H + k * H + h];
       }
       const float be = xs[1] * gm[1] * inv_sqrt_3;
       float g_al = gs[t * H + h] * inv_sqrt_2, g_be = 0.f, g_ga = 0.f;
@@ -652,17 +660,20 @@ inline void backward(Ctx& c, const Geometry& G, const float* h_in, const float* 
       for (int k = 0; k < 3; k++) {
         t_atomic_add(&g_X[a * 3 * H + k * H + h], gxs[k]);
         t_atomic_add(&g_X[t * 3 * H + k * H + h], gxs[k]);
-        g_RB[ee * 3 * H + k * H + h] = ggm[k] * D2[ee * 3 * H + k * H + h];
-        g_D2[ee * 3 * H + k * H + h] = ggm[k] * RB[ee * 3 * H + k * H + h];
+        g_RB[p * 3 * H + k * H + h] = ggm[k] * D2[p * 3 * H + k * H + h];
+        g_D2[p * 3 * H + k * H + h] = ggm[k] * RB[p * 3 * H + k * H + h];
       }
     });
     par_for(c.stream, (size_t)N * H, OARD_LAMBDA(size_t i) { gs[i] *= inv_sqrt_2; });  // g_s1 (from s2)
-    lin_bwd(c, E, 3 * H, R, rbf, R, c.w(ml + "rbf_proj.weight"), R, g_RB, 3 * H, nullptr, 0, 0.f, c.g(ml + "rbf_proj.weight"), nullptr);
-    float* g_d1 = c.A("g_d1", (size_t)E * 3 * H);
-    lin_bwd(c, E, 3 * H, 3 * H, act("d1_" + sl), 3 * H, c.w(ml + "dir_proj.2.weight"), 3 * H, g_D2, 3 * H, g_d1, 3 * H, 0.f,
+    lin_bwd(c, nA, 3 * H, R, act("rbfa"), R, c.w(ml + "rbf_proj.weight"), R, g_RB, 3 * H, nullptr, 0, 0.f, c.g(ml + "rbf_proj.weight"), nullptr);
+    float* g_d1 = c.A("g_d1", (size_t)nA * 3 * H);
+    lin_bwd(c, nA, 3 * H, 3 * H, act("d1_" + sl), 3 * H, c.w(ml + "dir_proj.2.weight"), 3 * H, g_D2, 3 * H, g_d1, 3 * H, 0.f,
             c.g(ml + "dir_proj.2.weight"), c.g(ml + "dir_proj.2.bias"));
-    silu_bwd(c, (size_t)E * 3 * H, act("d_pre_" + sl), g_d1, g_d1);
-    lin_bwd(c, E, 3 * H, D, e_new, D, c.w(ml + "dir_proj.0.weight"), D, g_d1, 3 * H, ge, D, 1.f, c.g(ml + "dir_proj.0.weight"), c.g(ml + "dir_proj.0.bias"));
+    silu_bwd(c, (size_t)nA * 3 * H, act("d_pre_" + sl), g_d1, g_d1);
+    float* g_ea = c.A("g_ea", (size_t)nA * D);
+    lin_bwd(c, nA, 3 * H, D, act("ea_" + sl), D, c.w(ml + "dir_proj.0.weight"), D, g_d1, 3 * H, g_ea, D, 0.f,
+            c.g(ml + "dir_proj.0.weight"), c.g(ml + "dir_proj.0.bias"));
+    par_for(c.stream, (size_t)nA * D, OARD_LAMBDA(size_t i) { ge[(size_t)aidx[i / D] * D + (i % D)] += g_ea[i]; });  // distinct rows
     float* g_xh = c.A("g_xh", (size_t)N * H); float* g_y = c.A("g_y", (size_t)N * H);
     lin_bwd(c, N, 3 * H, H, act("xh_" + sl), H, c.w(ml + "x_proj.2.weight"), H, g_X, 3 * H, g_xh, H, 0.f, c.g(ml + "x_proj.2.weight"), nullptr);
     silu_bwd(c, (size_t)N * H, act("xh_pre_" + sl), g_xh, g_xh);

@@ -21,9 +21,9 @@ extern "C" void emu_set_weight(const char* name, float* data, long numel) {
 }
 extern "C" void emu_forward_backward(const int* ei, const int* ej, const float* frame, const float* rb, const float* rbf,
                                      const float* inv_deg_i, const float* nodeframe, const float* pos_prjt,
-                                     const float* h_in, float* h_out, float* dpos, const float* g_hout, const float* g_dpos,
+                                     const int* act_idx, int n_act, const float* h_in, float* h_out, float* dpos, const float* g_hout, const float* g_dpos,
                                      float* g_hin) {
-  Geometry G{ei, ej, frame, rb, rbf, inv_deg_i, nodeframe, pos_prjt};
+  Geometry G{ei, ej, frame, rb, rbf, inv_deg_i, nodeframe, pos_prjt, act_idx, n_act};
   forward(g_ctx, G, h_in, h_out, dpos);
   if (g_hout) {
     for (auto& kv : g_ctx.dW) dev_zero(nullptr, kv.second, g_ctx.wn[kv.first]);

@@ -63,7 +63,9 @@ def _geometry(case):
     frame = torch.stack((cdiff * mask, ccross * mask, cvert * mask), dim=1)  # [E, 3(k), 3(xyz)]
     rb = 0.5 * (torch.cos(dist * math.pi / float(cfg["cutoff"])) + 1.0)
     deg = torch.zeros(N, dtype=torch.float64).index_add_(0, ei[0], torch.ones(ei.size(1), dtype=torch.float64))
-    return dict(frame=frame, rb=rb, rbf=dbg["rbf"], inv_deg=1.0 / deg.clamp(min=1), nodeframe=dbg["nodeframe"], pos_prjt=dbg["pos_prjt"], dbg=dbg)
+    act = torch.nonzero(dbg["mask"] > 0).flatten().to(torch.int32).contiguous()
+    return dict(frame=frame, rb=rb, rbf=dbg["rbf"], inv_deg=1.0 / deg.clamp(min=1), nodeframe=dbg["nodeframe"], pos_prjt=dbg["pos_prjt"],
+                act=act, dbg=dbg)
 
 
 @pytest.mark.parametrize("cfg_name,sizes,pos_scale", [("small", [4, 3], 1.5), ("small", [5, 2, 3], 3.0), ("mid", [4, 3], 1.5)])
@@ -95,7 +97,8 @@ def test_core_forward_and_backward_vs_oracle(emu, cfg_name, sizes, pos_scale):
     h32, A32, B32 = f32(case["h"]), f32(A), f32(B)
     ho, dp, gh = torch.zeros(N, Cin), torch.zeros(N, 3), torch.zeros(N, Cin)
     emu.emu_forward_backward(_p(ei32), _p(ej32), _p(t["frame"]), _p(t["rb"]), _p(t["rbf"]), _p(t["inv_deg"]), _p(t["nodeframe"]),
-                             _p(t["pos_prjt"]), _p(h32), _p(ho), _p(dp), _p(A32), _p(B32), _p(gh))
+                             _p(t["pos_prjt"]), _p(geo["act"]), C.c_int(geo["act"].numel()), _p(h32), _p(ho), _p(dp), _p(A32), _p(B32), _p(gh))
+    assert 0 < geo["act"].numel() < E  # both active and masked edges are exercised
     rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max().clamp(min=1e-30))
     e_h, e_p = rel(ho, h_out.detach()), rel(dp, dpos.detach())
     print(f"forward: h_out {e_h:.2e} dpos {e_p:.2e}")

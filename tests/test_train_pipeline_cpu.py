@@ -30,7 +30,8 @@ class _EmuFn(torch.autograd.Function):
         h32 = h.detach().to(torch.float32).contiguous()
         ho, dp = torch.zeros(N, h.size(1)), torch.zeros(N, 3)
         lib.emu_forward_backward(_p(ei32), _p(ej32), _p(geo["frame"]), _p(geo["rb"]), _p(geo["rbf"]), _p(geo["inv_deg"]),
-                                 _p(geo["nodeframe"]), _p(geo["pos_prjt"]), _p(h32), _p(ho), _p(dp), None, None, None)
+                                 _p(geo["nodeframe"]), _p(geo["pos_prjt"]), _p(geo["act"]), C.c_int(geo["act"].numel()), _p(h32), _p(ho),
+                                 _p(dp), None, None, None)
         ctx.saved = (lib, geo, ei32, ej32, h32, keep, names, [t.requires_grad for t in tensors])
         return ho, dp
 
@@ -42,7 +43,8 @@ class _EmuFn(torch.autograd.Function):
         gh, gd = g_h.contiguous().float(), g_dp.contiguous().float()
         # the emulation entry runs forward + backward in one call (activations live in its context)
         lib.emu_forward_backward(_p(ei32), _p(ej32), _p(geo["frame"]), _p(geo["rb"]), _p(geo["rbf"]), _p(geo["inv_deg"]),
-                                 _p(geo["nodeframe"]), _p(geo["pos_prjt"]), _p(h32), _p(ho), _p(dp), _p(gh), _p(gd), _p(gin))
+                                 _p(geo["nodeframe"]), _p(geo["pos_prjt"]), _p(geo["act"]), C.c_int(geo["act"].numel()), _p(h32), _p(ho),
+                                 _p(dp), _p(gh), _p(gd), _p(gin))
         grads = []
         for n, t, r in zip(names, keep, req):
             if not r:
@@ -72,7 +74,8 @@ def _make_emu_leftnet(lib):
                 f32 = lambda t: t.to(torch.float32).contiguous()
                 geo = dict(frame=f32(torch.stack((cdiff * mask, ccross * mask, cvert * mask), dim=1)),
                            rb=f32(0.5 * (torch.cos(dist * math.pi / float(cfg["cutoff"])) + 1.0)), rbf=f32(dbg["rbf"]),
-                           inv_deg=f32(1.0 / deg.clamp(min=1)), nodeframe=f32(dbg["nodeframe"]), pos_prjt=f32(dbg["pos_prjt"]))
+                           inv_deg=f32(1.0 / deg.clamp(min=1)), nodeframe=f32(dbg["nodeframe"]), pos_prjt=f32(dbg["pos_prjt"]),
+                           act=torch.nonzero(dbg["mask"] > 0).flatten().to(torch.int32).contiguous())
             names = [n for n in self._oard_tensors() if not n.startswith(("radial_emb.", "distance_embedding", "last_layer"))]
             tensors = [self._oard_tensors()[n] for n in names]
             h_out, dpos = _EmuFn.apply(lib, cfg, geo, edge_index, names, h, *tensors)
