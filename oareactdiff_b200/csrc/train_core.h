@@ -28,6 +28,8 @@
 #define OARD_LAMBDA [=]
 #else
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #define OARD_HD __host__ __device__
 #define OARD_LAMBDA [=] __host__ __device__
 #endif
@@ -42,6 +44,18 @@ OARD_HD inline float t_dsilu(float x) {  // d/dx [x sigmoid(x)]
 OARD_HD inline void t_atomic_add(float* p, float v) {
 #if defined(__CUDA_ARCH__)
   atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+// Same, for the case where ALL currently converged threads of the warp add to the SAME address (reductions of parameter
+// gradients over edges / nodes): one atomic per warp instead of 32 (cooperative-groups reduce over the coalesced threads,
+// valid for any active set).
+OARD_HD inline void t_atomic_add_uniform(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+  auto grp = cooperative_groups::coalesced_threads();
+  const float sum = cooperative_groups::reduce(grp, v, cooperative_groups::plus<float>());
+  if (grp.thread_rank() == 0) atomicAdd(p, sum);
 #else
   *p += v;
 #endif
@@ -86,21 +100,28 @@ inline float* dev_alloc(size_t n) {
 inline void dev_free(float* p) { cudaFree(p); }
 inline void dev_zero(void* stream, float* p, size_t n) { cudaMemsetAsync(p, 0, n * sizeof(float), (cudaStream_t)stream); }
 // Tiled SIMT GEMM with generic strides (64 x 64 tile, 16-deep K slices, 4 x 4 outputs per thread); exact fp32.
+// The tile loads walk the unit-stride dimension of each operand with consecutive threads (row- or column-major A / B).
+// ACC (beta == 1 only): the K range is split over blockIdx.z and the partial tiles are added with atomics — the
+// weight-gradient contractions reduce over up to 2e5 edge rows into a tile grid of ~100 CTAs.
+template <bool ACC>
 __global__ void __launch_bounds__(256) k_gemm_strided(int M, int N, int K, const float* __restrict__ A, long a_rs, long a_cs,
                                                        const float* __restrict__ B, long b_rs, long b_cs, float* __restrict__ C,
-                                                       long ldc, float beta) {
+                                                       long ldc, float beta, int k_per_z) {
   __shared__ float As[16][64 + 1], Bs[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kb0 = ACC ? blockIdx.z * k_per_z : 0, kb1 = ACC ? min(K, kb0 + k_per_z) : K;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kb0; k0 < kb1; k0 += 16) {
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int kk = i & 15, mm = i >> 4;  // A: consecutive threads along k (fast when a_cs == 1)
+      int kk, mm;
+      if (a_cs == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
       const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? A[(long)m * a_rs + (long)k * a_cs] : 0.f;
-      const int nn = i & 63, kb = i >> 6;  // B: consecutive threads along n (fast when b_cs == 1)
+      As[kk][mm] = (m < M && k < kb1) ? A[(long)m * a_rs + (long)k * a_cs] : 0.f;
+      int nn, kb;
+      if (b_cs == 1) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
       const int n = n0 + nn, k2 = k0 + kb;
-      Bs[kb][nn] = (n < N && k2 < K) ? B[(long)k2 * b_rs + (long)n * b_cs] : 0.f;
+      Bs[kb][nn] = (n < N && k2 < kb1) ? B[(long)k2 * b_rs + (long)n * b_cs] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -120,14 +141,24 @@ __global__ void __launch_bounds__(256) k_gemm_strided(int M, int N, int K, const
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-      if (m < M && n < N) C[(size_t)m * ldc + n] = (beta != 0.f ? beta * C[(size_t)m * ldc + n] : 0.f) + acc[i][j];
+      if (m < M && n < N) {
+        if (ACC) atomicAdd(&C[(size_t)m * ldc + n], acc[i][j]);
+        else C[(size_t)m * ldc + n] = (beta != 0.f ? beta * C[(size_t)m * ldc + n] : 0.f) + acc[i][j];
+      }
     }
 }
 inline void gemm(void* stream, int M, int N, int K, const float* A, long a_rs, long a_cs, const float* B, long b_rs,
                  long b_cs, float* C, long ldc, float beta) {
   if (M <= 0 || N <= 0) return;
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  if (beta == 1.f && K >= 8192 && tiles < 148 * 8) {  // long reduction into few tiles: split K
+    const int k_per_z = 2048;
+    dim3 grid((N + 63) / 64, (M + 63) / 64, (K + k_per_z - 1) / k_per_z);
+    k_gemm_strided<true><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, beta, k_per_z);
+    return;
+  }
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm_strided<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, beta);
+  k_gemm_strided<false><<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, beta, 0);
 }
 #endif
 
@@ -187,11 +218,16 @@ inline void lin_bwd(Ctx& c, int M, int N, int K, const float* X, long ldx, const
                     long ldy, float* dX, long lddx, float beta_dx, float* dWp, float* db) {
   if (dX) gemm(c.stream, M, K, N, dY, ldy, 1, Wp, ldw, 1, dX, lddx, beta_dx);
   if (dWp) gemm(c.stream, N, K, M, dY, 1, ldy, X, ldx, 1, dWp, ldw, 1.f);
-  if (db) par_for(c.stream, (size_t)N, OARD_LAMBDA(size_t n) {
-    float s = 0.f;
-    for (int m = 0; m < M; m++) s += dY[(size_t)m * ldy + n];
-    db[n] += s;
-  });
+  if (db) {  // column sums: 256-row chunks in parallel, one atomic per (chunk, column)
+    const int chunks = (M + 255) / 256;
+    par_for(c.stream, (size_t)chunks * N, OARD_LAMBDA(size_t i) {
+      const int ch = (int)(i / N), n = (int)(i % N);
+      const int m1 = (ch + 1) * 256 < M ? (ch + 1) * 256 : M;
+      float s = 0.f;
+      for (int m = ch * 256; m < m1; m++) s += dY[(size_t)m * ldy + n];
+      t_atomic_add(&db[n], s);
+    });
+  }
 }
 inline void silu_fwd(Ctx& c, size_t n, const float* pre, float* out) {
   par_for(c.stream, n, OARD_LAMBDA(size_t i) { out[i] = t_silu(pre[i]); });
@@ -242,7 +278,7 @@ inline void ln_bwd(Ctx& c, int rows, int H, const float* x, const float* add, co
       const float gn = gr[h] * (gamma ? gamma[h] : 1.f);
       const float v = rstd * (gn - s1 / (float)H - n * s2 / (float)H);
       gx[r * H + h] = acc_gx ? gx[r * H + h] + v : v;
-      if (ggamma) { t_atomic_add(&ggamma[h], gr[h] * n); t_atomic_add(&gbeta[h], gr[h]); }
+      if (ggamma) { t_atomic_add_uniform(&ggamma[h], gr[h] * n); t_atomic_add_uniform(&gbeta[h], gr[h]); }
     }
   });
 }
@@ -267,16 +303,15 @@ OARD_HD inline float lin3_eval(const Lin3Small& p, float s0, float s1, float s2)
 }
 // backward of lin3_eval for upstream gradient g: accumulates the weight gradients (atomics) and returns d/d(s0, s1, s2)
 OARD_HD inline void lin3_grad(const Lin3Small& p, float s0, float s1, float s2, float g, float& g0, float& g1, float& g2) {
-  g0 = g1 = g2 = 0.f;
-  if (g == 0.f) return;
+  g0 = g1 = g2 = 0.f;  // (no early exit for g == 0: every thread of the warp walks the same weights, see t_atomic_add_uniform)
   if (p.h2 == 0) {
-    t_atomic_add(&p.gb2[0], g);
+    t_atomic_add_uniform(&p.gb2[0], g);
     for (int m = 0; m < p.h1; m++) {
       const float z = p.w0[m * 3] * s0 + p.w0[m * 3 + 1] * s1 + p.w0[m * 3 + 2] * s2 + p.b0[m];
-      t_atomic_add(&p.gw2[m], g * t_silu(z));
+      t_atomic_add_uniform(&p.gw2[m], g * t_silu(z));
       const float gz = g * p.w2[m] * t_dsilu(z);
-      t_atomic_add(&p.gw0[m * 3], gz * s0); t_atomic_add(&p.gw0[m * 3 + 1], gz * s1); t_atomic_add(&p.gw0[m * 3 + 2], gz * s2);
-      t_atomic_add(&p.gb0[m], gz);
+      t_atomic_add_uniform(&p.gw0[m * 3], gz * s0); t_atomic_add_uniform(&p.gw0[m * 3 + 1], gz * s1); t_atomic_add_uniform(&p.gw0[m * 3 + 2], gz * s2);
+      t_atomic_add_uniform(&p.gb0[m], gz);
       g0 += gz * p.w0[m * 3]; g1 += gz * p.w0[m * 3 + 1]; g2 += gz * p.w0[m * 3 + 2];
     }
     return;
@@ -287,20 +322,20 @@ OARD_HD inline void lin3_grad(const Lin3Small& p, float s0, float s1, float s2, 
     const float u = t_silu(p.w0[m * 3] * s0 + p.w0[m * 3 + 1] * s1 + p.w0[m * 3 + 2] * s2 + p.b0[m]);
     for (int q = 0; q < p.h2; q++) a2[q] += p.w2[q * p.h1 + m] * u;
   }
-  t_atomic_add(&p.gb4[0], g);
+  t_atomic_add_uniform(&p.gb4[0], g);
   for (int q = 0; q < p.h2; q++) {
-    t_atomic_add(&p.gw4[q], g * t_silu(a2[q]));
+    t_atomic_add_uniform(&p.gw4[q], g * t_silu(a2[q]));
     ga2[q] = g * p.w4[q] * t_dsilu(a2[q]);
-    t_atomic_add(&p.gb2[q], ga2[q]);
+    t_atomic_add_uniform(&p.gb2[q], ga2[q]);
   }
   for (int m = 0; m < p.h1; m++) {
     const float z = p.w0[m * 3] * s0 + p.w0[m * 3 + 1] * s1 + p.w0[m * 3 + 2] * s2 + p.b0[m];
     const float u = t_silu(z);
     float gu = 0.f;
-    for (int q = 0; q < p.h2; q++) { t_atomic_add(&p.gw2[q * p.h1 + m], ga2[q] * u); gu += ga2[q] * p.w2[q * p.h1 + m]; }
+    for (int q = 0; q < p.h2; q++) { t_atomic_add_uniform(&p.gw2[q * p.h1 + m], ga2[q] * u); gu += ga2[q] * p.w2[q * p.h1 + m]; }
     const float gz = gu * t_dsilu(z);
-    t_atomic_add(&p.gw0[m * 3], gz * s0); t_atomic_add(&p.gw0[m * 3 + 1], gz * s1); t_atomic_add(&p.gw0[m * 3 + 2], gz * s2);
-    t_atomic_add(&p.gb0[m], gz);
+    t_atomic_add_uniform(&p.gw0[m * 3], gz * s0); t_atomic_add_uniform(&p.gw0[m * 3 + 1], gz * s1); t_atomic_add_uniform(&p.gw0[m * 3 + 2], gz * s2);
+    t_atomic_add_uniform(&p.gb0[m], gz);
     g0 += gz * p.w0[m * 3]; g1 += gz * p.w0[m * 3 + 1]; g2 += gz * p.w0[m * 3 + 2];
   }
 }
@@ -552,17 +587,17 @@ inline void backward(Ctx& c, const Geometry& G, const float* h_in, const float* 
     par_for(c.stream, (size_t)N, OARD_LAMBDA(size_t t) {
       float gg = 0.f;
       for (int cc = 0; cc < 3; cc++) gg += g_dpos[t * 3 + cc] * vdot2[t * 3 + cc];
-      t_atomic_add(&g_bu2[1], gg);
+      t_atomic_add_uniform(&g_bu2[1], gg);
       for (int h = 0; h < H; h++) {
         g_tu[t * H + h] = gg * wu2[H + h];
-        t_atomic_add(&g_wu2[H + h], gg * tu[t * H + h]);
+        t_atomic_add_uniform(&g_wu2[H + h], gg * tu[t * H + h]);
         float acc = 0.f;
         for (int cc = 0; cc < 3; cc++) {
           const float gv = g_dpos[t * 3 + cc] * gate[t];
           gvec[(t * 3 + cc) * H + h] = gv * wo2[h];
           acc += gv * vec[(t * 3 + cc) * H + h];
         }
-        t_atomic_add(&g_wo2[h], acc);
+        t_atomic_add_uniform(&g_wo2[h], acc);
       }
     });
   }
@@ -708,10 +743,10 @@ inline void backward(Ctx& c, const Geometry& G, const float* h_in, const float* 
           g_m[ee * H + h] = gmg * att;
         }
         const float ga = g_att * t_dsilu(a_pre[ee]);
-        t_atomic_add(&g_bat[0], ga);
+        t_atomic_add_uniform(&g_bat[0], ga);
         for (int h = 0; h < H; h++) {
           g_m[ee * H + h] += ga * wat[h];
-          t_atomic_add(&g_wat[h], ga * m[ee * H + h]);
+          t_atomic_add_uniform(&g_wat[h], ga * m[ee * H + h]);
         }
       });
     }
