@@ -365,6 +365,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train_grad":  # only the gradient fixtures
         case_train_grad("grad_small_train", SMALL_CFG, [5, 3, 4], seed=61, T=20, store_full=True)
         case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
+        case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)  # one sample drawn at t = 0: L0 terms
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":  # only the dataset / sampling-tools fixture
         case_dataset()
@@ -400,3 +401,4 @@ if __name__ == "__main__":
     case_dataset()
     case_train_grad("grad_small_train", SMALL_CFG, [5, 3, 4], seed=61, T=20, store_full=True)
     case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
+    case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)

@@ -49,8 +49,9 @@ def _loss_backward(name):
     return g, ddpm, float(loss)
 
 
-def test_training_step_gradients_small_config():
-    g, ddpm, loss = _loss_backward("grad_small_train")
+@pytest.mark.parametrize("name", ["grad_small_train", "grad_small_train_t0"])
+def test_training_step_gradients_small_config(name):
+    g, ddpm, loss = _loss_backward(name)
     assert abs(loss - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     worst, n = 0.0, 0
     for pn, prm in ddpm.dynamics.named_parameters():
@@ -62,7 +63,7 @@ def test_training_step_gradients_small_config():
         assert prm.grad is not None, pn
         n += 1
         worst = max(worst, float((prm.grad.cpu().double() - ref).abs().max()) / scale)
-    print(f"grad_small_train: loss {loss:.6f}, worst parameter-gradient error {worst:.2e} over {n} parameters")
+    print(f"{name}: loss {loss:.6f}, worst parameter-gradient error {worst:.2e} over {n} parameters")
     assert worst < 2e-3 and n > 80
 
 

@@ -93,8 +93,9 @@ class _Replay(ob.EnVariationalDiffusion):
         return [n.clone() for n in self._noises[self._k - 1]]
 
 
-def test_training_step_loss_and_gradients_vs_reference_golden(emu):  # noqa: F811
-    g = load_golden("grad_small_train")
+@pytest.mark.parametrize("name", ["grad_small_train", "grad_small_train_t0"])  # _t0: one sample drawn at t = 0 (L0 terms active)
+def test_training_step_loss_and_gradients_vs_reference_golden(emu, name):  # noqa: F811
+    g = load_golden(name)
     g["node_nfs"], g["condition_nf"] = np.array([9, 9, 9]), np.int64(1)
     dyn = ob.EGNNDynamics(model_config=g["cfg"], fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
                           model=_make_emu_leftnet(emu), device=torch.device("cpu"))
