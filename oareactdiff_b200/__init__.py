@@ -21,3 +21,4 @@ __all__ = ["LEFTNetB200", "LEFTNet", "EGNNDynamics", "EnVariationalDiffusion", "
            "PredefinedNoiseSchedule", "get_repaint_schedule", "Normalizer", "get_edges_index", "get_mask_for_frag",
            "get_n_frag_switch", "get_subgraph_mask"]
 from .data import ProcessedTS1x, assemble_sample_inputs, write_single_xyz, write_tmp_xyz  # noqa: E402,F401
+from .checkpoint import load_reference_checkpoint  # noqa: E402,F401

@@ -278,6 +278,16 @@ def case_train_grad(name, cfg, sizes, seed, T, store_full):
     print(name, "ok loss", float(out["loss"]), "f32", float(out["loss_f32"]), "params", len(names))
 
 
+def case_checkpoint(name="checkpoint_small"):
+    """State dict of the unmodified reference's EnVariationalDiffusion in the layout of a DDPMModule Lightning checkpoint
+    (`ddpm.` prefix, trainer/pl_trainer.py:77-140) plus keys a real checkpoint carries outside the diffusion model."""
+    ddpm, _ = build_ddpm(SMALL_CFG, 71, 20)
+    out = {"ddpm." + k: v.detach().numpy() for k, v in ddpm.state_dict().items()}
+    out["confidence.head.weight"] = np.ones((2, 3), dtype=np.float32)  # e.g. an auxiliary module of the LightningModule
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps(SMALL_CFG), T=np.int64(20), **out)
+    print(name, "ok", len(out), "tensors")
+
+
 def synthetic_raw_dataset(seed=7, n=9):
     """A raw Transition1x-style dict (the schema transition1x.py:46-85 reads) with ragged sizes, an excluded multi-fragment
     reaction and a `use_ind` subset."""
@@ -367,6 +377,9 @@ if __name__ == "__main__":
         case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
         case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)  # one sample drawn at t = 0: L0 terms
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        case_checkpoint()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":  # only the dataset / sampling-tools fixture
         case_dataset()
         sys.exit(0)
@@ -402,3 +415,4 @@ if __name__ == "__main__":
     case_train_grad("grad_small_train", SMALL_CFG, [5, 3, 4], seed=61, T=20, store_full=True)
     case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
     case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)
+    case_checkpoint()

@@ -77,3 +77,32 @@ def test_sampling_tools_match_reference(gold, tmp_path):
     assert sorted(os.listdir(tmp_path)) == names and len(names) == 6
     for fn in names:
         assert open(tmp_path / fn).read() == str(gold["xyz/" + fn]), fn
+
+
+def test_reference_checkpoint_layout_loads(tmp_path):
+    """A DDPMModule-style Lightning checkpoint of the UNMODIFIED reference (`ddpm.` prefix; fixture from
+    oracle/gen_golden.py::case_checkpoint) loads key for key into this package's EnVariationalDiffusion."""
+    import oareactdiff_b200 as ob
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "checkpoint_small.npz"), allow_pickle=False)
+    cfg = json.loads(str(z["cfg"]))
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("cfg", "T")}
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", int(z["T"]), 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True)
+    path = str(tmp_path / "ckpt.pt")
+    torch.save({"state_dict": sd, "epoch": 3, "global_step": 10}, path)
+    rep = ob.load_reference_checkpoint(ddpm, path)
+    assert rep["missing"] == [] and rep["unexpected"] == [] and rep["ignored"] == ["confidence.head.weight"]
+    own = ddpm.state_dict()
+    assert rep["loaded"] == len(own) == len(sd) - 1
+    for k, v in own.items():
+        assert torch.equal(v, sd["ddpm." + k]), k
+    # bare state dict (no prefix) and strictness
+    rep2 = ob.load_reference_checkpoint(ddpm, {k[5:]: v for k, v in sd.items() if k.startswith("ddpm.")})
+    assert rep2["loaded"] == len(own)
+    broken = {k: v for k, v in sd.items() if "embedding_out" not in k}
+    with pytest.raises(RuntimeError):
+        ob.load_reference_checkpoint(ddpm, {"state_dict": broken})
+    with pytest.raises(KeyError):
+        ob.load_reference_checkpoint(ddpm, {"state_dict": {"foo.bar": torch.zeros(1)}})
