@@ -20,19 +20,56 @@ from .normalizer import FEATURE_MAPPING, Normalizer
 from .schedule import DiffSchedule, get_repaint_schedule
 
 
-def remove_mean_batch(x: Tensor, indices: Tensor, n_seg: int) -> Tensor:
-    """x - segment_mean(x)[indices]  (diffusion/_utils.py:9-12), with the segment count supplied (no sync)."""
+def _n_seg(indices: Tensor, n_seg: Optional[int]) -> int:
+    # torch_scatter sizes its output from indices.max() (one host sync); the samplers pass the batch size instead
+    return int(indices.max()) + 1 if n_seg is None and indices.numel() else (n_seg or 0)
+
+
+def remove_mean_batch(x: Tensor, indices: Tensor, n_seg: Optional[int] = None) -> Tensor:
+    """x - segment_mean(x)[indices]  (diffusion/_utils.py:9-12); pass the segment count to avoid the host sync."""
+    n_seg = _n_seg(indices, n_seg)
     tot = torch.zeros(n_seg, x.size(1), device=x.device, dtype=x.dtype).index_add_(0, indices, x)
     cnt = torch.zeros(n_seg, device=x.device, dtype=x.dtype).index_add_(0, indices, torch.ones_like(indices, dtype=x.dtype))
     return x - (tot / cnt.clamp(min=1)[:, None])[indices]
 
 
-def assert_mean_zero_with_mask(x: Tensor, node_mask: Tensor, n_seg: int, eps: float = 1e-10):
+def assert_mean_zero_with_mask(x: Tensor, node_mask: Tensor, n_seg: Optional[int] = None, eps: float = 1e-10):
     """diffusion/_utils.py:15-19."""
+    n_seg = _n_seg(node_mask, n_seg)
     largest = x.abs().max().item()
     err = torch.zeros(n_seg, x.size(1), device=x.device, dtype=x.dtype).index_add_(0, node_mask, x).abs().max().item()
     rel = err / (largest + eps)
     assert rel < 1e-2, f"Mean is not zero, relative_error {rel}"
+
+
+def sample_center_gravity_zero_gaussian_batch(size: List[int], indices: List[Tensor]) -> Tensor:
+    """Standard normal projected on the zero-centre-of-mass subspace of every sample (diffusion/_utils.py:22-32)."""
+    assert len(size) == 2
+    return remove_mean_batch(torch.randn(size, device=indices[0].device), torch.cat(indices))
+
+
+def sum_except_batch(x: Tensor, indices: Tensor, dim_size: int) -> Tensor:
+    """Per-sample sum over nodes and channels (diffusion/_utils.py:35-36)."""
+    v = x.sum(-1)
+    return torch.zeros(dim_size, device=x.device, dtype=v.dtype).index_add_(0, indices, v)
+
+
+def cdf_standard_gaussian(x: Tensor) -> Tensor:
+    """diffusion/_utils.py:39-40."""
+    return 0.5 * (1.0 + torch.erf(x / math.sqrt(2)))
+
+
+def sample_gaussian(size, device) -> Tensor:
+    """diffusion/_utils.py:43-45."""
+    return torch.randn(size, device=device)
+
+
+def num_nodes_to_batch_mask(n_samples: int, num_nodes, device) -> Tensor:
+    """Sample id per node from per-sample node counts (diffusion/_utils.py:48-57)."""
+    assert isinstance(num_nodes, int) or len(num_nodes) == n_samples
+    if isinstance(num_nodes, Tensor):
+        num_nodes = num_nodes.to(device)
+    return torch.repeat_interleave(torch.arange(n_samples, device=device), num_nodes)
 
 
 class EnVariationalDiffusion(nn.Module):
@@ -128,6 +165,16 @@ class EnVariationalDiffusion(nn.Module):
         gamma_0 = self.schedule.gamma_module(torch.zeros((batch_size, 1), device=device))
         log_sigma_x = 0.5 * gamma_0.view(batch_size)
         return dof * (-log_sigma_x - 0.5 * math.log(2 * math.pi))
+
+    def kl_prior(self):
+        """Placeholder of the reference (en_diffusion.py:319-320): it RETURNS the exception class; forward() uses zeros."""
+        return NotImplementedError
+
+    @staticmethod
+    def gaussian_KL(q_mu_minus_p_mu_squared, q_sigma, p_sigma, d):
+        """KL(q || p) of two isotropic d-dimensional normals from ||mu_q - mu_p||^2 and the two scales
+        (en_diffusion.py:322-338)."""
+        return d * torch.log(p_sigma / q_sigma) + 0.5 * (d * q_sigma ** 2 + q_mu_minus_p_mu_squared) / (p_sigma ** 2) - 0.5 * d
 
     def log_pxh_given_z0_without_constants(self, representations, z_t, eps_xh, net_eps_xh, gamma_t, epsilon=1e-10):
         """L0 terms: Gaussian position term, discretised-Gaussian atom-type and charge terms (en_diffusion.py:340-454)."""
@@ -518,3 +565,13 @@ class EnVariationalDiffusion(nn.Module):
         self._check_com(pos)
         out_samples[0] = [torch.cat([pos[ii], cat[ii], charge[ii]], dim=1) for ii in range(len(pos))]
         return out_samples, masks
+
+    @torch.no_grad()
+    def inpaint_fixed(self, n_samples: int, fragments_nodes: List[Tensor], conditions: Optional[Tensor] = None,
+                      return_frames: int = 1, resamplings: int = 1, jump_length: int = 1, timesteps: Optional[int] = None,
+                      xh_fixed: Optional[List[Tensor]] = None, frag_fixed: Optional[List] = None):
+        """The reference keeps a second entry point whose body is statement for statement that of `inpaint`
+        (en_diffusion.py:887-1048 vs :722-883); same here."""
+        return self.inpaint(n_samples, fragments_nodes, conditions=conditions, return_frames=return_frames,
+                            resamplings=resamplings, jump_length=jump_length, timesteps=timesteps, xh_fixed=xh_fixed,
+                            frag_fixed=frag_fixed)

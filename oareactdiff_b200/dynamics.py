@@ -46,19 +46,27 @@ class BaseDynamics(nn.Module):
         self.embed_dim = model_config["in_node_nf"] - (1 if condition_time else 0) - max(condition_nf, 0)
         self.edge_embed_dim = 0
         assert self.embed_dim > 0
+        self.build_encoders_decoders(enforce_same_encoding, source)
+
+    def build_encoders_decoders(self, enfoce_name_encoding: Optional[List] = None, source: Optional[Dict] = None):
+        """Per-fragment encoder d -> 2d -> embed_dim and decoder embed_dim -> 2d -> d (_base.py:82-132; the keyword keeps
+        the reference's spelling).  No edge encoder / decoder: `in_edge_nf > 0` is rejected by the constructor."""
         self.encoders, self.decoders = nn.ModuleList(), nn.ModuleList()
-        for nf in node_nfs:
-            d = nf - pos_dim
+        for nf in self.node_nfs:
+            d = nf - self.pos_dim
             self.encoders.append(_EncDec(d, [2 * d, self.embed_dim]))
             self.decoders.append(_EncDec(self.embed_dim, [2 * d, d]))
-        if enforce_same_encoding is not None:
-            for ii in enforce_same_encoding:
+        if enfoce_name_encoding is not None:
+            for ii in enfoce_name_encoding:
                 self.encoders[ii] = self.encoders[0]
                 self.decoders[ii] = self.decoders[0]
         if source is not None:
             self.encoders.load_state_dict(source["encoders"])
             self.decoders.load_state_dict(source["decoders"])
         self.edge_encoder, self.edge_decoder = None, None
+
+    def forward(self):
+        raise NotImplementedError
 
 
 class EGNNDynamics(BaseDynamics):

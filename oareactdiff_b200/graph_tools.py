@@ -49,3 +49,8 @@ def get_edges_index(combined_mask: Tensor, pos: Optional[Tensor] = None, edge_cu
 def get_subgraph_mask(edge_index: Tensor, n_frag_switch: Tensor) -> Tensor:
     """1 for edges whose two ends lie in the same fragment (_graph_tools.py:39-59); stays on the device."""
     return (n_frag_switch[edge_index[0]] == n_frag_switch[edge_index[1]]).long()
+
+
+def get_inner_edge_index(subgraph_mask: Tensor) -> Tensor:
+    """Coordinates of the non-zero entries of a mask, one row per dimension (_graph_tools.py:99-100)."""
+    return torch.stack(torch.nonzero(subgraph_mask, as_tuple=True), dim=0)

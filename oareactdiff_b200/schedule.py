@@ -8,16 +8,21 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 
-def _alphas2_polynomial(timesteps: int, s: float, power: float) -> np.ndarray:
-    # _schedule.py:60-74 (+ clip_noise_schedule :43-57): alpha_t^2 = (1 - (t/T')^p)^2 with per-step ratio clipping
+def clip_noise_schedule(alphas2: np.ndarray, clip_value: float = 0.001) -> np.ndarray:
+    """Clip the per-step ratio alpha_t^2 / alpha_{t-1}^2 into [clip_value, 1] and re-accumulate (_schedule.py:43-57)."""
+    ratio = np.concatenate([alphas2[:1], alphas2[1:] / alphas2[:-1]])  # alpha_{-1}^2 = 1
+    return np.cumprod(np.clip(ratio, clip_value, 1.0))
+
+
+def polynomial_schedule(timesteps: int, s: float = 1e-4, power: float = 3.0) -> np.ndarray:
+    """alpha_t^2 = (1 - (t/T')^power)^2, ratio-clipped, squeezed into [s, 1 - s]; T+1 entries (_schedule.py:60-74)."""
     t = np.linspace(0, timesteps + 1, timesteps + 1)
     a2 = np.square(1.0 - (t / (timesteps + 1)) ** power)
-    ratio = np.clip(np.concatenate([a2[:1], a2[1:] / a2[:-1]]), 0.001, 1.0)
-    return (1 - 2 * s) * np.cumprod(ratio) + s
+    return (1 - 2 * s) * clip_noise_schedule(a2, clip_value=0.001) + s
 
 
-def _alphas2_cosine(timesteps: int, s: float = 0.008, raise_to_power: float = 1.0) -> np.ndarray:
-    # _schedule.py:9-26
+def cosine_beta_schedule(timesteps: int, s: float = 0.008, raise_to_power: float = 1) -> np.ndarray:
+    """Cumulative alpha^2 of the cosine schedule of Nichol & Dhariwal; T+1 entries (_schedule.py:9-26)."""
     x = np.linspace(0, timesteps + 2, timesteps + 2)
     f = np.cos((x / (timesteps + 2) + s) / (1 + s) * np.pi / 2) ** 2
     f = f / f[0]
@@ -25,12 +30,17 @@ def _alphas2_cosine(timesteps: int, s: float = 0.008, raise_to_power: float = 1.
     return a2 if raise_to_power == 1 else a2 ** raise_to_power
 
 
-def _alphas2_ccosine(timesteps, start, end, tau, clip_min=1e-9):
-    # _schedule.py:29-35
+def ccosine_schedule(timesteps: int, start: float = 0, end: float = 1, tau: float = 1, clip_min: float = 1e-9) -> np.ndarray:
+    """Continuous-time cosine schedule on [start, end] with exponent 2 tau; T+1 entries (_schedule.py:29-35)."""
     t = np.linspace(0, 1, timesteps + 1)
     lo, hi = np.cos(start * np.pi / 2) ** (2 * tau), np.cos(end * np.pi / 2) ** (2 * tau)
     out = (hi - np.cos((t * (end - start) + start) * np.pi / 2) ** (2 * tau)) / (hi - lo)
     return np.clip(out, clip_min, 1 - clip_min)
+
+
+def linear_schedule(timesteps: int, clip_min: float = 1e-9) -> np.ndarray:
+    """alpha_t^2 = 1 - t/T, clipped away from {0, 1}; T+1 entries (_schedule.py:38-41)."""
+    return np.clip(1 - np.linspace(0, 1, timesteps + 1), clip_min, 1 - clip_min)
 
 
 class PredefinedNoiseSchedule(nn.Module):
@@ -42,15 +52,15 @@ class PredefinedNoiseSchedule(nn.Module):
         parts = noise_schedule.split("_")
         if "cosine" in noise_schedule:
             assert len(parts) <= 2
-            a2 = _alphas2_cosine(timesteps, raise_to_power=1.0 if len(parts) == 1 else float(parts[1]))
+            a2 = cosine_beta_schedule(timesteps, raise_to_power=1.0 if len(parts) == 1 else float(parts[1]))
         elif "polynomial" in noise_schedule:
             assert len(parts) == 2
-            a2 = _alphas2_polynomial(timesteps, precision, float(parts[1]))
+            a2 = polynomial_schedule(timesteps, s=precision, power=float(parts[1]))
         elif "csin" in noise_schedule:
             assert len(parts) == 4
-            a2 = _alphas2_ccosine(timesteps, float(parts[1]), float(parts[2]), float(parts[3]))
+            a2 = ccosine_schedule(timesteps, start=float(parts[1]), end=float(parts[2]), tau=float(parts[3]))
         elif "linear" in noise_schedule:
-            a2 = np.clip(1 - np.linspace(0, 1, timesteps + 1), 1e-9, 1 - 1e-9)
+            a2 = linear_schedule(timesteps)
         else:
             raise ValueError(noise_schedule)
         gamma = -(np.log(a2) - np.log(1 - a2))

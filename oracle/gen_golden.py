@@ -288,6 +288,47 @@ def case_checkpoint(name="checkpoint_small"):
     print(name, "ok", len(out), "tensors")
 
 
+def case_api_helpers(name="api_helpers"):
+    """Outputs of the unmodified reference's module-level helpers a caller may import next to the samplers: the alpha^2
+    schedules (_schedule.py:9-74), the gamma tables of every schedule family, diffusion/_utils.py, get_inner_edge_index
+    and EnVariationalDiffusion.gaussian_KL."""
+    from oa_reactdiff.diffusion import _schedule as S
+    from oa_reactdiff.diffusion import _utils as U
+    from oa_reactdiff.utils._graph_tools import get_inner_edge_index
+    out = {}
+    for T in (10, 100, 1000):
+        out[f"poly2_{T}"] = S.polynomial_schedule(T, s=1e-5, power=2.0)
+        out[f"poly3_{T}"] = S.polynomial_schedule(T)
+        out[f"cos_{T}"] = S.cosine_beta_schedule(T)
+        out[f"cos2_{T}"] = S.cosine_beta_schedule(T, raise_to_power=2.0)
+        out[f"ccos_{T}"] = S.ccosine_schedule(T, start=0.1, end=0.9, tau=1.5)
+        out[f"lin_{T}"] = S.linear_schedule(T)
+        for fam in ("polynomial_2", "cosine", "cosine_2", "csin_0.1_0.9_2", "linear"):
+            out[f"gamma_{fam}_{T}"] = S.PredefinedNoiseSchedule(fam, T, 1e-5).gamma.detach().numpy()
+    rng = np.random.RandomState(5)
+    a2 = np.sort(rng.rand(50))[::-1].copy()
+    out["clip_in"], out["clip_out"] = a2, S.clip_noise_schedule(a2, clip_value=0.2)
+    idx = torch.tensor([0, 0, 2, 2, 2, 3, 5])  # samples 1 and 4 are empty
+    x = torch.from_numpy(rng.randn(7, 3)).float()
+    out["u_idx"], out["u_x"] = idx.numpy(), x.numpy()
+    out["u_remove_mean"] = U.remove_mean_batch(x, idx).numpy()
+    out["u_sum_except_batch"] = U.sum_except_batch(x, idx, dim_size=7).numpy()
+    out["u_cdf"] = U.cdf_standard_gaussian(x).numpy()
+    out["u_batch_mask"] = U.num_nodes_to_batch_mask(4, torch.tensor([2, 0, 3, 1]), torch.device("cpu")).numpy()
+    out["u_batch_mask_int"] = U.num_nodes_to_batch_mask(3, 2, torch.device("cpu")).numpy()
+    torch.manual_seed(123)
+    out["u_cog_noise"] = U.sample_center_gravity_zero_gaussian_batch([7, 3], [idx[:4], idx[4:]]).numpy()
+    torch.manual_seed(124)
+    out["u_gauss"] = U.sample_gaussian((5, 2), torch.device("cpu")).numpy()
+    m = torch.tensor([[0, 1, 0], [1, 1, 0]])
+    out["inner_in"], out["inner_out"] = m.numpy(), get_inner_edge_index(m).numpy()
+    q = torch.from_numpy(rng.rand(6)).float()
+    out["kl_in"] = q.numpy()
+    out["kl_out"] = EnVariationalDiffusion.gaussian_KL(q, q + 0.5, 2 * q + 0.1, 3.0).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", len(out), "arrays")
+
+
 def synthetic_raw_dataset(seed=7, n=9):
     """A raw Transition1x-style dict (the schema transition1x.py:46-85 reads) with ragged sizes, an excluded multi-fragment
     reaction and a `use_ind` subset."""
@@ -380,6 +421,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         case_checkpoint()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the module-level helper fixture
+        case_api_helpers()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":  # only the dataset / sampling-tools fixture
         case_dataset()
         sys.exit(0)
@@ -416,3 +460,4 @@ if __name__ == "__main__":
     case_train_grad("grad_trained_train_b3", TRAINED_CFG, [4, 9, 6], seed=62, T=100, store_full=False)
     case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)
     case_checkpoint()
+    case_api_helpers()
