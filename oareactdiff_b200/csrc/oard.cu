@@ -97,6 +97,12 @@ struct oard_handle {
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};  // [0]: subgraph_mask == NULL, [1]: with mask
   int64_t graph_launches = 0;
+  // OARD_FORK=k (off by default): per layer the node-level chain (node_mlp -> x_layernorm -> x_proj) runs on a side stream
+  // next to the edge-level chain (edge_out -> dir_proj / rbf_proj), which then leaves k SMs free; joined before the message
+  // kernel.  Works in eager mode and inside the captured graphs (fork / join become graph edges).
+  int fork_sms = 0;
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> fork_ev;  // [2 l] fork, [2 l + 1] join
   // profiling: CUDA-event timing per kernel class on sampled forwards
   int prof_every = 0;
   int64_t fwd_count = 0;
@@ -239,6 +245,13 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
                    cfg->hidden_channels <= 256 && ms_gemm_smem<4, 0>(2 * cfg->hidden_channels) <= 227 * 1024;
     const char* eg = getenv("OARD_GRAPH");  // "0" disables CUDA-graph replay of the forward
     h->use_graph = !(eg && strcmp(eg, "0") == 0);
+    const char* ef = getenv("OARD_FORK");  // SMs left to the node-level branch (0 / unset: one stream, the measured default)
+    h->fork_sms = ef ? std::max(0, std::min(atoi(ef), h->num_sms - 16)) : 0;
+    if (h->fork_sms > 0 && h->use_tc) {
+      CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+      h->fork_ev.resize(2 * (size_t)std::max(cfg->num_layers, 1));
+      for (auto& e : h->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    } else h->fork_sms = 0;
   }
   for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
   *out = h;
@@ -261,6 +274,8 @@ extern "C" void oard_destroy(oard_handle* h) {
     if (p) cudaFree(p);
   drop_graphs(h);
   h->tctx.release();
+  for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_map(h->ws);
   free_map(h->snaps);
@@ -925,6 +940,20 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
     else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
     KCHECK();
+    // OARD_FORK: from here the node-level chain (node_mlp, x_layernorm, x_proj: reads xa; writes tN, s, tmpH, X) and the
+    // edge-level chain (edge_out, dir_proj, rbf_proj: reads m2, att, ew, rbf_act; writes ew, ew_act, d1, RB, G) touch disjoint
+    // buffers; they meet again at the message kernel.  The edge-level GEMMs are persistent (one CTA per SM), so they are
+    // launched on num_sms - fork_sms CTAs to leave room for the node-level tiles.
+    const bool fork = h->fork_sms > 0 && E > 0 && !chain && !h->prof_now && !h->debug && 2 * (size_t)l + 1 < h->fork_ev.size();
+    cudaStream_t st_node = st;
+    struct SmGuard { int& v; int keep; ~SmGuard() { v = keep; } } sm_guard{h->num_sms, h->num_sms};
+    if (fork) {
+      CU(cudaEventRecord(h->fork_ev[2 * l], st));
+      CU(cudaStreamWaitEvent(h->side_stream, h->fork_ev[2 * l], 0));
+      st_node = h->side_stream;
+    }
+    {
+    cudaStream_t st = st_node;  // (the launch macros use `st`)
     if (chain) {
       MsGemmArgs m = msa(xa, 2 * H, 2 * H, h->Ms[l].n0, tN, H);
       m.bias = w.n0b; m.act = 1;
@@ -940,14 +969,19 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
       GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
     }
+    }
     if (E) {
+      if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
       g.prescale = h->buf<float>("att");  // attention gate of the edge (k_att_agg): W (att m) = att (W m)
       g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = ldD;  // compact copy of the active rows: contiguous operand for dir_proj
       if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
+      h->num_sms = sm_guard.keep;
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
+    {
+    cudaStream_t st = st_node;
     if (chain) {  // message x_layernorm fused into the staging of x_proj.0
       MsGemmArgs m = msa(s, H, H, h->Ms[l].x0, tmpH, H);
       m.ln = 1; m.gamma = w.mlnw; m.beta = w.mlnb; m.act = 1;
@@ -964,7 +998,9 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
       GEMM_TC("gemm_xproj2", g, h->T[l].x2);
     }
+    }
     if (E) {
+      if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(ew_act, ldD, w.d0w, D, d1, ld3H, E, 3 * H, D);
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
       if (P) GEMM_P16("gemm_dir_proj0", g, h->T[l].d0, true); else GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
@@ -974,6 +1010,11 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(d1, ld3H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
+      h->num_sms = sm_guard.keep;
+    }
+    if (fork) {  // join: the message kernel reads X (node branch) and G (edge branch)
+      CU(cudaEventRecord(h->fork_ev[2 * l + 1], h->side_stream));
+      CU(cudaStreamWaitEvent(st, h->fork_ev[2 * l + 1], 0));
     }
     PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
     {
