@@ -421,6 +421,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         case_checkpoint()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "noreflect":  # reflect_equiv=False (reference tests/model/test_equiv.py:40-41)
+        case_leftnet("leftnet_small_noreflect", dict(SMALL_CFG, reflect_equiv=False), 11, seed=14, cut=5, pos_scale=3.0)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the module-level helper fixture
         case_api_helpers()
         sys.exit(0)
@@ -437,6 +440,7 @@ if __name__ == "__main__":
     case_leftnet("leftnet_small_full", SMALL_CFG, 9, seed=11, pos_scale=3.0)
     case_leftnet("leftnet_small_cut", SMALL_CFG, 10, seed=12, cut=4, pos_scale=3.0)
     case_leftnet("leftnet_small_split", SMALL_CFG, 12, seed=13, cut=5, pos_scale=9.0)  # cutoff splits groups
+    case_leftnet("leftnet_small_noreflect", dict(SMALL_CFG, reflect_equiv=False), 11, seed=14, cut=5, pos_scale=3.0)
     # dynamics: reference fixture shape (ragged, an EMPTY fragment, per-fragment node_nf) tests/dynamics/test_egnn_dynamics.py:99-104
     case_dynamics("dyn_small_ragged", dict(SMALL_CFG, in_hidden_channels=8),
                   [torch.tensor([2, 0]), torch.tensor([2, 3]), torch.tensor([1, 2])], [4, 5, 6], 3, seed=21,

@@ -51,3 +51,20 @@ def test_fork_is_bitwise_identical(sizes, seed, k):
     for b in fork:
         assert torch.equal(b, base[0]), float((b - base[0]).abs().max())
     assert np.isfinite(base[0].numpy()).all()
+
+
+def test_leftnet_reflect_equiv_false_vs_reference_golden():
+    """`reflect_equiv=False` (the reference's own tests build such a LEFTNet: tests/model/test_equiv.py:40-41): no abs on the
+    frame's cross row and the `x * edge_cross` term in the messages (leftnet.py:268-269) — the node-per-block message kernel
+    (k_equi_reduce) instead of the group-staged one.  Golden from the unmodified reference; the oracle is pinned on it in
+    tests/test_oracle.py."""
+    from tests.test_gpu_parity import REL_TOL, make_leftnet
+    from tests.util import leftnet_state_dict, load_golden, rel_err
+    g = load_golden("leftnet_small_noreflect")
+    assert g["cfg"]["reflect_equiv"] is False
+    m = make_leftnet(g["cfg"], leftnet_state_dict(g))
+    h, pos = torch.from_numpy(g["h"]).float().to(DEV), torch.from_numpy(g["pos"]).float().to(DEV)
+    ho, po, _ = m(h, pos, torch.from_numpy(g["edge_index"]).to(DEV), subgraph_mask=torch.from_numpy(g["subgraph_mask"]).to(DEV))
+    e_h, e_p = rel_err(ho.cpu(), g["h_out_f64"]), rel_err((po - pos).cpu(), g["dpos_f64"])
+    print(f"noreflect: h {e_h:.2e} dpos {e_p:.2e}")
+    assert e_h < REL_TOL and e_p < REL_TOL

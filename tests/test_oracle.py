@@ -48,7 +48,7 @@ def test_repaint_schedule_identity():
 
 
 # ---- golden vectors from the unmodified reference
-@pytest.mark.parametrize("name", ["leftnet_small_full", "leftnet_small_cut", "leftnet_small_split"])
+@pytest.mark.parametrize("name", ["leftnet_small_full", "leftnet_small_cut", "leftnet_small_split", "leftnet_small_noreflect"])
 def test_leftnet_forward_matches_reference_fp64(name):
     g = load_golden(name)
     sd = leftnet_state_dict(g, torch.float64)

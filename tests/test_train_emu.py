@@ -68,9 +68,12 @@ def _geometry(case):
                 act=act, dbg=dbg)
 
 
-@pytest.mark.parametrize("cfg_name,sizes,pos_scale", [("small", [4, 3], 1.5), ("small", [5, 2, 3], 3.0), ("mid", [4, 3], 1.5)])
+@pytest.mark.parametrize("cfg_name,sizes,pos_scale", [("small", [4, 3], 1.5), ("small", [5, 2, 3], 3.0), ("mid", [4, 3], 1.5),
+                                                      ("small_noreflect", [4, 3], 1.5)])
 def test_core_forward_and_backward_vs_oracle(emu, cfg_name, sizes, pos_scale):
     cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2, cutoff=5.0)
+    if cfg_name == "small_noreflect":  # reflect_equiv=False: no abs on the frame's cross row, cross term in the messages
+        cfg["reflect_equiv"] = False
     if cfg_name == "mid":
         cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=52, num_radial=24, num_layers=3, cutoff=6.0)
     case = _case(cfg, sizes, seed=7 + len(sizes), pos_scale=pos_scale)
