@@ -90,6 +90,7 @@ struct oard_handle {
   // plan
   bool planned = false;
   int N = 0, E = 0, NC = 0, max_comp = 1;
+  bool complete = false;  // every component of the edge list is a complete graph (what get_edges_index builds per sample)
   std::map<std::string, DevBuf> ws;  // named workspace buffers
   size_t ws_bytes = 0;
   // CUDA graph of one forward (captured on an internal stream, replayed on the caller's stream)
@@ -563,7 +564,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
       {"mask", Ee}, {"att", Ee * 4}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
       {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"gsize", Nn * 4}, {"lead_list", Nn * 4}, {"lead_info", Nn * 8},
-      {"gm_node", Nn * 4}, {"gm_rap", Nn * 8}, {"act_rec", Ee * 8},
+      {"gm_node", (Nn + Ee) * 4}, {"gm_rap", (Nn + Ee) * 8}, {"act_rec", Ee * 8},
       {"n_lead", 16}, {"work_ctr", 64 * 4}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
       {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
       {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
@@ -590,6 +591,17 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   CU(cudaMemcpy(h->buf<int>("node_local"), node_local.data(), Nn * 4, cudaMemcpyHostToDevice));
   h->N = N; h->E = E; h->NC = NC;
   h->max_comp = count.empty() ? 1 : *std::max_element(count.begin(), count.end());
+  // The group-staged message kernel (k_equi_frag) takes "same fragment" for an equivalence relation whose classes are
+  // cliques: true for any fragment-derived subgraph_mask on complete per-sample graphs (the samplers' graphs), not for the
+  // hand-written sparse graphs of the reference's model tests (tests/model/test_equiv.py:30-32) — those take the
+  // node-per-block kernel (k_equi_reduce), which assumes nothing.  (gm_node / gm_rap are sized N + E, the bound of the
+  // member lists for ANY mask, so an inconsistent mask cannot write out of bounds.)
+  h->complete = true;
+  for (int i = 0; i < N && h->complete; i++) {
+    if (row_ptr[i + 1] - row_ptr[i] != count[comp_of[i]] - 1) h->complete = false;
+    for (int e = row_ptr[i]; e < row_ptr[i + 1] && h->complete; e++)
+      if (ecol[e] == i) h->complete = false;  // self loop
+  }
   h->planned = true;
   return OARD_OK;
 }
@@ -1025,7 +1037,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       const size_t ef_smem = CH == 28 ? ef_smem_bytes<28>(h->max_comp) : (CH == 32 ? ef_smem_bytes<32>(h->max_comp) : ef_smem_bytes<16>(h->max_comp));
       static int env_frag = -1;
       if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
-      const bool frag_ok = env_frag && c.reflect_equiv && l < 64 && ef_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
+      const bool frag_ok = env_frag && h->complete && c.reflect_equiv && l < 64 && ef_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
       if (frag_ok && E) {
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (ef_smem + 1024)));
         const int grid = h->num_sms * per_sm;

@@ -400,7 +400,7 @@ class EnVariationalDiffusion(nn.Module):
         cond = None
         if dyn.condition_nf > 0:
             cond = conditions.to(torch.float32).reshape(self._B, -1).contiguous()
-        self._dev = dict(eng=eng, nx=nx, nh=nh, views=views, cond=cond, sub=g["sub_flat"] if dyn.model.object_aware else None,
+        self._dev = dict(eng=eng, nx=nx, nh=nh, views=views, cond=cond, sub=g["sub_planned"] if dyn.model.object_aware else None,
                          H0=None if H0 is None else H0.to(torch.float32).contiguous())
 
     def _device_step(self, s_int: int, Z: Tensor, tab) -> Tensor:

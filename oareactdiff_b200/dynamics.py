@@ -32,7 +32,8 @@ class BaseDynamics(nn.Module):
             assert nf > pos_dim
         model_config = dict(model_config)
         model_config.setdefault("act_fn", "swish")
-        model_config.setdefault("in_node_nf", model_config["in_hidden_channels"])
+        if "in_node_nf" not in model_config:  # (the reference's own test configs give in_node_nf and no in_hidden_channels)
+            model_config["in_node_nf"] = model_config["in_hidden_channels"]
         if model_config.get("in_edge_nf", 0) > 0:
             raise NotImplementedError("edge attributes (in_edge_nf > 0) are not part of the LEFTNet hot path")
         self.model_config, self.node_nfs, self.edge_nf, self.condition_nf = model_config, node_nfs, edge_nf, condition_nf
@@ -106,6 +107,8 @@ class EGNNDynamics(BaseDynamics):
         if not (self.model.assume_static_weights and eng.weights_key is not None):
             eng.sync_weights(self.model)
         eng.plan(edge_index, combined_mask.numel())
+        if g.get("sub_planned_key") != eng.plan_key:  # same-fragment mask in the engine's edge order (same tensor if grouped by source)
+            g["sub_planned"], g["sub_planned_key"] = eng.edge_order(g["sub_flat"]), eng.plan_key
         if not (self.model.assume_static_weights and getattr(eng, "dyn_weights_key", None) is not None):
             eng.dyn_sync(self, len(self.fragment_names), self.node_nfs[0], self.condition_nf, self.condition_time)
         eng.dyn_plan(n_frag_switch, combined_mask, g["n_samples"])
@@ -121,7 +124,7 @@ class EGNNDynamics(BaseDynamics):
         if self.condition_time:
             tb = (t.reshape(1).expand(B) if t.numel() == 1 else t.reshape(-1)).to(torch.float32).contiguous()
         cond = conditions.to(torch.float32).reshape(B, -1).contiguous() if self.condition_nf > 0 else None
-        sub = g["sub_flat"] if self.model.object_aware else None
+        sub = g["sub_planned"] if self.model.object_aware else None
         eps = eng.dyn_forward(Z, tb, cond, sub, torch.empty_like(Z))
         fi = g["frag_index"]
         return [eps[fi[ii]:fi[ii + 1]] for ii in range(len(self.fragment_names))], None

@@ -129,6 +129,7 @@ class _Engine:
         self.names = [self.lib.oard_weight_name(self.h, i).decode() for i in range(self.lib.oard_num_weights(self.h))]
         self.weights_key = None
         self.plan_key = None
+        self.edge_perm = None
         self.N = self.E = 0
         self.debug = False
 
@@ -163,21 +164,36 @@ class _Engine:
         if key == self.plan_key:
             return
         ei = edge_index.detach().to("cpu", torch.int64).contiguous()
+        # oard_plan wants the edges grouped by source (the order get_edges_index produces).  Any other order of the same
+        # edges (e.g. the hand-written lists of the reference's tests/model/test_equiv.py:30-32) is brought into that form
+        # here; outputs are per node, so only the per-edge subgraph_mask has to follow (edge_order).
+        self.edge_perm = None
+        if ei.size(1) > 1 and bool((ei[0, 1:] < ei[0, :-1]).any()):
+            perm = torch.argsort(ei[0], stable=True)
+            ei = ei[:, perm].contiguous()
+            self.edge_perm = perm.to(self.device)
         _lib.check(self.lib.oard_plan(self.h, n_nodes, ei.size(1), C.c_void_p(ei.data_ptr())))
         self.plan_key, self.N, self.E = key, n_nodes, ei.size(1)
         self.dyn_plan_key = None
+
+    def edge_order(self, sub: Optional[Tensor]) -> Optional[Tensor]:
+        """Per-edge input of the caller (flat, caller's edge order) -> int64, contiguous, in the planned edge order."""
+        if sub is None:
+            return None
+        sub = sub.detach().reshape(-1).to(torch.int64)
+        if sub.numel() != self.E:
+            raise ValueError(f"subgraph_mask has {sub.numel()} entries, edge_index has {self.E} edges")
+        if self.edge_perm is not None:
+            sub = sub[self.edge_perm]
+        return sub.contiguous()
 
     def forward(self, h: Tensor, pos: Tensor, sub: Optional[Tensor]):
         h = h.detach().to(torch.float32).contiguous()
         pos = pos.detach().to(torch.float32).contiguous()
         h_out = torch.empty_like(h)
         dpos = torch.empty_like(pos)
-        sp = None
-        if sub is not None:
-            sub = sub.detach().reshape(-1).to(torch.int64).contiguous()
-            if sub.numel() != self.E:
-                raise ValueError(f"subgraph_mask has {sub.numel()} entries, edge_index has {self.E} edges")
-            sp = C.c_void_p(sub.data_ptr())
+        sub = self.edge_order(sub)
+        sp = None if sub is None else C.c_void_p(sub.data_ptr())
         _lib.check(self.lib.oard_forward(self.h, C.c_void_p(h.data_ptr()), C.c_void_p(pos.data_ptr()), sp,
                                          C.c_void_p(h_out.data_ptr()), C.c_void_p(dpos.data_ptr()),
                                          self._stream(self.device)))
@@ -239,12 +255,8 @@ class _Engine:
         h = h.detach().to(torch.float32).contiguous()
         pos = pos.detach().to(torch.float32).contiguous()
         h_out, dpos = torch.empty_like(h), torch.empty_like(pos)
-        sp = None
-        if sub is not None:
-            sub = sub.detach().reshape(-1).to(torch.int64).contiguous()
-            if sub.numel() != self.E:
-                raise ValueError(f"subgraph_mask has {sub.numel()} entries, edge_index has {self.E} edges")
-            sp = C.c_void_p(sub.data_ptr())
+        sub = self.edge_order(sub)
+        sp = None if sub is None else C.c_void_p(sub.data_ptr())
         st = self._stream(self.device)
         _lib.check(self.lib.oard_zero_grads(self.h, st))
         _lib.check(self.lib.oard_forward_train(self.h, self._ptr(h), self._ptr(pos), sp, self._ptr(h_out), self._ptr(dpos), st))
@@ -407,9 +419,11 @@ class LEFTNetB200(nn.Module):
             eng.sync_weights(self)
         eng.plan(edge_index, pos.size(0))
         h_out, dpos = eng.forward(h, pos, subgraph_mask if self.object_aware else None)
+        # the kernels compute in fp32; results go back in the caller's dtypes (the reference's tests run it in float64)
+        h_out, dpos = h_out.to(h.dtype), dpos.to(pos.dtype)
         if update_coords_mask is not None:
             dpos = update_coords_mask * dpos
-        pos_out = pos.to(torch.float32) + dpos
+        pos_out = pos + dpos
         if node_mask is not None:
             h_out = h_out * node_mask
         return h_out, pos_out, None

@@ -85,3 +85,58 @@ def test_schedule_matches_oracle():
         assert torch.equal(ob.PredefinedNoiseSchedule(name, T, 1e-5).gamma.data, oa_ref.gamma_table(name, T, 1e-5))
     for r, j, T in [(1, 1, 1000), (5, 5, 150), (5, 5, 1000), (2, 3, 12), (3, 7, 20), (1, 5, 3)]:
         assert ob.get_repaint_schedule(r, j, T) == oa_ref.get_repaint_schedule(r, j, T)
+
+
+def test_engine_plan_accepts_edges_not_grouped_by_source():
+    """The reference's own model tests hand-write edge lists in arbitrary order (tests/model/test_equiv.py:30-32); the shim
+    brings them into the source-grouped order oard_plan wants and permutes the per-edge subgraph_mask with them.  Checked
+    here against a recording stand-in for the C library (no CUDA needed for this host logic)."""
+    from oareactdiff_b200.leftnet import _Engine
+
+    seen = {}
+
+    class FakeLib:
+        def oard_plan(self, h, n_nodes, n_edges, ptr):
+            buf = (ctypes.c_int64 * (2 * n_edges)).from_address(ptr.value)
+            seen["ei"] = np.array(buf, dtype=np.int64).reshape(2, n_edges)
+            seen["n"] = n_nodes
+            return 0
+
+    eng = object.__new__(_Engine)
+    eng.lib, eng.h, eng.device, eng.plan_key, eng.edge_perm = FakeLib(), None, torch.device("cpu"), None, None
+    ei = torch.tensor([[0, 1, 1, 2, 3, 0], [1, 0, 2, 1, 0, 3]])
+    eng.plan(ei, 4)
+    assert seen["n"] == 4 and eng.E == 6
+    assert np.array_equal(seen["ei"], [[0, 0, 1, 1, 2, 3], [1, 3, 0, 2, 1, 0]])  # stable: (0,1) stays before (0,3)
+    sub = torch.tensor([[1], [0], [1], [1], [0], [1]])  # [E, 1] like the callers pass it
+    assert eng.edge_order(sub).tolist() == [1, 1, 0, 1, 1, 0]
+    assert eng.edge_order(None) is None
+    with pytest.raises(ValueError):
+        eng.edge_order(torch.ones(5))
+    # already grouped (what get_edges_index produces): passed through untouched, and the mask keeps its storage
+    ei2 = ob.get_edges_index(torch.tensor([0, 0, 0, 1, 1]), remove_self_edge=True)
+    eng.plan(ei2, 5)
+    assert eng.edge_perm is None and np.array_equal(seen["ei"], ei2.numpy())
+    flat = torch.ones(ei2.size(1), dtype=torch.int64)
+    assert eng.edge_order(flat).data_ptr() == flat.data_ptr()
+    del eng.h  # (nothing to destroy)
+
+
+def test_constructors_accept_the_reference_test_fixtures():
+    """Configs copied from the reference's own fixtures: tests/model/utils.py:24-32 (LEFTNet), tests/dynamics/
+    test_egnn_dynamics.py:50-62 and test_switch_fragments.py:34-50 (in_node_nf given, in_hidden_channels absent, edge_nf > 0
+    with no in_edge_nf)."""
+    left_config = dict(pos_require_grad=False, cutoff=20.0, num_layers=6, hidden_channels=32, num_radial=32, in_node_nf=8,
+                       reflect_equiv=True)
+    m = ob.LEFTNetB200(**left_config)
+    assert m.cfg["in_hidden_channels"] == 8 and m.cfg["reflect_equiv"] is True
+    assert ob.LEFTNetB200(**dict(left_config, reflect_equiv=False)).cfg["reflect_equiv"] is False
+    leftnet_config = dict(pos_require_grad=False, cutoff=5.0, num_layers=2, hidden_channels=32, num_radial=8, in_node_nf=8)
+    for node_nfs, names, edge_nf in (([4, 5, 6], ["inorg_node", "org_edge", "org_node"], 3), ([5, 5], ["A", "B"], 4)):
+        cfg = dict(leftnet_config)
+        dyn = ob.EGNNDynamics(model_config=cfg, node_nfs=node_nfs, edge_nf=edge_nf, condition_nf=3, fragment_names=names,
+                              pos_dim=3, update_pocket_coords=True, condition_time=True, edge_cutoff=None,
+                              model=ob.LEFTNetB200, device=torch.device("cpu"))
+        assert dyn.embed_dim == 8 - 1 - 3 and dyn.edge_encoder is None
+        assert [e.mlp[0].linear.in_features for e in dyn.encoders] == [n - 3 for n in node_nfs]
+        assert [d.mlp[1].linear.out_features for d in dyn.decoders] == [n - 3 for n in node_nfs]

@@ -10,7 +10,7 @@ mkdir -p $out
 export PYTHONUNBUFFERED=1
 echo "== default GPU suite";      timeout 600 python -m pytest tests -m gpu -x -q                       > $out/${tag}_pytest.log 2>&1; tail -2 $out/${tag}_pytest.log
 echo "== training path (opt-in)"; OARD_TRAIN_GPU=1 timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q -s   > $out/${tag}_pytest_train.log 2>&1; tail -3 $out/${tag}_pytest_train.log
-echo "== experimental (opt-in)";  OARD_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q > $out/${tag}_pytest_exp.log 2>&1; tail -3 $out/${tag}_pytest_exp.log
+echo "== experimental (opt-in)";  OARD_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_reference_suite.py -m gpu -q -s > $out/${tag}_pytest_exp.log 2>&1; tail -3 $out/${tag}_pytest_exp.log
 # OARD_FORK sweep on the device-resident reverse step (compact geometry, B = 64): device_step_ms is the number to compare
 for k in 0 16 24 32 48 64; do
   echo "== perf probe OARD_FORK=$k"
