@@ -1,0 +1,22 @@
+"""The plugin seam with the UNMODIFIED reference on the other side (build container only: skipped where /root/reference
+is absent): oracle/plug_into_reference.py hands `LEFTNetB200` to the reference's own `EGNNDynamics(model=<class>)` and lets
+the reference's own `sample()` drive it.  Run in a subprocess — the shims for torch_scatter / torch_geometric must not leak
+into this test session."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_leftnetb200_plugs_into_the_unmodified_reference():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "plug_into_reference.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["model_class"] == "LEFTNetB200" and out["missing"] == [] and out["unexpected"] == []
+    assert out["h_equal"] and max(out["trajectory_rel_err"]) < 1e-4, out
