@@ -67,12 +67,17 @@ int oard_commit_weights(oard_handle* h, void* stream);
 
 /* Build the static per-batch plan from the HOST edge list edge_index[2][E] (int64, edge_index[0] = source):
  * CSR rows, transposed-edge map, connected components (= reactions).  Requirements: edges grouped by source in
- * non-decreasing order, the graph symmetric, no duplicates, components of <= 256 nodes.  Allocates the workspace. */
+ * non-decreasing order, the graph symmetric, no duplicates, components of <= 256 nodes.  Allocates the workspace.
+ * Components need not be complete graphs: when every component is complete (what get_edges_index builds per sample) the
+ * message aggregation takes the group-staged kernel, otherwise the node-per-block kernel, which assumes nothing. */
 int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const int64_t* edge_index_host);
 size_t oard_workspace_bytes(const oard_handle* h);
 
 /* LEFTNet.forward (leftnet.py:724-891).  h_in[N,C], pos[N,3], subgraph_mask[E] (int64, may be NULL = all ones),
- * h_out[N,C], dpos[N,3] (the reference returns pos + dpos).  Device pointers; asynchronous on `stream`. */
+ * h_out[N,C], dpos[N,3] (the reference returns pos + dpos).  Device pointers; asynchronous on `stream`.
+ * subgraph_mask is in the order of the planned edge list.  On complete components it must be what
+ * get_subgraph_mask (_graph_tools.py:39-59) produces from per-node fragment ids, i.e. an equivalence relation — the
+ * group-staged message kernel relies on that (any other 0/1 mask: run with OARD_EQUI=node). */
 int oard_forward(oard_handle* h, const float* h_in, const float* pos, const int64_t* subgraph_mask, float* h_out,
                  float* dpos, void* stream);
 
