@@ -8,6 +8,20 @@
 
 namespace oard {
 
+// cudaFuncSetAttribute acts on the CURRENT device: a process that drives several GPUs (one handle per device) must opt in
+// to the large dynamic shared memory once per (kernel instantiation, device), not once per process.
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool first_time() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // MUFU wrappers with flush-to-zero: the non-ftz intrinsics (__expf, __fdividef) wrap every MUFU in range checks and

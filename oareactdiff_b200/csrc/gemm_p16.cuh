@@ -617,11 +617,10 @@ inline cudaError_t launch_gemm_p16_mlp2(const GemmArgs& g, const TcWeight& w1, c
   const size_t smem = (size_t)SA * P16_A_BYTES + (size_t)w2.k_chunks * P16_A_BYTES + (size_t)SW * 2 * w1.BN * TC_KC * 2 +
                       (size_t)(2 * SA + 2 * SW + 6) * 8 + 16;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr;
+  if (attr.first_time()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_p16_mlp2_kernel<SA, SW, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   gemm_p16_mlp2_kernel<SA, SW, EW><<<grid, (EW + 3) * 32, smem, st>>>(g, w1, w2, bias2, tmA, tmC);
   return cudaGetLastError();
@@ -635,12 +634,11 @@ inline size_t p16_smem_bytes(int BN, int sa, int sw, int ew, int nio) {
 template <int SA, int SW, int MODE, bool OUT_PAIR, int EW, int NIO>
 inline cudaError_t launch_gemm_p16_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, const CUtensorMap& tmA,
                                         const CUtensorMap& tmC, const CUtensorMap& tmX, cudaStream_t st) {
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static PerDeviceOnce attr;  // per instantiation
+  if (attr.first_time()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_p16_kernel<SA, SW, MODE, OUT_PAIR, EW, NIO>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   gemm_p16_kernel<SA, SW, MODE, OUT_PAIR, EW, NIO><<<grid, (EW + 3) * 32, smem, st>>>(g, w, tmA, tmC, tmX);
   return cudaGetLastError();

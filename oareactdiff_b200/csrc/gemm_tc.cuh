@@ -700,12 +700,11 @@ template <int STAGES, int RAW, int MODE, int NIO>
 inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int grid, size_t smem, TcDebugOpts dbg,
                                        const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmX,
                                        cudaStream_t st) {
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static PerDeviceOnce attr;  // per instantiation
+  if (attr.first_time()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<STAGES, RAW, MODE, NIO>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   gemm_tc_kernel<STAGES, RAW, MODE, NIO><<<grid, TC_THREADS, smem, st>>>(g, w, dbg, tmA, tmC, tmX);
   return cudaGetLastError();

@@ -412,12 +412,12 @@ inline size_t ms_gemm_smem(int K) {
 template <int MT, int NTW, int MODE, int NW>
 inline cudaError_t launch_ms_gemm(const MsGemmArgs& a, cudaStream_t st) {
   const size_t smem = ms_gemm_smem<MT, MODE>(a.K);
-  static size_t attr_smem = 0;  // per instantiation
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_ms_gemm<MT, NTW, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static PerDeviceOnce attr;  // per instantiation; the opt-in covers every K this kernel accepts
+  if (attr.first_time()) {
+    cudaError_t e = cudaFuncSetAttribute(k_ms_gemm<MT, NTW, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_smem = smem;
   }
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (a.K % 4 || a.K > 256 * (a.ln ? 1 : 4) || a.w.K != a.K || a.lda % 4 || a.w.NT8 % (MODE == 0 ? 1 : NTW)) return cudaErrorInvalidValue;
   const int groups = (a.w.NT8 + NTW - 1) / NTW;
   dim3 grid((a.M + (MODE == 1 ? 16 : 16 * MT) - 1) / (MODE == 1 ? 16 : 16 * MT), (groups + NW - 1) / NW);

@@ -1043,8 +1043,8 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
         const int grid = h->num_sms * per_sm;
 #define OARD_EF(CHV)                                                                                                   \
         {                                                                                                              \
-          static bool attr = false;                                                                                    \
-          if (!attr) { CU(cudaFuncSetAttribute(k_equi_frag<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+          static PerDeviceOnce attr;                                                                                   \
+          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_frag<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
           k_equi_frag<CHV><<<grid, 256, ef_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
               h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),     \
               h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                          \
