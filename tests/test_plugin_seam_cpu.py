@@ -20,3 +20,14 @@ def test_leftnetb200_plugs_into_the_unmodified_reference():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["model_class"] == "LEFTNetB200" and out["missing"] == [] and out["unexpected"] == []
     assert out["h_equal"] and max(out["trajectory_rel_err"]) < 1e-4, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_the_reference_own_test_files_pass_with_the_plugin_class():
+    """oracle/run_reference_tests.py: tests/model/test_equiv.py, test_subgraphs.py, tests/dynamics/test_switch_fragments.py and
+    test_egnn_dynamics.py of the reference, unmodified, with `oa_reactdiff.model.LEFTNet` replaced by `LEFTNetB200` (oracle as
+    engine; the confidence head keeps the reference's class)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_reference_tests.py")], capture_output=True, text=True,
+                       timeout=900, cwd="/tmp")
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["rc"] == 0 and out["failed"] == 0 and out["passed"] >= 18, (out, r.stdout[-3000:])
