@@ -319,7 +319,8 @@ class EnVariationalDiffusion(nn.Module):
         return len(set(self.node_nfs)) == 1 and not self.fixed_idx and not self.debug_asserts and own_noise
 
     def _tables(self, timesteps: int, device):
-        key = (timesteps, str(device), self.schedule.gamma_module.gamma.data_ptr())
+        gam = self.schedule.gamma_module.gamma  # callers swap `ddpm.schedule` / `ddpm.T` after construction (evaluate/utils.py:28-31)
+        key = (timesteps, str(device), id(self.schedule), gam.data_ptr(), gam._version, tuple(self.schedule.norm_values))
         if getattr(self, "_tab_key", None) == key:
             return self._tab
         steps = torch.arange(timesteps + 1, device=device)

@@ -44,3 +44,27 @@ def test_inpaint_trajectory_host_logic(oracle_engine, monkeypatch, fast, entry):
             return real(self, *a, **k)
         monkeypatch.setattr(ob.EnVariationalDiffusion, "inpaint", via_fixed)
     gp.test_inpaint_trajectory_vs_reference_golden()
+
+
+def test_schedule_swapped_after_construction_is_honoured(oracle_engine, monkeypatch):
+    """The reference's callers replace `ddpm.schedule` / `ddpm.T` on a built model (evaluate/utils.py:14-31,
+    pl_trainer.py:284-293: trained with one schedule, sampled with another): the tabulated fast path must follow — it is
+    compared with the reference-structured path, which reads the schedule directly."""
+    g = gp.load_golden("sample_small_T10")
+    sizes = [int(x) for x in g["sizes"]]
+    ddpm = gp._make_ddpm(g["cfg"], int(g["seed"]), 10, gp._CpuNoiseDiffusion)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, int(g["seed"]))
+
+    def run():
+        torch.manual_seed(3)
+        out, _ = ddpm.sample(len(sizes), nodes, cond, h0=h0)
+        return torch.cat([o[:, :3] for o in out[0]])
+
+    first = run()
+    ddpm.schedule = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_3", 6, 1e-5), norm_values=ddpm.norm_values)
+    ddpm.T = 6
+    fast = run()
+    assert ddpm.n_evals == 7 and not torch.allclose(fast, first)
+    monkeypatch.setattr(ob.EnVariationalDiffusion, "_fast_ok", lambda self: False)
+    structured = run()
+    assert torch.allclose(fast, structured, rtol=0, atol=1e-5 * float(structured.abs().max()))
