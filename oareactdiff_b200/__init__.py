@@ -23,5 +23,6 @@ __all__ = ["LEFTNetB200", "LEFTNet", "EGNNDynamics", "EnVariationalDiffusion", "
            "PredefinedNoiseSchedule", "get_repaint_schedule", "Normalizer", "get_edges_index", "get_mask_for_frag",
            "get_n_frag_switch", "get_subgraph_mask", "get_inner_edge_index", "polynomial_schedule", "cosine_beta_schedule",
            "ccosine_schedule", "linear_schedule", "clip_noise_schedule"]
-from .data import ProcessedTS1x, assemble_sample_inputs, write_single_xyz, write_tmp_xyz  # noqa: E402,F401
+from .data import (ProcessedTS1x, assemble_sample_inputs, write_single_xyz, write_tmp_xyz, set_new_schedule,  # noqa: E402,F401
+                   inplaint_batch, samples_to_pos_charge)
 from .checkpoint import load_reference_checkpoint  # noqa: E402,F401

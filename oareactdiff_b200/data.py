@@ -214,3 +214,47 @@ def write_tmp_xyz(fragments_nodes, out_samples, idx=[0], prefix="gen", localpath
             n = int(natoms)
             write_single_xyz(f"{localpath}/{prefix}_{jj + ex_ind}_{typemap[ii]}.xyz", n, out_samples[ii][start:start + n])
             start += n
+
+
+# ------------------------------------------------------------------------------------------------ evaluation-side callers
+# oa_reactdiff/evaluate/utils.py:14-63, 91-110 — the three helpers the reference's evaluation scripts put between a batch of
+# the dataset and `inpaint()`.  `ddpm_trainer` is whatever carries the diffusion model as `.ddpm` (the reference's
+# LightningModule); a bare `EnVariationalDiffusion` is accepted as well.
+def _ddpm_of(obj):
+    return getattr(obj, "ddpm", obj)
+
+
+def set_new_schedule(ddpm_trainer, timesteps: int = 250, device: torch.device = torch.device("cuda"),
+                     noise_schedule: str = "polynomial_2"):
+    """Replace the noise schedule of a built model — sampling with fewer steps than it was trained with
+    (evaluate/utils.py:14-32; precision 1e-5, the model's own norm_values)."""
+    from .schedule import DiffSchedule, PredefinedNoiseSchedule
+    ddpm = _ddpm_of(ddpm_trainer)
+    ddpm.schedule = DiffSchedule(gamma_module=PredefinedNoiseSchedule(noise_schedule=noise_schedule, timesteps=timesteps,
+                                                                       precision=1e-5), norm_values=ddpm.norm_values)
+    ddpm.T = timesteps
+    return ddpm_trainer.to(device)
+
+
+def inplaint_batch(batch: List, ddpm_trainer, resamplings: int = 1, jump_length: int = 1, frag_fixed: List = [0, 2]):
+    """One collated batch -> RePaint inpainting with the fragments `frag_fixed` clamped to the batch's own geometry
+    (evaluate/utils.py:35-63; the name keeps the reference's spelling).  Returns (out_samples[0], xh_fixed, fragments_nodes)."""
+    from .normalizer import FEATURE_MAPPING
+    representations, conditions = batch
+    xh_fixed = [torch.cat([rep[k] for k in FEATURE_MAPPING], dim=1) for rep in representations]
+    fragments_nodes = [rep["size"] for rep in representations]
+    out_samples, _ = _ddpm_of(ddpm_trainer).inpaint(
+        n_samples=representations[0]["size"].size(0), fragments_nodes=fragments_nodes, conditions=conditions, return_frames=1,
+        resamplings=resamplings, jump_length=jump_length, timesteps=None, xh_fixed=xh_fixed, frag_fixed=frag_fixed)
+    return out_samples[0], xh_fixed, fragments_nodes
+
+
+def samples_to_pos_charge(out_samples, fragments_nodes):
+    """Per-reaction numpy positions of the three fragments, atomic numbers and atom counts from `out_samples[0]`
+    (evaluate/utils.py:91-110; all three fragments are split with the first fragment's sizes, as in the reference)."""
+    cuts = torch.cumsum(fragments_nodes[0], dim=0).to("cpu")[:-1]
+    parts = [torch.tensor_split(out_samples[ii], cuts) for ii in range(3)]
+    pos = {name: [x[:, :3].cpu().numpy() for x in parts[ii]] for ii, name in enumerate(FRAG_KEYS)}
+    z = [x[:, -1].long().cpu().numpy() for x in parts[0]]
+    natoms = [f.cpu().item() for f in fragments_nodes[0]]
+    return pos, z, natoms

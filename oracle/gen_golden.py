@@ -393,6 +393,68 @@ def case_dataset(name="dataset_small"):
     print(name, "ok", [k for k in out if k.endswith("/len")], [int(out[k]) for k in out if k.endswith("/len")])
 
 
+def _reference_evaluate_utils():
+    """oa_reactdiff/evaluate/utils.py, unmodified.  Its module-level imports of the Lightning trainer and the pyscf-based
+    geometry tools (absent here, and unused by the three helpers wanted) are satisfied by empty stand-in modules."""
+    import types
+    for name, attrs in (("oa_reactdiff.trainer.pl_trainer", {"DDPMModule": object}),
+                        ("oa_reactdiff.analyze.geomopt", {"calc_deltaE": None, "compute_efh": None})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            pkg = name.rsplit(".", 1)[0]
+            if pkg not in sys.modules:
+                sys.modules[pkg] = types.ModuleType(pkg)
+                sys.modules[pkg].__path__ = []
+    import importlib
+    return importlib.import_module("oa_reactdiff.evaluate.utils")
+
+
+def case_eval_pipeline(name="eval_pipeline_small", seed=81):
+    """The evaluation-side callers of the path, end to end with the unmodified reference: ProcessedTS1x batch (dataset/
+    transition1x.py) -> set_new_schedule -> inplaint_batch -> samples_to_pos_charge (evaluate/utils.py:14-63, 91-110)."""
+    import copy
+    import tempfile
+    from oa_reactdiff.dataset.transition1x import ProcessedTS1x
+    EU = _reference_evaluate_utils()
+    raw = synthetic_raw_dataset()
+    kw = dict(single_frag_only=True, use_by_ind=False, swapping_react_prod=False)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "raw.pkl")
+        pickle.dump(copy.deepcopy(raw), open(path, "wb"))
+        ds = ProcessedTS1x(path, **kw)
+        idxs = [4, 0, 2]
+        batch = ProcessedTS1x.collate_fn([ds[i] for i in idxs])
+    ddpm, _ = build_ddpm(SMALL_CFG, seed, 20)
+
+    class Trainer:  # what the helpers need of the LightningModule: `.ddpm` and `.to()`
+        def __init__(self, d):
+            self.ddpm = d
+
+        def to(self, device):
+            self.ddpm.to(device)
+            return self
+
+    tr = EU.set_new_schedule(Trainer(ddpm), timesteps=8, device=torch.device("cpu"), noise_schedule="polynomial_3")
+    torch.manual_seed(seed)
+    out, xh_fixed, fragments_nodes = EU.inplaint_batch(batch, tr, resamplings=2, jump_length=2, frag_fixed=[0, 2])
+    pos, z, natoms = EU.samples_to_pos_charge(out, fragments_nodes)
+    res = {"raw": json.dumps(raw), "kw": json.dumps(kw), "idxs": np.array(idxs), "seed": np.int64(seed), "T0": np.int64(20),
+           "gamma_new": tr.ddpm.schedule.gamma_module.gamma.detach().numpy(), "T_new": np.int64(tr.ddpm.T),
+           "natoms": np.array(natoms)}
+    for f in range(3):
+        res[f"out{f}"] = out[f].numpy()
+        res[f"xh_fixed{f}"] = xh_fixed[f].numpy()
+    for k, v in pos.items():
+        for i, a in enumerate(v):
+            res[f"pos/{k}/{i}"] = a
+    for i, a in enumerate(z):
+        res[f"z/{i}"] = a
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps(SMALL_CFG), **res)
+    print(name, "ok", natoms)
+
+
 def t1x_histogram():
     path = "/root/reference/oa_reactdiff/data/transition1x/train.pkl"
     with open(path, "rb") as fh:
@@ -423,6 +485,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "noreflect":  # reflect_equiv=False (reference tests/model/test_equiv.py:40-41)
         case_leftnet("leftnet_small_noreflect", dict(SMALL_CFG, reflect_equiv=False), 11, seed=14, cut=5, pos_scale=3.0)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":  # only the evaluation-pipeline fixture
+        case_eval_pipeline()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the module-level helper fixture
         case_api_helpers()
@@ -465,3 +530,4 @@ if __name__ == "__main__":
     case_train_grad("grad_small_train_t0", SMALL_CFG, [4, 5, 3], seed=77, T=20, store_full=True)
     case_checkpoint()
     case_api_helpers()
+    case_eval_pipeline()
