@@ -9,7 +9,9 @@ this proves is that the CLASS — constructor kwargs of the reference's fixtures
 forward signature incl. positional `edge_attr`, return convention, float64 callers, use inside the reference's
 `EGNNDynamics` — satisfies the reference's own tests; the kernels are judged on the GPU.
 Files: tests/model/test_equiv.py, tests/model/test_subgraphs.py, tests/dynamics/test_switch_fragments.py,
-tests/dynamics/test_egnn_dynamics.py (their EGNN halves run on the reference's EGNN, untouched)."""
+tests/dynamics/test_egnn_dynamics.py (their EGNN halves run on the reference's EGNN, untouched); tests/utils/
+test_graph_tools.py and tests/datasets/test_transition1x.py with this package's graph helpers / packed dataset swapped in
+— i.e. the reference's whole test suite."""
 import json
 import os
 import sys
@@ -38,6 +40,15 @@ def _plug(**cfg):
 
 ref_model.LEFTNet = _plug  # the test modules do `from oa_reactdiff.model import EGNN, LEFTNet`
 
+# tests/utils/test_graph_tools.py and tests/datasets/test_transition1x.py: this package's graph helpers and packed dataset
+# under the reference's names (`from oa_reactdiff.utils import ...`, `from oa_reactdiff.dataset.transition1x import ...`)
+import oa_reactdiff.dataset.transition1x as ref_t1x  # noqa: E402
+import oa_reactdiff.utils as ref_utils  # noqa: E402
+
+for _n in ("get_edges_index", "get_subgraph_mask", "get_n_frag_switch", "get_mask_for_frag"):
+    setattr(ref_utils, _n, getattr(ob, _n))
+ref_t1x.ProcessedTS1x = ob.ProcessedTS1x
+
 
 class _Count:
     def __init__(self):
@@ -58,7 +69,7 @@ class _Count:
 def main():
     t = "/root/reference/oa_reactdiff/tests/"
     files = [t + "model/test_equiv.py", t + "model/test_subgraphs.py", t + "dynamics/test_switch_fragments.py",
-             t + "dynamics/test_egnn_dynamics.py"]
+             t + "dynamics/test_egnn_dynamics.py", t + "utils/test_graph_tools.py", t + "datasets/test_transition1x.py"]
     c = _Count()
     rc = pytest.main(["-q", "-x", "-p", "no:cacheprovider", "--rootdir", "/tmp", *files], plugins=[c])
     print(json.dumps({"rc": int(rc), "passed": c.passed, "failed": c.failed, "failed_ids": c.names}))
