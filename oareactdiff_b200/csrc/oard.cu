@@ -600,7 +600,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   for (int i = 0; i < N && h->complete; i++) {
     if (row_ptr[i + 1] - row_ptr[i] != count[comp_of[i]] - 1) h->complete = false;
     for (int e = row_ptr[i]; e < row_ptr[i + 1] && h->complete; e++)
-      if (ecol[e] == i) h->complete = false;  // self loop
+      if (ecol[e] == i || (e > row_ptr[i] && ecol[e] <= ecol[e - 1])) h->complete = false;  // self loop / row not ascending
   }
   h->planned = true;
   return OARD_OK;

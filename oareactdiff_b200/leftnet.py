@@ -164,14 +164,16 @@ class _Engine:
         if key == self.plan_key:
             return
         ei = edge_index.detach().to("cpu", torch.int64).contiguous()
-        # oard_plan wants the edges grouped by source (the order get_edges_index produces).  Any other order of the same
-        # edges (e.g. the hand-written lists of the reference's tests/model/test_equiv.py:30-32) is brought into that form
-        # here; outputs are per node, so only the per-edge subgraph_mask has to follow (edge_order).
+        # oard_plan wants the edges sorted by (source, target), the order get_edges_index produces.  Any other order of the
+        # same edges (e.g. the hand-written lists of the reference's tests/model/test_equiv.py:30-32) is brought into that
+        # form here; outputs are per node, so only the per-edge subgraph_mask has to follow (edge_order).
         self.edge_perm = None
-        if ei.size(1) > 1 and bool((ei[0, 1:] < ei[0, :-1]).any()):
-            perm = torch.argsort(ei[0], stable=True)
-            ei = ei[:, perm].contiguous()
-            self.edge_perm = perm.to(self.device)
+        if ei.size(1) > 1:
+            rank = ei[0] * int(n_nodes) + ei[1]
+            if bool((rank[1:] < rank[:-1]).any()):
+                perm = torch.argsort(rank, stable=True)
+                ei = ei[:, perm].contiguous()
+                self.edge_perm = perm.to(self.device)
         _lib.check(self.lib.oard_plan(self.h, n_nodes, ei.size(1), C.c_void_p(ei.data_ptr())))
         self.plan_key, self.N, self.E = key, n_nodes, ei.size(1)
         self.dyn_plan_key = None

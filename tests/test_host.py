@@ -113,7 +113,13 @@ def test_engine_plan_accepts_edges_not_grouped_by_source():
     assert eng.edge_order(None) is None
     with pytest.raises(ValueError):
         eng.edge_order(torch.ones(5))
-    # already grouped (what get_edges_index produces): passed through untouched, and the mask keeps its storage
+    # grouped by source but targets not ascending inside a row: sorted as well (the group-staged message kernel walks the
+    # members of a fragment in row order and addresses them by rank)
+    ei3 = torch.tensor([[0, 0, 1, 1, 2, 2], [2, 1, 0, 2, 1, 0]])
+    eng.plan(ei3, 3)
+    assert np.array_equal(seen["ei"], [[0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]])
+    assert eng.edge_order(torch.tensor([10, 11, 12, 13, 14, 15])).tolist() == [11, 10, 12, 13, 15, 14]
+    # already sorted (what get_edges_index produces): passed through untouched, and the mask keeps its storage
     ei2 = ob.get_edges_index(torch.tensor([0, 0, 0, 1, 1]), remove_self_edge=True)
     eng.plan(ei2, 5)
     assert eng.edge_perm is None and np.array_equal(seen["ei"], ei2.numpy())
