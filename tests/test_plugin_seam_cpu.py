@@ -32,3 +32,11 @@ def test_the_reference_own_test_files_pass_with_the_plugin_class():
                        timeout=900, cwd="/tmp")
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["rc"] == 0 and out["failed"] == 0 and out["passed"] >= 24, (out, r.stdout[-3000:])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_graph_helpers_bit_exact_vs_the_unmodified_reference_on_random_inputs():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_graph_tools.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["n_mismatches"] == 0 and out["checks"] > 2000, out
