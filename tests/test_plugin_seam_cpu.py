@@ -40,3 +40,12 @@ def test_graph_helpers_bit_exact_vs_the_unmodified_reference_on_random_inputs():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["n_mismatches"] == 0 and out["checks"] > 2000, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_loss_terms_match_the_unmodified_reference_over_its_option_space():
+    """oracle/fuzz_loss_options.py: loss_type {l2, vlb} x pos_only x training / eval x fixed_idx, native random streams."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_loss_options.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["cases"] == 16 and out["bad"] == 0 and out["worst"] < 1e-5, out
