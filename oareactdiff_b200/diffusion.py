@@ -340,6 +340,7 @@ class EnVariationalDiffusion(nn.Module):
             "alpha": self.schedule.alpha(gamma, ref).flatten().tolist(),
             "sigma_abs": self.schedule.sigma(gamma, ref).flatten().tolist(),
             "sigma_ts": sigma_ts.flatten().tolist(),
+            "gamma": gamma.detach().float().cpu().flatten(),        # gamma(k / timesteps): the jump-back of inpaint() pairs any s < t
         }
         self._tab_key, self._tab = key, tab
         return tab
@@ -508,7 +509,7 @@ class EnVariationalDiffusion(nn.Module):
         if self._fast_ok():
             tab = self._tables(timesteps, dev)
             self._seg_setup(masks)
-            gamma_cpu = self.schedule.gamma_module.gamma.detach().float().cpu()
+            gamma_cpu = tab["gamma"]  # indexed by step of THIS trajectory (timesteps may differ from the schedule's T)
             Z = torch.cat(z).to(torch.float32).contiguous()
             Xf = torch.cat(xh_fixed).to(torch.float32)
             H0 = torch.cat(h0).to(Z.dtype)

@@ -49,3 +49,14 @@ def test_loss_terms_match_the_unmodified_reference_over_its_option_space():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["cases"] == 16 and out["bad"] == 0 and out["worst"] < 1e-5, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_samplers_match_the_unmodified_reference_over_their_option_space():
+    """oracle/fuzz_sampler_options.py: sample (pos_only x return_frames x timesteps x fixed_idx) and inpaint (pos_only x
+    resamplings / jump_length x frag_fixed x timesteps), native random streams, both host formulations of this package."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_sampler_options.py")], capture_output=True, text=True,
+                       timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["cases"] == 40 and out["bad"] == 0 and out["worst"] < 1e-5, out

@@ -18,6 +18,10 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(gp, "DEV", torch.device("cpu"))
     monkeypatch.setattr(ob.LEFTNetB200, "forward", _oracle_forward)
     monkeypatch.setattr(ob.EGNNDynamics, "fused_ok", lambda self, device: False)
+    # the GPU twins draw the noise on the CPU through a subclass, which (by design) switches the tabulated fast path off; on the
+    # CPU the package's own noise function already produces the reference's stream, so the plain class is used and the
+    # `fast` parameter below really selects between the two host formulations
+    monkeypatch.setattr(gp, "_CpuNoiseDiffusion", ob.EnVariationalDiffusion)
 
 
 @pytest.mark.parametrize("fast", [True, False])
@@ -65,6 +69,27 @@ def test_schedule_swapped_after_construction_is_honoured(oracle_engine, monkeypa
     ddpm.T = 6
     fast = run()
     assert ddpm.n_evals == 7 and not torch.allclose(fast, first)
+    monkeypatch.setattr(ob.EnVariationalDiffusion, "_fast_ok", lambda self: False)
+    structured = run()
+    assert torch.allclose(fast, structured, rtol=0, atol=1e-5 * float(structured.abs().max()))
+
+
+def test_inpaint_with_fewer_steps_than_the_schedule_jumps_back_correctly(oracle_engine, monkeypatch):
+    """`timesteps` below the schedule's T (en_diffusion.py:736) with RePaint jump-backs: the forward jump z_s -> z_t needs
+    gamma at s / timesteps and t / timesteps, not at the raw step indices (regression: the tabulated path used the latter)."""
+    g = gp.load_golden("inpaint_small_T12_r2_j3")
+    sizes = [int(x) for x in g["sizes"]]
+    ddpm = gp._make_ddpm(g["cfg"], int(g["seed"]), int(g["T"]), gp._CpuNoiseDiffusion)
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, int(g["seed"]))
+    xh_fixed = [torch.from_numpy(g[f"xh_fixed{f}"]) for f in range(3)]
+
+    def run():
+        torch.manual_seed(5)
+        out, _ = ddpm.inpaint(len(sizes), nodes, cond, resamplings=3, jump_length=2, timesteps=6,
+                              xh_fixed=[x.clone() for x in xh_fixed], frag_fixed=[0, 2])
+        return torch.cat([o[:, :3] for o in out[0]])
+
+    fast = run()
     monkeypatch.setattr(ob.EnVariationalDiffusion, "_fast_ok", lambda self: False)
     structured = run()
     assert torch.allclose(fast, structured, rtol=0, atol=1e-5 * float(structured.abs().max()))
