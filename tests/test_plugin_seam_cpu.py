@@ -60,3 +60,14 @@ def test_samplers_match_the_unmodified_reference_over_their_option_space():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["cases"] == 40 and out["bad"] == 0 and out["worst"] < 1e-5, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_dynamics_wrapper_matches_the_unmodified_reference_over_its_option_space():
+    """oracle/fuzz_dynamics_options.py: condition_time x condition_nf x t layout x per-fragment node_nf x fragment sets (incl. an
+    empty fragment) x shared encoders, weights handed over through `source`."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_dynamics_options.py")], capture_output=True, text=True,
+                       timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["cases"] >= 100 and out["bad"] == 0 and out["worst"] < 1e-6, out
