@@ -71,3 +71,15 @@ def test_dynamics_wrapper_matches_the_unmodified_reference_over_its_option_space
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["cases"] >= 100 and out["bad"] == 0 and out["worst"] < 1e-6, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_oracle_leftnet_matches_the_unmodified_reference_over_graphs_and_options():
+    """oracle/fuzz_oracle_leftnet.py: 576 float64 cases (graph shapes incl. sparse / disconnected / shuffled edge lists, masks,
+    cut-offs that split groups, reflect_equiv, object_aware, update, depth) — the checker of the kernels pinned on the reference
+    itself, beyond the committed golden vectors."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_oracle_leftnet.py")], capture_output=True, text=True,
+                       timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["cases"] >= 500 and out["bad"] == 0 and out["worst"] < 1e-9, out
