@@ -68,3 +68,46 @@ def test_leftnet_reflect_equiv_false_vs_reference_golden():
     e_h, e_p = rel_err(ho.cpu(), g["h_out_f64"]), rel_err((po - pos).cpu(), g["dpos_f64"])
     print(f"noreflect: h {e_h:.2e} dpos {e_p:.2e}")
     assert e_h < REL_TOL and e_p < REL_TOL
+
+
+def _grid_graphs():
+    def full(n):
+        return torch.tensor([[i, j] for i in range(n) for j in range(n) if i != j]).T.contiguous()
+    g = torch.Generator().manual_seed(0)
+    e8 = full(8)
+    return {"complete9": (9, full(9)), "path": (4, torch.tensor([[0, 1, 1, 2, 3, 0], [1, 0, 2, 1, 0, 3]])),
+            "two_components": (7, torch.tensor([[0, 1, 1, 2, 0, 3, 4, 6, 4, 5], [1, 0, 2, 1, 3, 0, 6, 4, 5, 4]])),
+            "complete8_shuffled": (8, e8[:, torch.randperm(e8.size(1), generator=g)]),
+            "two_cliques": (11, torch.cat([full(5), full(6) + 5], dim=1))}
+
+
+@pytest.mark.parametrize("gname", ["complete9", "path", "two_components", "complete8_shuffled", "two_cliques"])
+def test_leftnet_option_grid_vs_oracle(gname):
+    """The grid on which oracle/fuzz_oracle_leftnet.py pins the oracle to the unmodified reference (graph shapes, masks,
+    cut-offs that split groups, reflect_equiv, object_aware, update, depth), now CUDA vs that oracle (fp64), REL_TOL = 1e-3."""
+    import itertools
+    from tests.test_gpu_parity import REL_TOL, make_leftnet
+    from tests.util import rel_err
+    n, ei = _grid_graphs()[gname]
+    g = torch.Generator().manual_seed(1)
+    worst = 0.0
+    for reflect, oa, update, layers, cut, cutoff, scale in itertools.product([True, False], [True, False], [True, False], [1, 3],
+                                                                          [None, 3], [20.0, 2.5], [1.0, 3.0]):
+        if n < 5 and cut:
+            continue
+        cfg = dict(cutoff=cutoff, num_layers=layers, hidden_channels=16, num_radial=8, in_hidden_channels=6, reflect_equiv=reflect,
+                   legacy=True, update=update, object_aware=oa)
+        sd = oa_ref.make_state_dict(oa_ref.leftnet_param_shapes(cfg), 3, cfg, dtype=torch.float64)
+        h = torch.rand(n, 6, generator=g, dtype=torch.float64)
+        pos = torch.rand(n, 3, generator=g, dtype=torch.float64) * scale
+        sub = None
+        if cut:
+            s = (ei < cut).sum(0)
+            sub = ((s == 2) | (s == 0)).long()[:, None]
+        ho_ref, dpos_ref = oa_ref.leftnet_forward(sd, cfg, h, pos, ei, sub)
+        m = make_leftnet(cfg, {k: v.float() for k, v in sd.items()})
+        ho, po, _ = m(h.float().to(DEV), pos.float().to(DEV), ei.to(DEV), subgraph_mask=None if sub is None else sub.to(DEV))
+        e = max(rel_err(ho.cpu(), ho_ref), rel_err((po.cpu() - pos.float()), dpos_ref))
+        worst = max(worst, e)
+        assert e < REL_TOL, (gname, reflect, oa, update, layers, cut, cutoff, scale, e)
+    print(f"{gname}: worst rel err over the grid {worst:.2e}")
