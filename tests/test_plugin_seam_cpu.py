@@ -83,3 +83,17 @@ def test_oracle_leftnet_matches_the_unmodified_reference_over_graphs_and_options
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["cases"] >= 500 and out["bad"] == 0 and out["worst"] < 1e-9, out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_plugin_class_inside_the_reference_real_trainer_module():
+    """oracle/trainer_seam.py: the reference's `DDPMModule` (pl_trainer.py, unmodified; Lightning / torchmetrics stand-ins) built
+    with `model=LEFTNetB200` from train_ts1x.py's configuration: same checkpoint keys, `compute_loss` over loss_type x pos_only x
+    mode equal to the `model=LEFTNet` module AND to this package's own `compute_loss` on the packed batch producer,
+    `training_step` / `validation_step` / the sampling half of `eval_inplaint_batch` equal."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "trainer_seam.py")], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["compute_loss_cases"] == 8 and out["worst"] < 1e-6, out
+    assert all(c["finite"] and c["info_keys_equal"] for c in out["report"])
+    assert max(out["training_step"], out["validation_step"], out["eval_inpaint_samples"]) < 1e-6
