@@ -3,19 +3,64 @@ model as `self.ddpm`, so a Lightning checkpoint is `{"state_dict": {"ddpm.<key>"
 `<key>` = the state-dict keys of `EnVariationalDiffusion` — which this repo's modules reproduce one to one
 (`dynamics.model.*`, `dynamics.encoders.*`, `dynamics.decoders.*`, `schedule.gamma_module.gamma`).
 `demo.py:269` (`DDPMModule.load_from_checkpoint`) is therefore replaced by `load_reference_checkpoint(ddpm, path)`."""
+import os
+import pickle
+import types
 from typing import Dict, Union
 
 import torch
 from torch import Tensor, nn
 
 
-def load_reference_checkpoint(ddpm: nn.Module, ckpt: Union[str, Dict], prefix: str = "ddpm.", strict: bool = True) -> Dict:
+class _Absent:
+    """Stands in for a pickled object whose class cannot be imported here (see _read)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        pass
+
+    def __call__(self, *a, **k):
+        return self
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except Exception:
+            return _Absent
+
+
+_tolerant_pickle = types.SimpleNamespace(Unpickler=_TolerantUnpickler, load=pickle.load, loads=pickle.loads,
+                                         __name__="pickle")
+
+
+def _read(path: str, allow_pickle: bool):
+    """`DDPMModule.save_hyperparameters()` (pl_trainer.py:147) puts the constructor arguments into the checkpoint, among them
+    `model=<class LEFTNet>`: a Lightning checkpoint of the reference therefore pickles a CLASS of the reference package and
+    does not open with `weights_only=True`, nor at all where `oa_reactdiff` is not installed.  With `allow_pickle=True` (a
+    file you trust: unpickling can run code) it is read with an unpickler that replaces what cannot be imported by a
+    placeholder; only the tensors of `state_dict` are used afterwards."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:
+        if not allow_pickle:
+            raise RuntimeError(f"{path}: not loadable with weights_only=True ({type(e).__name__}: {str(e)[:200]}).  Lightning "
+                               "checkpoints of the reference pickle its model class in `hyper_parameters`; if you trust the file, "
+                               "call load_reference_checkpoint(..., allow_pickle=True).") from e
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_tolerant_pickle)
+
+
+def load_reference_checkpoint(ddpm: nn.Module, ckpt: Union[str, Dict], prefix: str = "ddpm.", strict: bool = True,
+                              allow_pickle: bool = False) -> Dict:
     """Copy the weights of a reference checkpoint (path or already-loaded dict; plain state dict or Lightning layout) into
     `ddpm` (an `EnVariationalDiffusion` of this package).  Returns {"loaded": n, "ignored": [keys outside `prefix`],
     "missing": [...], "unexpected": [...]}; with strict=True missing / unexpected keys under the prefix raise like
-    `load_state_dict` does."""
-    if isinstance(ckpt, str):
-        ckpt = torch.load(ckpt, map_location="cpu", weights_only=True)
+    `load_state_dict` does.  `allow_pickle`: see `_read`."""
+    if isinstance(ckpt, (str, os.PathLike)):
+        ckpt = _read(os.fspath(ckpt), allow_pickle)
     sd = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
     if not isinstance(sd, dict) or not all(isinstance(v, Tensor) for v in sd.values()):
         raise ValueError("checkpoint does not hold a state dict of tensors")

@@ -106,3 +106,39 @@ def test_reference_checkpoint_layout_loads(tmp_path):
         ob.load_reference_checkpoint(ddpm, {"state_dict": broken})
     with pytest.raises(KeyError):
         ob.load_reference_checkpoint(ddpm, {"state_dict": {"foo.bar": torch.zeros(1)}})
+
+
+def test_lightning_checkpoint_that_pickles_the_reference_model_class(tmp_path):
+    """A real checkpoint of the reference carries `hyper_parameters["model"] = <class LEFTNet>` (save_hyperparameters,
+    pl_trainer.py:147): a pickled class of a package that is not installed here.  Refused with a pointer by default, read with
+    placeholders under allow_pickle=True; only the tensors are used."""
+    import sys
+    import types
+
+    import oareactdiff_b200 as ob
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "checkpoint_small.npz"), allow_pickle=False)
+    cfg, T = json.loads(str(z["cfg"])), int(z["T"])
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("cfg", "T")}
+    mod = types.ModuleType("oa_reactdiff_absent_pkg")
+
+    class LEFTNet:  # stands for oa_reactdiff.model.leftnet.LEFTNet at save time
+        pass
+    LEFTNet.__module__, LEFTNet.__qualname__ = "oa_reactdiff_absent_pkg", "LEFTNet"
+    mod.LEFTNet = LEFTNet
+    sys.modules["oa_reactdiff_absent_pkg"] = mod
+    path = tmp_path / "ddpm-epoch=1.ckpt"
+    try:
+        torch.save({"epoch": 1, "global_step": 10, "pytorch-lightning_version": "1.8.6", "state_dict": sd,
+                    "hyper_parameters": {"model": LEFTNet, "model_config": cfg, "scales": [1.0, 2.0, 1.0], "probe": LEFTNet()}}, path)
+    finally:
+        del sys.modules["oa_reactdiff_absent_pkg"]  # ... and is not importable at load time
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), (1.0, 1.0, 1.0)),
+                                     normalizer=ob.Normalizer(), pos_only=True)
+    with pytest.raises(RuntimeError, match="allow_pickle=True"):
+        ob.load_reference_checkpoint(ddpm, str(path))
+    res = ob.load_reference_checkpoint(ddpm, path, allow_pickle=True)
+    assert res["missing"] == [] and res["unexpected"] == [] and res["loaded"] == len(ddpm.state_dict())
+    for k, v in ddpm.state_dict().items():
+        assert torch.equal(v, sd["ddpm." + k]), k
