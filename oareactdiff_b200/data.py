@@ -87,6 +87,12 @@ class ProcessedTS1x(Dataset):
                 self.Z[f, o:o + n] = torch.from_numpy(z.astype(np.int64))
                 self.pos[f, o:o + n] = p
                 o += n
+        # dtype of the per-atom "charge" feature: the reference builds it with torch.tensor(raw charges) (base_dataset.py:179-185),
+        # so it follows the raw container — int32 for the numpy arrays of the shipped Transition1x files, int64 for Python lists
+        self.charge_dtype = torch.int64
+        if self.n_samples:
+            src, i = per_frag["reactant"][0]
+            self.charge_dtype = torch.tensor(raw[src]["charges"][i][:int(raw[src]["num_atoms"][i])]).dtype
         lut = torch.full((int(self.Z.max()) + 1,), -1, dtype=torch.int64)
         for z, c in ATOM_MAPPING.items():
             if z < lut.numel():
@@ -107,7 +113,7 @@ class ProcessedTS1x(Dataset):
             out[f"size_{f}"] = self.sizes[idx].to(self.device)
             out[f"pos_{f}"] = self.pos[f, a:b].to(self.device)
             out[f"one_hot_{f}"] = F.one_hot(self.cls[f, a:b], num_classes=n_element).to(self.device)
-            ch = torch.zeros(b - a, 1, dtype=torch.int64) if self.zero_charge else self.Z[f, a:b].view(-1, 1)
+            ch = torch.zeros(b - a, 1, dtype=torch.int64) if self.zero_charge else self.Z[f, a:b].view(-1, 1).to(self.charge_dtype)
             out[f"charge_{f}"] = ch.to(self.device)
             out[f"mask_{f}"] = torch.zeros(b - a, dtype=torch.int64, device=self.device)
         out["condition"] = torch.zeros(1, 1, dtype=torch.int64, device=self.device)
@@ -170,6 +176,8 @@ class ProcessedTS1x(Dataset):
                 ch.zero_()
             else:
                 torch.index_select(self.Z[f], 0, rows, out=ch.view(-1))
+            if not self.zero_charge and self.charge_dtype != torch.int64:
+                ch = ch.to(self.charge_dtype)
             out.append({"size": sz.to(device, non_blocking=nb), "pos": pos.to(device, non_blocking=nb),
                         "one_hot": oh.to(device, non_blocking=nb), "charge": ch.to(device, non_blocking=nb),
                         "mask": mask.to(device, non_blocking=nb)})

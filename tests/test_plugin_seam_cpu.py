@@ -97,3 +97,13 @@ def test_plugin_class_inside_the_reference_real_trainer_module():
     assert out["compute_loss_cases"] == 8 and out["worst"] < 1e-6, out
     assert all(c["finite"] and c["info_keys_equal"] for c in out["report"])
     assert max(out["training_step"], out["validation_step"], out["eval_inpaint_samples"]) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/oa_reactdiff/data/transition1x/train.pkl"), reason="needs the Transition1x file shipped with the reference")
+def test_packed_dataset_bit_exact_on_the_real_transition1x_file():
+    """oracle/fuzz_dataset.py: 13 466 (trainer options) / 10 073 reactions; random items and collated batches, dtypes included
+    (the shipped file stores atomic numbers as int32 arrays, which the reference's `charge` feature inherits)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "fuzz_dataset.py")], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["n_mismatches"] == 0 and out["checks"] >= 300 and out["lens"]["trainer"] == [13466, 13466], out
