@@ -146,3 +146,65 @@ def test_constructors_accept_the_reference_test_fixtures():
         assert dyn.embed_dim == 8 - 1 - 3 and dyn.edge_encoder is None
         assert [e.mlp[0].linear.in_features for e in dyn.encoders] == [n - 3 for n in node_nfs]
         assert [d.mlp[1].linear.out_features for d in dyn.decoders] == [n - 3 for n in node_nfs]
+
+
+def test_fused_dynamics_plumbing_with_a_recording_engine():
+    """The Python side of the device-resident path (`EGNNDynamics._forward_fused`, `EnVariationalDiffusion._device_setup` /
+    `_device_step`, sample() around them) cannot run without CUDA, but its plumbing can: a recording stand-in for the engine
+    (real `plan` / `edge_order`, no kernels) checks which tensors reach the C calls — shapes, dtypes, the same-fragment mask in
+    the planned edge order, persistence of the state buffer across steps."""
+    from oareactdiff_b200.leftnet import _Engine
+
+    calls = []
+
+    class FakeLib:
+        def oard_plan(self, h, n_nodes, n_edges, ptr):
+            return 0
+
+    class Rec(_Engine):
+        def __init__(self):
+            self.lib, self.h, self.device, self.plan_key, self.edge_perm = FakeLib(), None, torch.device("cpu"), None, None
+            self.weights_key = self.dyn_weights_key = None
+            self.N = self.E = 0
+
+        def __del__(self):
+            pass
+
+        def sync_weights(self, module, force=False):
+            self.weights_key = 1
+
+        def dyn_sync(self, dynamics, n_frag, node_nf, condition_nf, condition_time):
+            self.dyn_weights_key = (n_frag, node_nf, condition_nf, condition_time)
+
+        def dyn_plan(self, nfs, cm, n_samples):
+            calls.append(("dyn_plan", nfs.numel(), cm.numel(), n_samples))
+
+        def dyn_forward(self, xh, t, cond, sub, out):
+            calls.append(("dyn_forward", tuple(xh.shape), xh.dtype, None if t is None else tuple(t.shape), None if cond is None else tuple(cond.shape),
+                          None if sub is None else (sub.dtype, sub.numel(), sub.is_contiguous())))
+            return out.zero_()
+
+        def reverse_step(self, z, nx, nh, h0, cond, sub, t, alpha_ts, coef, sigma):
+            calls.append(("reverse_step", z.data_ptr(), tuple(nx.shape), nh is None, None if h0 is None else tuple(h0.shape), float(t)))
+
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    eng = Rec()
+    dyn.model.engine = lambda device: eng
+    dyn.fused_ok = lambda device: True
+    sizes = [3, 5]
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 0)
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", 5, 1e-5), (1.0, 1.0, 1.0)),
+                                     normalizer=ob.Normalizer(), pos_only=True)
+    torch.manual_seed(0)
+    out, masks = ddpm.sample(len(sizes), nodes, cond, h0=h0)
+    N, E = 3 * sum(sizes), sum(3 * n * (3 * n - 1) for n in sizes)
+    steps = [c for c in calls if c[0] == "reverse_step"]
+    assert len(steps) == 5 and len({c[1] for c in steps}) == 1  # one persistent state buffer: the step graph is keyed by it
+    assert steps[0][2] == (N, 3) and steps[0][3] and steps[0][4] == (N, 6) and [round(c[5] * 5) for c in steps] == [5, 4, 3, 2, 1]
+    fwd = [c for c in calls if c[0] == "dyn_forward"]
+    assert len(fwd) == 1 and fwd[0][1] == (N, 9) and fwd[0][2] == torch.float32 and fwd[0][3] == (2,) and fwd[0][4] == (2, 1)
+    assert fwd[0][5] == (torch.int64, E, True)
+    assert ("dyn_plan", N, N, 2) in calls and ddpm.n_evals == 6
+    assert [tuple(o.shape) for o in out[0]] == [(sum(sizes), 9)] * 3
