@@ -148,11 +148,8 @@ def test_constructors_accept_the_reference_test_fixtures():
         assert [d.mlp[1].linear.out_features for d in dyn.decoders] == [n - 3 for n in node_nfs]
 
 
-def test_fused_dynamics_plumbing_with_a_recording_engine():
-    """The Python side of the device-resident path (`EGNNDynamics._forward_fused`, `EnVariationalDiffusion._device_setup` /
-    `_device_step`, sample() around them) cannot run without CUDA, but its plumbing can: a recording stand-in for the engine
-    (real `plan` / `edge_order`, no kernels) checks which tensors reach the C calls — shapes, dtypes, the same-fragment mask in
-    the planned edge order, persistence of the state buffer across steps."""
+def _recording_dynamics():
+    """EGNNDynamics whose engine is a recording stand-in (real `plan` / `edge_order`, no kernels); -> (dynamics, calls)."""
     from oareactdiff_b200.leftnet import _Engine
 
     calls = []
@@ -193,6 +190,15 @@ def test_fused_dynamics_plumbing_with_a_recording_engine():
     eng = Rec()
     dyn.model.engine = lambda device: eng
     dyn.fused_ok = lambda device: True
+    return dyn, calls
+
+
+def test_fused_dynamics_plumbing_with_a_recording_engine():
+    """The Python side of the device-resident path (`EGNNDynamics._forward_fused`, `EnVariationalDiffusion._device_setup` /
+    `_device_step`, sample() / inpaint() around them) cannot run without CUDA, but its plumbing can: a recording stand-in for
+    the engine checks which tensors reach the C calls — shapes, dtypes, the same-fragment mask in the planned edge order,
+    persistence of the state buffer across steps (the step graph is keyed by it), the step order incl. RePaint jump-backs."""
+    dyn, calls = _recording_dynamics()
     sizes = [3, 5]
     nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 0)
     ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", 5, 1e-5), (1.0, 1.0, 1.0)),
@@ -208,3 +214,18 @@ def test_fused_dynamics_plumbing_with_a_recording_engine():
     assert fwd[0][5] == (torch.int64, E, True)
     assert ("dyn_plan", N, N, 2) in calls and ddpm.n_evals == 6
     assert [tuple(o.shape) for o in out[0]] == [(sum(sizes), 9)] * 3
+    # RePaint: known fragments blended in place, jump-backs copied into the same buffer
+    del calls[:]
+    xh_fixed = [torch.cat([torch.randn(h.size(0), 3), h.float()], dim=1) for h in h0]
+    ddpm.inpaint(len(sizes), nodes, cond, resamplings=2, jump_length=2, timesteps=4, xh_fixed=xh_fixed, frag_fixed=[0, 2])
+    steps = [c for c in calls if c[0] == "reverse_step"]
+    sched = ob.get_repaint_schedule(2, 2, 4)
+    assert len(steps) == sum(sched) == ddpm.n_evals - 1 and len({c[1] for c in steps}) == 1
+    want, s = [], 3
+    for i, n in enumerate(sched):
+        for j in range(n):
+            want.append(s + 1)
+            if j == n - 1 and i < len(sched) - 1:
+                s += 2
+            s -= 1
+    assert [round(c[5] * 4) for c in steps] == want
