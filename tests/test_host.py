@@ -229,3 +229,77 @@ def test_fused_dynamics_plumbing_with_a_recording_engine():
                 s += 2
             s -= 1
     assert [round(c[5] * 4) for c in steps] == want
+
+
+def test_training_path_autograd_plumbing_with_a_recording_engine():
+    """`enable_training_path`: LEFTNetB200.forward as an autograd node over oard_forward_train / oard_backward / oard_get_grad.
+    With a stand-in engine that returns recognisable values, check the routing: every parameter (by reference name) receives
+    the gradient buffer of ITS name, buffers and positions receive none, the node-feature gradient flows on into the encoders
+    of EGNNDynamics, inference mode and torch.no_grad() keep using the inference entry."""
+    from oareactdiff_b200.leftnet import _Engine
+
+    calls = []
+
+    class FakeLib:
+        def oard_plan(self, h, n_nodes, n_edges, ptr):
+            return 0
+
+    class Rec(_Engine):
+        def __init__(self, names):
+            self.lib, self.h, self.device, self.plan_key, self.edge_perm = FakeLib(), None, torch.device("cpu"), None, None
+            self.weights_key, self.names, self.N, self.E = None, names, 0, 0
+
+        def __del__(self):
+            pass
+
+        def sync_weights(self, module, force=False):
+            self.weights_key = 1
+
+        def forward_train(self, h, pos, sub):
+            calls.append(("forward_train", tuple(h.shape), None if sub is None else self.edge_order(sub).numel()))
+            return 2.0 * h.detach(), torch.ones_like(pos)
+
+        def forward(self, h, pos, sub):
+            calls.append(("forward",))
+            return torch.zeros_like(h), torch.zeros_like(pos)
+
+        def backward(self, g_h, g_dpos):
+            calls.append(("backward", float(g_h.sum()), float(g_dpos.sum())))
+            return 2.0 * g_h
+
+        def get_grad(self, name, like):
+            return torch.full(like.shape, float(len(name)))
+
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    model = dyn.model
+    names = [n for n in model._oard_tensors() if not n.startswith(("distance_embedding", "last_layer"))]
+    eng = Rec(names)
+    model.engine = lambda device: eng
+    sizes = [3, 4]
+    nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, 0)
+    masks = [ob.get_mask_for_frag(n) for n in nodes]
+    cm = torch.cat(masks)
+    ei, nfs = ob.get_edges_index(cm, remove_self_edge=True), ob.get_n_frag_switch(nodes)
+    xh = [torch.cat([torch.randn(h.size(0), 3), h.float()], dim=1) for h in h0]
+    t = torch.rand(len(sizes), 1)
+    out, _ = dyn(xh, ei, t, cond, nfs, cm)  # default: inference entry, no graph
+    assert calls == [("forward",)]
+    model.enable_training_path = True
+    with torch.no_grad():
+        dyn(xh, ei, t, cond, nfs, cm)
+    assert calls == [("forward",), ("forward",)]
+    out, _ = dyn(xh, ei, t, cond, nfs, cm)
+    assert calls[-1] == ("forward_train", (cm.numel(), 8), ei.size(1)) and out[0].requires_grad
+    sum(o.sum() for o in out).backward()
+    assert calls[-1][0] == "backward"
+    params = dict(model.named_parameters())
+    for n in names:
+        if n in params:
+            assert params[n].grad is not None and torch.equal(params[n].grad, torch.full_like(params[n], float(len(n)))), n
+    for n, p in params.items():
+        if n not in names:
+            assert p.grad is None, n  # distance_embedding / last_layer: present in the state dict, unused by forward
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dyn.encoders.parameters())  # through g_h_in
+    assert all(p.grad is not None for p in dyn.decoders.parameters())
