@@ -15,7 +15,11 @@ tests/dynamics/test_egnn_dynamics.py:142-153), re-stated in
 tests/test_oracle.py, and (ii) outputs of the UNMODIFIED reference imported in
 the build container through oracle/shims (script: oracle/gen_golden.py),
 committed as tests/golden/*.npz.  tests/test_oracle.py checks this file against
-those vectors to 1e-12 (fp64).
+those vectors to 1e-12 (fp64); (iii) in the build container, directly against the
+unmodified reference over 576 float64 cases of graph shape (complete, sparse,
+disconnected, shuffled edge lists), mask, cut-off and option (reflect_equiv,
+object_aware, update, depth): oracle/fuzz_oracle_leftnet.py, run by
+tests/test_plugin_seam_cpu.py (2e-12).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/oa_reactdiff/).  The op structure deliberately mirrors the
