@@ -111,3 +111,45 @@ def test_leftnet_option_grid_vs_oracle(gname):
         worst = max(worst, e)
         assert e < REL_TOL, (gname, reflect, oa, update, layers, cut, cutoff, scale, e)
     print(f"{gname}: worst rel err over the grid {worst:.2e}")
+
+
+def test_device_resident_path_on_ragged_fragments_with_an_empty_one():
+    """The device-resident dynamics wrapper and reverse step (oard_dyn_forward / oard_reverse_step) on the reference's ragged
+    fixture shape — fragments of different sizes, one of them EMPTY in a sample (tests/dynamics/test_egnn_dynamics.py:100-104)
+    — with equal node_nf so the fused path is taken: against the torch-composed wrapper around the same kernels, and a short
+    sample() against the host fast path."""
+    from tests.test_gpu_parity import make_dynamics
+    from tests.util import rel_err
+    import oareactdiff_b200 as ob
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=2, cutoff=5.0)
+    sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 4, cfg, prefix_model="model.")
+    dyn = make_dynamics(cfg, sd)
+    assert dyn.fused_ok(DEV)
+    g = torch.Generator().manual_seed(0)
+    nodes = [torch.tensor([2, 0]), torch.tensor([2, 3]), torch.tensor([1, 2])]
+    masks = [ob.get_mask_for_frag(n) for n in nodes]
+    cm = torch.cat(masks)
+    ei, nfs = ob.get_edges_index(cm, remove_self_edge=True), ob.get_n_frag_switch(nodes)
+    h0 = [torch.cat([torch.nn.functional.one_hot(torch.randint(0, 5, (int(n.sum()),), generator=g), 5),
+                     torch.randint(1, 9, (int(n.sum()), 1), generator=g)], dim=1) for n in nodes]
+    xh = [torch.cat([oa_ref.remove_mean_batch(torch.randn(h.size(0), 3, generator=g), m), h.float()], dim=1) for h, m in zip(h0, masks)]
+    t, cond = torch.rand(2, 1, generator=g), torch.rand(2, 1, generator=g)
+    args = ([x.to(DEV) for x in xh], ei.to(DEV), t.to(DEV), cond.to(DEV), nfs.to(DEV), cm.to(DEV))
+    for _ in range(3):
+        fused, _ = dyn(*args)
+    dyn.use_fused = False
+    host, _ = dyn(*args)
+    dyn.use_fused = True
+    ref = oa_ref.dynamics_forward({k: v.double() for k, v in sd.items()}, cfg, [x.double() for x in xh], ei, t.double(), cond.double(), nfs, cm)
+    for f in range(3):
+        assert fused[f].shape == xh[f].shape
+        assert rel_err(fused[f].cpu(), host[f].cpu()) < 1e-4 and rel_err(fused[f].cpu(), ref[f]) < 1e-3
+    sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", 6, 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True).to(DEV)
+    outs = []
+    for fused_on in (True, False):
+        dyn.use_fused = fused_on
+        torch.manual_seed(3)
+        out, _ = ddpm.sample(2, [n.to(DEV) for n in nodes], cond.to(DEV), h0=[h.to(DEV) for h in h0])
+        outs.append(torch.cat([o[:, :3].cpu() for o in out[0]]))
+    assert rel_err(outs[0], outs[1]) < 1e-3
