@@ -22,22 +22,9 @@ from oa_reactdiff.utils import get_edges_index, get_mask_for_frag, get_n_frag_sw
 
 import oareactdiff_b200 as ob  # noqa: E402
 
-_engines = {}
+from oracle.ref_engine import install  # noqa: E402
 
-
-def _ref_engine_forward(self, h, pos, edge_index, edge_attr=None, node_mask=None, edge_mask=None, update_coords_mask=None,
-                        subgraph_mask=None):
-    if id(self) not in _engines:
-        st = torch.get_rng_state()
-        m = RLeft(**self.cfg)
-        torch.set_rng_state(st)
-        m.load_state_dict(self.state_dict(), strict=True)
-        _engines[id(self)] = (m, self)
-    return _engines[id(self)][0](h, pos, edge_index, None, subgraph_mask=subgraph_mask)
-
-
-ob.LEFTNetB200.forward = _ref_engine_forward
-ob.EGNNDynamics.fused_ok = lambda self, d: False
+install()
 
 
 def main():

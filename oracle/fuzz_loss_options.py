@@ -20,19 +20,8 @@ from oa_reactdiff.diffusion._normalizer import Normalizer as RN
 from oa_reactdiff.diffusion.en_diffusion import EnVariationalDiffusion as RDiff
 import oareactdiff_b200 as ob
 from oracle import oa_ref
-_ref_cache = {}
-def _ref_engine_forward(self, h, pos, edge_index, edge_attr=None, node_mask=None, edge_mask=None, update_coords_mask=None, subgraph_mask=None):
-    # the reference's own fp32 LEFTNet as the engine: isolates the HOST logic of the loss code
-    key = id(self)
-    if key not in _ref_cache:
-        st = torch.get_rng_state()  # building a module draws its initial weights: keep the caller's stream intact
-        m = RLeft(**{k: v for k, v in self.cfg.items()})
-        torch.set_rng_state(st)
-        m.load_state_dict(self.state_dict(), strict=True)
-        _ref_cache[key] = m
-    return _ref_cache[key](h, pos, edge_index, None, subgraph_mask=subgraph_mask)
-ob.LEFTNetB200.forward = _ref_engine_forward
-ob.EGNNDynamics.fused_ok = lambda self, d: False
+from oracle.ref_engine import install
+install()
 cfg = dict(cutoff=5.0, num_layers=2, hidden_channels=32, num_radial=16, in_hidden_channels=8, reflect_equiv=True, legacy=True, update=True, object_aware=True)
 seed=5; sizes=[4,6,3]
 sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg,[9,9,9],1), seed, cfg, prefix_model="model.")

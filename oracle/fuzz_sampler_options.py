@@ -24,22 +24,9 @@ from oa_reactdiff.model import LEFTNet as RLeft  # noqa: E402
 import oareactdiff_b200 as ob  # noqa: E402
 from oracle import oa_ref  # noqa: E402
 
-_engines = {}
+from oracle.ref_engine import install  # noqa: E402
 
-
-def _ref_engine_forward(self, h, pos, edge_index, edge_attr=None, node_mask=None, edge_mask=None, update_coords_mask=None,
-                        subgraph_mask=None):
-    if id(self) not in _engines:
-        st = torch.get_rng_state()  # building a module draws its initial weights: keep the caller's stream intact
-        m = RLeft(**self.cfg)
-        torch.set_rng_state(st)
-        m.load_state_dict(self.state_dict(), strict=True)
-        _engines[id(self)] = (m, self)  # (keep `self` alive so the id is not reused)
-    return _engines[id(self)][0](h, pos, edge_index, None, subgraph_mask=subgraph_mask)
-
-
-ob.LEFTNetB200.forward = _ref_engine_forward
-ob.EGNNDynamics.fused_ok = lambda self, d: False
+install()
 CFG = dict(cutoff=5.0, num_layers=2, hidden_channels=32, num_radial=16, in_hidden_channels=8, reflect_equiv=True, legacy=True,
            update=True, object_aware=True)
 SEED, SIZES, T = 9, [4, 6, 3], 12

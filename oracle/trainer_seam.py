@@ -71,22 +71,9 @@ from oa_reactdiff.dataset.transition1x import ProcessedTS1x  # noqa: E402
 import oareactdiff_b200 as ob  # noqa: E402
 from oracle.gen_golden import synthetic_raw_dataset  # noqa: E402  (the raw-dataset maker of the fixtures; imports the reference too)
 
-_engines = {}
+from oracle.ref_engine import install  # noqa: E402
 
-
-def _ref_engine_forward(self, h, pos, edge_index, edge_attr=None, node_mask=None, edge_mask=None, update_coords_mask=None,
-                        subgraph_mask=None):
-    if id(self) not in _engines:
-        st = torch.get_rng_state()
-        m = LEFTNet(**self.cfg)
-        torch.set_rng_state(st)
-        m.load_state_dict(self.state_dict(), strict=True)
-        _engines[id(self)] = (m, self)
-    return _engines[id(self)][0](h, pos, edge_index, None, subgraph_mask=subgraph_mask)
-
-
-ob.LEFTNetB200.forward = _ref_engine_forward
-ob.EGNNDynamics.fused_ok = lambda self, d: False
+install()
 
 # trainer/train_ts1x.py:43-121, with a narrower network so the check runs in seconds on the CPU
 LEFTNET_CONFIG = dict(pos_require_grad=False, cutoff=10.0, num_layers=2, hidden_channels=32, num_radial=16, in_hidden_channels=8,
