@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <unordered_map>
@@ -221,6 +222,7 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
   if (device < 0 || device >= ndev) return fail(OARD_ECUDA, "device %d not available (%d devices)", device, ndev);
   CU(cudaSetDevice(device));
   auto* h = new oard_handle();
+  std::unique_ptr<oard_handle, void (*)(oard_handle*)> guard(h, oard_destroy);  // an error return below frees what exists so far
   h->cfg = *cfg;
   h->device = device;
   build_specs(h);
@@ -255,7 +257,7 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     } else h->fork_sms = 0;
   }
   for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
-  *out = h;
+  *out = guard.release();
   return OARD_OK;
 }
 
