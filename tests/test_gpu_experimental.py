@@ -95,7 +95,7 @@ def test_leftnet_option_grid_vs_oracle(gname):
                                                                           [None, 3], [20.0, 2.5], [1.0, 3.0]):
         if n < 5 and cut:
             continue
-        cfg = dict(cutoff=cutoff, num_layers=layers, hidden_channels=16, num_radial=8, in_hidden_channels=6, reflect_equiv=reflect,
+        cfg = dict(cutoff=cutoff, num_layers=layers, hidden_channels=32, num_radial=16, in_hidden_channels=6, reflect_equiv=reflect,
                    legacy=True, update=update, object_aware=oa)
         sd = oa_ref.make_state_dict(oa_ref.leftnet_param_shapes(cfg), 3, cfg, dtype=torch.float64)
         h = torch.rand(n, 6, generator=g, dtype=torch.float64)
