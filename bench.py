@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--profile-every", type=int, default=97, help="bracket kernels with CUDA events every n-th forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the realistic-geometry replay line")
+    ap.add_argument("--replay-geometry", default="synthetic", choices=["synthetic", "real"],
+                    help="replay states from compact synthetic clouds (default, the measured configuration) or from the frozen "
+                         "REAL Transition1x geometries of tests/golden/t1x_geometries_b512.npz (oracle/gen_t1x_geometries.py)")
     ap.add_argument("--cpu-evals", type=int, default=2, help="denoiser evaluations timed for cpu_baseline")
     return ap.parse_args()
 
@@ -244,6 +247,14 @@ def run_b200(args, rank, world, local_rank):
     for f in range(3):
         xs = [gp + 0.3 * torch.randn(gp.shape, generator=gen) for gp in geo]
         x_frag.append(torch.cat([x - x.mean(0, keepdim=True) for x in xs]).to(dev))
+    if args.replay_geometry == "real":
+        # reactant / transition-state / product geometries of real Transition1x reactions with exactly these atom counts
+        import numpy as np
+        fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "t1x_geometries_b512.npz"))
+        if hi > len(fx["sizes"]) or [int(v) for v in fx["sizes"][lo:hi]] != list(sizes):
+            raise SystemExit("--replay-geometry real: the fixture holds the first 512 reactions of t1x_sizes(., seed=0) only")
+        off = np.concatenate([[0], np.cumsum(fx["sizes"])])
+        x_frag = [torch.from_numpy(fx[k][off[lo]:off[hi]]).to(dev) for k in ("reactant", "transition_state", "product")]
     xh0_d = [torch.cat([x_frag[f], h0_d[f]], dim=1) for f in range(3)]
 
     replay_Z = torch.empty(sum(h.size(0) for h in h0_d), 9, device=dev)
@@ -328,8 +339,11 @@ def run_b200(args, rank, world, local_rank):
         af = prof_rp.get("_active_fraction")
         replay = {"value": len(all_sizes) / (ms_rp / 1e3), "unit": UNIT, "ms_per_step": ms_rp, "steps": 1,
                   "active_edge_fraction": (af["flops"] / max(af["launches"], 1)) if af else None,
-                  "note": "same per-step work on z_t = alpha_t x + sigma_t eps from compact synthetic geometries "
-                          "(what a trained model sees; every same-fragment edge inside the cutoff)",
+                  "geometry": args.replay_geometry,
+                  "note": "same per-step work on z_t = alpha_t x + sigma_t eps from "
+                          + ("REAL Transition1x reactant / TS / product geometries (tests/golden/t1x_geometries_b512.npz) "
+                             if args.replay_geometry == "real" else "compact synthetic geometries ")
+                          + "(what a trained model sees; every same-fragment edge inside the cutoff)",
                   "kernels_ms_per_launch": {k: round(v["ms"] / max(v["launches"], 1), 5) for k, v in
                                             sorted(prof_rp.items(), key=lambda kv: -kv[1]["ms"])[:10] if not k.startswith("_")}}
 

@@ -25,3 +25,4 @@ except Exception as e:
 EOF
 done
 echo "== bench (N = 1)"; timeout 900 python bench.py --steps 2 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; head -c 600 $out/${tag}_bench.json; echo
+echo "== bench replay on REAL Transition1x geometries"; timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --replay-geometry real > $out/${tag}_bench_real.json 2> $out/${tag}_bench_real.err; python -c "import json; d=json.load(open(\"$out/${tag}_bench_real.json\")); print(d[\"replay\"][\"value\"], d[\"replay\"][\"active_edge_fraction\"])"
