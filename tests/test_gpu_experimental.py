@@ -153,3 +153,39 @@ def test_device_resident_path_on_ragged_fragments_with_an_empty_one():
         out, _ = ddpm.sample(2, [n.to(DEV) for n in nodes], cond.to(DEV), h0=[h.to(DEV) for h in h0])
         outs.append(torch.cat([o[:, :3].cpu() for o in out[0]]))
     assert rel_err(outs[0], outs[1]) < 1e-3
+
+
+def test_dynamics_on_real_transition1x_geometries_vs_oracle():
+    """Trained configuration on REAL Transition1x geometries (fixture tests/golden/t1x_geometries_b512.npz: reactant / TS /
+    product of the first reactions the bench draws), noised to a mid-trajectory state: CUDA vs the fp64 oracle."""
+    import numpy as np
+    from tests.test_gpu_parity import REL_TOL, make_dynamics
+    from tests.util import rel_err
+    import oareactdiff_b200 as ob
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "t1x_geometries_b512.npz"))
+    k = 5
+    sizes = [int(v) for v in fx["sizes"][:k]]
+    n_at = sum(sizes)
+    cfg = dict(oa_ref.TRAINED_CFG)
+    sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), 8, cfg, prefix_model="model.")
+    nodes = [torch.tensor(sizes)] * 3
+    masks = [ob.get_mask_for_frag(n) for n in nodes]
+    cm = torch.cat(masks)
+    ei, nfs = ob.get_edges_index(cm, remove_self_edge=True), ob.get_n_frag_switch(nodes)
+    z = torch.from_numpy(fx["Z"][:n_at])
+    lut = {1: 0, 6: 1, 7: 2, 8: 3, 9: 4}
+    h = torch.cat([torch.nn.functional.one_hot(torch.tensor([lut[int(v)] for v in z]), 5).float(), z.float()[:, None]], dim=1)
+    g = torch.Generator().manual_seed(2)
+    xh = []
+    for key in ("reactant", "transition_state", "product"):
+        x = torch.from_numpy(fx[key][:n_at])
+        x = 0.8 * x + 0.6 * oa_ref.remove_mean_batch(torch.randn(n_at, 3, generator=g), masks[0])  # q(z_t | x) at alpha = 0.8
+        xh.append(torch.cat([x, h], dim=1))
+    t, cond = torch.full((k, 1), 0.35), torch.zeros(k, 1)
+    ref = oa_ref.dynamics_forward({kk: v.double() for kk, v in sd.items()}, cfg, [x.double() for x in xh], ei, t.double(), cond.double(), nfs, cm)
+    dyn = make_dynamics(cfg, sd)
+    out, _ = dyn([x.to(DEV) for x in xh], ei.to(DEV), t.to(DEV), cond.to(DEV), nfs.to(DEV), cm.to(DEV))
+    for f in range(3):
+        e = rel_err(out[f].cpu(), ref[f])
+        print(f"real geometries frag{f}: {e:.2e}")
+        assert e < REL_TOL
