@@ -1417,6 +1417,7 @@ extern "C" int oard_dyn_plan(oard_handle* h, const int64_t* node_frag, const int
   CU(cudaMemcpy(h->buf<int>("dyn_seg_ptr"), seg_ptr.data(), (size_t)(S + 1) * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->buf<int>("dyn_seg_frag"), seg_frag.data(), (size_t)S * 4, cudaMemcpyHostToDevice));
   CU(cudaMemset(h->buf<float>("dyn_prm"), 0, 64));
+  CU(cudaStreamSynchronize(0));  // (NULL-stream clear: callers may launch on non-blocking streams, which do not wait for it)
   h->dyn_S = S; h->dyn_B = (int)n_samples;
   h->dyn_planned = true;
   for (auto& s : h->gslots)

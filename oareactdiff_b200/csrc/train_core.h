@@ -94,7 +94,10 @@ inline void par_for(void* stream, size_t n, F f) {
 inline float* dev_alloc(size_t n) {
   float* p = nullptr;
   if (cudaMalloc(&p, (n ? n : 1) * sizeof(float)) != cudaSuccess) return nullptr;
+  // cleared on the NULL stream and waited for: the caller's stream may be a non-blocking one (PyTorch's side streams are),
+  // which is not ordered against the NULL stream — the clear must not land after the first kernel that writes the buffer
   cudaMemset(p, 0, (n ? n : 1) * sizeof(float));
+  cudaStreamSynchronize(0);
   return p;
 }
 inline void dev_free(float* p) { cudaFree(p); }
