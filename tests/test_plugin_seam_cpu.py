@@ -107,3 +107,13 @@ def test_packed_dataset_bit_exact_on_the_real_transition1x_file():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["n_mismatches"] == 0 and out["checks"] >= 300 and out["lens"]["trainer"] == [13466, 13466], out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/oa_reactdiff"), reason="the reference only exists in the build container")
+def test_default_initialisation_scheme_matches_the_reference_constructors():
+    """oracle/init_parity.py: trained configuration, 246 tensors — constants (zero biases, LayerNorm, RBF buffers) equal, large
+    random tensors agree in spread and bound: training from scratch starts from the same distribution."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "init_parity.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["n_bad"] == 0 and out["tensors"] == 246 and out["random_checked"] > 50 and out["constants_checked"] > 20, out
