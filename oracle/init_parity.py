@@ -27,10 +27,18 @@ KW = dict(fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condit
 
 def main():
     torch.manual_seed(0)
-    a = RDyn(model_config=dict(CFG), model=LEFTNet, **KW).state_dict()
+    ma = RDyn(model_config=dict(CFG), model=LEFTNet, **KW)
     torch.manual_seed(1)
-    b = ob.EGNNDynamics(model_config=dict(CFG), model=ob.LEFTNetB200, **KW).state_dict()
+    mb = ob.EGNNDynamics(model_config=dict(CFG), model=ob.LEFTNetB200, **KW)
+    a, b = ma.state_dict(), mb.state_dict()
     bad, n_const, n_rand = [], 0, 0
+    # parameters() order and requires_grad: optimizer states of a reference checkpoint are stored by POSITION
+    pa = [(k, tuple(v.shape), v.requires_grad) for k, v in ma.named_parameters()]
+    pb = [(k, tuple(v.shape), v.requires_grad) for k, v in mb.named_parameters()]
+    if pa != pb:
+        bad.append(("named_parameters order / flags", len(pa), len(pb)))
+    if [k for k, _ in ma.named_buffers()] != [k for k, _ in mb.named_buffers()]:
+        bad.append(("named_buffers",))
     if list(a) != list(b):
         bad.append(("key order", len(a), len(b)))
     for k in a:
