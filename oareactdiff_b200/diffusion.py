@@ -342,7 +342,7 @@ class EnVariationalDiffusion(nn.Module):
             "sigma_ts": sigma_ts.flatten().tolist(),
             "gamma": gamma.detach().float().cpu().flatten(),        # gamma(k / timesteps): the jump-back of inpaint() pairs any s < t
         }
-        self._tab_key, self._tab = key, tab
+        self._tab_key, self._tab, self._tab_refs = key, tab, (self.schedule, gam)  # (identity keys: keep the keyed objects alive)
         return tab
 
     def _seg_setup(self, masks):

@@ -90,6 +90,9 @@ class EGNNDynamics(BaseDynamics):
             self._graph = dict(sub=sub[:, None], sub_flat=sub.to(torch.int64).contiguous(), frag_index=frag_index, seg=seg,
                                n_seg=max(n_seg, 1), n_samples=n_samples, inv_cnt=(1.0 / cnt.clamp(min=1))[:, None])
             self._graph_key = key
+            # the key identifies the inputs by address and version: keep them alive while cached, so that no OTHER tensor can
+            # take their address (the caching allocators hand a freed block straight to the next request of that size)
+            self._graph_refs = (edge_index, n_frag_switch, combined_mask)
         return self._graph
 
     # ---- device-resident path: prologue, LEFTNet and epilogue behind the C ABI (oard_dyn_forward / oard_reverse_step)

@@ -113,6 +113,10 @@ class _EquiOutput(nn.Module):  # :500-519
         self.output_network = nn.ModuleList([_Gated(H, 1)])
 
 
+def _no_engine():
+    return None
+
+
 class _Engine:
     """One C-ABI handle (device workspace + weights + plan) for one module on one device."""
 
@@ -132,6 +136,15 @@ class _Engine:
         self.edge_perm = None
         self.N = self.E = 0
         self.debug = False
+
+    # A handle belongs to ONE module object: copies and pickles of a model (the reference's trainer deep-copies the whole
+    # diffusion model before every sampling evaluation, pl_trainer.py:291; torch.save(model) pickles it) carry no engine and
+    # build their own at the first forward (LEFTNetB200.engine).
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_engine, ())
 
     def __del__(self):
         try:
@@ -157,7 +170,7 @@ class _Engine:
                 t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
             _lib.check(self.lib.oard_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), 1, st))
         _lib.check(self.lib.oard_commit_weights(self.h, st))
-        self.weights_key = key
+        self.weights_key, self._weights_refs = key, list(sd.values())  # (address + version keys: keep the keyed tensors alive)
 
     def plan(self, edge_index: Tensor, n_nodes: int):
         key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n_nodes)
@@ -176,6 +189,7 @@ class _Engine:
                 self.edge_perm = perm.to(self.device)
         _lib.check(self.lib.oard_plan(self.h, n_nodes, ei.size(1), C.c_void_p(ei.data_ptr())))
         self.plan_key, self.N, self.E = key, n_nodes, ei.size(1)
+        self._plan_ref = edge_index  # see sync_weights
         self.dyn_plan_key = None
 
     def edge_order(self, sub: Optional[Tensor]) -> Optional[Tensor]:
@@ -221,7 +235,7 @@ class _Engine:
             if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
             _lib.check(self.lib.oard_dyn_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), t.numel(), 1, st))
-        self.dyn_weights_key = key
+        self.dyn_weights_key, self._dyn_weights_refs = key, [sd[n] for n in self.dyn_names]
 
     def dyn_plan(self, n_frag_switch: Tensor, combined_mask: Tensor, n_samples: int):
         key = (self.plan_key, n_frag_switch.data_ptr(), n_frag_switch._version, combined_mask.data_ptr(),
@@ -233,7 +247,7 @@ class _Engine:
         if nf.numel() != self.N or cm.numel() != self.N:
             raise ValueError(f"n_frag_switch / combined_mask must have {self.N} entries")
         _lib.check(self.lib.oard_dyn_plan(self.h, C.c_void_p(nf.data_ptr()), C.c_void_p(cm.data_ptr()), n_samples))
-        self.dyn_plan_key = key
+        self.dyn_plan_key, self._dyn_plan_refs = key, (n_frag_switch, combined_mask)
 
     @staticmethod
     def _ptr(t: Optional[Tensor]):

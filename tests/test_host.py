@@ -286,6 +286,9 @@ def test_training_path_autograd_plumbing_with_a_recording_engine():
     t = torch.rand(len(sizes), 1)
     out, _ = dyn(xh, ei, t, cond, nfs, cm)  # default: inference entry, no graph
     assert calls == [("forward",)]
+    # caches keyed by (address, version) keep the keyed tensors alive: a freed block would be handed to the next tensor of
+    # that size, and a different graph at the same address must not hit the cache
+    assert dyn._graph_refs[0] is ei and dyn._graph_refs[1] is nfs and dyn._graph_refs[2] is cm and eng._plan_ref is ei
     model.enable_training_path = True
     with torch.no_grad():
         dyn(xh, ei, t, cond, nfs, cm)
@@ -303,3 +306,38 @@ def test_training_path_autograd_plumbing_with_a_recording_engine():
             assert p.grad is None, n  # distance_embedding / last_layer: present in the state dict, unused by forward
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dyn.encoders.parameters())  # through g_h_in
     assert all(p.grad is not None for p in dyn.decoders.parameters())
+
+
+def test_models_with_live_engines_can_be_copied_and_pickled():
+    """The reference's trainer deep-copies the diffusion model before every sampling evaluation (pl_trainer.py:291) and
+    `torch.save(model)` pickles it; a live engine (a C handle) must neither break that nor be shared: the copy carries none
+    and builds its own at its first forward."""
+    import copy
+    import ctypes as C
+    import io
+    import pickle
+
+    from oareactdiff_b200.leftnet import _Engine
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", 5, 1e-5), (1.0, 1.0, 1.0)),
+                                     normalizer=ob.Normalizer(), pos_only=True)
+    eng = object.__new__(_Engine)  # what a forward on a GPU leaves behind: a ctypes library object and a handle
+    eng.lib, eng.h, eng.device = C.CDLL(None), None, torch.device("cpu")
+    dyn.model._engines[torch.device("cpu")] = eng
+    dyn._nan_gen = torch.Generator()
+    dyn._graph, dyn._graph_key = dict(sub=torch.ones(4, 1)), (1, 2)
+    ddpm._dev = dict(eng=eng, nx=torch.zeros(3, 3), views=[torch.zeros(2)], cond=None, sub=None, H0=None)
+
+    def via_torch_save(m):
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        return torch.load(buf, weights_only=False)
+
+    for clone in (copy.deepcopy, lambda m: pickle.loads(pickle.dumps(m)), via_torch_save):
+        c = clone(ddpm)
+        assert c.dynamics.model._engines == {torch.device("cpu"): None} and c._dev["eng"] is None
+        assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(c.parameters(), ddpm.parameters()))
+    assert dyn.model._engines[torch.device("cpu")] is eng  # the original keeps its engine
