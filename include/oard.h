@@ -10,7 +10,8 @@
  * Conventions: plain C, no exceptions across the boundary; every entry point returns 0 on success or a negative
  * OARD_E* code and records a message retrievable with oard_last_error().  All tensor pointers passed to
  * oard_forward are DEVICE pointers owned by the caller, fp32 row-major, valid until the stream reaches the end of the
- * call's work; the call is asynchronous on `stream` (a cudaStream_t passed as void*).  One handle per device; a handle
+ * call's work; the call is asynchronous on `stream` (a cudaStream_t passed as void*, blocking or not).  Entry points run on
+ * the handle's device and restore the caller's current device before returning.  One handle per device; a handle
  * is not thread-safe.  There is no CPU fallback: without a CUDA device every compute entry point fails with
  * OARD_ECUDA.
  */

@@ -27,6 +27,23 @@
 
 using namespace oard;
 
+// Entry points run on the handle's device and leave the caller's current device as they found it (a process that drives
+// several GPUs — or PyTorch, whose current_device() is cudaGetDevice — must not see it change under its feet).
+struct DeviceScope {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) prev = cur;
+    if (cur != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -220,7 +237,8 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(OARD_ECUDA, "device %d not available (%d devices)", device, ndev);
-  CU(cudaSetDevice(device));
+  DeviceScope dev_scope(device);
+  CU(dev_scope.err);
   auto* h = new oard_handle();
   std::unique_ptr<oard_handle, void (*)(oard_handle*)> guard(h, oard_destroy);  // an error return below frees what exists so far
   h->cfg = *cfg;
@@ -269,7 +287,7 @@ static void free_map(std::map<std::string, DevBuf>& m) {
 
 extern "C" void oard_destroy(oard_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceScope dev_scope(h->device);
   for (float* p : h->wdev)
     if (p) cudaFree(p);
   for (void* p : h->tc_bufs) cudaFree(p);
@@ -301,7 +319,8 @@ extern "C" int oard_set_weight(oard_handle* h, const char* name, const float* da
   const WeightSpec& s = h->specs[it->second];
   if (numel != s.numel) return fail(OARD_EINVAL, "weight '%s': expected %lld elements, got %lld", name,
                                     (long long)s.numel, (long long)numel);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   CU(cudaMemcpyAsync(h->wdev[it->second], data, numel * sizeof(float),
                      is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
   h->wset[it->second] = 1;
@@ -352,7 +371,8 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
     w.l4w = W(u + "lin3.4.weight"); w.l4b = W(u + "lin3.4.bias");
   }
   drop_graphs(h);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   for (void* p : h->tc_bufs) cudaFree(p);
   h->tc_bufs.clear();
   {  // stacked P/Q weight of the GCL edge MLP's node part: one [N, H] x [H, 2H] GEMM instead of two
@@ -494,7 +514,8 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   if (!h || (!ei && n_edges > 0)) return fail(OARD_EINVAL, "null argument");
   if (n_nodes <= 0 || n_nodes > (1 << 28) || n_edges < 0 || n_edges > (int64_t)1 << 30)
     return fail(OARD_EINVAL, "bad sizes N=%lld E=%lld", (long long)n_nodes, (long long)n_edges);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   const int N = (int)n_nodes, E = (int)n_edges;
   const int64_t* src = ei;
   const int64_t* dst = ei + n_edges;
@@ -1143,7 +1164,8 @@ extern "C" int oard_forward(oard_handle* h, const float* h_in, const float* pos,
   if (!h || !h_in || !pos || !h_out || !dpos) return fail(OARD_EINVAL, "null argument");
   if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
   if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
   h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
   h->fwd_count++;
@@ -1233,7 +1255,8 @@ extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float
   if (!h->committed) return fail(OARD_ESTATE, "oard_commit_weights has not been called");
   if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
   if (!h->cfg.update || !h->cfg.legacy) return fail(OARD_EINVAL, "training path implements update=1, legacy=1 only");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = train_setup(h);
   if (rc) return rc;
@@ -1277,7 +1300,8 @@ extern "C" int oard_forward_train(oard_handle* h, const float* h_in, const float
 extern "C" int oard_backward(oard_handle* h, const float* g_h_out, const float* g_dpos, float* g_h_in, void* stream) {
   if (!h || !g_h_out || !g_dpos || !g_h_in) return fail(OARD_EINVAL, "null argument");
   if (!h->train_fwd_done) return fail(OARD_ESTATE, "oard_forward_train has not been called for the current plan");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   oard_train::Ctx& c = h->tctx;
   c.stream = stream;
   oard_train::Geometry G{h->buf<int>("esrc"), h->buf<int>("ecol"), c.act.at("geo_frame"), c.act.at("geo_rb"), c.act.at("geo_rbf"),
@@ -1291,7 +1315,8 @@ extern "C" int oard_backward(oard_handle* h, const float* g_h_out, const float* 
 
 extern "C" int oard_zero_grads(oard_handle* h, void* stream) {
   if (!h) return fail(OARD_EINVAL, "null handle");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   int rc = train_setup(h);
   if (rc) return rc;
   for (auto& kv : h->tctx.dW) CU(cudaMemsetAsync(kv.second, 0, h->tctx.wn[kv.first] * sizeof(float), (cudaStream_t)stream));
@@ -1303,7 +1328,8 @@ extern "C" int oard_get_grad(oard_handle* h, const char* name, float* dst, int64
   auto it = h->tctx.dW.find(name);
   if (it == h->tctx.dW.end()) return fail(OARD_EINVAL, "no gradient buffer '%s' (call oard_forward_train first)", name);
   if ((size_t)numel != h->tctx.wn[name]) return fail(OARD_EINVAL, "gradient '%s': expected %zu elements, got %lld", name, h->tctx.wn[name], (long long)numel);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   CU(cudaMemcpyAsync(dst, it->second, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return OARD_OK;
 }
@@ -1318,7 +1344,8 @@ extern "C" int oard_dyn_configure(oard_handle* h, int n_frag, int node_nf, int c
   if (d <= 0 || d > DYN_MAX_D) return fail(OARD_EINVAL, "node_nf - 3 must be in [1,%d], got %d", DYN_MAX_D, d);
   if (emb <= 0 || emb > DYN_MAX_D) return fail(OARD_EINVAL, "embed width %d (= in_hidden_channels - time - conditions) out of range", emb);
   if (condition_nf < 0) return fail(OARD_EINVAL, "condition_nf < 0");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   for (float* p : h->ddev)
     if (p) cudaFree(p);
   h->dspecs.clear(); h->dspec_idx.clear(); h->ddev.clear(); h->dset.clear();
@@ -1360,7 +1387,8 @@ extern "C" int oard_dyn_set_weight(oard_handle* h, const char* name, const float
   const WeightSpec& s = h->dspecs[it->second];
   if (numel != s.numel) return fail(OARD_EINVAL, "weight '%s': expected %lld elements, got %lld", name,
                                     (long long)s.numel, (long long)numel);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   CU(cudaMemcpyAsync(h->ddev[it->second], data, numel * sizeof(float),
                      is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
   h->dset[it->second] = 1;
@@ -1385,7 +1413,8 @@ extern "C" int oard_dyn_plan(oard_handle* h, const int64_t* node_frag, const int
   if (!h->dyn_cfg) return fail(OARD_ESTATE, "oard_dyn_configure has not been called");
   if (!h->planned) return fail(OARD_ESTATE, "oard_plan has not been called");
   if (n_samples <= 0) return fail(OARD_EINVAL, "n_samples must be > 0");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   const int N = h->N;
   std::vector<int> nfrag(N), nsamp(N), seg_ptr, seg_frag;
   std::unordered_map<uint64_t, int> seen;
@@ -1533,7 +1562,8 @@ extern "C" int oard_dyn_forward(oard_handle* h, const float* xh, const float* t,
   if (!xh || !eps) return fail(OARD_EINVAL, "null argument");
   if (h->dyn_ctime && !t) return fail(OARD_EINVAL, "condition_time is set: t[B] is required");
   if (h->dyn_cnd > 0 && !cond) return fail(OARD_EINVAL, "condition_nf > 0: conditions[B, condition_nf] is required");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   return dyn_run(h, 0, xh, t, cond, sub, eps, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -1544,7 +1574,8 @@ extern "C" int oard_reverse_step(oard_handle* h, float* z, const float* noise, c
   if (rc) return rc;
   if (!z || !noise) return fail(OARD_EINVAL, "null argument");
   if (h->dyn_cnd > 0 && !cond) return fail(OARD_EINVAL, "condition_nf > 0: conditions[B, condition_nf] is required");
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
   k_set_params<<<1, 1, 0, st>>>(h->buf<float>("dyn_prm"), t, alpha_ts, coef, sigma, h->nan_counter++);
   CU(cudaGetLastError());
@@ -1565,7 +1596,8 @@ extern "C" int oard_test_gemm(int device, int M, int N, int K, const float* A, c
 extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
                                  float* C, int use_tc, int act, int swap_lbo_sbo, int mode, const float* aux, int ablate,
                                  int reps, float* ms_out, void* stream) {
-  CU(cudaSetDevice(device));
+  DeviceScope dev_scope(device);
+  CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
   GemmArgs g = mk(A, K, W, K, C, N, M, N, K);
   g.bias = bias; g.act = act;
@@ -1611,7 +1643,8 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
 extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
                                   float* C, int mode, const float* aux, int out_pair, int act, float* c2_out, int ew,
                                   int reps, float* ms_out, void* stream) {
-  CU(cudaSetDevice(device));
+  DeviceScope dev_scope(device);
+  CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -1693,7 +1726,8 @@ extern "C" int oard_debug_read(oard_handle* h, const char* name, void* dst, size
   auto it = h->snaps.find(name);
   if (it == h->snaps.end()) return fail(OARD_EINVAL, "no snapshot '%s' (debug off or forward not run)", name);
   if (bytes > it->second.bytes) return fail(OARD_EINVAL, "snapshot '%s' has %zu bytes, asked %zu", name, it->second.bytes, bytes);
-  CU(cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(dst, it->second.p, bytes, cudaMemcpyDeviceToHost));
   return OARD_OK;
