@@ -330,6 +330,7 @@ class _LeftnetTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, names, h, pos, sub, *tensors):
         h_out, dpos = eng.forward_train(h, pos, sub)
+        eng._train_token = ctx.token = getattr(eng, "_train_token", 0) + 1  # the handle keeps the activations of ONE forward
         ctx.eng, ctx.names = eng, names
         ctx.meta = [(t.shape, t.dtype, t.requires_grad) for t in tensors]
         ctx.h_dtype = h.dtype
@@ -338,6 +339,10 @@ class _LeftnetTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_h, g_dpos):
         eng = ctx.eng
+        if ctx.token != getattr(eng, "_train_token", 0):
+            raise RuntimeError("LEFTNetB200 training path: the activations of this forward were overwritten by a later forward on the "
+                               "same model (the engine keeps ONE forward's activations); run backward before the next "
+                               "differentiable forward, or wrap forwards that need no gradient in torch.no_grad()")
         g_in = eng.backward(g_h, g_dpos).to(ctx.h_dtype)
         grads = []
         for name, (shape, dtype, req) in zip(ctx.names, ctx.meta):

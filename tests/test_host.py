@@ -306,6 +306,12 @@ def test_training_path_autograd_plumbing_with_a_recording_engine():
             assert p.grad is None, n  # distance_embedding / last_layer: present in the state dict, unused by forward
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dyn.encoders.parameters())  # through g_h_in
     assert all(p.grad is not None for p in dyn.decoders.parameters())
+    # the handle keeps ONE forward's activations: backward through an older forward must fail loudly, not silently use the newer ones
+    first, _ = dyn(xh, ei, t, cond, nfs, cm)
+    second, _ = dyn(xh, ei, t, cond, nfs, cm)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        sum(o.sum() for o in first).backward()
+    sum(o.sum() for o in second).backward()
 
 
 def test_models_with_live_engines_can_be_copied_and_pickled():
