@@ -11,7 +11,7 @@ gathers into pinned staging buffers and one host->device copy per tensor — the
 `sample()` and `inpaint()` without per-sample Python work.
 """
 import pickle
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -8,7 +8,7 @@ start and end of a trajectory unless `debug_asserts=True`.  The RNG draw order o
 fragment: positions, then features).  Training `forward()` (loss terms) is a later row of SURVEY §8f.
 """
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F

@@ -20,7 +20,6 @@ import sys
 import tempfile
 import types
 
-import numpy as np
 import torch
 from torch import nn
 
