@@ -26,3 +26,5 @@ EOF
 done
 echo "== bench (N = 1)"; timeout 900 python bench.py --steps 2 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; head -c 600 $out/${tag}_bench.json; echo
 echo "== bench replay on REAL Transition1x geometries"; timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --replay-geometry real > $out/${tag}_bench_real.json 2> $out/${tag}_bench_real.err; python -c "import json; d=json.load(open(\"$out/${tag}_bench_real.json\")); print(d[\"replay\"][\"value\"], d[\"replay\"][\"active_edge_fraction\"])"
+echo "== probe: tcgen05.mma with the A operand in tensor memory (DESIGN 11.1)"
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/probe_ts tools/probe_ts_mma.cu > $out/${tag}_probe_ts.log 2>&1 && timeout 60 /tmp/probe_ts >> $out/${tag}_probe_ts.log 2>&1; tail -3 $out/${tag}_probe_ts.log
