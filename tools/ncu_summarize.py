@@ -15,17 +15,18 @@ import re
 import subprocess
 import sys
 
-WANT = [  # (column label, regex on the metric name, unit scale)
-    ("us", r"^gpu__time_duration\.sum$", None),
-    ("regs", r"^launch__registers_per_thread$", None),
-    ("dram rd MB", r"^dram__bytes_read\.sum$", "bytes"),
-    ("dram wr MB", r"^dram__bytes_write\.sum$", "bytes"),
-    ("dram %", r"^gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$", None),
-    ("L2 hit %", r"^lts__t_sector_hit_rate\.pct$", None),
-    ("tensor %", r"^sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_active$|^sm__inst_executed_pipe_tensor.*pct_of_peak_sustained_active$", None),
-    ("occ %", r"^sm__warps_active\.avg\.pct_of_peak_sustained_active$", None),
-    ("issue %", r"^sm__inst_issued\.avg\.pct_of_peak_sustained_active$|^smsp__issue_active\.avg\.pct$", None),
-    ("IPC", r"^sm__inst_executed\.avg\.per_cycle_active$|^smsp__inst_executed\.avg\.per_cycle_active$", None),
+WANT = [  # (column label, exact metric names in order of preference, kind)
+    ("us", ["gpu__time_duration.sum"], None),
+    ("regs", ["launch__registers_per_thread"], None),
+    ("dram rd MB", ["dram__bytes_read.sum"], "bytes"),
+    ("dram wr MB", ["dram__bytes_write.sum"], "bytes"),
+    ("dram %", ["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"], None),
+    ("L2 hit %", ["lts__t_sector_hit_rate.pct"], None),
+    ("tensor %", ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                  "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"], None),
+    ("occ %", ["sm__warps_active.avg.pct_of_peak_sustained_active"], None),
+    ("issue %", ["smsp__issue_active.avg.pct", "sm__inst_issued.avg.pct_of_peak_sustained_active"], None),
+    ("IPC", ["sm__inst_executed.avg.per_cycle_active", "smsp__inst_executed.avg.per_cycle_active"], None),
 ]
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
@@ -57,10 +58,10 @@ def main():
         rows.pop(0)
     header, units, data = rows[0], rows[1], rows[2:]
     cols = {}
-    for label, pat, kind in WANT:
-        for i, h in enumerate(header):
-            if re.search(pat, h.split(".")[-1]) or re.search(pat, ".".join(h.split(".")[-4:])) or re.search(pat, h):
-                cols[label] = (i, kind)
+    for label, names, kind in WANT:
+        for name in names:
+            if name in header:
+                cols[label] = (header.index(name), kind)
                 break
     stall = [(i, h) for i, h in enumerate(header) if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")] or \
             [(i, h) for i, h in enumerate(header) if "average_warp" in h and "issue_stalled" in h and h.endswith(".ratio")]
