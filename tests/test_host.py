@@ -347,3 +347,16 @@ def test_models_with_live_engines_can_be_copied_and_pickled():
         assert c.dynamics.model._engines == {torch.device("cpu"): None} and c._dev["eng"] is None
         assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(c.parameters(), ddpm.parameters()))
     assert dyn.model._engines[torch.device("cpu")] is eng  # the original keeps its engine
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No built library -> RuntimeError naming the build command; a library that lacks a declared symbol -> AttributeError."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "liboard_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        _lib.load()
+    emu = os.path.join(ROOT, "oareactdiff_b200", "libtrain_emu.so")  # a real shared library without the oard_* entry points
+    if os.path.exists(emu):
+        monkeypatch.setattr(_lib, "LIB_PATH", emu)
+        with pytest.raises(AttributeError):
+            _lib.load()
