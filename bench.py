@@ -4,10 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host cores (oracle port)
 
-One "step" = one full `EnVariationalDiffusion.sample()` of a B=64 batch: 1000 reverse steps + the final p(x|z0)
-decode = 1001 denoiser evaluations (config.workload names it).  Weak scaling: every rank samples its own B=64 batch.
-`value` = reactions per second with inputs resident in HBM; `e2e` = the same through the public API with HOST (pinned)
-inputs copied in and results copied out inside the timed region.  Prints ONE JSON line on rank 0.
+One "step" = one full reverse diffusion of a B=64 batch: 1000 reverse steps (denoiser evaluation + posterior sampling)
++ the final p(x|z0) decode = 1001 LEFTNet evaluations, on the states a TRAINED model visits: z_t = alpha_t x + sigma_t eps
+re-drawn every step from frozen real Transition1x reactant / TS / product geometries (workloads.replay_trajectory; active
+edge fraction ~0.32).  The literal `sample()` with random-init weights is reported beside it (`literal_sample`): there the
+positions drift out of the 10 A cutoff and most of the message-passing work is (exactly) skipped, which flatters the number.
+Weak scaling: every rank runs its own B=64 batch.  `value` = reactions per second with inputs resident in HBM; `e2e` = the
+same with HOST (pinned) inputs copied in and results copied out inside the timed region.  Further legs in the same JSON
+line (1 GPU only): `inpaint` (BASELINE config 4: RePaint r=1/j=1 and r=5/j=5) and `train_step` (config 5: B=128 forward +
+backward with loss / gradient errors against the oracle and its CPU timing).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -19,9 +24,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO prints it on stdout) is silenced
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "reactions/sec full 1000-step reverse diffusion, Transition1x-shaped batch"
 UNIT = "reactions/s"
@@ -37,10 +39,16 @@ def parse():
     ap.add_argument("--denoise-steps", type=int, default=1000, help="T of the reverse diffusion (BASELINE: 1000)")
     ap.add_argument("--profile-every", type=int, default=97, help="bracket kernels with CUDA events every n-th forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-replay", action="store_true", help="skip the realistic-geometry replay line")
-    ap.add_argument("--replay-geometry", default="synthetic", choices=["synthetic", "real"],
-                    help="replay states from compact synthetic clouds (default, the measured configuration) or from the frozen "
-                         "REAL Transition1x geometries of tests/golden/t1x_geometries_b512.npz (oracle/gen_t1x_geometries.py)")
+    ap.add_argument("--geometry", default="real", choices=["real", "synthetic"],
+                    help="reference geometries of the trained-model states: frozen REAL Transition1x R/TS/P coordinates "
+                         "(tests/golden/t1x_geometries_b512.npz, oracle/gen_t1x_geometries.py; default) or compact synthetic clouds")
+    ap.add_argument("--no-literal", action="store_true", help="skip the literal random-weight sample() line")
+    ap.add_argument("--no-inpaint", action="store_true", help="skip the TS-inpainting legs (BASELINE config 4)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE config 5)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default: min(steps, 5), at least 3)")
+    ap.add_argument("--train-batch", type=int, default=128)
+    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--train-check", type=int, default=4, help="reactions of the training batch checked against / timed on the oracle")
     ap.add_argument("--cpu-evals", type=int, default=2, help="denoiser evaluations timed for cpu_baseline")
     return ap.parse_args()
 
@@ -92,12 +100,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_workloads():
+    """oareactdiff_b200/workloads.py by file path: the reference arm must not import the package (which loads the CUDA library)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_oard_workloads", os.path.join(ROOT, "oareactdiff_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def tune_cpu_threads():
     """Eager PyTorch on many-core hosts is often fastest well below the core count (oversubscription of small ops):
     time one small denoiser evaluation at a few thread counts and keep the best, so the CPU baseline is a fair one."""
     import torch
     from oracle import oa_ref
-    from oareactdiff_b200 import workloads
+    workloads = load_workloads()
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
     cfg = dict(oa_ref.TRAINED_CFG)
@@ -132,7 +149,7 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import oa_ref
-    from oareactdiff_b200 import workloads
+    workloads = load_workloads()
     tune_cpu_threads()
     cfg = dict(oa_ref.TRAINED_CFG)
     T = args.denoise_steps
@@ -172,10 +189,9 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
-def cpu_baseline(args, T):
+def cpu_baseline(args, T, workloads):
     import torch
     from oracle import oa_ref
-    from oareactdiff_b200 import workloads
     tune_cpu_threads()
     cfg = dict(oa_ref.TRAINED_CFG)
     sizes = workloads.t1x_sizes(args.batch, seed=0)
@@ -190,14 +206,129 @@ def cpu_baseline(args, T):
     val = len(sizes) / (per_eval * (T + 1))
     return {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
             "sample": f"{smp.n_evals} denoiser evaluations of the same B={args.batch} batch via oracle Sampler.sample "
-                      f"({per_eval:.2f} s/eval), extrapolated to {T + 1}"}
+                      f"({per_eval:.2f} s/eval; the reference's cost per evaluation does not depend on the geometry: dense "
+                      f"masked compute over all edges), extrapolated to {T + 1}"}
+
+
+def train_leg(args, ob, workloads, dev, cfg, T):
+    """BASELINE config 5: one training step (l2 objective: EnVariationalDiffusion.compute_loss -> mean -> backward through
+    the CUDA denoiser) on B = 128 noised real-geometry reaction triples; plus, on the first `train_check` reactions, the same
+    step against the oracle's fp32 forward + torch autograd on the host cores (timed: the CPU baseline of this leg) and its
+    fp64 run (the parity figure: loss and worst parameter-gradient error relative to max|grad|)."""
+    import torch
+    from oracle import oa_ref  # checker + CPU baseline of this leg
+
+    class ReplayDraws(ob.EnVariationalDiffusion):  # replays given draws so that both sides see the same t and noise
+        def set_draws(self, t_int, noises):
+            self._t_int, self._noises, self._k = t_int, noises, 0
+
+        def _draw_t_int(self, num_sample, device):
+            return self._t_int.to(device).view(num_sample, 1)
+
+        def sample_combined_position_feature_noise(self, masks):
+            out = [n.to(masks[0].device) for n in self._noises[self._k]]
+            self._k += 1
+            return out
+
+    Bt = args.train_batch
+    sizes = workloads.t1x_sizes(Bt, seed=0)
+    x_ref = workloads.real_geometries(0, Bt, sizes)
+    _, h0, _ = workloads.reaction_batch(sizes, seed=0)
+    torch.manual_seed(0)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0,
+                          condition_nf=1, model=ob.LEFTNetB200, device=dev).to(dev)
+    dyn.model.enable_training_path = True
+    sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
+    ddpm = ReplayDraws(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True).to(dev)
+    ddpm.train(True)
+    gen = torch.Generator().manual_seed(7)
+
+    def draws(szs):
+        t_int = torch.randint(1, T + 1, (len(szs), 1), generator=gen).float()
+        mask = torch.repeat_interleave(torch.arange(len(szs)), torch.tensor(szs))
+        noise = []
+        for _ in range(3):
+            x = torch.randn(sum(szs), 3, generator=gen)
+            mean = torch.zeros(len(szs), 3).index_add_(0, mask, x) / torch.tensor(szs, dtype=torch.float32)[:, None]
+            noise.append(torch.cat([x - mean[mask], torch.zeros(sum(szs), 6)], dim=1))
+        return t_int, noise, mask
+
+    def step(szs, xr, hh, t_int, noise):
+        reps, cond = workloads.training_batch(szs, xr, hh, dev)
+        ddpm.set_draws(t_int, [noise])
+        for prm in dyn.parameters():
+            prm.grad = None
+        nll, _ = ddpm.compute_loss((reps, cond), scales=(1.0, 2.0, 1.0), training=True)
+        loss = nll.mean()
+        loss.backward()
+        return loss
+
+    t_int, noise, _ = draws(sizes)
+    step(sizes, x_ref, h0, t_int, noise)  # warm-up (allocations, first-call attributes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for _ in range(args.train_steps):
+        e0.record()
+        loss = step(sizes, x_ref, h0, t_int, noise)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    times.sort()
+    out = {"workload": f"batch={Bt} noised Transition1x reaction triples (real R/TS/P geometries), l2 objective, forward + backward "
+                       f"through encoders / LEFTNet / decoders (exact-fp32 SIMT training kernels, csrc/train_core.h)",
+           "ms_per_step": times[len(times) // 2], "ms_min": times[0], "ms_max": times[-1], "steps": len(times),
+           "reactions_per_s": Bt / (times[len(times) // 2] * 1e-3), "loss": float(loss),
+           "grads_finite": all(bool(torch.isfinite(p_.grad).all()) for p_ in dyn.parameters() if p_.grad is not None)}
+    # ---- parity + CPU baseline on a sub-batch
+    k = args.train_check
+    if k > 0:
+        sub_sizes = sizes[:k]
+        n_sub = sum(sub_sizes)
+        xr = [x[:n_sub] for x in x_ref]
+        hh = [h[:n_sub] for h in h0]
+        t_sub, noise_sub, mask_sub = draws(sub_sizes)
+        loss_gpu = float(step(sub_sizes, xr, hh, t_sub, noise_sub))
+        grads = {n_: p_.grad.detach().cpu().double() for n_, p_ in dyn.named_parameters() if p_.grad is not None}
+        sd = {n_: p_.detach().cpu() for n_, p_ in dyn.state_dict().items()}
+        gamma = sched.gamma_module.gamma.detach().cpu()
+        xh = [torch.cat([x - (torch.zeros(k, 3).index_add_(0, mask_sub, x) / torch.tensor(sub_sizes, dtype=torch.float32)[:, None])[mask_sub], h], dim=1)
+              for x, h in zip(xr, hh)]
+        res = {}
+        for dt_, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            sd_ = {n_: v.to(dt_).requires_grad_(v.is_floating_point()) if v.is_floating_point() else v for n_, v in sd.items()}
+            tune_cpu_threads()
+            t0 = time.perf_counter()
+            l_ = oa_ref.train_loss_l2(sd_, cfg, gamma.to(dt_), [x.to(dt_) for x in xh], [mask_sub] * 3, torch.tensor(sub_sizes),
+                                      torch.zeros(k, 1), t_sub.view(-1), [n_.to(dt_) for n_ in noise_sub])
+            l_.backward()
+            res[tag] = (float(l_), {n_: v.grad.double() for n_, v in sd_.items() if getattr(v, "grad", None) is not None},
+                        time.perf_counter() - t0)
+        l64, g64, _ = res["f64"]
+        worst, worst32, n_cmp = 0.0, 0.0, 0
+        for n_, gref in g64.items():
+            sc = float(gref.abs().max())
+            if sc == 0.0 or n_ not in grads:
+                continue
+            n_cmp += 1
+            worst = max(worst, float((grads[n_] - gref).abs().max()) / sc)
+            worst32 = max(worst32, float((res["f32"][1][n_] - gref).abs().max()) / sc)
+        out["check"] = {"reactions": k, "loss_rel_err": abs(loss_gpu - l64) / abs(l64), "grad_rel_err_worst": worst,
+                        "parameters_compared": n_cmp, "oracle_fp32_grad_rel_err_worst": worst32,
+                        "against": "oracle fp64 forward + torch autograd on the same draws (pinned on the unmodified reference's "
+                                   "gradient goldens, tests/test_oracle_grad.py)"}
+        import torch as _t
+        out["cpu_baseline"] = {"value": k / res["f32"][2], "unit": "reactions/s", "cores": _t.get_num_threads(), "kind": "port",
+                               "sample": f"oracle fp32 forward + autograd backward of {k} of the {Bt} reactions "
+                                         f"({res['f32'][2]:.2f} s), cost linear in the reactions"}
+    return out
 
 
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import oareactdiff_b200 as ob
-    from oareactdiff_b200 import workloads
+    from oareactdiff_b200 import parallel, workloads
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local_rank)
@@ -210,7 +341,6 @@ def run_b200(args, rank, world, local_rank):
     torch.manual_seed(0)
     dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0,
                           condition_nf=1, model=ob.LEFTNetB200, device=dev).to(dev)
-    from oareactdiff_b200 import parallel
     bcast_bytes = parallel.broadcast_module_(dyn, src=0)  # the one collective of the path: rank 0's weights (42.6 MB), NCCL
     sched = ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", T, 1e-5), norm_values=(1.0, 1.0, 1.0))
     ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=sched, normalizer=ob.Normalizer(), pos_only=True).to(dev)
@@ -223,78 +353,38 @@ def run_b200(args, rank, world, local_rank):
     sizes = all_sizes[lo:hi]
     B = len(sizes)
     nodes_h, h0_h, cond_h = workloads.reaction_batch(sizes, seed=rank)
+    geometry = args.geometry
+    if geometry == "real" and hi > 512:
+        geometry = "synthetic"  # the fixture covers 512 reactions
+    x_h = workloads.real_geometries(lo, hi, sizes) if geometry == "real" else workloads.synthetic_geometries(sizes, rank)
     pin = lambda t: t.pin_memory()
-    nodes_h, h0_h, cond_h = [pin(x) for x in nodes_h], [pin(x) for x in h0_h], pin(cond_h)
-    nodes_d, h0_d, cond_d = [x.to(dev) for x in nodes_h], [x.to(dev) for x in h0_h], cond_h.to(dev)
+    nodes_h, h0_h, cond_h, x_h = [pin(x) for x in nodes_h], [pin(x) for x in h0_h], pin(cond_h), [pin(x) for x in x_h]
+    nodes_d, h0_d, cond_d, x_d = [x.to(dev) for x in nodes_h], [x.to(dev) for x in h0_h], cond_h.to(dev), [x.to(dev) for x in x_h]
     eng = dyn.model.engine(dev)
+    out_host = [torch.empty(h.size(0), 3).pin_memory() for h in h0_h]
 
+    # ---- headline step: a full reverse diffusion on trained-model states built from the reference geometries
     def step_resident():
+        torch.manual_seed(4321 + rank)
+        return workloads.replay_trajectory(ddpm, B, nodes_d, cond_d, h0_d, x_d, T)
+
+    def step_e2e():  # host (pinned) inputs -> device inside the timed region, result back to the host
+        torch.manual_seed(4321 + rank)
+        nd = [x.to(dev, non_blocking=True) for x in nodes_h]
+        hd = [x.to(dev, non_blocking=True) for x in h0_h]
+        xd = [x.to(dev, non_blocking=True) for x in x_h]
+        cd = cond_h.to(dev, non_blocking=True)
+        pos = workloads.replay_trajectory(ddpm, B, nd, cd, hd, xd, T)
+        for dst, src in zip(out_host, pos):
+            dst.copy_(src.to(torch.float32), non_blocking=True)
+        return pos
+
+    def step_literal():  # the literal sample() with random weights: the trajectory drifts out of the cutoff
         torch.manual_seed(1234 + rank)
         out, _ = ddpm.sample(B, nodes_d, cond_d, h0=h0_d)
         return out[0]
 
-    # Replay (SURVEY §8d realism caveat): the same per-step work (denoiser + posterior sampling) on states
-    # z_t = alpha_t x + sigma_t eps built from compact synthetic geometries, i.e. what a TRAINED model sees: every
-    # same-fragment edge stays inside the 10 A cutoff.  With random weights the literal sample() drifts to |x| ~ 1e2 A.
-    gen = torch.Generator().manual_seed(99 + rank)
-    geo = []
-    for n in sizes:
-        r = 1.2 * n ** (1.0 / 3.0)
-        pts = torch.randn(n, 3, generator=gen)
-        pts = pts / pts.norm(dim=1, keepdim=True) * (torch.rand(n, 1, generator=gen) ** (1 / 3)) * r
-        geo.append(pts - pts.mean(0, keepdim=True))
-    x_frag = []
-    for f in range(3):
-        xs = [gp + 0.3 * torch.randn(gp.shape, generator=gen) for gp in geo]
-        x_frag.append(torch.cat([x - x.mean(0, keepdim=True) for x in xs]).to(dev))
-    if args.replay_geometry == "real":
-        # reactant / transition-state / product geometries of real Transition1x reactions with exactly these atom counts
-        import numpy as np
-        fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "t1x_geometries_b512.npz"))
-        if hi > len(fx["sizes"]) or [int(v) for v in fx["sizes"][lo:hi]] != list(sizes):
-            raise SystemExit("--replay-geometry real: the fixture holds the first 512 reactions of t1x_sizes(., seed=0) only")
-        off = np.concatenate([[0], np.cumsum(fx["sizes"])])
-        x_frag = [torch.from_numpy(fx[k][off[lo]:off[hi]]).to(dev) for k in ("reactant", "transition_state", "product")]
-    xh0_d = [torch.cat([x_frag[f], h0_d[f]], dim=1) for f in range(3)]
-
-    replay_Z = torch.empty(sum(h.size(0) for h in h0_d), 9, device=dev)
-
-    def step_replay():
-        torch.manual_seed(4321 + rank)
-        masks, edge_index, nfs = ddpm._setup(B, nodes_d)
-        tab = ddpm._tables(T, dev)
-        ddpm._seg_setup(masks)
-        X = torch.cat(xh0_d)
-        H0 = torch.cat(h0_d)
-        on_device = ddpm._device_ok(dev)
-        if on_device:
-            ddpm._device_setup(replay_Z, masks, edge_index, nfs, cond_d, H0)
-        for s_int in reversed(range(T)):
-            # state a trained model would see at t = s+1: q(z_t | x); then the usual reverse step (denoiser + posterior)
-            Z = tab["alpha"][s_int + 1] * X + tab["sigma_abs"][s_int + 1] * ddpm._noise_cat(masks)
-            Z[:, 3:] = H0
-            if on_device:  # the device step replays one CUDA graph on a persistent state buffer
-                replay_Z.copy_(Z)
-                ddpm._device_step(s_int, replay_Z, tab)
-            else:
-                Z = ddpm._fast_step(s_int, Z, tab, edge_index, nfs, masks, cond_d)
-        Z0 = tab["alpha"][0] * X + tab["sigma_abs"][0] * ddpm._noise_cat(masks)
-        Z0[:, 3:] = H0
-        return ddpm.sample_p_xh_given_z0(ddpm._views(Z0), edge_index, nfs, masks, B, cond_d)[0]
-
-    out_host = [torch.empty(h.size(0), 9).pin_memory() for h in h0_h]
-
-    def step_e2e():
-        torch.manual_seed(1234 + rank)
-        nd = [x.to(dev, non_blocking=True) for x in nodes_h]
-        hd = [x.to(dev, non_blocking=True) for x in h0_h]
-        cd = cond_h.to(dev, non_blocking=True)
-        out, _ = ddpm.sample(B, nd, cd, h0=hd)
-        for dst, src in zip(out_host, out[0]):
-            dst.copy_(src.to(torch.float32), non_blocking=True)
-        return out[0]
-
-    h2d =sum(x.numel() * x.element_size() for x in nodes_h + h0_h + [cond_h])
+    h2d = sum(x.numel() * x.element_size() for x in nodes_h + h0_h + x_h + [cond_h])
     d2h = sum(x.numel() * x.element_size() for x in out_host)
 
     def barrier():
@@ -305,16 +395,24 @@ def run_b200(args, rank, world, local_rank):
     host_ms = {}
 
     def timed(fn, k):
+        """-> (total ms of k steps, max over ranks; per-step ms of this rank)."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        evs[0].record()
         t0 = time.perf_counter()
-        for _ in range(k):
+        for i in range(k):
             fn()
+            evs[i + 1].record()
         host_ms[fn.__name__] = (time.perf_counter() - t0) * 1e3 / k  # host enqueue time (no sync inside the loop)
-        e1.record()
         barrier()
-        return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(k)]
+        return parallel.max_over_ranks(evs[0].elapsed_time(evs[k]), dev), per
+
+    def profile_of(prof):
+        return {k: dict(ms_per_launch=v["ms"] / max(v["launches"], 1), launches=v["launches"], ms=v["ms"],
+                        tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
+                        gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0, flops=v["flops"], bytes=v["bytes"])
+                for k, v in prof.items() if not k.startswith("_")}
 
     for _ in range(args.warmup):
         step_resident()
@@ -322,107 +420,139 @@ def run_b200(args, rank, world, local_rank):
     l0 = eng.total_launches()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms = timed(step_resident, args.steps)
+    ms, per_step = timed(step_resident, args.steps)
     clk = clocks.stop()
     launches = eng.total_launches() - l0
     prof = eng.profile()
     eng.set_profile(0)
-    ms_e2e = timed(step_e2e, args.steps)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, 5))
+    ms_e2e, per_e2e = timed(step_e2e, e2e_steps)
     finite = all(bool(torch.isfinite(o).all()) for o in out_host)
-    replay = None
-    if not args.no_replay:
-        step_replay()
+
+    literal = None
+    if not args.no_literal:
+        step_literal()
         eng.set_profile(args.profile_every)
-        ms_rp = timed(step_replay, 1)
-        prof_rp = eng.profile()
+        ms_lit, _ = timed(step_literal, 1)
+        prof_lit = eng.profile()
         eng.set_profile(0)
-        af = prof_rp.get("_active_fraction")
-        replay = {"value": len(all_sizes) / (ms_rp / 1e3), "unit": UNIT, "ms_per_step": ms_rp, "steps": 1,
-                  "active_edge_fraction": (af["flops"] / max(af["launches"], 1)) if af else None,
-                  "geometry": args.replay_geometry,
-                  "note": "same per-step work on z_t = alpha_t x + sigma_t eps from "
-                          + ("REAL Transition1x reactant / TS / product geometries (tests/golden/t1x_geometries_b512.npz) "
-                             if args.replay_geometry == "real" else "compact synthetic geometries ")
-                          + "(what a trained model sees; every same-fragment edge inside the cutoff)",
-                  "kernels_ms_per_launch": {k: round(v["ms"] / max(v["launches"], 1), 5) for k, v in
-                                            sorted(prof_rp.items(), key=lambda kv: -kv[1]["ms"])[:10] if not k.startswith("_")}}
+        af = prof_lit.get("_active_fraction")
+        literal = {"value": len(all_sizes) / (ms_lit / 1e3), "unit": UNIT, "ms_per_step": ms_lit, "steps": 1,
+                   "active_edge_fraction": (af["flops"] / max(af["launches"], 1)) if af else None,
+                   "note": "EnVariationalDiffusion.sample() taken literally with random-init weights: positions drift to "
+                           "|x| ~ 1e2 A, the cutoff empties and the active-edge stages shrink (exactly skipped work)"}
+
+    inpaint = None
+    if world == 1 and not args.no_inpaint:
+        inpaint = {}
+        for r_, j_ in ((1, 1), (5, 5)):
+            try:
+                def step_inpaint():
+                    torch.manual_seed(77 + rank)
+                    xf = [torch.cat([x, h], dim=1) for x, h in zip(x_d, h0_d)]
+                    out, _ = ddpm.inpaint(B, nodes_d, cond_d, resamplings=r_, jump_length=j_, xh_fixed=xf, frag_fixed=[0, 2])
+                    return out[0]
+                if (r_, j_) == (1, 1):
+                    step_inpaint()
+                ms_i, _ = timed(step_inpaint, 1)
+                inpaint[f"r{r_}_j{j_}"] = {"value": B / (ms_i / 1e3), "unit": UNIT, "ms_per_step": ms_i, "denoiser_evaluations": ddpm.n_evals,
+                                           "ms_per_evaluation": ms_i / ddpm.n_evals, "host_enqueue_ms": host_ms.get("step_inpaint")}
+            except Exception as ex:  # noqa: BLE001
+                inpaint[f"r{r_}_j{j_}"] = {"error": repr(ex)[:300]}
+        inpaint["workload"] = (f"TS inpainting (RePaint): reactant + product clamped to real Transition1x geometries, TS resampled; "
+                               f"batch={B}, {T} steps, 1xB200 (BASELINE config 4)")
+
+    train = None
+    if world == 1 and not args.no_train:
+        try:
+            del step_inpaint
+        except Exception:  # noqa: BLE001
+            pass
+        try:
+            train = train_leg(args, ob, workloads, dev, cfg, T)
+        except Exception as ex:  # noqa: BLE001
+            train = {"error": repr(ex)[:400]}
 
     total_reactions = len(all_sizes) * args.steps
     value = total_reactions / (ms / 1e3)
-    e2e_v = total_reactions / (ms_e2e / 1e3)
+    e2e_v = len(all_sizes) * e2e_steps / (ms_e2e / 1e3)
     if rank != 0:
         return
     pk = peaks()
-    af_lit = prof.pop("_active_fraction", None)
-    kernels = {k: dict(ms_per_launch=v["ms"] / max(v["launches"], 1), launches=v["launches"],
-                       tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
-                       gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
-                       share=v["ms"]) for k, v in prof.items()}
-    tot = sum(v["share"] for v in kernels.values()) or 1.0
+    af_rep = prof.pop("_active_fraction", None)
+    active_fraction = (af_rep["flops"] / max(af_rep["launches"], 1)) if af_rep else None
+    kernels = profile_of(prof)
+    tot = sum(v["ms"] for v in kernels.values()) or 1.0
     for v in kernels.values():
-        v["share"] = v["share"] / tot
+        v["share"] = v["ms"] / tot
     dom = max(kernels, key=lambda k: kernels[k]["share"]) if kernels else None
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if dom and os.path.exists(tpath):
-        t_ = json.load(open(tpath)).get(dom)
+        tj = json.load(open(tpath))
+        t_ = tj.get(dom)
         traffic = t_.get("dram_bytes_per_launch") if isinstance(t_, dict) else t_  # ncu dram read+write bytes of one launch
+        traffic_src = tj.get("_source")
     roof = None
     ridge = pk["tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)  # FLOP per byte where the two roofs meet (bf16 tensor vs HBM)
+    mp = kernels.get("k_equi_msg")
+    mp_roof = None if not mp else {
+        "kernel": "k_equi_tgt (EquiMessage message + aggregation at the target)", "bound": "hbm", "achieved": mp["gbs"],
+        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": mp["gbs"] / pk["hbm_gbs"], "ms_per_launch": mp["ms_per_launch"],
+        "share_of_step": mp["share"], "algorithmic_bytes": "E_act * (3H*4 + 24): G row + geometry / index record per active edge",
+        "measured_on": "the timed run (trained-model geometry)"}
     if dom:
         kd = kernels[dom]
-        pv = prof[dom]
         # tensor pipe executes 3 bf16 MMAs per algorithmic fp32 product (bf16x3 split): that is what competes with HBM
-        intensity = (3.0 * pv["flops"] / pv["bytes"]) if pv["bytes"] > 0 else float("inf")
+        intensity = (3.0 * kd["flops"] / kd["bytes"]) if kd["bytes"] > 0 else float("inf")
+        common = {"kernel": dom, "traffic": traffic, "traffic_source": traffic_src, "share_of_step": kd["share"],
+                  "ms_per_launch": kd["ms_per_launch"], "active_edge_fraction": active_fraction, "message_passing": mp_roof}
         if dom.startswith("gemm") and intensity >= ridge:
-            roof = {"kernel": dom, "bound": "tensor", "achieved": kd["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": kd["tflops"] / pk["tflops"], "traffic": traffic, "share_of_step": kd["share"],
-                    "mma_issued_tflops": 3.0 * kd["tflops"],
+            roof = {"bound": "tensor", "achieved": kd["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": kd["tflops"] / pk["tflops"], **common, "mma_issued_tflops": 3.0 * kd["tflops"],
                     "note": f"achieved = algorithmic fp32-equivalent flops (2MNK, inactive edges skipped) / CUDA-event launch time; "
                             f"the kernel issues 3 bf16 MMAs per product (bf16x3 split), so its own ceiling is peak/3; "
                             f"peak = bf16 cuBLAS sustained ({pk['src']})"}
         else:
-            roof = {"kernel": dom, "bound": "hbm", "achieved": kd["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": kd["gbs"] / pk["hbm_gbs"], "traffic": traffic, "share_of_step": kd["share"],
+            roof = {"bound": "hbm", "achieved": kd["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": kd["gbs"] / pk["hbm_gbs"], **common,
                     "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
                     "note": f"achieved = algorithmic bytes (operand read + residual read + result write, fp32) / CUDA-event "
                             f"launch time; arithmetic intensity (bf16 MMA flops per byte) is below the ridge, so HBM is the "
                             f"bound; peak = copy bandwidth ({pk['src']})"}
-    # the message-passing kernel's roofline is quoted on the replay (trained-model geometry, active fraction ~0.32): in the
-    # literal random-weight trajectory the cutoff empties and the kernel has almost no edges to stream
-    mp = kernels.get("k_equi_reduce")
-    mp_src = "literal sample()"
-    if replay is not None and "k_equi_reduce" in prof_rp and prof_rp["k_equi_reduce"]["ms"] > 0:
-        v = prof_rp["k_equi_reduce"]
-        mp = dict(gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, ms_per_launch=v["ms"] / max(v["launches"], 1))
-        mp_src = "replay"
     gemm_tab = {k: {"tflops_alg": round(v["tflops"], 1), "frac_of_bf16x3_ceiling": round(3.0 * v["tflops"] / pk["tflops"], 3),
                     "gbs_alg": round(v["gbs"], 1), "frac_hbm": round(v["gbs"] / pk["hbm_gbs"], 3)}
                 for k, v in kernels.items() if k.startswith("gemm")}
+    srt = sorted(per_step)
+    geo_txt = ("frozen REAL Transition1x reactant / TS / product coordinates (tests/golden/t1x_geometries_b512.npz)"
+               if geometry == "real" else "compact synthetic clouds of molecular density")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batch={args.batch} Transition1x-shaped reactions (<=23 atoms) per GPU, {T} steps "
-                                   f"(sample(): {T + 1} LEFTNet evaluations), trained LEFTNet config (6 layers, H=196, R=96)",
+            "dtype": "f32 (bf16x3 split on tcgen05, pair16 edge storage; fp64 frames)", "data": "synthetic",
+            "config": {"workload": f"batch={args.batch} Transition1x-shaped reactions (<=23 atoms) per GPU, {T} reverse steps + decode "
+                                   f"({T + 1} LEFTNet evaluations), trained LEFTNet config (6 layers, H=196, R=96), states of a "
+                                   f"trained model: z_t = alpha_t x + sigma_t eps re-drawn every step from {geo_txt}",
+                       "geometry": geometry, "active_edge_fraction": active_fraction,
+                       "literal_sample": literal,
                        "global_batch": len(all_sizes), "denoise_steps": T, "weights_broadcast_bytes": int(bcast_bytes), "nodes_per_gpu": int(sum(sizes) * 3),
                        "edges_per_gpu": workloads.edge_count(sizes), "parallelism": f"dp{world} (reactions sharded, no "
                        "per-step collective)", "l2": "working set per evaluation (edge state 4*E*684 B = "
                        f"{workloads.edge_count(sizes) * 684 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
                        "weights": "torch.manual_seed(0) default init (checkpoint is a git-LFS pointer)"},
             "clocks": clk, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
+            "spread": {"ms_per_step_min": srt[0], "ms_per_step_median": srt[len(srt) // 2], "ms_per_step_max": srt[-1],
+                       "repeats": len(srt), "e2e_ms_per_step": [round(x, 1) for x in per_e2e]},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps, "outputs_finite": finite},
-            "active_edge_fraction": (af_lit["flops"] / max(af_lit["launches"], 1)) if af_lit else None,
-            "replay": replay,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "outputs_finite": finite},
             "roofline": roof,
-            "message_passing_roofline": None if not mp else {
-                "kernel": "k_equi_reduce", "bound": "hbm", "achieved": mp["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": mp["gbs"] / pk["hbm_gbs"], "ms_per_launch": mp["ms_per_launch"], "measured_on": mp_src},
+            "literal_sample": literal,
+            "inpaint": inpaint,
+            "train_step": train,
             "gemm_rooflines": gemm_tab,
-            "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()}
-                        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share"])[:12]}}
+            "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk not in ("flops", "bytes", "ms")}
+                        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["share"])[:14]}}
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(args, T)
+        line["cpu_baseline"] = cpu_baseline(args, T, workloads)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -58,7 +58,7 @@ __global__ void k_edge_mask(int E, const int* __restrict__ esrc, const int* __re
                             uint8_t* __restrict__ mask, uint8_t* __restrict__ sub8) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  sub8[e] = (sub == nullptr || sub[e] > 0);  // same-fragment relation (an equivalence): groups of k_equi_frag
+  sub8[e] = (sub == nullptr || sub[e] > 0);  // same-fragment relation (an equivalence): groups of k_equi_tgt
   const int i = esrc[e], j = ecol[e];
   const float dx = pos[i * 3 + 0] - pos[j * 3 + 0], dy = pos[i * 3 + 1] - pos[j * 3 + 1],
               dz = pos[i * 3 + 2] - pos[j * 3 + 2];
@@ -77,7 +77,7 @@ template <int MAXC>
 __global__ void __launch_bounds__(128) k_group_frame(
     const int* __restrict__ comp_ptr, const int* __restrict__ comp_nodes, const int* __restrict__ node_local,
     const int* __restrict__ row_ptr, const int* __restrict__ ecol, const uint8_t* __restrict__ mask,
-    const float* __restrict__ pos, float* __restrict__ pf, float* __restrict__ nodeframe,
+    const float* __restrict__ pos, float* __restrict__ pf, double* __restrict__ pf64, float* __restrict__ nodeframe,
     float* __restrict__ pos_prjt, int* __restrict__ owner, uint8_t* __restrict__ opener) {
   __shared__ int lab[MAXC];
   __shared__ double p[MAXC][3];
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(128) k_group_frame(
     q[n][0] = p[n][0] - sx / cnt; q[n][1] = p[n][1] - sy / cnt; q[n][2] = p[n][2] - sz / cnt;
     const int t = nodes[n];
     pf[t * 3 + 0] = (float)q[n][0]; pf[t * 3 + 1] = (float)q[n][1]; pf[t * 3 + 2] = (float)q[n][2];
+    pf64[t * 3 + 0] = q[n][0]; pf64[t * 3 + 1] = q[n][1]; pf64[t * 3 + 2] = q[n][2];
     owner[t] = nodes[own];
     opener[t] = (own == n);
   }
@@ -167,16 +168,20 @@ __global__ void k_group_ids(int N, const int* __restrict__ owner, const uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// (E) edge geometry on pos_frame, masked (leftnet.py:693-705,764-771,785): geo[e] = (u_x,u_y,u_z,dist), rb[e];
-// also counts the row's active edges.  One warp per CSR row.
+// (E) edge geometry on pos_frame, masked (leftnet.py:693-705,764-771,785): geo[e] = (u_x,u_y,u_z,dist), rb[e],
+// ecross[e] = unit cross of pos_frame_i x pos_frame_j; also counts the row's active edges.  One warp per CSR row.
+// Evaluated in fp64 on the fp64 frame positions: inside a group of two (or a collinear group) the centred positions are
+// exactly (anti)parallel, so the cross product is pure rounding noise in fp32 — against the 1e-6 of its normalisation that
+// noise is O(1) in the reference's fp32, while fp64 gives the clean ~0 of the fp64 oracle (same argument as the node frame).
 __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* __restrict__ ecol,
                             const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sub8,
-                            const float* __restrict__ pf, float cutoff, float4* __restrict__ geo, float* __restrict__ rb,
+                            const double* __restrict__ pf64, float cutoff, float4* __restrict__ geo,
+                            float4* __restrict__ ecross, float* __restrict__ rb,
                             int* __restrict__ row_cnt, int* __restrict__ leader, int* __restrict__ glocal,
                             int* __restrict__ gsize) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= N) return;
-  const float ax = pf[t * 3 + 0], ay = pf[t * 3 + 1], az = pf[t * 3 + 2];
+  const double ax = pf64[t * 3 + 0], ay = pf64[t * 3 + 1], az = pf64[t * 3 + 2];
   int cnt = 0, lead = t, below = 0, gsz = 0;
   for (int e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) {
     if (sub8[e]) {  // same-group neighbour: the group's leader is its smallest node id, glocal = rank inside the group
@@ -185,18 +190,23 @@ __global__ void k_edge_geom(int N, const int* __restrict__ row_ptr, const int* _
       below += j < t;
       gsz++;
     }
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), cr = g;
     float r = 1.0f;  // 0.5*(cos(0)+1)
     if (mask[e]) {
       const int j = ecol[e];
-      const float dx = ax - pf[j * 3 + 0], dy = ay - pf[j * 3 + 1], dz = az - pf[j * 3 + 2];
-      const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-      const float inv = 1.0f / (d + OARD_EPS);
-      g = make_float4(dx * inv, dy * inv, dz * inv, d);
-      r = 0.5f * (cosf(d * (float)OARD_PI / cutoff) + 1.0f);
+      const double bx = pf64[j * 3 + 0], by = pf64[j * 3 + 1], bz = pf64[j * 3 + 2];
+      const double dx = ax - bx, dy = ay - by, dz = az - bz;
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      const double inv = 1.0 / (d + (double)OARD_EPS);
+      g = make_float4((float)(dx * inv), (float)(dy * inv), (float)(dz * inv), (float)d);
+      const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      const double cinv = 1.0 / (sqrt(cx * cx + cy * cy + cz * cz) + (double)OARD_EPS);
+      cr = make_float4((float)(cx * cinv), (float)(cy * cinv), (float)(cz * cinv), 0.f);
+      r = 0.5f * (cosf(g.w * (float)OARD_PI / cutoff) + 1.0f);
       cnt++;
     }
     geo[e] = g;
+    ecross[e] = cr;
     rb[e] = r;
   }
   cnt = (int)warp_sum((float)cnt);
@@ -226,7 +236,7 @@ __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restr
   int run = sm[tid];
   for (int i = b; i < e; i++) { row_act_ptr[i] = run; run += row_cnt[i]; }
   if (tid == T - 1) { row_act_ptr[N] = sm[T]; *n_act = sm[T]; }
-  // ordered compaction of the group leaders (leader[t] == t) and reset of the per-layer work counters of k_equi_frag
+  // ordered compaction of the group leaders (leader[t] == t) and reset of the per-layer work counters of k_equi_tgt
   __syncthreads();
   s = 0;
   for (int i = b; i < e; i++) s += leader[i] == i;
@@ -259,7 +269,8 @@ __global__ void k_scan_rows(int N, const int* __restrict__ row_cnt, int* __restr
 
 // ordered compaction of active edges: act_idx[p] = e, act_pos[e] = p or -1.  One warp per row.
 __global__ void k_compact(int N, const int* __restrict__ row_ptr, const uint8_t* __restrict__ mask,
-                          const int* __restrict__ row_act_ptr, int* __restrict__ act_idx, int* __restrict__ act_pos) {
+                          const int* __restrict__ row_act_ptr, int* __restrict__ act_idx, int* __restrict__ act_pos,
+                          int* __restrict__ act_pos_t) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= N) return;
   int base = row_act_ptr[t];
@@ -271,7 +282,7 @@ __global__ void k_compact(int N, const int* __restrict__ row_ptr, const uint8_t*
     const int off = __popc(bal & ((1u << lane) - 1u));
     if (e < r1) {
       if (a) { act_idx[base + off] = e; act_pos[e] = base + off; }
-      else act_pos[e] = -1;
+      else { act_pos[e] = -1; act_pos_t[e] = -1; }
     }
     base += __popc(bal);
   }
@@ -474,21 +485,26 @@ __global__ void k_att_agg(int H, const int* __restrict__ row_ptr, const float* _
   }
 }
 
-// Per-step lists over the compact active edges: for p = (t -> a), the compact position of the transposed edge (a -> t), the
-// neighbour a and the geometry of p (the transposed edge's unit vector is its exact negation).  They turn the
-// target-side aggregations into walks over contiguous index ranges [row_act_ptr[t], row_act_ptr[t+1]) with independent loads.
+// Per-step lists over the compact active edges: for p = (t -> a), the neighbour a and the geometry of p (the transposed
+// edge's unit vector is its exact negation), and per EDGE e the compact position of its transposed edge, act_pos_t[e]: the
+// row where edge_out puts e's compact copy, so that the compact rows are in TARGET order (rows [row_act_ptr[t],
+// row_act_ptr[t+1]) = the edges arriving at t) and the target-side aggregation walks one contiguous block.  The distance
+// and the same-fragment relation are symmetric, so e is active iff its transposed edge is.
 __global__ void k_act_lists(const int* __restrict__ n_act, int cap, const int* __restrict__ act_idx,
                             const int* __restrict__ act_pos, const int* __restrict__ rev, const int* __restrict__ ecol,
-                            const float4* __restrict__ geo, const int* __restrict__ glocal, int* __restrict__ act_tr,
-                            int* __restrict__ act_col, float4* __restrict__ act_geo, int2* __restrict__ act_rec) {
+                            const float4* __restrict__ geo, const float4* __restrict__ ecross,
+                            const int* __restrict__ glocal, int* __restrict__ act_pos_t,
+                            int* __restrict__ act_col, float4* __restrict__ act_geo, float4* __restrict__ act_cross,
+                            int2* __restrict__ act_rec) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= min(*n_act, cap)) return;
   const int e = act_idx[p];
   const int tr = act_pos[rev[e]], a = ecol[e];
-  act_tr[p] = tr;
+  act_pos_t[e] = tr;
   act_col[p] = a;
   act_geo[p] = geo[e];
-  act_rec[p] = make_int2(tr, glocal[a]);  // k_equi_frag: G row of the message edge, source's rank inside its group
+  act_cross[p] = ecross[e];
+  act_rec[p] = make_int2(tr, glocal[a]);  // k_equi_tgt: (source-ordered position of the message edge, source's rank inside its group)
 }
 
 // Member lists of the groups, once per forward: gm_node[off + i] = i-th member (ascending), gm_rap[off + i] = its range of
@@ -523,9 +539,8 @@ __global__ void k_group_members(const int* __restrict__ n_lead, const int* __res
 // s = (s + dx)/sqrt2, vec_out = vec_in + dvec.
 template <int NG>
 __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
-    int H, int reflect, const int* __restrict__ row_act_ptr, const int* __restrict__ act_tr,
-    const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float* __restrict__ G,
-    const float* __restrict__ X, const float* __restrict__ pf, const float* __restrict__ vec_in,
+    int H, int reflect, const int* __restrict__ row_act_ptr, const int* __restrict__ act_col, const float4* __restrict__ act_geo, const float4* __restrict__ act_cross,
+    const float* __restrict__ G, const float* __restrict__ X, const float* __restrict__ vec_in,
     float* __restrict__ vec_out, float* __restrict__ s) {
   extern __shared__ __align__(16) float4 eq_part[];  // [NG][4][H/4]
   const int t = blockIdx.x, grp = threadIdx.x >> 6, h = (threadIdx.x & 63) * 4, H4 = H / 4;
@@ -537,24 +552,20 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
   if (on) {
     const float* Xt = X + (size_t)t * 3 * H;
     const float4 x0 = ld4(Xt + h), x1 = ld4(Xt + H + h), x2 = ld4(Xt + 2 * H + h);
-    float tx = 0.f, ty = 0.f, tz = 0.f;
-    if (!reflect) { tx = pf[t * 3]; ty = pf[t * 3 + 1]; tz = pf[t * 3 + 2]; }
     auto edge = [&](int p) {
-      const int pr = act_tr[p], a = act_col[p];
+      const int a = act_col[p];
       const float4 gm = act_geo[p];  // geometry of (t -> a); the message edge (a -> t) has the negated unit vector
       const float ux = -gm.x, uy = -gm.y, uz = -gm.z;
-      const float* g = G + (size_t)pr * 3 * H;
+      const float* g = G + (size_t)p * 3 * H;  // compact rows are in target order: row p = message (a -> t) of edge p = (t -> a)
       const float* Xa = X + (size_t)a * 3 * H;
       const float* va = vec_in + (size_t)a * 3 * H;
       const float4 g0 = ld4(g + h), g1 = ld4(g + H + h), g2 = ld4(g + 2 * H + h);
       const float4 a0 = ld4(Xa + h), a1 = ld4(Xa + H + h), a2 = ld4(Xa + 2 * H + h);
       const float4 v0 = ld4(va + h), v1 = ld4(va + H + h), v2 = ld4(va + 2 * H + h);
       float cx = 0.f, cy = 0.f, cz = 0.f;
-      if (!reflect) {  // + x * edge_cross (leftnet.py:268-269); cross of pos_frame_a x pos_frame_t, unit
-        const float ax = pf[a * 3], ay = pf[a * 3 + 1], az = pf[a * 3 + 2];
-        cx = ay * tz - az * ty; cy = az * tx - ax * tz; cz = ax * ty - ay * tx;
-        const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
-        cx *= cinv; cy *= cinv; cz *= cinv;
+      if (!reflect) {  // + x * edge_cross (leftnet.py:268-269): unit cross of pos_frame_a x pos_frame_t = -(t x a) of edge p
+        const float4 cr = act_cross[p];
+        cx = -cr.x; cy = -cr.y; cz = -cr.z;
       }
 #define OARD_EQ(c)                                                                         \
       {                                                                                    \
@@ -591,226 +602,105 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
   }
 }
 
-// EquiMessage message + aggregation, group-staged form of k_equi_reduce (reflect_equiv only; same arithmetic).  A "group"
-// is a class of the same-fragment relation (sub8): every active source of a target lies in the target's group, so the
-// X and vec rows a group needs (the L2 gather traffic that bounded k_equi_reduce: 2 x 3H floats per edge) are staged ONCE
-// in shared memory and the kernel streams only G[E_act, 3H] from HBM.  Work item = (group, channel slice of CH channels);
-// items are handed out through an atomic counter whose next value is fetched while the current item runs (dynamic
-// balance; results do not depend on the assignment).  Per item the dependent memory round trips are: member list + edge
-// ranges (k_group_members, once per forward) -> {X / vec rows, edge records} -> G rows.  Each warp takes the group's
-// targets round-robin; lane = (q, e4): float4 column q of the slice, edge slot e4 of 4 edges in flight (x2 unrolled); the
-// four partial sums are combined by a fixed shuffle tree (bitwise reproducible).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+// ---------------------------------------------------------------------------------------------------------------
+// EquiMessage message + aggregation at the target, round-2 form (reflect_equiv only; same arithmetic as k_equi_reduce).
+// The compact rows of the active edges are kept in TARGET order (edge_out scatters the row of edge e to the compact
+// position of its transposed edge), so the G rows of all messages arriving at target t are the contiguous block
+// [row_act_ptr[t], row_act_ptr[t+1]) and G row p belongs to the message (a -> t) of the compact edge p = (t -> a).
+// Work item = (group, CH-channel slice), one item per CTA turn (atomic counter); the group's X / vec rows of the slice are
+// staged once in shared memory.  Thread = (target slot, float4 column): it walks the target's block of G rows with the next
+// row's three 16-byte loads in flight and accumulates in registers — no cross-thread reduction, no shuffles, fixed edge
+// order (bitwise reproducible).  Latency is hidden by the co-resident CTAs (4-5 per SM), not by an in-CTA pipeline.
+template <int CH>
+inline size_t et_smem_bytes(int gmax) {
+  return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * (4 + 8);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int EF_CE = 8;  // edges per chunk (one cp.async group)
+constexpr int ET_THREADS = 192;
 template <int CH>
-__host__ __device__ constexpr int ef_stage_f4() { return EF_CE * 3 * (CH / 4) + EF_CE + 2; }  // G rows | geometry | source ranks
-template <int CH>
-inline size_t ef_smem_bytes(int gmax) {
-  return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * 2 * (4 + 8) + (size_t)8 * 2 * ef_stage_f4<CH>() * 16;
-}
-
-// Messages are STAGED THROUGH SHARED MEMORY: a warp walks the chunks (<= 8 edges) of its targets; the G rows of chunk k+1
-// are in flight as one cp.async group (and the edge records of chunk k+2 as plain loads) while chunk k is evaluated, so
-// the only exposed latency per item is the first chunk's.
-template <int CH>
-__global__ void __launch_bounds__(256) k_equi_frag(
+__global__ void __launch_bounds__(ET_THREADS, 4) k_equi_tgt(
     int H, int NS, int gmax, const int* __restrict__ n_lead, const int2* __restrict__ lead_info,
-    int* __restrict__ work_ctr, const int* __restrict__ gm_node,
-    const int2* __restrict__ gm_rap, const int2* __restrict__ act_rec, const float4* __restrict__ act_geo,
-    const float* __restrict__ G, const float* __restrict__ X, const float* __restrict__ vec_in,
-    float* __restrict__ vec_out, float* __restrict__ s) {
-  constexpr int Q = CH / 4;  // float4 columns per slice
-  constexpr int STG = ef_stage_f4<CH>();
-  extern __shared__ __align__(16) float4 ef_sm[];
-  float4* Xs = ef_sm;                         // [gmax][3][Q]
-  float4* Vs = ef_sm + (size_t)gmax * 3 * Q;  // [gmax][3][Q]
+    int* __restrict__ work_ctr, const int* __restrict__ gm_node, const int2* __restrict__ gm_rap,
+    const int2* __restrict__ act_rec, const float4* __restrict__ act_geo, const float* __restrict__ G,
+    const float* __restrict__ X, const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
+  constexpr int Q = CH / 4;              // float4 columns per slice
+  constexpr int NSLOT = ET_THREADS / Q;  // targets in flight per CTA
+  extern __shared__ __align__(16) float4 et_sm[];
+  float4* Xs = et_sm;                         // [gmax][3][Q]
+  float4* Vs = et_sm + (size_t)gmax * 3 * Q;  // [gmax][3][Q]
   const int gpad = (gmax + 3) & ~3;
-  int* mem_node_all = reinterpret_cast<int*>(Vs + (size_t)gmax * 3 * Q);     // [2][gpad]   (double-buffered descriptors)
-  int2* mem_rap_all = reinterpret_cast<int2*>(mem_node_all + 2 * gpad);      // [2][gpad]
-  float4* wb_all = reinterpret_cast<float4*>(mem_rap_all + 2 * gpad);        // [8 warps][2 stages][STG]
-  __shared__ int w_sm[2];
-  __shared__ int2 info_sm[2];  // (group size, number of active edges inside the group)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int q = lane >> 2, e4 = lane & 3;
-  const bool on = q < Q;
-  float4* wb = wb_all + (size_t)warp * 2 * STG;
+  int2* mem_rap = reinterpret_cast<int2*>(Vs + (size_t)gmax * 3 * Q);  // [gpad]
+  int* mem_node = reinterpret_cast<int*>(mem_rap + gpad);               // [gpad]
+  __shared__ int w_sm;
+  const int tid = threadIdx.x;
+  const int slot = tid / Q, q = tid - slot * Q;
   const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
-  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
   const int total = *n_lead * NS;
-  const int nwk = nw - 1;  // worker warps; the last warp fetches the NEXT item's descriptor while the workers run
-  // next work item -> (w, member-list offset/size, member list + edge ranges) in descriptor buffer b: three dependent
-  // global round trips that never sit on the workers' critical path
-  auto fetch_desc = [&](int b) {
-    int w2 = 0;
-    if (lane == 0) w2 = atomicAdd(work_ctr, 1);
-    w2 = __shfl_sync(0xffffffffu, w2, 0);
-    int2 inf = make_int2(0, 0);
-    int ne = 0;
-    if (w2 < total) {
-      inf = lead_info[w2 / NS];
-      for (int i = lane; i < inf.y; i += 32) {
-        const int2 rap = gm_rap[inf.x + i];
-        mem_node_all[b * gpad + i] = gm_node[inf.x + i];
-        mem_rap_all[b * gpad + i] = rap;
-        ne += rap.y - rap.x;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ne += __shfl_xor_sync(0xffffffffu, ne, o);
-    if (lane == 0) { w_sm[b] = w2; info_sm[b] = make_int2(inf.y, ne); }
-  };
-  int cur = 0;
-  if (warp == nw - 1) fetch_desc(0);
-  __syncthreads();
-  for (;; cur ^= 1) {
-    const int w = w_sm[cur];
+  const size_t H3 = (size_t)3 * H;
+  for (;;) {
+    if (tid == 0) w_sm = atomicAdd(work_ctr, 1);
+    __syncthreads();
+    const int w = w_sm;
     if (w >= total) break;
     const int gi = w / NS, h0 = (w - gi * NS) * CH;
-    const int gs = info_sm[cur].x;
-    const int* mem_node = mem_node_all + cur * gpad;
-    const int2* mem_rap = mem_rap_all + cur * gpad;
-    if (info_sm[cur].y == 0) {
-      // no active edge inside the group (cutoff emptied): s <- s / sqrt2, vec_out <- vec_in, no staging (block-uniform branch)
-      __syncthreads();  // everyone has read the descriptor
-      if (warp == nw - 1) fetch_desc(cur ^ 1);
-      for (int i = tid; i < gs * 4 * Q; i += blockDim.x) {
-        const int m = i / (4 * Q), r = i - m * 4 * Q, c = r / Q, qq = r - c * Q;
-        const int t = mem_node[m];
-        if (c == 0) {
-          float* sp = s + (size_t)t * H + h0 + 4 * qq;
-          float4 v = ld4(sp);
-          v.x *= inv_sqrt_2; v.y *= inv_sqrt_2; v.z *= inv_sqrt_2; v.w *= inv_sqrt_2;
-          *reinterpret_cast<float4*>(sp) = v;
-        } else {
-          const size_t o = (size_t)t * 3 * H + (size_t)(c - 1) * H + h0 + 4 * qq;
-          *reinterpret_cast<float4*>(vec_out + o) = ld4(vec_in + o);
-        }
-      }
-      __syncthreads();
-      continue;
-    }
-    for (int i = tid; i < gs * 3 * Q; i += blockDim.x) {
+    const int2 inf = lead_info[gi];
+    const int gs = inf.y;
+    for (int i = tid; i < gs; i += ET_THREADS) { mem_node[i] = gm_node[inf.x + i]; mem_rap[i] = gm_rap[inf.x + i]; }
+    for (int i = tid; i < gs * 3 * Q; i += ET_THREADS) {
       const int m = i / (3 * Q), r = i - m * 3 * Q, c = r / Q, qq = r - c * Q;
-      const size_t o = (size_t)mem_node[m] * 3 * H + (size_t)c * H + h0 + 4 * qq;
+      const size_t o = (size_t)gm_node[inf.x + m] * H3 + (size_t)c * H + h0 + 4 * qq;
       Xs[i] = ld4(X + o);
       Vs[i] = ld4(vec_in + o);
     }
-    // ---- this warp's chunk walk (all control flow below is warp-uniform)
-    struct Chunk { int tl, p, pend, n; bool valid; };
-    auto mk_chunk = [&](int tl, int p, int pend) {
-      Chunk c;
-      c.tl = tl; c.p = p; c.pend = pend; c.valid = tl < gs; c.n = c.valid ? min(EF_CE, max(pend - p, 0)) : 0;
-      return c;
-    };
-    auto first_of = [&](int tl) {
-      if (tl >= gs) return mk_chunk(tl, 0, 0);
-      const int2 rap = mem_rap[tl];
-      return mk_chunk(tl, rap.x, rap.y);
-    };
-    auto advance = [&](const Chunk& c) {
-      if (!c.valid) return c;
-      if (c.p + EF_CE < c.pend) return mk_chunk(c.tl, c.p + EF_CE, c.pend);
-      return first_of(c.tl + nwk);
-    };
-    auto load_rec = [&](const Chunk& c, int2& r, float4& gm) {
-      r = make_int2(0, 0); gm = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < c.n) { r = act_rec[c.p + lane]; gm = act_geo[c.p + lane]; }
-    };
-    auto issue_g = [&](const Chunk& c, const int2 r, const float4 gm, int stage) {
-      float4* gb = wb + (size_t)stage * STG;
-      if (lane < EF_CE) {
-        gb[EF_CE * 3 * Q + lane] = gm;
-        reinterpret_cast<int*>(gb + EF_CE * 3 * Q + EF_CE)[lane] = r.y;
-      }
-      const int tot = c.n * 3 * Q;
-      for (int i0 = 0; i0 < tot; i0 += 32) {
-        const int i = i0 + lane, e = min(i / (3 * Q), EF_CE - 1), rr = i - e * 3 * Q, cc = rr / Q, qq = rr - cc * Q;
-        const int tr = __shfl_sync(0xffffffffu, r.x, e);
-        if (i < tot) cp_async16(gb + i, G + (size_t)tr * 3 * H + (size_t)cc * H + h0 + 4 * qq);
-      }
-      cp_async_commit();
-    };
-    Chunk c0 = first_of(warp < nwk ? warp : gs), c1 = advance(c0);
-    int2 r0, r1;
-    float4 gm0, gm1;
-    load_rec(c0, r0, gm0);
-    load_rec(c1, r1, gm1);
-    __syncthreads();  // tiles staged
-    if (warp == nw - 1) fetch_desc(cur ^ 1);
-    if (c0.valid) issue_g(c0, r0, gm0, 0);
-    int stage = 0;
-    float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx, x0 = dx, x1 = dx, x2 = dx, sv = dx;
-    while (c0.valid) {
-      const Chunk c2 = advance(c1);
-      int2 r2;
-      float4 gm2;
-      load_rec(c2, r2, gm2);
-      if (c1.valid) { issue_g(c1, r1, gm1, stage ^ 1); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
-      __syncwarp();
-      const int tl = c0.tl;
-      if (c0.p == mem_rap[tl].x) {  // first chunk of the target
-        dx = make_float4(0.f, 0.f, 0.f, 0.f); d0 = dx; d1 = dx; d2 = dx;
-        if (on) { x0 = Xs[(tl * 3 + 0) * Q + q]; x1 = Xs[(tl * 3 + 1) * Q + q]; x2 = Xs[(tl * 3 + 2) * Q + q]; }
-        if (on && e4 == 0) sv = ld4(s + (size_t)mem_node[tl] * H + h0 + 4 * q);  // consumed when the target's last chunk is done
-      }
-      const float4* gb = wb + (size_t)stage * STG;
-      if (on) {
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int j = e4 + 4 * jj;
-          if (j < c0.n) {
-            const float4 gm = gb[EF_CE * 3 * Q + j];
-            const int al = reinterpret_cast<const int*>(gb + EF_CE * 3 * Q + EF_CE)[j];
-            const float4 g0 = gb[(j * 3 + 0) * Q + q], g1 = gb[(j * 3 + 1) * Q + q], g2 = gb[(j * 3 + 2) * Q + q];
-            const float ux = -gm.x, uy = -gm.y, uz = -gm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
-            const float4 a0 = Xs[(al * 3 + 0) * Q + q], a1 = Xs[(al * 3 + 1) * Q + q], a2 = Xs[(al * 3 + 2) * Q + q];
-            const float4 v0 = Vs[(al * 3 + 0) * Q + q], v1 = Vs[(al * 3 + 1) * Q + q], v2 = Vs[(al * 3 + 2) * Q + q];
-#define OARD_EQF(c)                                                                          \
-            {                                                                                \
-              const float al_ = (a0.c + x0.c) * g0.c;                                        \
-              const float be = (a1.c + x1.c) * g1.c * inv_sqrt_3;                            \
-              const float ga = (a2.c + x2.c) * g2.c;                                         \
-              const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
-              dx.c += al_;                                                                   \
-              d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
-            }
-            OARD_EQF(x) OARD_EQF(y) OARD_EQF(z) OARD_EQF(w)
-#undef OARD_EQF
-          }
-        }
-      }
-      if (c0.p + EF_CE >= c0.pend) {  // last chunk of the target: fixed-order combination of the four edge slots, write
+    __syncthreads();
+    if (slot < NSLOT) {
+      for (int tl = slot; tl < gs; tl += NSLOT) {
+        const int2 rap = mem_rap[tl];
         const int t = mem_node[tl];
-#define OARD_RED4(v)                                                                                    \
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, 1); v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);       \
-        v.z += __shfl_xor_sync(0xffffffffu, v.z, 1); v.w += __shfl_xor_sync(0xffffffffu, v.w, 1);       \
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, 2); v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);       \
-        v.z += __shfl_xor_sync(0xffffffffu, v.z, 2); v.w += __shfl_xor_sync(0xffffffffu, v.w, 2);
-        OARD_RED4(dx) OARD_RED4(d0) OARD_RED4(d1) OARD_RED4(d2)
-#undef OARD_RED4
-        if (on && e4 == 0) {
-          const size_t o = (size_t)t * 3 * H + h0 + 4 * q;
-          float* sp = s + (size_t)t * H + h0 + 4 * q;
-          sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
-          *reinterpret_cast<float4*>(sp) = sv;
-          const float4 w0 = Vs[(tl * 3 + 0) * Q + q], w1 = Vs[(tl * 3 + 1) * Q + q], w2 = Vs[(tl * 3 + 2) * Q + q];
-          *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
-          *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
-          *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
+        const float4 x0 = Xs[(tl * 3 + 0) * Q + q], x1 = Xs[(tl * 3 + 1) * Q + q], x2 = Xs[(tl * 3 + 2) * Q + q];
+        float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
+        const float* gp = G + (size_t)rap.x * H3 + h0 + 4 * q;
+        float4 g0, g1, g2, gm;
+        int al = 0;
+        if (rap.x < rap.y) {
+          g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+          al = act_rec[rap.x].y; gm = act_geo[rap.x];
         }
+        for (int p = rap.x; p < rap.y; p++) {
+          const float4 c0 = g0, c1 = g1, c2 = g2, cm = gm;
+          const int ca = al;
+          if (p + 1 < rap.y) {  // next row in flight while this one is evaluated
+            gp += H3;
+            g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+            al = act_rec[p + 1].y; gm = act_geo[p + 1];
+          }
+          const float ux = -cm.x, uy = -cm.y, uz = -cm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
+          const float4 a0 = Xs[(ca * 3 + 0) * Q + q], a1 = Xs[(ca * 3 + 1) * Q + q], a2 = Xs[(ca * 3 + 2) * Q + q];
+          const float4 v0 = Vs[(ca * 3 + 0) * Q + q], v1 = Vs[(ca * 3 + 1) * Q + q], v2 = Vs[(ca * 3 + 2) * Q + q];
+#define OARD_EQT(c)                                                                          \
+          {                                                                                  \
+            const float al_ = (a0.c + x0.c) * c0.c;                                          \
+            const float be = (a1.c + x1.c) * c1.c * inv_sqrt_3;                              \
+            const float ga = (a2.c + x2.c) * c2.c;                                           \
+            const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
+            dx.c += al_;                                                                     \
+            d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+          }
+          OARD_EQT(x) OARD_EQT(y) OARD_EQT(z) OARD_EQT(w)
+#undef OARD_EQT
+        }
+        float* sp = s + (size_t)t * H + h0 + 4 * q;
+        float4 sv = *reinterpret_cast<const float4*>(sp);
+        sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
+        *reinterpret_cast<float4*>(sp) = sv;
+        const size_t o = (size_t)t * H3 + h0 + 4 * q;
+        const float4 w0 = Vs[(tl * 3 + 0) * Q + q], w1 = Vs[(tl * 3 + 1) * Q + q], w2 = Vs[(tl * 3 + 2) * Q + q];
+        *reinterpret_cast<float4*>(vec_out + o) = make_float4(w0.x + d0.x, w0.y + d0.y, w0.z + d0.z, w0.w + d0.w);
+        *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
+        *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
       }
-      __syncwarp();  // the stage is free for the chunk after next
-      c0 = c1; c1 = c2; r1 = r2; gm1 = gm2; stage ^= 1;
     }
-    __syncthreads();  // tiles dead, next descriptor published
+    __syncthreads();  // tiles dead before the next item stages
   }
 }
 
@@ -1058,7 +948,7 @@ struct EdgeInitIn { int e; float a0, a1, a2, b0, b1, b2, gx, gy, gz, cx, cy, cz,
 template <bool PAIR>
 __global__ void __launch_bounds__(256, 4) k_edge_init_act(
     int H, int R, int reflect, int ld, int cap, const int* __restrict__ n_act, const int* __restrict__ act_idx,
-    const int* __restrict__ esrc, const int* __restrict__ ecol, const float* __restrict__ pf,
+    const int* __restrict__ esrc, const int* __restrict__ ecol, const float4* __restrict__ ecross,
     const float4* __restrict__ geo, const float* __restrict__ rb, const float* __restrict__ NE1,
     const float* __restrict__ f_act, const float* __restrict__ rbf_act, const __grid_constant__ Lin3E W,
     float* __restrict__ ew) {
@@ -1078,10 +968,9 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
       const float4 g = geo[in.e];
       in.gx = g.x; in.gy = g.y; in.gz = g.z;
       in.rbe = rb[in.e];
-      // edge frame columns: u (unit diff), c (unit cross of pos_frame_i x pos_frame_j), v = u x c   (:693-705)
-      const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2];
-      const float bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
-      in.cx = ay * bz - az * by; in.cy = az * bx - ax * bz; in.cz = ax * by - ay * bx;
+      // edge frame columns: u (unit diff), c (unit cross of pos_frame_i x pos_frame_j, k_edge_geom), v = u x c   (:693-705)
+      const float4 cr = ecross[in.e];
+      in.cx = cr.x; in.cy = cr.y; in.cz = cr.z;
       const float* ni = NE1 + (size_t)i * 3 * H;
       const float* nj = NE1 + (size_t)j * 3 * H;
       in.a0 = ni[t]; in.a1 = ni[H + t]; in.a2 = ni[2 * H + t];
@@ -1099,8 +988,7 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
     if (t < H) row[2 * H + t] = cur.fv;
     if (t < R) row[3 * H + t] = cur.rv;
     if (t < H) {
-      const float cinv = 1.0f / (sqrtf(cur.cx * cur.cx + cur.cy * cur.cy + cur.cz * cur.cz) + OARD_EPS);
-      const float cx = cur.cx * cinv, cy = cur.cy * cinv, cz = cur.cz * cinv;
+      const float cx = cur.cx, cy = cur.cy, cz = cur.cz;
       const float vx = cur.gy * cz - cur.gz * cy, vy = cur.gz * cx - cur.gx * cz, vz = cur.gx * cy - cur.gy * cx;
       const float s0 = cur.a0 * cur.gx + cur.a1 * cur.gy + cur.a2 * cur.gz;
       float s1 = cur.a0 * cx + cur.a1 * cy + cur.a2 * cz;

@@ -585,11 +585,11 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   struct { const char* n; size_t b; } allocs[] = {
       {"row_ptr", (Nn + 1) * 4}, {"esrc", Ee * 4}, {"ecol", Ee * 4}, {"rev", Ee * 4}, {"comp_ptr", (size_t)(NC + 1) * 4},
       {"comp_nodes", Nn * 4}, {"node_local", Nn * 4},
-      {"mask", Ee}, {"att", Ee * 4}, {"geo", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_tr", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
+      {"mask", Ee}, {"att", Ee * 4}, {"geo", Ee * 16}, {"ecross", Ee * 16}, {"act_cross", Ee * 16}, {"rb", Ee * 4}, {"act_idx", Ee * 4}, {"act_pos", Ee * 4}, {"act_pos_t", Ee * 4}, {"act_col", Ee * 4}, {"act_geo", Ee * 16}, {"row_cnt", Nn * 4},
       {"row_act_ptr", (Nn + 1) * 4}, {"n_act", 16}, {"sub8", Ee}, {"leader", Nn * 4}, {"glocal", Nn * 4}, {"gsize", Nn * 4}, {"lead_list", Nn * 4}, {"lead_info", Nn * 8},
       {"gm_node", (Nn + Ee) * 4}, {"gm_rap", (Nn + Ee) * 8}, {"act_rec", Ee * 8},
       {"n_lead", 16}, {"work_ctr", 64 * 4}, {"owner", Nn * 4}, {"opener", Nn}, {"group", Nn * 4},
-      {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
+      {"rank_tmp", Nn * 4}, {"pf", Nn * 12}, {"pf64", Nn * 24}, {"nodeframe", Nn * 36}, {"pos_prjt", Nn * 12}, {"f0", H * 4}, {"c3", 16},
       {"z_emb", Nn * H * 4}, {"ne", Nn * H * 4}, {"s", Nn * H * 4}, {"tmpH", Nn * H * 4}, {"q", Nn * H * 4},
       {"NE1", Nn * 3 * H * 4}, {"pe_t", Nn * (H / 2) * 4}, {"pe", Nn * H * 4}, {"xa", Nn * 2 * H * 4},
       {"PQ", Nn * 2 * H * 4}, {"tN", Nn * H * 4}, {"X", Nn * 3 * H * 4}, {"vecA", Nn * 3 * H * 4},
@@ -614,7 +614,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
   CU(cudaMemcpy(h->buf<int>("node_local"), node_local.data(), Nn * 4, cudaMemcpyHostToDevice));
   h->N = N; h->E = E; h->NC = NC;
   h->max_comp = count.empty() ? 1 : *std::max_element(count.begin(), count.end());
-  // The group-staged message kernel (k_equi_frag) takes "same fragment" for an equivalence relation whose classes are
+  // The group-staged message kernel (k_equi_tgt) takes "same fragment" for an equivalence relation whose classes are
   // cliques: true for any fragment-derived subgraph_mask on complete per-sample graphs (the samplers' graphs), not for the
   // hand-written sparse graphs of the reference's model tests (tests/model/test_equiv.py:30-32) — those take the
   // node-per-block kernel (k_equi_reduce), which assumes nothing.  (gm_node / gm_rap are sized N + E, the bound of the
@@ -819,7 +819,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     k_edge_mask<<<(E + 255) / 256, 256, 0, st>>>(E, esrc, ecol, pos, sub, c.cutoff, mask, h->buf<uint8_t>("sub8")); KCHECK(); }
   PB("k_group_frame", 0, N*64.0, 0);
   k_group_frame<256><<<h->NC, 128, 0, st>>>(h->buf<int>("comp_ptr"), h->buf<int>("comp_nodes"),
-                                            h->buf<int>("node_local"), row_ptr, ecol, mask, pos, pf, nodeframe, pos_prjt,
+                                            h->buf<int>("node_local"), row_ptr, ecol, mask, pos, pf, h->buf<double>("pf64"), nodeframe, pos_prjt,
                                             h->buf<int>("owner"), h->buf<uint8_t>("opener"));
   KCHECK();
   if (h->debug) {
@@ -829,7 +829,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     KCHECK();
   }
   PB("k_edge_geom", 0, E*25.0, 0);
-  k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, h->buf<uint8_t>("sub8"), pf, c.cutoff, geo, rb,
+  k_edge_geom<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, ecol, mask, h->buf<uint8_t>("sub8"), h->buf<double>("pf64"), c.cutoff, geo, h->buf<float4>("ecross"), rb,
                                                     h->buf<int>("row_cnt"), h->buf<int>("leader"), h->buf<int>("glocal"), h->buf<int>("gsize"));
   KCHECK();
   PB("k_scan_rows", 0, N*8.0, 0);
@@ -838,13 +838,13 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
                                   h->buf<int>("work_ctr"), 64);
   KCHECK();
   PB("k_compact", 0, E*9.0, 0);
-  k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos);
+  k_compact<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, row_ptr, mask, h->buf<int>("row_act_ptr"), act_idx, act_pos, h->buf<int>("act_pos_t"));
   KCHECK();
   if (E) {
     PB("k_act_lists", 0, E*40.0, 1);
-    k_act_lists<<<(E + 255) / 256, 256, 0, st>>>(n_act, E, act_idx, act_pos, rev, ecol, geo, h->buf<int>("glocal"),
-                                                 h->buf<int>("act_tr"), h->buf<int>("act_col"), h->buf<float4>("act_geo"),
-                                                 h->buf<int2>("act_rec"));
+    k_act_lists<<<(E + 255) / 256, 256, 0, st>>>(n_act, E, act_idx, act_pos, rev, ecol, geo, h->buf<float4>("ecross"),
+                                                 h->buf<int>("glocal"), h->buf<int>("act_pos_t"), h->buf<int>("act_col"),
+                                                 h->buf<float4>("act_geo"), h->buf<float4>("act_cross"), h->buf<int2>("act_rec"));
     KCHECK();
     PB("k_group_members", 0, N*24.0, 0);
     k_group_members<<<(N * 32 + 255) / 256, 256, 0, st>>>(h->buf<int>("n_lead"), h->buf<int>("lead_list"), h->buf<int2>("lead_info"),
@@ -899,10 +899,10 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     const int ei_grid = std::min(E, h->num_sms * 4);  // = resident blocks (launch bounds 256 x 4)
     if (P)
       k_edge_init_act<true><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                 pf, geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
+                                                                 h->buf<float4>("ecross"), geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
     else
       k_edge_init_act<false><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                  pf, geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
+                                                                  h->buf<float4>("ecross"), geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
     h->launches += 2;
     KCHECK();
   }
@@ -1010,7 +1010,9 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
       g.prescale = h->buf<float>("att");  // attention gate of the edge (k_att_agg): W (att m) = att (W m)
-      g.C2 = ew_act; g.c2idx = act_pos; g.ldc2 = ldD;  // compact copy of the active rows: contiguous operand for dir_proj
+      // compact copy of the active rows in TARGET order (row of e = compact position of its transposed edge): contiguous
+      // operand for dir_proj, and the G rows of the messages arriving at one target form one contiguous block
+      g.C2 = ew_act; g.c2idx = h->buf<int>("act_pos_t"); g.ldc2 = ldD;
       if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
       h->num_sms = sm_guard.keep;
     }
@@ -1051,33 +1053,35 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       CU(cudaEventRecord(h->fork_ev[2 * l + 1], h->side_stream));
       CU(cudaStreamWaitEvent(st, h->fork_ev[2 * l + 1], 0));
     }
-    PB("k_equi_reduce", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
+    PB("k_equi_msg", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
     {
-      // group-staged kernel (k_equi_frag): channel slice CH = largest multiple of 4 that divides H and is <= 32
+      // group-staged kernel (k_equi_tgt): channel slice CH = largest multiple of 4 that divides H and is <= 32
       int CH = 0;
       for (int cch = 32; cch >= 4; cch -= 4)
         if (H % cch == 0) { CH = cch; break; }
-      const size_t ef_smem = CH == 28 ? ef_smem_bytes<28>(h->max_comp) : (CH == 32 ? ef_smem_bytes<32>(h->max_comp) : ef_smem_bytes<16>(h->max_comp));
+      const size_t et_smem = CH == 28 ? et_smem_bytes<28>(h->max_comp) : (CH == 32 ? et_smem_bytes<32>(h->max_comp) : et_smem_bytes<16>(h->max_comp));
       static int env_frag = -1;
       if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
-      const bool frag_ok = env_frag && h->complete && c.reflect_equiv && l < 64 && ef_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
+      const bool frag_ok = env_frag && h->complete && c.reflect_equiv && l < 64 && et_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
       if (frag_ok && E) {
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (ef_smem + 1024)));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (220 * 1024) / (et_smem + 1024)));
         const int grid = h->num_sms * per_sm;
-#define OARD_EF(CHV)                                                                                                   \
+#define OARD_ET(CHV)                                                                                                   \
         {                                                                                                              \
+        if (et_smem > 48 * 1024) {                                                                                     \
           static PerDeviceOnce attr;                                                                                   \
-          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_frag<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-          k_equi_frag<CHV><<<grid, 256, ef_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
-              h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),     \
-              h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                          \
+          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_tgt<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        }                                                                                                              \
+        k_equi_tgt<CHV><<<grid, ET_THREADS, et_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
+            h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),       \
+            h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                            \
         }
-        if (CH == 28) OARD_EF(28) else if (CH == 32) OARD_EF(32) else OARD_EF(16)
-#undef OARD_EF
+        if (CH == 28) OARD_ET(28) else if (CH == 32) OARD_ET(32) else OARD_ET(16)
+#undef OARD_ET
       } else {
         k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(
-            H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_tr"), h->buf<int>("act_col"),
-            h->buf<float4>("act_geo"), G, X, pf, vec, vec2, s);
+            H, c.reflect_equiv, h->buf<int>("row_act_ptr"), h->buf<int>("act_col"),
+            h->buf<float4>("act_geo"), h->buf<float4>("act_cross"), G, X, vec, vec2, s);
       }
     }
     KCHECK();
@@ -1206,17 +1210,14 @@ static void train_adapter(oard_handle* h, float* frame, float* rbf_dense, float*
   const int *esrc = h->buf<int>("esrc"), *ecol = h->buf<int>("ecol"), *row_ptr = h->buf<int>("row_ptr"), *act_pos = h->buf<int>("act_pos");
   const uint8_t* mask = h->buf<uint8_t>("mask");
   const float4* geo = h->buf<float4>("geo");
-  const float *pf = h->buf<float>("pf"), *rbf_act = h->buf<float>("rbf_act");
+  const float* rbf_act = h->buf<float>("rbf_act");
+  const float4* ecross = h->buf<float4>("ecross");
   oard_train::par_for(st, (size_t)E, [=] __host__ __device__(size_t e) {
     float* f = frame + e * 9;
     for (int k = 0; k < 9; k++) f[k] = 0.f;
     if (mask[e]) {
-      const int i = esrc[e], j = ecol[e];
-      const float4 g = geo[e];
-      const float ax = pf[i * 3], ay = pf[i * 3 + 1], az = pf[i * 3 + 2], bx = pf[j * 3], by = pf[j * 3 + 1], bz = pf[j * 3 + 2];
-      float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-      const float cinv = 1.0f / (sqrtf(cx * cx + cy * cy + cz * cz) + OARD_EPS);
-      cx *= cinv; cy *= cinv; cz *= cinv;
+      const float4 g = geo[e], cr = ecross[e];
+      const float cx = cr.x, cy = cr.y, cz = cr.z;
       f[0] = g.x; f[1] = g.y; f[2] = g.z;
       f[3] = cx; f[4] = cy; f[5] = cz;
       f[6] = g.y * cz - g.z * cy; f[7] = g.z * cx - g.x * cz; f[8] = g.x * cy - g.y * cx;

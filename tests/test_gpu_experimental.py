@@ -1,10 +1,6 @@
-"""Opt-in GPU checks of code paths that are written but have NOT run on hardware yet (round 1's GPU budget was spent
-before they existed): set OARD_TEST_EXPERIMENTAL=1.  They are off by default both here and in the library.
-
-* OARD_FORK=<k>: per layer the node-level chain runs on a side stream next to the edge-level chain, whose persistent
-  GEMMs leave k SMs free (csrc/oard.cu, layer loop).  Same kernels, same per-kernel summation order, only the overlap
-  changes, so the outputs must be BITWISE identical to the single-stream forward — eager, graph-replayed, and through the
-  device-resident reverse step."""
+"""GPU checks of the less-travelled paths: `reflect_equiv=False`, sparse / shuffled / split graphs over the option grid on which
+the oracle is pinned to the unmodified reference, the device-resident path on ragged fragments with an empty one, and
+parity on real Transition1x geometries."""
 import os
 
 import numpy as np
@@ -14,43 +10,7 @@ import torch
 from oracle import oa_ref
 from tests.test_gpu_parity import DEV, _oracle_inputs, make_dynamics
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OARD_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental paths not yet run on hardware; set OARD_TEST_EXPERIMENTAL=1")]
-
-
-def _run(cfg, sizes, seed, env, n_calls=4):
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        nodes, h0, cond, masks, cm, ei, nfs, xh, t = _oracle_inputs(cfg, sizes, seed=seed)
-        sd = oa_ref.make_state_dict(oa_ref.dynamics_param_shapes(cfg, [9, 9, 9], 1), seed, cfg, prefix_model="model.")
-        dyn = make_dynamics(cfg, sd)  # the engine (and its OARD_* switches) is created at the first forward
-        outs = []
-        for _ in range(n_calls):  # call 1 is eager, later calls replay the captured graph
-            out, _ = dyn([x.to(DEV) for x in xh], ei.to(DEV), t.to(DEV), cond.to(DEV), nfs.to(DEV), cm.to(DEV))
-            outs.append(torch.cat([o.cpu() for o in out]))
-        torch.cuda.synchronize()
-        return outs
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-
-
-@pytest.mark.parametrize("sizes,seed", [([6, 13, 9], 5), ([23] * 16 + [4] * 8, 6)])
-@pytest.mark.parametrize("k", ["24", "48"])
-def test_fork_is_bitwise_identical(sizes, seed, k):
-    cfg = dict(oa_ref.TRAINED_CFG)
-    base = _run(cfg, sizes, seed, {"OARD_FORK": "0"})
-    fork = _run(cfg, sizes, seed, {"OARD_FORK": k})
-    for a in base[1:]:
-        assert torch.equal(a, base[0])
-    for b in fork:
-        assert torch.equal(b, base[0]), float((b - base[0]).abs().max())
-    assert np.isfinite(base[0].numpy()).all()
+pytestmark = pytest.mark.gpu
 
 
 def test_leftnet_reflect_equiv_false_vs_reference_golden():
@@ -84,10 +44,12 @@ def _grid_graphs():
 @pytest.mark.parametrize("gname", ["complete9", "path", "two_components", "complete8_shuffled", "two_cliques"])
 def test_leftnet_option_grid_vs_oracle(gname):
     """The grid on which oracle/fuzz_oracle_leftnet.py pins the oracle to the unmodified reference (graph shapes, masks,
-    cut-offs that split groups, reflect_equiv, object_aware, update, depth), now CUDA vs that oracle (fp64), REL_TOL = 1e-3."""
+    cut-offs that split groups, reflect_equiv, object_aware, update, depth), now CUDA vs that oracle (fp64), REL_TOL = 2e-4.
+    Graphs with almost no active edge have a position update of ~1e-7 of the positions: dpos is measured against
+    max(max|dpos_ref|, 1e-3 max|pos|), like the reference's own tests, which compare pos + dpos."""
     import itertools
     from tests.test_gpu_parity import REL_TOL, make_leftnet
-    from tests.util import rel_err
+    from tests.util import rel_err, rel_err_floor
     n, ei = _grid_graphs()[gname]
     g = torch.Generator().manual_seed(1)
     worst = 0.0
@@ -107,7 +69,7 @@ def test_leftnet_option_grid_vs_oracle(gname):
         ho_ref, dpos_ref = oa_ref.leftnet_forward(sd, cfg, h, pos, ei, sub)
         m = make_leftnet(cfg, {k: v.float() for k, v in sd.items()})
         ho, po, _ = m(h.float().to(DEV), pos.float().to(DEV), ei.to(DEV), subgraph_mask=None if sub is None else sub.to(DEV))
-        e = max(rel_err(ho.cpu(), ho_ref), rel_err((po.cpu() - pos.float()), dpos_ref))
+        e = max(rel_err(ho.cpu(), ho_ref), rel_err_floor(po.cpu() - pos.float(), dpos_ref, 1e-3 * float(pos.abs().max())))
         worst = max(worst, e)
         assert e < REL_TOL, (gname, reflect, oa, update, layers, cut, cutoff, scale, e)
     print(f"{gname}: worst rel err over the grid {worst:.2e}")

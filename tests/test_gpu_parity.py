@@ -3,7 +3,8 @@ fp64 oracle on identical inputs, against golden vectors of the unmodified refere
 properties at the full BASELINE size.
 
 Tolerances (stated): integer artefacts (mask, group ids, active list) bit-exact; floats
-max|x - ref64| / max|ref64| <= REL_TOL, where the reference's own fp32-vs-fp64 gap is ~2e-4 on this model.
+max|x - ref64| / max|ref64| <= REL_TOL = 2e-4 for one forward and its stages (measured on the B200: 1e-7 ... 4e-5; the
+reference's own fp32-vs-fp64 gap is 2e-4 ... 6e-3 on this model), TRAJ_TOL = 1e-3 for the 11-evaluation trajectories.
 """
 import numpy as np
 import pytest
@@ -14,7 +15,8 @@ from oracle import oa_ref
 from tests.util import dyn_state_dict, leftnet_state_dict, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
-REL_TOL = 1e-3
+REL_TOL = 2e-4
+TRAJ_TOL = 1e-3
 DEV = torch.device("cuda:0")
 
 
@@ -172,7 +174,7 @@ def test_sample_trajectory_vs_reference_golden(name):
     for f in range(3):
         e = rel_err(out[0][f][:, :3].cpu(), g[f"out{f}"][:, :3])
         print(f"{name} frag{f}: trajectory rel err {e:.2e}")
-        assert e < 5e-3  # 11 chained evaluations amplify the per-forward 1e-4 gap
+        assert e < TRAJ_TOL  # 11 chained evaluations amplify the per-forward gap
         assert np.array_equal(out[0][f][:, 3:].cpu().numpy(), g[f"out{f}"][:, 3:])
 
 
@@ -189,7 +191,7 @@ def test_inpaint_trajectory_vs_reference_golden():
     for f in range(3):
         e = rel_err(out[0][f][:, :3].cpu(), g[f"out{f}"][:, :3])
         print(f"inpaint frag{f}: {e:.2e}")
-        assert e < 5e-3
+        assert e < TRAJ_TOL
 
 
 def _rot(seed):
@@ -227,19 +229,59 @@ def test_full_size_properties_b64():
         assert (rot[f][:, :3] - base[f][:, :3]).abs().max() < 2e-3 * scale
     for f in range(3):
         assert (rot[f][:, 3:] - base[f][:, 3:]).abs().max() < 2e-3 * max(1.0, float(base[f][:, 3:].abs().max()))
-    # sub-batch agreement with the fp64 oracle: first 3 reactions evaluated alone by the oracle
-    k = 3
-    sub_nodes = [n[:k] for n in nodes]
-    sub_masks = [oa_ref.get_mask_for_frag(n) for n in sub_nodes]
-    sub_cm = torch.cat(sub_masks)
-    sub_xh = [x[: int(n[:k].sum())] for x, n in zip(xh, nodes)]
-    ref = oa_ref.dynamics_forward({kk: v.double() for kk, v in sd.items()}, cfg, [x.double() for x in sub_xh],
-                                  oa_ref.get_edges_index(sub_cm, remove_self_edge=True), t[:k].double(),
-                                  cond[:k].double(), oa_ref.get_n_frag_switch(sub_nodes), sub_cm)
-    for f in range(3):
-        e = rel_err(base[f][: sub_xh[f].size(0)].cpu(), ref[f])
-        print(f"B=64 sub-batch frag{f}: {e:.2e}")
-        assert e < REL_TOL
+    # the WHOLE batch against the fp64 oracle: reactions are independent, so the oracle evaluates it in chunks of 8
+    worst = 0.0
+    node_off = [torch.cat([torch.zeros(1, dtype=torch.long), n.cumsum(0)]) for n in nodes]
+    sd64 = {kk: v.double() for kk, v in sd.items()}
+    for k0 in range(0, B, 8):
+        k1 = min(B, k0 + 8)
+        sub_nodes = [n[k0:k1] for n in nodes]
+        sub_masks = [oa_ref.get_mask_for_frag(n) for n in sub_nodes]
+        sub_cm = torch.cat(sub_masks)
+        sub_xh = [x[int(o[k0]):int(o[k1])] for x, o in zip(xh, node_off)]
+        ref = oa_ref.dynamics_forward(sd64, cfg, [x.double() for x in sub_xh], oa_ref.get_edges_index(sub_cm, remove_self_edge=True),
+                                      t[k0:k1].double(), cond[k0:k1].double(), oa_ref.get_n_frag_switch(sub_nodes), sub_cm)
+        for f in range(3):
+            worst = max(worst, rel_err(base[f][int(node_off[f][k0]):int(node_off[f][k1])].cpu(), ref[f]))
+    print(f"B=64 whole batch vs fp64 oracle: {worst:.2e}")
+    assert worst < REL_TOL
+
+
+def test_cutoff_boundary_mask_is_bit_exact():
+    """The edge mask is an integer contract (leftnet.py:747-753): `dist_raw < cutoff` with the reference's fp32 rounding
+    sequence.  Pairs of atoms are placed so that the computed fp32 distance lands within a few ulp of the cutoff (both
+    sides, and exactly on it); the CUDA mask and the greedy group labels that follow from it must equal the oracle's
+    evaluated in fp32."""
+    cutoff = 2.5
+    cfg = dict(cutoff=cutoff, num_layers=1, hidden_channels=32, num_radial=16, in_hidden_channels=6, reflect_equiv=True,
+               legacy=True, update=True, object_aware=True)
+    g = torch.Generator().manual_seed(11)
+    n = 96
+    pos = torch.zeros(n, 3)
+    pos[0::2] = torch.rand(n // 2, 3, generator=g) * 40.0  # pairs far from each other: only the partner is near the cutoff
+    u = torch.randn(n // 2, 3, generator=g)
+    u = u / u.norm(dim=1, keepdim=True)
+    u[:8] = torch.eye(3).repeat(3, 1)[:8]  # axis-aligned pairs: the distance is computed exactly
+    k = torch.randint(-4, 5, (n // 2, 1), generator=g).float()
+    d = torch.tensor(cutoff) * (1.0 + k * 2.0 ** -23)
+    d[:8] = torch.tensor([cutoff, float(np.nextafter(np.float32(cutoff), np.float32(0))),
+                          float(np.nextafter(np.float32(cutoff), np.float32(9))), cutoff, cutoff, cutoff, cutoff, cutoff])[:, None]
+    pos[1::2] = pos[0::2] + u * d
+    ei = torch.tensor([[i, j] for i in range(n) for j in range(n) if i != j]).T.contiguous()
+    h = torch.rand(n, 6, generator=g)
+    dist = (pos[ei[0]] - pos[ei[1]]).pow(2).sum(dim=-1).sqrt()  # the reference's expression (leftnet.py:747), fp32 on the CPU
+    ref_mask = (dist < cutoff)
+    near = (dist - cutoff).abs() < 4e-6
+    assert int(near.sum()) >= n // 2 and 0 < int((ref_mask & near).sum()) < int(near.sum())  # both sides are populated
+    sd = oa_ref.make_state_dict(oa_ref.leftnet_param_shapes(cfg), 3, cfg)
+    m = make_leftnet(cfg, sd)
+    eng = m.engine(DEV)
+    eng.set_debug(True)
+    m(h.to(DEV), pos.to(DEV), ei.to(DEV), subgraph_mask=None)
+    assert torch.equal(eng.read("mask", torch.uint8).bool(), ref_mask)
+    group = oa_ref.assemble_nodemask(ei[:, ref_mask], n)
+    assert np.array_equal(eng.read("group", torch.int32).numpy().astype(np.int64), group.numpy())
+    eng.set_debug(False)
 
 
 def test_c_abi_error_codes():

@@ -6,9 +6,8 @@ kernels compute in fp32, so "equal" is max|a - b| <= TOL * max(1, max|b|) with T
 tolerance) and "different" keeps the reference's thresholds.  Inputs are float64 like the reference's (the module returns
 the caller's dtype).
 
-Opt-in (OARD_TEST_EXPERIMENTAL=1) until its first hardware run: written after round 1's GPU budget was spent.  It drives
-code that had no GPU coverage before: sparse / non-complete graphs (node-per-block message kernel), edge lists in arbitrary
-order, `reflect_equiv=False`, float64 callers."""
+It drives sparse / non-complete graphs (node-per-block message kernel), edge lists in arbitrary order,
+`reflect_equiv=False` and float64 callers."""
 import os
 
 import numpy as np
@@ -18,9 +17,7 @@ from torch import nn
 
 import oareactdiff_b200 as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OARD_TEST_EXPERIMENTAL") != "1",
-                                 reason="restated reference suite not yet run on hardware; set OARD_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 TOL = 2e-3
 F64 = torch.float64

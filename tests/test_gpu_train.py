@@ -2,11 +2,10 @@
 `oard_forward_train` / `oard_backward` against golden gradients of the UNMODIFIED reference's autograd
 (oracle/gen_golden.py::case_train_grad, fp64; inputs and random draws replayed).
 
-STATUS: the kernels behind these entry points are the same source as the host-emulation build that
-tests/test_train_emu.py validates on the CPU (forward 2e-7, every parameter gradient < 1e-5 of the fp64 oracle), but
-they have not run on hardware yet: round 1's GPU budget was exhausted before they were written.  The tests are therefore
-opt-in (OARD_TRAIN_GPU=1) until a GPU run has confirmed them.  Tolerance: 2e-3 of max|grad| per parameter (the
-reference's own fp32 autograd is up to 7e-2 away from its fp64 run on these fixtures)."""
+The kernels behind these entry points are the same source as the host-emulation build that tests/test_train_emu.py
+validates on the CPU (forward 2e-7, every parameter gradient < 1e-5 of the fp64 oracle).  Measured on the B200: worst
+parameter-gradient error 9.3e-6 / 1.1e-6 of max|grad| on the two small fixtures.  Tolerance: 2e-4 of max|grad| per parameter
+(the reference's own fp32 autograd is up to 7e-2 away from its fp64 run on these fixtures)."""
 import json
 import os
 
@@ -19,9 +18,7 @@ from tests.test_gpu_loss import _ReplayDraws
 from tests.test_gpu_parity import DEV, make_dynamics
 from tests.util import dyn_state_dict, load_golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OARD_TRAIN_GPU") != "1",
-                                 reason="training kernels validated in host emulation only; set OARD_TRAIN_GPU=1 to run on the device")]
+pytestmark = pytest.mark.gpu
 
 
 def _setup(name):
@@ -64,7 +61,7 @@ def test_training_step_gradients_small_config(name):
         n += 1
         worst = max(worst, float((prm.grad.cpu().double() - ref).abs().max()) / scale)
     print(f"{name}: loss {loss:.6f}, worst parameter-gradient error {worst:.2e} over {n} parameters")
-    assert worst < 2e-3 and n > 80
+    assert worst < 2e-4 and n > 80
 
 
 def test_training_step_gradient_checksums_trained_config():
@@ -81,7 +78,7 @@ def test_training_step_gradient_checksums_trained_config():
         gr = prm.grad.cpu().double()
         worst = max(worst, abs(float(gr.norm()) - gn) / gn, abs(float((gr * direction).sum()) - gp) / gn)
     print(f"grad_trained_train_b3: worst |norm| / projection deviation {worst:.2e}")
-    assert worst < 5e-3
+    assert worst < 2e-4  # measured 3.0e-6 on the B200
 
 
 def test_one_sgd_step_reduces_the_loss():

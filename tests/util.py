@@ -26,7 +26,14 @@ def leftnet_state_dict(g, dtype=torch.float32):
     return oa_ref.make_state_dict(oa_ref.leftnet_param_shapes(g["cfg"]), int(g["seed"]), g["cfg"], dtype=dtype)
 
 
+def rel_err_floor(a, b, floor):
+    """max|a-b| / max(max|b|, floor): for outputs that can legitimately be ~0 (a position update of a graph with almost no
+    active edge is 1e-7 of the positions; its relative error against itself is rounding noise over nothing)."""
+    a, b = torch.as_tensor(a, dtype=torch.float64).detach(), torch.as_tensor(b, dtype=torch.float64).detach()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=floor))
+
+
 def rel_err(a, b):
     """max|a-b| / max|b| — the parity figure SURVEY §8d asks for."""
-    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    a, b = torch.as_tensor(a, dtype=torch.float64).detach(), torch.as_tensor(b, dtype=torch.float64).detach()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
