@@ -278,7 +278,7 @@ def train_leg(args, ob, workloads, dev, cfg, T):
     out = {"workload": f"batch={Bt} noised Transition1x reaction triples (real R/TS/P geometries), l2 objective, forward + backward "
                        f"through encoders / LEFTNet / decoders (exact-fp32 SIMT training kernels, csrc/train_core.h)",
            "ms_per_step": times[len(times) // 2], "ms_min": times[0], "ms_max": times[-1], "steps": len(times),
-           "reactions_per_s": Bt / (times[len(times) // 2] * 1e-3), "loss": float(loss),
+           "reactions_per_s": Bt / (times[len(times) // 2] * 1e-3), "loss": float(loss.detach()),
            "grads_finite": all(bool(torch.isfinite(p_.grad).all()) for p_ in dyn.parameters() if p_.grad is not None)}
     # ---- parity + CPU baseline on a sub-batch
     k = args.train_check
@@ -288,7 +288,7 @@ def train_leg(args, ob, workloads, dev, cfg, T):
         xr = [x[:n_sub] for x in x_ref]
         hh = [h[:n_sub] for h in h0]
         t_sub, noise_sub, mask_sub = draws(sub_sizes)
-        loss_gpu = float(step(sub_sizes, xr, hh, t_sub, noise_sub))
+        loss_gpu = float(step(sub_sizes, xr, hh, t_sub, noise_sub).detach())
         grads = {n_: p_.grad.detach().cpu().double() for n_, p_ in dyn.named_parameters() if p_.grad is not None}
         sd = {n_: p_.detach().cpu() for n_, p_ in dyn.state_dict().items()}
         gamma = sched.gamma_module.gamma.detach().cpu()
@@ -296,13 +296,13 @@ def train_leg(args, ob, workloads, dev, cfg, T):
               for x, h in zip(xr, hh)]
         res = {}
         for dt_, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
-            sd_ = {n_: v.to(dt_).requires_grad_(v.is_floating_point()) if v.is_floating_point() else v for n_, v in sd.items()}
+            sd_ = {n_: v.detach().to(dt_).clone().requires_grad_(True) if v.is_floating_point() else v for n_, v in sd.items()}
             tune_cpu_threads()
             t0 = time.perf_counter()
             l_ = oa_ref.train_loss_l2(sd_, cfg, gamma.to(dt_), [x.to(dt_) for x in xh], [mask_sub] * 3, torch.tensor(sub_sizes),
                                       torch.zeros(k, 1), t_sub.view(-1), [n_.to(dt_) for n_ in noise_sub])
             l_.backward()
-            res[tag] = (float(l_), {n_: v.grad.double() for n_, v in sd_.items() if getattr(v, "grad", None) is not None},
+            res[tag] = (float(l_.detach()), {n_: v.grad.double() for n_, v in sd_.items() if getattr(v, "grad", None) is not None},
                         time.perf_counter() - t0)
         l64, g64, _ = res["f64"]
         worst, worst32, n_cmp = 0.0, 0.0, 0

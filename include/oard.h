@@ -112,6 +112,20 @@ int oard_dyn_forward(oard_handle* h, const float* xh, const float* t, const floa
 int oard_reverse_step(oard_handle* h, float* z, const float* noise_pos, const float* noise_feat, const float* h0,
                       const float* conditions, const int64_t* subgraph_mask, float t, float alpha_ts, float coef,
                       float sigma, void* stream);
+/* One RePaint step (en_diffusion.py:788-853, the body of inpaint()'s inner loop) IN PLACE on z: oard_reverse_step for the
+ * fragments being generated, and for the clamped fragments f (bit f of known_frag_bits) a fresh draw from
+ *   q(z_s | x_fixed) = alpha_s x_fixed + sigma_s eps'      (noised_representation, :260-279)
+ * with eps' = noise_known_pos[N, 3] (projected on the zero-CoM subspace per (fragment, sample)) / noise_known_feat (NULL:
+ * zero); then the h0 overwrite.  x_fixed[N, node_nf] holds the clamped fragments' data (other rows are ignored).  The whole
+ * call is ONE CUDA-graph launch keyed by the pointers and known_frag_bits. */
+int oard_inpaint_step(oard_handle* h, float* z, const float* noise_pos, const float* noise_feat, const float* h0,
+                      const float* conditions, const int64_t* subgraph_mask, float t, float alpha_ts, float coef,
+                      float sigma, const float* x_fixed, int known_frag_bits, const float* noise_known_pos,
+                      const float* noise_known_feat, float alpha_s, float sigma_s, void* stream);
+/* The RePaint jump-back z_s -> z_t (en_diffusion.py:1050-1074, sample_p_zt_given_zs) IN PLACE on z:
+ *   z = alpha_ts z + sigma_ts eps, eps positions CoM-free per (fragment, sample), then the CoM of the new positions removed. */
+int oard_jump_back(oard_handle* h, float* z, const float* noise_pos, const float* noise_feat, float alpha_ts,
+                   float sigma_ts, void* stream);
 
 /* ---- Training: differentiable forward + backward (BASELINE config 5) ----
  *   oa_reactdiff/model/leftnet.py:724-891 under torch autograd  -> oard_forward_train + oard_backward

@@ -19,10 +19,13 @@ struct DynCodec {  // encoders[f] / decoders[f]: MLP(d -> 2d -> out), SiLU betwe
   const float *dw0[DYN_MAX_FRAG], *db0[DYN_MAX_FRAG], *dw1[DYN_MAX_FRAG], *db1[DYN_MAX_FRAG];
 };
 
-// step_params[0..3] = t, alpha_ts, coef, sigma ; [4] = nan-guard draw counter (as int bits)
-__global__ void k_set_params(float* __restrict__ prm, float t, float alpha_ts, float coef, float sigma, int counter) {
+// step_params[0..3] = t, alpha_ts, coef, sigma ; [4] = nan-guard draw counter (as int bits) ; [5..6] = alpha_s, sigma_s of the
+// RePaint blend (q(z_s | x) of the clamped fragments)
+__global__ void k_set_params(float* __restrict__ prm, float t, float alpha_ts, float coef, float sigma, int counter,
+                             float alpha_s, float sigma_s) {
   prm[0] = t; prm[1] = alpha_ts; prm[2] = coef; prm[3] = sigma;
   reinterpret_cast<int*>(prm)[4] = counter;
+  prm[5] = alpha_s; prm[6] = sigma_s;
 }
 
 // Prologue (egnn_dynamics.py:91-119): pos = xh[:, :3]; h = [encoder_f(xh[:, 3:]) | t | condition[sample]].
@@ -87,16 +90,35 @@ __device__ __forceinline__ float dyn_gauss(uint32_t counter, uint32_t idx) {
 //   zero-CoM subspace per segment (_utils.py:9-12, en_diffusion.py:281-304, 627-631); noise_h == NULL: feature noise is
 //   zero (pos_only); h0 != NULL: the features are overwritten by h0 (en_diffusion.py:524-527).  Same fp32 operation order as the host formulas
 //   (division kept, no contraction).  One warp per segment.
+// MODE 2: MODE 1 + the RePaint blend (en_diffusion.py:803-851): segments of the fragments in `known_bits` are not stepped but
+//   re-drawn from q(z_s | x_fixed) = alpha_s x_fixed + sigma_s eps' (noised_representation, :260-279) with the second set of
+//   raw draws noise2_x / noise2_h (position noise CoM-free per segment; noise2_h == NULL: zero), then the h0 overwrite.
 template <int MODE>
 __global__ void k_dyn_post(int S, int nf, int d, int emb, int C, const int* __restrict__ seg_ptr,
                            const int* __restrict__ seg_frag, DynCodec cd, const float* __restrict__ vel,
                            const float* __restrict__ h_out, const int* __restrict__ nan_flag,
                            const float* __restrict__ prm, float* __restrict__ eps_out, float* __restrict__ z,
                            const float* __restrict__ noise_x, const float* __restrict__ noise_h,
-                           const float* __restrict__ h0) {
+                           const float* __restrict__ h0, const float* __restrict__ x_fixed = nullptr, int known_bits = 0,
+                           const float* __restrict__ noise2_x = nullptr, const float* __restrict__ noise2_h = nullptr) {
   const int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (sgm >= S) return;
   const int n0 = seg_ptr[sgm], n1 = seg_ptr[sgm + 1], f = seg_frag[sgm];
+  if (MODE == 2 && ((known_bits >> f) & 1)) {  // clamped fragment: z_s ~ q(z_s | x_fixed)
+    const float alpha_s = prm[5], sigma_s = prm[6];
+    const float cntk = (float)max(n1 - n0, 1);
+    float sk[3] = {0.f, 0.f, 0.f};
+    for (int n = n0 + lane; n < n1; n += 32)
+      for (int c = 0; c < 3; c++) sk[c] += noise2_x[n * 3 + c];
+    for (int c = 0; c < 3; c++) sk[c] = warp_sum(sk[c]) / cntk;
+    for (int n = n0 + lane; n < n1; n += 32)
+      for (int k = 0; k < nf; k++) {
+        const float nz = k < 3 ? noise2_x[n * 3 + k] - sk[k] : (noise2_h ? noise2_h[(size_t)n * d + (k - 3)] : 0.f);
+        const float v = __fadd_rn(__fmul_rn(alpha_s, x_fixed[(size_t)n * nf + k]), __fmul_rn(sigma_s, nz));
+        z[(size_t)n * nf + k] = (k >= 3 && h0) ? h0[(size_t)n * (nf - 3) + (k - 3)] : v;
+      }
+    return;
+  }
   const bool bad = *nan_flag != 0;
   const uint32_t ctr = (uint32_t)reinterpret_cast<const int*>(prm)[4];
   const float cnt = (float)max(n1 - n0, 1);
@@ -106,9 +128,9 @@ __global__ void k_dyn_post(int S, int nf, int d, int emb, int C, const int* __re
   for (int n = n0 + lane; n < n1; n += 32)
     for (int c = 0; c < 3; c++) {
       sv[c] += vload(n, c);
-      if (MODE == 1) sn[c] += noise_x[n * 3 + c];
+      if (MODE >= 1) sn[c] += noise_x[n * 3 + c];
     }
-  for (int c = 0; c < 3; c++) { sv[c] = warp_sum(sv[c]) / cnt; if (MODE == 1) sn[c] = warp_sum(sn[c]) / cnt; }
+  for (int c = 0; c < 3; c++) { sv[c] = warp_sum(sv[c]) / cnt; if (MODE >= 1) sn[c] = warp_sum(sn[c]) / cnt; }
   const float *w0 = cd.dw0[f], *b0 = cd.db0[f], *w1 = cd.dw1[f], *b1 = cd.db1[f];
   auto eps_of = [&](int n, float* e) {  // e[0..nf)
     for (int c = 0; c < 3; c++) e[c] = vload(n, c) - sv[c];
@@ -158,6 +180,35 @@ __global__ void k_dyn_post(int S, int nf, int d, int emb, int C, const int* __re
     zs_of(n, o);
     for (int c = 0; c < 3; c++) z[(size_t)n * nf + c] = o[c] - sz[c];
     for (int k = 3; k < nf; k++) z[(size_t)n * nf + k] = h0 ? h0[(size_t)n * (nf - 3) + (k - 3)] : o[k];
+  }
+}
+
+// The RePaint jump-back z_s -> z_t (en_diffusion.py:1050-1074, sample_p_zt_given_zs) IN PLACE: z = alpha_ts z + sigma_ts eps with
+// eps = the caller's raw draws (position noise CoM-free per segment, feature noise NULL = zero), then the centre of mass of
+// the new positions is removed per segment.  One warp per segment, fixed summation order.
+__global__ void k_dyn_jump(int S, int nf, int d, const int* __restrict__ seg_ptr, float alpha_ts, float sigma_ts,
+                           float* __restrict__ z, const float* __restrict__ noise_x, const float* __restrict__ noise_h) {
+  const int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (sgm >= S) return;
+  const int n0 = seg_ptr[sgm], n1 = seg_ptr[sgm + 1];
+  const float cnt = (float)max(n1 - n0, 1);
+  float sn[3] = {0.f, 0.f, 0.f};
+  for (int n = n0 + lane; n < n1; n += 32)
+    for (int c = 0; c < 3; c++) sn[c] += noise_x[n * 3 + c];
+  for (int c = 0; c < 3; c++) sn[c] = warp_sum(sn[c]) / cnt;
+  auto zt_of = [&](int n, int k) {
+    const float nz = k < 3 ? noise_x[n * 3 + k] - sn[k] : (noise_h ? noise_h[(size_t)n * d + (k - 3)] : 0.f);
+    return __fadd_rn(__fmul_rn(alpha_ts, z[(size_t)n * nf + k]), __fmul_rn(sigma_ts, nz));
+  };
+  float sz[3] = {0.f, 0.f, 0.f};
+  for (int n = n0 + lane; n < n1; n += 32)
+    for (int c = 0; c < 3; c++) sz[c] += zt_of(n, c);
+  for (int c = 0; c < 3; c++) sz[c] = warp_sum(sz[c]) / cnt;
+  __syncwarp();
+  for (int n = n0 + lane; n < n1; n += 32) {
+    float o[3 + DYN_MAX_D];
+    for (int k = 0; k < nf; k++) o[k] = zt_of(n, k);
+    for (int k = 0; k < nf; k++) z[(size_t)n * nf + k] = k < 3 ? o[k] - sz[k] : o[k];
   }
 }
 

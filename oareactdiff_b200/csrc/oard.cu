@@ -151,7 +151,7 @@ struct oard_handle {
   std::vector<char> dset;
   DynCodec codec{};
   int nan_counter = 0;
-  struct GraphSlot { int kind; std::array<const void*, 6> key; cudaGraphExec_t exec; int64_t launches; };
+  struct GraphSlot { int kind; std::array<const void*, 10> key; cudaGraphExec_t exec; int64_t launches; };
   std::vector<GraphSlot> gslots;  // whole-call graphs of oard_dyn_forward (kind 0) / oard_reverse_step (kind 1), keyed by pointers
 
   template <typename T>
@@ -1064,19 +1064,22 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
       const bool frag_ok = env_frag && h->complete && c.reflect_equiv && l < 64 && et_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
       if (frag_ok && E) {
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (220 * 1024) / (et_smem + 1024)));
+        // variants (edges in flight per thread, CTAs per SM the registers allow): OARD_ET=42 (default) | 33 | 24
+        static int env_et = -1;
+        if (env_et < 0) { const char* e = getenv("OARD_ET"); env_et = e ? atoi(e) : 42; if (env_et != 33 && env_et != 24) env_et = 42; }
+        const int minb = env_et % 10;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(minb, (220 * 1024) / (et_smem + 1024)));
         const int grid = h->num_sms * per_sm;
-#define OARD_ET(CHV)                                                                                                   \
+#define OARD_ET(CHV, U, MB)                                                                                            \
         {                                                                                                              \
-        if (et_smem > 48 * 1024) {                                                                                     \
           static PerDeviceOnce attr;                                                                                   \
-          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_tgt<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        }                                                                                                              \
-        k_equi_tgt<CHV><<<grid, ET_THREADS, et_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
-            h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),       \
-            h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                            \
+          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_tgt<CHV, U, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+          k_equi_tgt<CHV, U, MB><<<grid, ET_THREADS, et_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
+              h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),     \
+              h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                          \
         }
-        if (CH == 28) OARD_ET(28) else if (CH == 32) OARD_ET(32) else OARD_ET(16)
+        if (CH == 28) { if (env_et == 33) OARD_ET(28, 3, 3) else if (env_et == 24) OARD_ET(28, 2, 4) else OARD_ET(28, 4, 2) }
+        else if (CH == 32) OARD_ET(32, 4, 2) else OARD_ET(16, 4, 2)
 #undef OARD_ET
       } else {
         k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(
@@ -1457,9 +1460,11 @@ extern "C" int oard_dyn_plan(oard_handle* h, const int64_t* node_frag, const int
 }
 
 // prologue -> LEFTNet forward -> epilogue (mode 0: eps out; mode 1: in-place reverse step) on stream st
+struct InpaintArgs { const float* x_fixed = nullptr; int known_bits = 0; const float* noise2 = nullptr; const float* noise2_h = nullptr; };
+
 static int dyn_impl(oard_handle* h, int mode, const float* xh, const float* t_dev, const float* cond, const int64_t* sub,
                     float* eps, float* z, const float* noise, const float* noise_h, const float* h0, cudaStream_t st,
-                    bool fwd_graph = false) {
+                    bool fwd_graph = false, const InpaintArgs& ip = InpaintArgs()) {
   const int N = h->N, C = h->cfg.in_hidden_channels, nf = h->dyn_nf, d = h->dyn_d, emb = h->dyn_emb;
   float *gh = h->buf<float>("g_h_in"), *gp = h->buf<float>("g_pos"), *gho = h->buf<float>("g_h_out"),
         *gdp = h->buf<float>("g_dpos"), *vel = h->buf<float>("dyn_vel"), *prm = h->buf<float>("dyn_prm");
@@ -1493,16 +1498,21 @@ static int dyn_impl(oard_handle* h, int mode, const float* xh, const float* t_de
   if (mode == 0)
     k_dyn_post<0><<<grid, 128, 0, st>>>(S, nf, d, emb, C, h->buf<int>("dyn_seg_ptr"), h->buf<int>("dyn_seg_frag"), h->codec,
                                         vel, gho, flag, prm, eps, nullptr, nullptr, nullptr, nullptr);
-  else
+  else if (mode == 1)
     k_dyn_post<1><<<grid, 128, 0, st>>>(S, nf, d, emb, C, h->buf<int>("dyn_seg_ptr"), h->buf<int>("dyn_seg_frag"), h->codec,
                                         vel, gho, flag, prm, nullptr, z, noise, noise_h, h0);
+  else
+    k_dyn_post<2><<<grid, 128, 0, st>>>(S, nf, d, emb, C, h->buf<int>("dyn_seg_ptr"), h->buf<int>("dyn_seg_frag"), h->codec,
+                                        vel, gho, flag, prm, nullptr, z, noise, noise_h, h0, ip.x_fixed, ip.known_bits,
+                                        ip.noise2, ip.noise2_h);
   KCHECK();
   h->launches += 1;  // k_dyn_pre (issued before forward_impl reset the counter)
   return OARD_OK;
 }
 
 static int dyn_run(oard_handle* h, int mode, const float* xh, const float* t_dev, const float* cond, const int64_t* sub,
-                   float* eps, float* z, const float* noise, const float* noise_h, const float* h0, cudaStream_t st) {
+                   float* eps, float* z, const float* noise, const float* noise_h, const float* h0, cudaStream_t st,
+                   const InpaintArgs& ip = InpaintArgs()) {
   h->prof_now = h->prof_every > 0 && (h->fwd_count % h->prof_every) == 0;
   h->fwd_count++;
   if (!h->cfg.object_aware) sub = nullptr;
@@ -1510,14 +1520,15 @@ static int dyn_run(oard_handle* h, int mode, const float* xh, const float* t_dev
   if (eager || mode == 0) {
     // mode 0 (dyn_forward) is called with fresh tensors (loss terms, final decode): its wrapper kernels are issued
     // directly around the cached forward graph; the whole-call graph below is for the reverse step's persistent buffers
-    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, st, !eager);
+    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, st, !eager, ip);
     if (rc) return rc;
     h->total_launches += h->launches;
     return prof_harvest(h, st);
   }
-  const std::array<const void*, 6> key = {mode == 0 ? (const void*)xh : (const void*)z, mode == 0 ? (const void*)eps : (const void*)noise,
-                                          mode == 0 ? (const void*)t_dev : (const void*)noise_h, (const void*)cond, (const void*)sub,
-                                          (const void*)h0};
+  const std::array<const void*, 10> key = {mode == 0 ? (const void*)xh : (const void*)z, mode == 0 ? (const void*)eps : (const void*)noise,
+                                           mode == 0 ? (const void*)t_dev : (const void*)noise_h, (const void*)cond, (const void*)sub,
+                                           (const void*)h0, (const void*)ip.x_fixed, (const void*)(intptr_t)ip.known_bits,
+                                           (const void*)ip.noise2, (const void*)ip.noise2_h};
   oard_handle::GraphSlot* slot = nullptr;
   for (auto& s : h->gslots)
     if (s.kind == mode && s.key == key) { slot = &s; break; }
@@ -1530,7 +1541,7 @@ static int dyn_run(oard_handle* h, int mode, const float* xh, const float* t_dev
     CU(cudaStreamSynchronize(st));
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, h->cap_stream);
+    const int rc = dyn_impl(h, mode, xh, t_dev, cond, sub, eps, z, noise, noise_h, h0, h->cap_stream, false, ip);
     cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return fail(OARD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
@@ -1578,11 +1589,47 @@ extern "C" int oard_reverse_step(oard_handle* h, float* z, const float* noise, c
   DeviceScope dev_scope(h->device);
   CU(dev_scope.err);
   cudaStream_t st = (cudaStream_t)stream;
-  k_set_params<<<1, 1, 0, st>>>(h->buf<float>("dyn_prm"), t, alpha_ts, coef, sigma, h->nan_counter++);
+  k_set_params<<<1, 1, 0, st>>>(h->buf<float>("dyn_prm"), t, alpha_ts, coef, sigma, h->nan_counter++, 0.f, 0.f);
   CU(cudaGetLastError());
   rc = dyn_run(h, 1, nullptr, nullptr, cond, sub, nullptr, z, noise, noise_h, h0, st);
   h->total_launches += 1;
   return rc;
+}
+
+extern "C" int oard_inpaint_step(oard_handle* h, float* z, const float* noise, const float* noise_h, const float* h0,
+                                 const float* cond, const int64_t* sub, float t, float alpha_ts, float coef, float sigma,
+                                 const float* x_fixed, int known_frag_bits, const float* noise_known,
+                                 const float* noise_known_h, float alpha_s, float sigma_s, void* stream) {
+  int rc = dyn_ready(h);
+  if (rc) return rc;
+  if (!z || !noise || !x_fixed || !noise_known) return fail(OARD_EINVAL, "null argument");
+  if (h->dyn_cnd > 0 && !cond) return fail(OARD_EINVAL, "condition_nf > 0: conditions[B, condition_nf] is required");
+  if (known_frag_bits < 0 || known_frag_bits >= (1 << DYN_MAX_FRAG)) return fail(OARD_EINVAL, "known_frag_bits out of range");
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_set_params<<<1, 1, 0, st>>>(h->buf<float>("dyn_prm"), t, alpha_ts, coef, sigma, h->nan_counter++, alpha_s, sigma_s);
+  CU(cudaGetLastError());
+  InpaintArgs ip;
+  ip.x_fixed = x_fixed; ip.known_bits = known_frag_bits; ip.noise2 = noise_known; ip.noise2_h = noise_known_h;
+  rc = dyn_run(h, 2, nullptr, nullptr, cond, sub, nullptr, z, noise, noise_h, h0, st, ip);
+  h->total_launches += 1;
+  return rc;
+}
+
+extern "C" int oard_jump_back(oard_handle* h, float* z, const float* noise, const float* noise_h, float alpha_ts,
+                              float sigma_ts, void* stream) {
+  int rc = dyn_ready(h);
+  if (rc) return rc;
+  if (!z || !noise) return fail(OARD_EINVAL, "null argument");
+  DeviceScope dev_scope(h->device);
+  CU(dev_scope.err);
+  const int S = h->dyn_S;
+  k_dyn_jump<<<(S * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, h->dyn_nf, h->dyn_d, h->buf<int>("dyn_seg_ptr"), alpha_ts,
+                                                                    sigma_ts, z, noise, noise_h);
+  CU(cudaGetLastError());
+  h->total_launches += 1;
+  return OARD_OK;
 }
 
 extern "C" int oard_test_gemm_ex(int, int, int, int, const float*, const float*, const float*, float*, int, int, int, int,

@@ -416,6 +416,40 @@ class EnVariationalDiffusion(nn.Module):
                                tab["sigma"][s_int])
         return Z
 
+    # RePaint on the device: the draw for the clamped fragments, the reverse step, the blend and the jump-back
+    def _device_setup_inpaint(self, Xf: Tensor, frag_fixed):
+        dv = self._dev
+        N, p, d = Xf.size(0), self.pos_dim, self.node_nfs[0] - self.pos_dim
+        kx, kh = torch.empty(N, p, device=Xf.device), torch.empty(N, d, device=Xf.device)
+        o = self._frag_off
+        views = []
+        for f in range(len(o) - 1):  # noised_representation draws first (en_diffusion.py:806), same per-fragment order
+            views += [kx[o[f]:o[f + 1]], kh[o[f]:o[f + 1]]]
+        bits = 0
+        for f in frag_fixed:
+            bits |= 1 << int(f)
+        dv.update(kx=kx, kh=kh, kviews=views, Xf=Xf.to(torch.float32).contiguous(), known_bits=bits)
+
+    def _device_inpaint_step(self, s_int: int, Z: Tensor, tab) -> Tensor:
+        dv = self._dev
+        for v in dv["kviews"]:  # z_known's noise, then the reverse step's: the reference's draw order
+            v.normal_()
+        for v in dv["views"]:
+            v.normal_()
+        self.n_evals += 1
+        dv["eng"].inpaint_step(Z, dv["nx"], None if self.pos_only else dv["nh"], dv["H0"] if self.pos_only else None,
+                               dv["cond"], dv["sub"], tab["t"][s_int + 1], tab["alpha_ts"][s_int], tab["coef"][s_int],
+                               tab["sigma"][s_int], dv["Xf"], dv["known_bits"], dv["kx"], None if self.pos_only else dv["kh"],
+                               tab["alpha"][s_int], tab["sigma_abs"][s_int])
+        return Z
+
+    def _device_jump_back(self, Z: Tensor, alpha_ts: float, sigma_ts: float) -> Tensor:
+        dv = self._dev
+        for v in dv["views"]:
+            v.normal_()
+        dv["eng"].jump_back(Z, dv["nx"], None if self.pos_only else dv["nh"], alpha_ts, sigma_ts)
+        return Z
+
     # ---------------------------------------------------------------- drivers
     def _setup(self, n_samples, fragments_nodes):
         masks = [get_mask_for_frag(n) for n in fragments_nodes]
@@ -515,28 +549,31 @@ class EnVariationalDiffusion(nn.Module):
             H0 = torch.cat(h0).to(Z.dtype)
             known = torch.cat([torch.full((len(m), 1), ii in frag_fixed, dtype=torch.bool, device=dev)
                                for ii, m in enumerate(masks)])
-            on_device = self._device_ok(dev)
+            on_device = self._device_ok(dev) and len(masks) <= 8
             if on_device:
                 self._device_setup(Z, masks, edge_index, nfs, conditions, H0 if self.pos_only else None)
+                self._device_setup_inpaint(Xf, frag_fixed)
             for i, n_denoise_steps in enumerate(schedule):
                 for j in range(n_denoise_steps):
                     # known fragments: q(z_s | x) (noised_representation); unknown: reverse step from z_t
-                    Z_known = tab["alpha"][s] * Xf + tab["sigma_abs"][s] * self._noise_cat(masks)
-                    if on_device:
-                        self._device_step(s, Z, tab)
-                        torch.where(known, Z_known, Z, out=Z)
+                    if on_device:  # both draws, the step, the blend and the h0 overwrite: one CUDA-graph launch
+                        self._device_inpaint_step(s, Z, tab)
                     else:
+                        Z_known = tab["alpha"][s] * Xf + tab["sigma_abs"][s] * self._noise_cat(masks)
                         Z_unknown = self._fast_step(s, Z, tab, edge_index, nfs, masks, conditions)
                         Z = torch.where(known, Z_known, Z_unknown)
-                    if self.pos_only:
-                        Z[:, p:] = H0
+                        if self.pos_only:
+                            Z[:, p:] = H0
                     if j == n_denoise_steps - 1 and i < len(schedule) - 1:  # jump back `jump_length` steps
                         t = s + jump_length
                         g_s, g_t = gamma_cpu[s].view(1, 1), gamma_cpu[t].view(1, 1)
                         _, sigma_ts, alpha_ts = self.schedule.sigma_and_alpha_t_given_s(g_t, g_s, g_s)
-                        Zj = float(alpha_ts) * Z + float(sigma_ts) * self._noise_cat(masks)
-                        Zj[:, :p] = self._remove_mean_cat(Zj[:, :p])
-                        Z = Z.copy_(Zj) if on_device else Zj  # the device step replays a graph on Z's storage
+                        if on_device:
+                            self._device_jump_back(Z, float(alpha_ts), float(sigma_ts))
+                        else:
+                            Zj = float(alpha_ts) * Z + float(sigma_ts) * self._noise_cat(masks)
+                            Zj[:, :p] = self._remove_mean_cat(Zj[:, :p])
+                            Z = Zj
                         s = t
                     s = s - 1
             z = self._views(Z)

@@ -266,6 +266,20 @@ class _Engine:
                                               self._ptr(cond), self._ptr(sub), t, alpha_ts, coef, sigma,
                                               self._stream(self.device)))
 
+    def inpaint_step(self, z: Tensor, noise_x: Tensor, noise_h: Optional[Tensor], h0: Optional[Tensor], cond: Optional[Tensor],
+                     sub: Optional[Tensor], t: float, alpha_ts: float, coef: float, sigma: float, x_fixed: Tensor,
+                     known_bits: int, noise_kx: Tensor, noise_kh: Optional[Tensor], alpha_s: float, sigma_s: float):
+        """One RePaint step in place (one CUDA-graph launch): reverse step + q(z_s | x_fixed) for the clamped fragments."""
+        _lib.check(self.lib.oard_inpaint_step(self.h, self._ptr(z), self._ptr(noise_x), self._ptr(noise_h), self._ptr(h0),
+                                              self._ptr(cond), self._ptr(sub), t, alpha_ts, coef, sigma, self._ptr(x_fixed),
+                                              int(known_bits), self._ptr(noise_kx), self._ptr(noise_kh), alpha_s, sigma_s,
+                                              self._stream(self.device)))
+
+    def jump_back(self, z: Tensor, noise_x: Tensor, noise_h: Optional[Tensor], alpha_ts: float, sigma_ts: float):
+        """RePaint jump-back z_s -> z_t in place (sample_p_zt_given_zs)."""
+        _lib.check(self.lib.oard_jump_back(self.h, self._ptr(z), self._ptr(noise_x), self._ptr(noise_h), alpha_ts, sigma_ts,
+                                           self._stream(self.device)))
+
     # ---- training: differentiable forward + backward behind the C ABI (include/oard.h, csrc/train_core.h)
     def forward_train(self, h: Tensor, pos: Tensor, sub: Optional[Tensor]):
         h = h.detach().to(torch.float32).contiguous()

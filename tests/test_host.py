@@ -184,6 +184,13 @@ def _recording_dynamics():
         def reverse_step(self, z, nx, nh, h0, cond, sub, t, alpha_ts, coef, sigma):
             calls.append(("reverse_step", z.data_ptr(), tuple(nx.shape), nh is None, None if h0 is None else tuple(h0.shape), float(t)))
 
+        def inpaint_step(self, z, nx, nh, h0, cond, sub, t, alpha_ts, coef, sigma, x_fixed, known_bits, kx, kh, alpha_s, sigma_s):
+            calls.append(("inpaint_step", z.data_ptr(), tuple(nx.shape), nh is None, None if h0 is None else tuple(h0.shape), float(t),
+                          tuple(x_fixed.shape), int(known_bits), kx.data_ptr() != nx.data_ptr(), kh is None, float(alpha_s), float(sigma_s)))
+
+        def jump_back(self, z, nx, nh, alpha_ts, sigma_ts):
+            calls.append(("jump_back", z.data_ptr(), tuple(nx.shape), nh is None, float(alpha_ts), float(sigma_ts)))
+
     cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1)
     dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
                           model=ob.LEFTNetB200, device=torch.device("cpu"))
@@ -214,13 +221,18 @@ def test_fused_dynamics_plumbing_with_a_recording_engine():
     assert fwd[0][5] == (torch.int64, E, True)
     assert ("dyn_plan", N, N, 2) in calls and ddpm.n_evals == 6
     assert [tuple(o.shape) for o in out[0]] == [(sum(sizes), 9)] * 3
-    # RePaint: known fragments blended in place, jump-backs copied into the same buffer
+    # RePaint: one oard_inpaint_step per step (clamped fragments as a bit mask, their own noise buffers), jump-backs in place on
+    # the same state buffer
     del calls[:]
     xh_fixed = [torch.cat([torch.randn(h.size(0), 3), h.float()], dim=1) for h in h0]
     ddpm.inpaint(len(sizes), nodes, cond, resamplings=2, jump_length=2, timesteps=4, xh_fixed=xh_fixed, frag_fixed=[0, 2])
-    steps = [c for c in calls if c[0] == "reverse_step"]
+    steps = [c for c in calls if c[0] == "inpaint_step"]
     sched = ob.get_repaint_schedule(2, 2, 4)
     assert len(steps) == sum(sched) == ddpm.n_evals - 1 and len({c[1] for c in steps}) == 1
+    assert all(c[6] == (N, 9) and c[7] == 0b101 and c[8] and c[9] and 0 < c[10] <= 1 and 0 <= c[11] < 1 for c in steps)
+    jumps = [c for c in calls if c[0] == "jump_back"]
+    assert len(jumps) == len(sched) - 1 and {c[1] for c in jumps} == {steps[0][1]} and all(0 < c[4] <= 1 for c in jumps)
+    assert not [c for c in calls if c[0] == "reverse_step"]
     want, s = [], 3
     for i, n in enumerate(sched):
         for j in range(n):

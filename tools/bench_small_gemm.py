@@ -1,5 +1,5 @@
 """Timing helper (not a pytest file): node-level GEMM shapes (M = 2 613 rows) on the fp32-A tcgen05 kernel (gemm_tc.cuh) and
-on the pair16 kernel (gemm_p16.cuh) for several tile widths.  `python tests/bench_small_gemm.py`"""
+on the pair16 kernel (gemm_p16.cuh) for several tile widths.  `python tools/bench_small_gemm.py`"""
 import os
 import subprocess
 import sys

@@ -1,5 +1,5 @@
 """Bring-up / timing helper (not a pytest file) for the pair16 tcgen05 GEMM (csrc/gemm_p16.cuh) through
-oard_test_gemm_p16.  `python tests/bringup_p16.py` prints accuracy for every mode and a timing table next to the
+oard_test_gemm_p16.  `python tools/bringup_p16.py` prints accuracy for every mode and a timing table next to the
 fp32-A kernel (gemm_tc.cuh) on the B=64 edge shapes."""
 import ctypes as C
 import os

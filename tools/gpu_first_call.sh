@@ -14,7 +14,7 @@ echo "== experimental (opt-in)";  OARD_TEST_EXPERIMENTAL=1 timeout 900 python -m
 # OARD_FORK sweep on the device-resident reverse step (compact geometry, B = 64): device_step_ms is the number to compare
 for k in 0 16 24 32 48 64; do
   echo "== perf probe OARD_FORK=$k"
-  OARD_FORK=$k timeout 300 python tests/perf_probe.py 40 > $out/${tag}_probe_fork$k.json 2> $out/${tag}_probe_fork$k.err
+  OARD_FORK=$k timeout 300 python tools/perf_probe.py 40 > $out/${tag}_probe_fork$k.json 2> $out/${tag}_probe_fork$k.err
   python - <<EOF
 import json
 try:

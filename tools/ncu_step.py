@@ -1,6 +1,6 @@
 """Profiling target (not a test): n device-resident reverse steps of the B=64 Transition1x-shaped batch on a compact
 state (every same-fragment edge inside the cutoff, active fraction 0.317), one CUDA graph per step.
-    python tests/ncu_step.py [n_steps] [eager]
+    python tools/ncu_step.py [n_steps] [eager]
 Used under `ncu --metrics gpu__time_duration.sum` (launch list) and `ncu --set full -k regex:...` (profiles/)."""
 import os
 import sys

@@ -1,7 +1,7 @@
 """GPU probe (not a test): where does a reverse step's time go?  Times, with CUDA events on the current stream,
 (a) the LEFTNet evaluation alone through the C ABI (CUDA-graph replay and eager), (b) EGNNDynamics.forward,
 (c) the full reverse step of the sampler, all on the same compact B=64 Transition1x-shaped state.
-    python tests/perf_probe.py [reps]"""
+    python tools/perf_probe.py [reps]"""
 import json
 import os
 import sys
