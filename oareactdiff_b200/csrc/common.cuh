@@ -1,5 +1,8 @@
 // Shared device helpers for the OA-ReactDiff B200 hot path (sm_100a).
 #pragma once
+#include <cstdlib>
+#include <cstring>
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 

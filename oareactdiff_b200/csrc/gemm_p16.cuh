@@ -118,9 +118,6 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + EW * NIO);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
-  const int m_tiles = (M + TC_BM - 1) / TC_BM;
-  const int total_tiles = m_tiles * w.n_tiles;
   const int k_chunks = w.k_chunks;
   const int k16_total = (g.K + 15) / 16;
 
@@ -136,10 +133,14 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
+  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int total_tiles = m_tiles * w.n_tiles;
 
   if (warp == EW + 1) {
     // ===================== A loader: 2-D TMA boxes {32 floats, 128 rows}, SWIZZLE_128B =====================
     if (lane == 0) {
+      const uint64_t polA = ptx::l2_policy(g.hintA);
       ptx::tma_prefetch_desc(&tmA);
       uint32_t gchunk = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -148,7 +149,7 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
           const int s = gchunk % SA;
           ptx::mbar_wait(&empty_a[s], ((gchunk / SA) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_a[s], P16_A_BYTES);
-          ptx::tma_load_2d(a_ring + (size_t)s * P16_A_BYTES, &tmA, kc * TC_KC, m0, &full_a[s]);
+          ptx::tma_load_2d_h(a_ring + (size_t)s * P16_A_BYTES, &tmA, kc * TC_KC, m0, &full_a[s], g.hintA, polA);
         }
       }
     }
@@ -207,6 +208,7 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
     const int nblocks = (BN + 31) / 32;
     const int sw = lane & 7;
     constexpr bool HAS_AUX = (MODE == 2 || MODE == 3);
+    const uint64_t polX = ptx::l2_policy(g.hintX), polC = ptx::l2_policy(g.hintC);
     // Buffer ring per warp: block i uses buffer i % NIO from its aux load until its store has read it.  Aux loads run PF
     // blocks ahead; the buffer of block nb + PF was last read by the store of block nb + PF - NIO, so at most
     // PEND = NIO - 1 - PF newer stores may still be reading when it is refilled (NIO 2: PF 1, PEND 0; NIO 3: PF 1, PEND 1).
@@ -224,8 +226,8 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
       if (pf_tile >= total_tiles) return;
       const int b = npf % NIO;
       ptx::mbar_arrive_expect_tx(&xbar[b], TC_IO_BYTES);
-      ptx::tma_load_2d(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
-                       (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b]);
+      ptx::tma_load_2d_h(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
+                         (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b], g.hintX, polX);
       npf++;
       pf_next();
     };
@@ -336,7 +338,7 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
         ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES);
+          ptx::tma_store_2d_h(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES, g.hintC, polC);
           ptx::bulk_commit();
         }
         __syncwarp();

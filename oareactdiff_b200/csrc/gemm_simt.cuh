@@ -25,6 +25,9 @@ struct GemmArgs {
   const float* resid; int ldres;                     // + resid[m, n]   (may alias C)
   // optional second, row-scattered copy of the result: C2[c2idx[m], n] = C[m, n] for rows with c2idx[m] >= 0
   float* C2; const int* c2idx; int ldc2;
+  // L2 eviction-priority hints of the tensor-core kernels' TMA streams (gemm_tc.cuh l2_policy): A operand, aux (mul / resid)
+  // blocks, C stores.  0 none, 1 evict_first, 2 evict_last.
+  int hintA, hintX, hintC;
 };
 
 constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;

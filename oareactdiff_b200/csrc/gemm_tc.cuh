@@ -138,6 +138,28 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
                "r"(c1), "r"(smem_u32(src))
                : "memory");
 }
+// L2 eviction-priority hints for the TMA streams (0 none, 1 evict_first: data read / written once and too large to stay
+// resident — it should leave L2 before the activations the NEXT kernel reads; 2 evict_last).  createpolicy + .L2::cache_hint.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  uint64_t p = 0;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_h(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, int kind, uint64_t pol) {
+  if (kind == 0) { tma_load_2d(dst, tm, c0, c1, bar); return; }
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_h(const CUtensorMap* tm, int c0, int c1, const void* src, int kind, uint64_t pol) {
+  if (kind == 0) { tma_store_2d(tm, c0, c1, src); return; }
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tm),
+               "r"(c0), "r"(c1), "r"(smem_u32(src)), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -249,9 +271,6 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + TC_EPI_WARPS * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
-  const int m_tiles = (M + TC_BM - 1) / TC_BM;
-  const int total_tiles = m_tiles * w.n_tiles;
   const int k_chunks = w.k_chunks;
   const int k16_total = (g.K + 15) / 16;
 
@@ -276,6 +295,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
+  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int total_tiles = m_tiles * w.n_tiles;
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= TC_EPI_WARPS + TC_CTRL_WARPS) {
@@ -393,6 +415,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   } else if (warp == TC_EPI_WARPS + 2) {
     // ===================== A loader: 2-D TMA boxes {32 floats, 128 rows} into the raw ring =====================
     if (RAW > 0 && lane == 0) {
+      const uint64_t polA = ptx::l2_policy(g.hintA);
       ptx::tma_prefetch_desc(&tmA);
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -402,7 +425,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           ptx::mbar_wait(&raw_empty[r], ((c / (RAW > 0 ? RAW : 1)) & 1) ^ 1);
           if (dbg.ablate & 1) { ptx::mbar_arrive(&raw_full[r]); continue; }
           ptx::mbar_arrive_expect_tx(&raw_full[r], TC_RAW_BYTES);
-          ptx::tma_load_2d(raw_base + (size_t)r * TC_RAW_BYTES, &tmA, kc * TC_KC, m0, &raw_full[r]);
+          ptx::tma_load_2d_h(raw_base + (size_t)r * TC_RAW_BYTES, &tmA, kc * TC_KC, m0, &raw_full[r], g.hintA, polA);
         }
       }
     }
@@ -443,6 +466,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
     // ===================== epilogue warps 0-7 =====================
     // warp e reads TMEM lanes 32*(e%4).. (its row quarter) and takes the 32-column blocks with parity e/4.
     if constexpr (NIO > 0) {
+      const uint64_t polX = ptx::l2_policy(g.hintX), polC = ptx::l2_policy(g.hintC);
       // ---- TMA epilogue: thread = output row.  A block is 32 rows x 32 columns (4 KB, 128-byte rows, 128B-swizzled so
       // that both the row-per-thread accesses here and the TMA engine are bank-conflict free).  Residual / multiplier blocks
       // are fetched by TMA one block ahead; results leave by TMA store.  No LSU traffic except bias and gathered rows.
@@ -467,8 +491,8 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         if (!pf_valid()) return;
         const int b = npf % NIO;
         ptx::mbar_arrive_expect_tx(&xbar[b], TC_IO_BYTES);
-        ptx::tma_load_2d(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
-                         (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b]);
+        ptx::tma_load_2d_h(io + (size_t)b * TC_IO_BYTES, &tmX, (pf_tile % w.n_tiles) * BN + pf_blk * 32,
+                           (pf_tile / w.n_tiles) * TC_BM + rq * 32, &xbar[b], g.hintX, polX);
         npf++;
         pf_next();
       };
@@ -537,7 +561,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
-            if (!(dbg.ablate & 2)) ptx::tma_store_2d(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES);
+            if (!(dbg.ablate & 2)) ptx::tma_store_2d_h(&tmC, nblk, m0r, io + (size_t)b * TC_IO_BYTES, g.hintC, polC);
             ptx::bulk_commit();
             if (HAS_AUX && NIO == 1) { ptx::bulk_wait_read0(); issue_aux(); }
           }

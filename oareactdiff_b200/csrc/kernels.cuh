@@ -608,33 +608,29 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
 // position of its transposed edge), so the G rows of all messages arriving at target t are the contiguous block
 // [row_act_ptr[t], row_act_ptr[t+1]) and G row p belongs to the message (a -> t) of the compact edge p = (t -> a).
 // Work item = (group, CH-channel slice), one item per CTA turn (atomic counter); the group's X / vec rows of the slice are
-// staged once in shared memory.  Threads accumulate in registers over contiguous G rows (layout below); latency is hidden by
-// the loads in flight per thread and the co-resident CTAs (3 per SM), not by an in-CTA pipeline.
-constexpr int ET_THREADS = 192;
+// staged once in shared memory.  Thread = (target slot, float4 column): it walks the target's block of G rows with the next
+// row's three 16-byte loads in flight and accumulates in registers — no cross-thread reduction, no shuffles, fixed edge
+// order (bitwise reproducible).  Latency is hidden by the co-resident CTAs (4 per SM), not by an in-CTA pipeline.
+// (Edge slots, deeper register staging, a loader warp and L2 prefetches were all measured slower: profiles/r2_experiments.md.)
 template <int CH>
 inline size_t et_smem_bytes(int gmax) {
-  return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * (4 + 8) + (size_t)ET_THREADS * 4 * 16;
+  return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * (4 + 8);
 }
-// Thread = (target slot tl, edge slot es, float4 column q): a group of gs targets uses ES = NSLOT / gs edge slots per target
-// (small groups spread every target's edges over several threads so that all items take about the same time); a thread walks
-// its edges p0 + es, p0 + es + ES, .. in chunks of ET_U with all 3 ET_U 16-byte G loads issued before the first use.  The ES
-// partial sums of a target are combined through shared memory in slot order (bitwise reproducible).
-// ET_U = edges whose G rows are in flight per thread (register-staged), MINB = CTAs per SM the register budget is set for.
-template <int CH, int ET_U, int MINB>
-__global__ void __launch_bounds__(ET_THREADS, MINB) k_equi_tgt(
+constexpr int ET_THREADS = 192;
+template <int CH>
+__global__ void __launch_bounds__(ET_THREADS, 4) k_equi_tgt(
     int H, int NS, int gmax, const int* __restrict__ n_lead, const int2* __restrict__ lead_info,
     int* __restrict__ work_ctr, const int* __restrict__ gm_node, const int2* __restrict__ gm_rap,
     const int2* __restrict__ act_rec, const float4* __restrict__ act_geo, const float* __restrict__ G,
     const float* __restrict__ X, const float* __restrict__ vec_in, float* __restrict__ vec_out, float* __restrict__ s) {
   constexpr int Q = CH / 4;              // float4 columns per slice
-  constexpr int NSLOT = ET_THREADS / Q;  // (target, edge slot) pairs in flight per CTA
+  constexpr int NSLOT = ET_THREADS / Q;  // targets in flight per CTA
   extern __shared__ __align__(16) float4 et_sm[];
   float4* Xs = et_sm;                         // [gmax][3][Q]
   float4* Vs = et_sm + (size_t)gmax * 3 * Q;  // [gmax][3][Q]
-  float4* part = Vs + (size_t)gmax * 3 * Q;   // [NSLOT][Q][4]  partial sums (dx, d0, d1, d2)
   const int gpad = (gmax + 3) & ~3;
-  int2* mem_rap = reinterpret_cast<int2*>(part + (size_t)ET_THREADS * 4);  // [gpad]
-  int* mem_node = reinterpret_cast<int*>(mem_rap + gpad);                   // [gpad]
+  int2* mem_rap = reinterpret_cast<int2*>(Vs + (size_t)gmax * 3 * Q);  // [gpad]
+  int* mem_node = reinterpret_cast<int*>(mem_rap + gpad);               // [gpad]
   __shared__ int w_sm;
   const int tid = threadIdx.x;
   const int slot = tid / Q, q = tid - slot * Q;
@@ -658,64 +654,42 @@ __global__ void __launch_bounds__(ET_THREADS, MINB) k_equi_tgt(
       Vs[i] = ld4(vec_in + o);
     }
     __syncthreads();
-    const int ES = max(1, min(NSLOT / max(gs, 1), 8));  // edge slots per target
-    const int per_round = NSLOT / ES;                    // targets per round
-    for (int t0 = 0; t0 < gs; t0 += per_round) {         // (one round unless the group is larger than NSLOT)
-      const int tls = slot % per_round, es = slot / per_round;
-      const int tl = t0 + tls;
-      const bool live = slot < per_round * ES && tl < gs;
-      float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
-      if (live) {
+    if (slot < NSLOT) {
+      for (int tl = slot; tl < gs; tl += NSLOT) {
         const int2 rap = mem_rap[tl];
-        const float4 x0 = Xs[(tl * 3 + 0) * Q + q], x1 = Xs[(tl * 3 + 1) * Q + q], x2 = Xs[(tl * 3 + 2) * Q + q];
-        for (int pb = rap.x + es; pb < rap.y; pb += ES * ET_U) {
-          float4 g0[ET_U], g1[ET_U], g2[ET_U], gm[ET_U];
-          int al[ET_U];
-#pragma unroll
-          for (int u = 0; u < ET_U; u++) {
-            const int p = pb + u * ES;
-            if (p < rap.y) {
-              const float* gp = G + (size_t)p * H3 + h0 + 4 * q;
-              g0[u] = ld4(gp); g1[u] = ld4(gp + H); g2[u] = ld4(gp + 2 * H);
-              al[u] = act_rec[p].y; gm[u] = act_geo[p];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < ET_U; u++) {
-            if (pb + u * ES < rap.y) {
-              const float ux = -gm[u].x, uy = -gm[u].y, uz = -gm[u].z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
-              const int ca = al[u];
-              const float4 a0 = Xs[(ca * 3 + 0) * Q + q], a1 = Xs[(ca * 3 + 1) * Q + q], a2 = Xs[(ca * 3 + 2) * Q + q];
-              const float4 v0 = Vs[(ca * 3 + 0) * Q + q], v1 = Vs[(ca * 3 + 1) * Q + q], v2 = Vs[(ca * 3 + 2) * Q + q];
-#define OARD_EQT(c)                                                                          \
-              {                                                                              \
-                const float al_ = (a0.c + x0.c) * g0[u].c;                                   \
-                const float be = (a1.c + x1.c) * g1[u].c * inv_sqrt_3;                       \
-                const float ga = (a2.c + x2.c) * g2[u].c;                                    \
-                const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
-                dx.c += al_;                                                                 \
-                d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
-              }
-              OARD_EQT(x) OARD_EQT(y) OARD_EQT(z) OARD_EQT(w)
-#undef OARD_EQT
-            }
-          }
-        }
-      }
-      if (ES > 1) {  // block-uniform
-        float4* mine = part + (size_t)tid * 4;
-        mine[0] = dx; mine[1] = d0; mine[2] = d1; mine[3] = d2;
-        __syncthreads();
-        if (live && es == 0) {
-          auto add4 = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
-          for (int e2 = 1; e2 < ES; e2++) {
-            const float4* o = part + (size_t)((e2 * per_round + tls) * Q + q) * 4;
-            add4(dx, o[0]); add4(d0, o[1]); add4(d1, o[2]); add4(d2, o[3]);
-          }
-        }
-      }
-      if (live && es == 0) {
         const int t = mem_node[tl];
+        const float4 x0 = Xs[(tl * 3 + 0) * Q + q], x1 = Xs[(tl * 3 + 1) * Q + q], x2 = Xs[(tl * 3 + 2) * Q + q];
+        float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), d0 = dx, d1 = dx, d2 = dx;
+        const float* gp = G + (size_t)rap.x * H3 + h0 + 4 * q;
+        float4 g0, g1, g2, gm;
+        int al = 0;
+        if (rap.x < rap.y) {
+          g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+          al = act_rec[rap.x].y; gm = act_geo[rap.x];
+        }
+        for (int p = rap.x; p < rap.y; p++) {
+          const float4 c0 = g0, c1 = g1, c2 = g2, cm = gm;
+          const int ca = al;
+          if (p + 1 < rap.y) {  // next row in flight while this one is evaluated
+            gp += H3;
+            g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+            al = act_rec[p + 1].y; gm = act_geo[p + 1];
+          }
+          const float ux = -cm.x, uy = -cm.y, uz = -cm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)
+          const float4 a0 = Xs[(ca * 3 + 0) * Q + q], a1 = Xs[(ca * 3 + 1) * Q + q], a2 = Xs[(ca * 3 + 2) * Q + q];
+          const float4 v0 = Vs[(ca * 3 + 0) * Q + q], v1 = Vs[(ca * 3 + 1) * Q + q], v2 = Vs[(ca * 3 + 2) * Q + q];
+#define OARD_EQT(c)                                                                          \
+          {                                                                                  \
+            const float al_ = (a0.c + x0.c) * c0.c;                                          \
+            const float be = (a1.c + x1.c) * c1.c * inv_sqrt_3;                              \
+            const float ga = (a2.c + x2.c) * c2.c;                                           \
+            const float m0 = fmaf(v0.c, be, ga * ux), m1 = fmaf(v1.c, be, ga * uy), m2 = fmaf(v2.c, be, ga * uz); \
+            dx.c += al_;                                                                     \
+            d0.c = fmaf(m0, inv_sqrt_h, d0.c); d1.c = fmaf(m1, inv_sqrt_h, d1.c); d2.c = fmaf(m2, inv_sqrt_h, d2.c); \
+          }
+          OARD_EQT(x) OARD_EQT(y) OARD_EQT(z) OARD_EQT(w)
+#undef OARD_EQT
+        }
         float* sp = s + (size_t)t * H + h0 + 4 * q;
         float4 sv = *reinterpret_cast<const float4*>(sp);
         sv.x = (sv.x + dx.x) * inv_sqrt_2; sv.y = (sv.y + dx.y) * inv_sqrt_2; sv.z = (sv.z + dx.z) * inv_sqrt_2; sv.w = (sv.w + dx.w) * inv_sqrt_2;
@@ -726,7 +700,6 @@ __global__ void __launch_bounds__(ET_THREADS, MINB) k_equi_tgt(
         *reinterpret_cast<float4*>(vec_out + o + H) = make_float4(w1.x + d1.x, w1.y + d1.y, w1.z + d1.z, w1.w + d1.w);
         *reinterpret_cast<float4*>(vec_out + o + 2 * H) = make_float4(w2.x + d2.x, w2.y + d2.y, w2.z + d2.z, w2.w + d2.w);
       }
-      if (ES > 1) __syncthreads();  // partials dead before the next round
     }
     __syncthreads();  // tiles dead before the next item stages
   }

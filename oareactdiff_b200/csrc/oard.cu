@@ -813,6 +813,12 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
   };
   const bool P = h->use_p16;
   const int ldD = h->ldD, ldH = h->ldH, ld3H = h->ld3H;
+  // L2 residency plan: operands that are streamed once and are too large to stay (the edge state) or are dead after this
+  // read (hidden activations at their last use) are loaded / stored with evict_first, so that what the NEXT kernel reads
+  // (hid1, m2, d1, RB, G: 80-85 MB each, the L2 holds 126 MB) is what survives.  OARD_L2HINT=0: no hints.
+  static int env_hint = -1;
+  if (env_hint < 0) { const char* e = getenv("OARD_L2HINT"); env_hint = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  const int EF = env_hint ? 1 : 0;
 
   // ---- per-step graph artefacts: mask, groups, CoM, frames, active-edge compaction
   if (E) { PB("k_edge_mask", 0, E*29.0, 0);
@@ -946,6 +952,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
+      g.hintA = EF;  // the edge state streams through
       static int env_mlp2 = -1;
       // OARD_MLP2=1: both layers of the edge MLP in one kernel (gemm_p16_mlp2_kernel).  Parity-green, but measured slower
       // (160 vs 97 + 43 us per layer): with 512 TMEM columns and 227 KB of shared memory there is room for ONE accumulator
@@ -968,6 +975,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
         if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
         g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
         g.bias = w.e1b; g.act = 1;
+        g.hintA = EF;  // last use of hid1
         if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
       }
     }
@@ -1010,6 +1018,8 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
       g.prescale = h->buf<float>("att");  // attention gate of the edge (k_att_agg): W (att m) = att (W m)
+      // (no hints here: the m2 tile is re-read for each of the three column tiles, and hints on the in-place edge-state stream
+      // itself measured slower, 194 vs 170 us)
       // compact copy of the active rows in TARGET order (row of e = compact position of its transposed edge): contiguous
       // operand for dir_proj, and the G rows of the messages arriving at one target form one contiguous block
       g.C2 = ew_act; g.c2idx = h->buf<int>("act_pos_t"); g.ldc2 = ldD;
@@ -1040,12 +1050,14 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(ew_act, ldD, w.d0w, D, d1, ld3H, E, 3 * H, D);
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
+      g.hintA = EF;  // last use of the compact copy
       if (P) GEMM_P16("gemm_dir_proj0", g, h->T[l].d0, true); else GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
       g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
       g.m_dev = n_act;
       GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
       g = mk(d1, ld3H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
+      g.hintA = EF; g.hintX = EF;  // last use of d1 and RB; G stays for the message kernel
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
       h->num_sms = sm_guard.keep;
     }
@@ -1064,22 +1076,17 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       if (env_frag < 0) { const char* e = getenv("OARD_EQUI"); env_frag = (e && strcmp(e, "node") == 0) ? 0 : 1; }
       const bool frag_ok = env_frag && h->complete && c.reflect_equiv && l < 64 && et_smem <= 200 * 1024 && (CH == 28 || CH == 32 || CH == 16);
       if (frag_ok && E) {
-        // variants (edges in flight per thread, CTAs per SM the registers allow): OARD_ET=42 (default) | 33 | 24
-        static int env_et = -1;
-        if (env_et < 0) { const char* e = getenv("OARD_ET"); env_et = e ? atoi(e) : 42; if (env_et != 33 && env_et != 24) env_et = 42; }
-        const int minb = env_et % 10;
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(minb, (220 * 1024) / (et_smem + 1024)));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (et_smem + 1024)));
         const int grid = h->num_sms * per_sm;
-#define OARD_ET(CHV, U, MB)                                                                                            \
+#define OARD_ET(CHV)                                                                                                   \
         {                                                                                                              \
           static PerDeviceOnce attr;                                                                                   \
-          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_tgt<CHV, U, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-          k_equi_tgt<CHV, U, MB><<<grid, ET_THREADS, et_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
+          if (attr.first_time()) CU(cudaFuncSetAttribute(k_equi_tgt<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+          k_equi_tgt<CHV><<<grid, ET_THREADS, et_smem, st>>>(H, H / CHV, h->max_comp, h->buf<int>("n_lead"), h->buf<int2>("lead_info"), \
               h->buf<int>("work_ctr") + l, h->buf<int>("gm_node"), h->buf<int2>("gm_rap"), h->buf<int2>("act_rec"),     \
               h->buf<float4>("act_geo"), G, X, vec, vec2, s);                                                          \
         }
-        if (CH == 28) { if (env_et == 33) OARD_ET(28, 3, 3) else if (env_et == 24) OARD_ET(28, 2, 4) else OARD_ET(28, 4, 2) }
-        else if (CH == 32) OARD_ET(32, 4, 2) else OARD_ET(16, 4, 2)
+        if (CH == 28) OARD_ET(28) else if (CH == 32) OARD_ET(32) else OARD_ET(16)
 #undef OARD_ET
       } else {
         k_equi_reduce<8><<<N, 512, (size_t)8 * 4 * (H / 4) * sizeof(float4), st>>>(

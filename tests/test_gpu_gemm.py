@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("M,N,K", [(128, 16, 32), (300, 196, 684), (1000, 684, 196), (257, 588, 588), (5000, 588, 96),
                                    (33, 32, 112), (20000, 196, 684)])
 def test_gemm_tc_and_simt(M, N, K):
-    from tests.bringup_tc import run
+    from tools.bringup_tc import run
     tc = run(M, N, K, 1)
     simt = run(M, N, K, 0)
     tcs = run(M, N, K, 1, act=1)
@@ -25,7 +25,7 @@ def test_gemm_tc_and_simt(M, N, K):
 def test_gemm_tc_epilogue_modes(M, N, K, mode):
     """Epilogue modes (two gathered adds / multiplier / in-place residual) incl. multi-tile-per-CTA sizes, on the TMA paths
     and with the LSU fallbacks forced (ablate bits 16 / 32)."""
-    from tests.bringup_tc import run_mode
+    from tools.bringup_tc import run_mode
     for ab in (0, 16, 32, 48):
         res = run_mode(M, N, K, mode, ab)
         assert res.startswith("rel_err=") and float(res.split()[0].split("=")[1]) < 3e-5 and res.endswith("nan=0"), (ab, res)
@@ -38,7 +38,7 @@ def test_gemm_p16(M, N, K, mode, out_pair):
     """pair16 GEMM (A operand and optionally C / residual / compact copy stored as split-bf16 pairs in the UMMA operand
     layout) against fp64: 3e-5 of max|ref| like the fp32-A kernel (the operands carry the same 16 mantissa bits; a
     pair16 output adds one 2^-17 rounding)."""
-    from tests.bringup_p16 import run_p16
+    from tools.bringup_p16 import run_p16
     for ew in ((8, 16) if (mode, out_pair) != (3, 0) else (8,)):
         res = run_p16(M, N, K, mode, out_pair, act=1, c2=(mode in (0, 3)), ew=ew)
         assert "error" not in res, res
