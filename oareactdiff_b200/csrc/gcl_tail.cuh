@@ -1,0 +1,507 @@
+// Fused tail of the GCL edge chain (leftnet.py:160-183) — one persistent tcgen05 kernel instead of three launches:
+//
+//   m    = SiLU(hid W_b^T + b_b)                       second layer of edge_mlp            (was gemm_gcl_edge2)
+//   att  = SiLU(w_att . m + b_att)                     attention gate, per edge            (was part of k_att_agg)
+//   e   += SiLU(att (m W_eo^T) + b_eo)                 edge_out_trans residual             (was gemm_gcl_edge_out)
+//
+// The hidden tile m never goes through HBM on its way into the third contraction: epilogue 2 writes it as split-bf16 pairs
+// straight into TENSOR MEMORY, and tcgen05.mma takes its A operand from there (tools/probe_ts_mma.cu established the
+// layout: lane = row, one 32-bit column = two K-adjacent bf16, k even in the low half; a K step of 16 = 8 columns).
+// Tensor-memory plan per CTA (512 columns x 128 lanes):
+//   [0, 208)    acc2 = hid W_b^T (N 196 -> 208)          then, once epilogue 2 has drained it, accumulator B of layer 3
+//   [208, 312)  m_hi   (K 196 -> 208 = 13 K steps x 8 columns)
+//   [312, 416)  m_lo
+//   [416, 512)  accumulator A of layer 3 (96 columns)
+// Layer 3 runs in 8 column tiles of 96 (684 -> 768) that alternate between the accumulators A and B, so the MMAs of tile
+// nt + 1 overlap the epilogue of tile nt.  Per 128-edge tile the kernel reads hid (pair16) and the edge state and writes the
+// edge state (+ the compact copy of the active rows, + m for the aggregation kernel): m2 is no longer read back by
+// edge_out, att no longer round-trips, two launches disappear.
+//
+// Warp roles (15 warps, 1 CTA/SM, persistent over row tiles):
+//   warps 0..11  epilogue: warp e owns TMEM lanes 32 (e % 4).. and column blocks e / 4 (+3, +6 in epilogue 2)
+//   warp  12     MMA issuer (one lane), owns the tensor-memory allocation
+//   warp  13     A loader: 2-D TMA boxes of the pair16 hidden activation (128 rows x 128 B, SWIZZLE_128B)
+//   warp  14     W loader: TMA bulk copies of the pre-tiled weight slabs of layer 2, then of the 8 x 7 slabs of layer 3
+#pragma once
+#include "gemm_p16.cuh"
+#include "kernels.cuh"  // packed f32x2 helpers, silu4_shared_rcp2
+
+namespace oard {
+
+struct GclTailArgs {
+  const float* hid; int ldh;        // A of layer 2: pair16 [E, ldh]
+  float* P; int ldp;                // partial sums of att * m per (32-row group, run of equal sources): [ceil(E/32) * 32, ldp]
+  int* Psrc;                        // source node of every run ([ceil(E/32) * 32], -1 = unused; set by oard_plan)
+  const int* esrc;                  // source node per edge (rows are sorted by it)
+  float* ew; int lde;               // edge state, pair16 [E, lde], updated in place
+  float* ew_act; const int* c2idx;  // compact copy of the active rows (row index per edge or -1), same pitch as ew
+  const float* b2; const float* attw; const float* attb; const float* b3;
+  float* att;                       // [E] attention gate (diagnostics / training adapter), may be NULL
+  long long* ts;                    // optional [16 warps][64] clock64 timestamps of CTA 0's third row tile (timeline probe)
+  int E, H, D;
+};
+
+constexpr int GT_EW = 12;                          // epilogue warps
+constexpr int GT_THREADS = (GT_EW + 4) * 32;       // 512
+constexpr int GT_BN3 = 96;                         // column tile of layer 3
+constexpr int GT_COL_ACC2 = 0, GT_COL_MHI = 208, GT_COL_MLO = 312, GT_COL_ACCA = 416;
+
+// tcgen05.mma with the A operand in tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 / 8 consecutive 32-bit columns from registers into tensor memory (thread t -> lane base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ inline int gcl_tail_wslot(int bn2) {
+  const int a = 2 * bn2 * TC_KC * 2, b = 4 * GT_BN3 * TC_KC * 2;
+  return ((a > b ? a : b) + 1023) / 1024 * 1024;
+}
+
+// 32 lanes x 16 consecutive 32-bit columns as raw words
+__device__ __forceinline__ void tmem_ld16_u32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+#define GT_TS(k) do { if (g.ts && blockIdx.x == 0 && it == 2 && lane == 0) g.ts[warp * 64 + (k)] = clock64(); } while (0)
+
+template <int SH, int SR, int SW>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmE) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int EW = GT_EW;
+  const int W2_PART = w2.BN * TC_KC * 2, W3_PART = GT_BN3 * TC_KC * 2;
+  // ring slot = one slab of layer 2 or TWO consecutive slabs of layer 3 (12 KB each: pairs keep twice the bytes in flight
+  // on the L2 -> shared-memory stream that feeds the 8 x 7 weight slabs of layer 3 to every row tile)
+  const int W_SLOT = gcl_tail_wslot(w2.BN);
+  uint8_t* h_ring = smem;                                        // [SH][16 KB]  hidden activation chunks (A of layer 2)
+  uint8_t* r_ring = h_ring + (size_t)SH * P16_A_BYTES;           // [SR][16 KB]  edge-state residual blocks, 128 rows x 32 columns
+  uint8_t* w_ring = r_ring + (size_t)SR * P16_A_BYTES;           // [SW][W_SLOT]
+  uint8_t* out_all = w_ring + (size_t)SW * W_SLOT;               // [EW][4 KB]   output staging / transpose scratch per warp
+  float* att_part = reinterpret_cast<float*>(out_all + (size_t)EW * TC_IO_BYTES);  // [3][128]
+  float* b3s = att_part + 3 * TC_BM;                                               // [J * 32] bias of layer 3 (zero padded)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + ((g.D + 31) / 32) * 32);
+  uint64_t* full_h = bars;               // [SH]
+  uint64_t* empty_h = full_h + SH;       // [SH]  tcgen05.commit
+  uint64_t* full_r = empty_h + SH;       // [SR]
+  uint64_t* empty_r = full_r + SR;       // [SR]  count 4: the four row-quarter warps of the block's column group
+  uint64_t* full_w = empty_r + SR;       // [SW]
+  uint64_t* empty_w = full_w + SW;       // [SW]
+  uint64_t* acc2_full = empty_w + SW;    // layer-2 MMAs retired
+  uint64_t* m_full = acc2_full + 1;      // count EW: m tile written to tensor memory (and acc2 drained)
+  uint64_t* acc3_full = m_full + 1;      // [2]
+  uint64_t* acc3_empty = acc3_full + 2;  // [2] count EW (every epilogue warp arrives for every column tile)
+  uint64_t* tile_done = acc3_empty + 2;  // count EW: epilogue 3 of the tile finished (accumulators and m are dead)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.E + TC_BM - 1) / TC_BM;
+  const int k2_chunks = w2.k_chunks, k16_2 = (w2.K + 15) / 16;  // layer 2: K = H
+  const int k3_chunks = w3.k_chunks, k16_3 = (w3.K + 15) / 16;  // layer 3: K = H
+  const int n3_tiles = w3.n_tiles;
+  const int J = (g.D + 31) / 32;  // residual / output blocks per row tile, in (column tile, column group) order
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SH; s++) { ptx::mbar_init(&full_h[s], 1); ptx::mbar_init(&empty_h[s], 1); }
+    for (int s = 0; s < SR; s++) { ptx::mbar_init(&full_r[s], 1); ptx::mbar_init(&empty_r[s], 4); }
+    for (int s = 0; s < SW; s++) { ptx::mbar_init(&full_w[s], 1); ptx::mbar_init(&empty_w[s], 1); }
+    ptx::mbar_init(acc2_full, 1);
+    ptx::mbar_init(m_full, EW);
+    for (int b = 0; b < 2; b++) { ptx::mbar_init(&acc3_full[b], 1); ptx::mbar_init(&acc3_empty[b], EW); }
+    ptx::mbar_init(tile_done, EW);
+    ptx::fence_barrier_init();
+  }
+  if (warp == EW) ptx::tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < J * 32; i += GT_THREADS) b3s[i] = i < g.D ? g.b3[i] : 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == EW + 1) {
+    // ===================== hidden-activation loader (A of layer 2) =====================
+    if (lane == 0) {
+      const uint64_t pol = ptx::l2_policy(1);  // last use of hid1
+      ptx::tma_prefetch_desc(&tmA);
+      uint32_t gchunk = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        const int m0 = tile * TC_BM;
+        for (int kc = 0; kc < k2_chunks; kc++, gchunk++) {
+          const int s = gchunk % SH;
+          ptx::mbar_wait(&empty_h[s], ((gchunk / SH) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_h[s], P16_A_BYTES);
+          ptx::tma_load_2d_h(h_ring + (size_t)s * P16_A_BYTES, &tmA, kc * TC_KC, m0, &full_h[s], 1, pol);
+        }
+      }
+    }
+  } else if (warp == EW + 3) {
+    // ===================== residual loader: the edge-state blocks of epilogue 3, 128 rows x 32 columns each, running ahead of
+    // the epilogue by the depth of the ring (they do not depend on the contractions)
+    if (lane == 0) {
+      ptx::tma_prefetch_desc(&tmR);
+      uint32_t gi = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        const int m0 = tile * TC_BM;
+        for (int f = 0; f < J; f++, gi++) {
+          const int s = gi % SR;
+          ptx::mbar_wait(&empty_r[s], ((gi / SR) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_r[s], P16_A_BYTES);
+          ptx::tma_load_2d(r_ring + (size_t)s * P16_A_BYTES, &tmR, f * 32, m0, &full_r[s]);
+        }
+      }
+    }
+  } else if (warp == EW + 2) {
+    // ===================== W loader: 7 slabs of layer 2, then 8 x 7 slabs of layer 3 in pairs, per row tile =====================
+    if (lane == 0) {
+      uint32_t gchunk = 0;
+      const uint8_t* src2 = reinterpret_cast<const uint8_t*>(w2.data);
+      const uint8_t* src3 = reinterpret_cast<const uint8_t*>(w3.data);
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < k2_chunks; kc++, gchunk++) {
+          const int s = gchunk % SW;
+          ptx::mbar_wait(&empty_w[s], ((gchunk / SW) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W2_PART);
+          ptx::bulk_g2s(w_ring + (size_t)s * W_SLOT, src2 + (size_t)kc * 2 * W2_PART, 2 * W2_PART, &full_w[s]);
+        }
+        const int total3 = n3_tiles * k3_chunks;
+        for (int c = 0; c < total3; c += 2, gchunk++) {  // two consecutive slabs per slot
+          const int s = gchunk % SW;
+          const uint32_t bytes = (uint32_t)min(2, total3 - c) * 2 * W3_PART;
+          ptx::mbar_wait(&empty_w[s], ((gchunk / SW) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_w[s], bytes);
+          ptx::bulk_g2s(w_ring + (size_t)s * W_SLOT, src3 + (size_t)c * 2 * W3_PART, bytes, &full_w[s]);
+        }
+      }
+    }
+  } else if (warp == EW) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc2 = tc_idesc(TC_BM, w2.BN), idesc3 = tc_idesc(TC_BM, GT_BN3);
+      uint32_t ga = 0, gw = 0, it = 0, g3 = 0;
+      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
+        // the accumulators and the m tile of the previous row tile are dead once its epilogue 3 has finished
+        GT_TS(0);
+        ptx::mbar_wait(tile_done, (it & 1) ^ 1);
+        ptx::tc_fence_after();
+        GT_TS(1);
+        // ---- layer 2 -> acc2
+        for (int kc = 0; kc < k2_chunks; kc++, ga++, gw++) {
+          const int sa = ga % SH, sw_ = gw % SW;
+          ptx::mbar_wait(&full_w[sw_], (gw / SW) & 1);
+          ptx::mbar_wait(&full_h[sa], (ga / SH) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(h_ring + (size_t)sa * P16_A_BYTES);
+          const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT), w_lo = w_hi + W2_PART;
+          const int steps = min(TC_KC / 16, k16_2 - kc * (TC_KC / 16));
+          for (int j = 0; j < steps; j++) {
+            const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
+            const uint32_t kw = j * 2 * TC_CORE_BYTES;
+            const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwh, idesc2, (kc | j) != 0);
+            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwl, idesc2, 1);
+            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dal, dwh, idesc2, 1);
+          }
+          ptx::umma_commit(&empty_h[sa]);
+          ptx::umma_commit(&empty_w[sw_]);
+        }
+        ptx::umma_commit(acc2_full);
+        GT_TS(2);
+        // ---- layer 3: A = m in tensor memory, 8 column tiles alternating between the accumulators A and B
+        ptx::mbar_wait(m_full, it & 1);
+        ptx::tc_fence_after();
+        GT_TS(3);
+        const int total3 = n3_tiles * k3_chunks;
+        int sw_ = 0;
+        for (int nt = 0; nt < n3_tiles; nt++, g3++) {
+          const int buf = g3 & 1;
+          ptx::mbar_wait(&acc3_empty[buf], ((g3 >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          GT_TS(4 + 2 * nt);
+          const uint32_t d_tmem = tmem_base + (buf ? GT_COL_ACC2 : GT_COL_ACCA);
+          for (int kc = 0; kc < k3_chunks; kc++) {
+            const int c = nt * k3_chunks + kc;  // flat slab index of the row tile: slot = c / 2, half = c % 2
+            if ((c & 1) == 0) {
+              sw_ = gw % SW;
+              ptx::mbar_wait(&full_w[sw_], (gw / SW) & 1);
+              ptx::tc_fence_after();
+            }
+            const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT + (size_t)(c & 1) * 2 * W3_PART), w_lo = w_hi + W3_PART;
+            const int steps = min(TC_KC / 16, k16_3 - kc * (TC_KC / 16));
+            for (int j = 0; j < steps; j++) {
+              const uint32_t ks = (uint32_t)(kc * (TC_KC / 16) + j) * 8;  // 8 columns per K step of 16
+              const uint32_t kw = j * 2 * TC_CORE_BYTES;
+              const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwh, idesc3, (kc | j) != 0);
+              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwl, idesc3, 1);
+              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MLO + ks, dwh, idesc3, 1);
+            }
+            if ((c & 1) == 1 || c == total3 - 1) { ptx::umma_commit(&empty_w[sw_]); gw++; }
+          }
+          ptx::umma_commit(&acc3_full[buf]);
+          GT_TS(5 + 2 * nt);
+        }
+      }
+    }
+  } else if (warp < EW) {
+    // ===================== epilogue warps: thread = edge row =====================
+    const int rq = warp & 3, cg = warp >> 2;  // row quarter, column group (0..2)
+    const uint32_t lane_base = (uint32_t)(rq * 32) << 16;
+    uint8_t* stg = out_all + (size_t)warp * TC_IO_BYTES;
+    float* T = reinterpret_cast<float*>(stg);  // 32 x 32 transpose scratch of the aggregation (same 4 KB)
+    const int sw = lane & 7;
+    const int nb2 = (w2.BN + 31) / 32;  // column blocks of the hidden tile (7)
+    if (lane == 0) ptx::tma_prefetch_desc(&tmE);
+    const float batt = g.attb[0];
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
+      const int m0r = tile * TC_BM + rq * 32;
+      const int m = m0r + lane;
+      const bool ok = m < g.E;
+      const int c2 = (ok && g.ew_act) ? g.c2idx[m] : -1;
+      const int src = ok ? g.esrc[m] : -1;  // rows are sorted by source: a run of equal sources = the edges of one node
+      // ---------------- epilogue 2, pass 1: m = SiLU(acc2 + b2) -> tensor memory (split bf16); att partial dots
+      GT_TS(0);
+      ptx::mbar_wait(acc2_full, it & 1);
+      ptx::tc_fence_after();
+      GT_TS(1);
+      float dot = 0.f;
+      for (int blk = cg; blk < nb2; blk += 3) {
+        float v[32];
+        ptx::tmem_ld32(tmem_base + lane_base + GT_COL_ACC2 + blk * 32, v);  // warp-collective
+        const int nblk = blk * 32;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int n = nblk + q * 4;
+          const bool nin = n < g.H;
+          float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (nin) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(g.b2 + n));
+            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+          }
+          x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w);
+          if (!nin || !ok) x = make_float4(0.f, 0.f, 0.f, 0.f);  // K padding of layer 3 / rows beyond E: exact zeros
+          if (nin) {
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(g.attw + n));
+            dot = fmaf(x.x, wa.x, fmaf(x.y, wa.y, fmaf(x.z, wa.z, fmaf(x.w, wa.w, dot))));
+          }
+          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        uint4 cell[8];
+        p16_split8(v, cell[0], cell[2]);
+        p16_split8(v + 8, cell[1], cell[3]);
+        p16_split8(v + 16, cell[4], cell[6]);
+        p16_split8(v + 24, cell[5], cell[7]);
+        // tensor memory: hi words of columns nblk .. nblk+31 = cells 0,1,4,5 (two bf16 per word, k even in the low half)
+        const uint32_t hi[16] = {cell[0].x, cell[0].y, cell[0].z, cell[0].w, cell[1].x, cell[1].y, cell[1].z, cell[1].w,
+                                 cell[4].x, cell[4].y, cell[4].z, cell[4].w, cell[5].x, cell[5].y, cell[5].z, cell[5].w};
+        const uint32_t lo[16] = {cell[2].x, cell[2].y, cell[2].z, cell[2].w, cell[3].x, cell[3].y, cell[3].z, cell[3].w,
+                                 cell[6].x, cell[6].y, cell[6].z, cell[6].w, cell[7].x, cell[7].y, cell[7].z, cell[7].w};
+        const uint32_t c16 = (uint32_t)blk * 16;
+        if ((blk + 1) * 32 <= k16_3 * 16) {
+          tmem_st16(tmem_base + lane_base + GT_COL_MHI + c16, hi);
+          tmem_st16(tmem_base + lane_base + GT_COL_MLO + c16, lo);
+        } else {  // last block: only the first 16 columns lie inside the padded K
+          tmem_st8(tmem_base + lane_base + GT_COL_MHI + c16, hi);
+          tmem_st8(tmem_base + lane_base + GT_COL_MLO + c16, lo);
+        }
+      }
+      tmem_wait_st();
+      GT_TS(2);
+      att_part[cg * TC_BM + rq * 32 + lane] = dot;
+      ptx::tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(GT_EW * 32) : "memory");  // the 12 epilogue warps: partial dots visible, m complete
+      if (lane == 0) ptx::mbar_arrive(m_full);  // (after the barrier: every warp's columns of m are in tensor memory)
+      GT_TS(3);
+      const float att = silu((att_part[rq * 32 + lane] + att_part[TC_BM + rq * 32 + lane]) + att_part[2 * TC_BM + rq * 32 + lane] + batt);
+      if (cg == 0 && ok && g.att) g.att[m] = att;
+      // ---------------- epilogue 2, pass 2: aggregation at the source (leftnet.py:170-183).  The rows of this warp hold runs of
+      // equal sources; the sum of att * m over a run goes to the partial-sum row (32-row group, run index), a node's mean is
+      // completed by k_agg_runs from the 1-3 groups its edges span.  Transpose through shared memory: lane = column, fixed
+      // row order (bitwise reproducible).
+      {
+        const int prev = __shfl_up_sync(0xffffffffu, src, 1);
+        const unsigned starts = __ballot_sync(0xffffffffu, lane == 0 || src != prev);
+        const int grp = m0r >> 5;
+        if (cg == 0 && ((starts >> lane) & 1u) && src >= 0)
+          g.Psrc[(size_t)grp * 32 + (__popc(starts & ((2u << lane) - 1u)) - 1)] = src;
+        const unsigned valid_rows = __ballot_sync(0xffffffffu, src >= 0);
+        for (int blk = cg; blk < nb2; blk += 3) {
+          uint32_t hw[16], lw[16];
+          tmem_ld16_u32(tmem_base + lane_base + GT_COL_MHI + blk * 16, hw);
+          tmem_ld16_u32(tmem_base + lane_base + GT_COL_MLO + blk * 16, lw);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the scratch was a store's source
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float a = (__uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16)) * att;
+            const float b = (__uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u)) * att;
+            T[lane * 32 + ((2 * j) ^ lane)] = a;
+            T[lane * 32 + ((2 * j + 1) ^ lane)] = b;
+          }
+          __syncwarp();
+          const int n = blk * 32 + lane;  // this lane's column
+          float sum = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; r++) {
+            sum += T[r * 32 + (lane ^ r)];
+            const bool last = r == 31 || ((starts >> (r + 1)) & 1u);
+            if (last) {
+              if (n < g.H && ((valid_rows >> r) & 1u))
+                g.P[((size_t)grp * 32 + (__popc(starts & ((2u << r) - 1u)) - 1)) * g.ldp + n] = sum;
+              sum = 0.f;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      GT_TS(4);
+      // ---------------- epilogue 3: e += SiLU(att * acc3 + b3) per column tile
+      for (int nt = 0; nt < n3_tiles; nt++) {
+        const int g3 = (int)it * n3_tiles + nt;
+        const int buf = g3 & 1;
+        const int f = nt * 3 + cg;  // block index inside the row tile
+        const int n0 = f * 32;
+        if (f < J) {
+          // Order matters for the residual ring's phase parity: a warp may only wait for block f of the ring after every warp
+          // has consumed its block of column tile nt - 2 (they hand accumulator nt - 2 back AFTER their ring read, and this
+          // warp is past acc3_full(nt)), so the oldest unconsumed block is at most 5 positions back: less than the 2 * SR = 8
+          // at which a parity wait would be satisfied by a stale phase.
+          ptx::mbar_wait(&acc3_full[buf], (g3 >> 1) & 1);
+          ptx::tc_fence_after();
+          GT_TS(8 + 4 * nt);
+          const uint32_t ri = it * (uint32_t)J + (uint32_t)f;
+          const int rs = ri % SR;
+          ptx::mbar_wait(&full_r[rs], (ri / SR) & 1);
+          GT_TS(9 + 4 * nt);
+          const uint8_t* rb = r_ring + (size_t)rs * P16_A_BYTES + (size_t)(rq * 32 + lane) * 128;
+          uint4 cell[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) cell[q] = *reinterpret_cast<const uint4*>(rb + ((q ^ sw) << 4));
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&empty_r[rs]);
+          float e[32];
+          p16_join8(cell[0], cell[2], e);
+          p16_join8(cell[1], cell[3], e + 8);
+          p16_join8(cell[4], cell[6], e + 16);
+          p16_join8(cell[5], cell[7], e + 24);
+          float v[32];
+          ptx::tmem_ld32(tmem_base + lane_base + (buf ? GT_COL_ACC2 : GT_COL_ACCA) + cg * 32, v);  // warp-collective
+          // this accumulator block is in registers: the MMA warp may refill it as soon as every warp has arrived
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc3_empty[buf]);
+          const f32x2 att2 = pk2(att, att);
+          const float2* bp = reinterpret_cast<const float2*>(b3s + n0);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {  // 8 values per round: x = SiLU(att * acc + b3), four SiLUs per reciprocal pair
+            f32x2 u0 = fma2(pk2(v[8 * q], v[8 * q + 1]), att2, ld2(bp[4 * q])), u1 = fma2(pk2(v[8 * q + 2], v[8 * q + 3]), att2, ld2(bp[4 * q + 1]));
+            f32x2 u2 = fma2(pk2(v[8 * q + 4], v[8 * q + 5]), att2, ld2(bp[4 * q + 2])), u3 = fma2(pk2(v[8 * q + 6], v[8 * q + 7]), att2, ld2(bp[4 * q + 3]));
+            silu4_shared_rcp2(u0, u1, u2, u3);
+            u0 = add2(u0, pk2(e[8 * q], e[8 * q + 1])); u1 = add2(u1, pk2(e[8 * q + 2], e[8 * q + 3]));
+            u2 = add2(u2, pk2(e[8 * q + 4], e[8 * q + 5])); u3 = add2(u3, pk2(e[8 * q + 6], e[8 * q + 7]));
+            upk2(u0, v[8 * q], v[8 * q + 1]); upk2(u1, v[8 * q + 2], v[8 * q + 3]);
+            upk2(u2, v[8 * q + 4], v[8 * q + 5]); upk2(u3, v[8 * q + 6], v[8 * q + 7]);
+          }
+          p16_split8(v, cell[0], cell[2]);
+          p16_split8(v + 8, cell[1], cell[3]);
+          p16_split8(v + 16, cell[4], cell[6]);
+          p16_split8(v + 24, cell[5], cell[7]);
+          GT_TS(10 + 4 * nt);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has read the staging
+          __syncwarp();
+          GT_TS(11 + 4 * nt);
+          uint8_t* iob = stg + lane * 128;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            *reinterpret_cast<uint4*>(iob + ((q ^ sw) << 4)) = cell[q];
+            if (c2 >= 0 && (n0 + (q >> 2) * 16) < g.lde)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.ew_act + (size_t)c2 * g.lde + n0) + q * 16) = cell[q];
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmE, n0, m0r, stg);
+            ptx::bulk_commit();
+          }
+          __syncwarp();
+        } else {  // no block of this column tile for this warp: just hand the accumulator back
+          ptx::mbar_wait(&acc3_full[buf], (g3 >> 1) & 1);
+          ptx::tc_fence_after();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc3_empty[buf]);
+        }
+      }
+      GT_TS(40);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tile_done);
+    }
+    if (lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == EW) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline size_t gcl_tail_smem_bytes(int bn2, int D, int sh, int sr, int sw) {
+  return (size_t)(sh + sr) * P16_A_BYTES + (size_t)sw * gcl_tail_wslot(bn2) + (size_t)GT_EW * TC_IO_BYTES + 3 * TC_BM * 4 +
+         (size_t)((D + 31) / 32) * 32 * 4 + (size_t)(2 * sh + 2 * sr + 2 * sw + 7) * 8 + 16;
+}
+
+// hid: pair16 [E, ldh]; w2 packed with one column tile (BN <= 208, K = H); w3 packed with BN = 96 (K = H, N = D).
+// Returns cudaErrorInvalidValue when the shape does not fit this kernel (the caller then takes the three-launch path).
+inline cudaError_t launch_gcl_tail(const GclTailArgs& g, const TcWeight& w2, const TcWeight& w3, int num_sms, cudaStream_t st) {
+  if (g.E <= 0) return cudaSuccess;
+  if (w2.n_tiles != 1 || w2.BN > 208 || w2.BN % 16 || w2.K != g.H || w2.N != g.H || w3.BN != GT_BN3 || w3.K != g.H ||
+      w3.N != g.D || w3.k_chunks != w2.k_chunks || g.H % 4 || g.D % 4 || g.ldh % 16 || g.ldh < g.H || g.lde % 16 ||
+      g.lde < g.D || g.ldp < g.H || !g.P || !g.Psrc || !g.esrc || ((w3.K + 15) / 16) * 8 > 104 || g.H > 208)
+    return cudaErrorInvalidValue;
+  const int m_tiles = (g.E + TC_BM - 1) / TC_BM;
+  const int grid = m_tiles < num_sms ? m_tiles : num_sms;
+  CUtensorMap tmA, tmR, tmE;
+  memset(&tmA, 0, sizeof tmA); memset(&tmR, 0, sizeof tmR); memset(&tmE, 0, sizeof tmE);
+  if (!tc_make_map(&tmA, g.hid, g.E, p16_ld(g.H), g.ldh, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
+  if (!tc_make_map(&tmR, g.ew, g.E, p16_ld(g.D), g.lde, 32, TC_BM, true)) return cudaErrorInvalidValue;
+  if (!tc_make_map(&tmE, g.ew, g.E, p16_ld(g.D), g.lde, 32, 32, true)) return cudaErrorInvalidValue;
+  constexpr int SH = 2, SR = 4, SW = 3;
+  const size_t smem = gcl_tail_smem_bytes(w2.BN, g.D, SH, SR, SW);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceOnce attr;
+  if (attr.first_time()) {
+    cudaError_t e = cudaFuncSetAttribute(gcl_tail_kernel<SH, SR, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  gcl_tail_kernel<SH, SR, SW><<<grid, GT_THREADS, smem, st>>>(g, w2, w3, tmA, tmR, tmE);
+  return cudaGetLastError();
+}
+
+}  // namespace oard

@@ -1029,6 +1029,24 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
   }
 }
 
+// Mean aggregation at the edge source from the per-run partial sums of the fused GCL tail (gcl_tail.cuh): node t's edges
+// are the rows [row_ptr[t], row_ptr[t+1]) and span 1-3 groups of 32 rows; in every group they form exactly one run, found by
+// its source id.  Summed in group order (bitwise reproducible).  One block per node, thread = channel.
+__global__ void k_agg_runs(int H, const int* __restrict__ row_ptr, const float* __restrict__ P, int ldp,
+                           const int* __restrict__ Psrc, float* __restrict__ xa, int ldxa) {
+  const int t = blockIdx.x, h = threadIdx.x, lane = threadIdx.x & 31;
+  const int r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  float sum = 0.f;
+  if (r1 > r0) {
+    for (int gq = r0 >> 5; gq <= (r1 - 1) >> 5; gq++) {
+      const unsigned hit = __ballot_sync(0xffffffffu, Psrc[(size_t)gq * 32 + lane] == t);
+      const int slot = __ffs(hit) - 1;  // (every warp of the block finds the same slot)
+      if (slot >= 0 && h < H) sum += P[((size_t)gq * 32 + slot) * ldp + h];
+    }
+  }
+  if (h < H) xa[(size_t)t * ldxa + H + h] = sum / (float)(r1 > r0 ? r1 - r0 : 1);
+}
+
 // GCL attention gate + mean aggregation at the edge source on a pair16 m2 (row pitch ld floats, H <= ld).
 // One block per node; warps take the row's edges round-robin; lane l < ld/8 owns 8 consecutive columns.
 __global__ void k_att_agg_p16(int H, int ld, const int* __restrict__ row_ptr, const float* __restrict__ m2,

@@ -20,6 +20,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_p16.cuh"
+#include "gcl_tail.cuh"
 #include "kernels.cuh"
 #include "dynamics.cuh"
 #include "node_chain.cuh"
@@ -95,7 +96,7 @@ struct oard_handle {
   bool use_p16 = false;  // edge-level activations (edge state, GCL hidden, dir_proj hidden) stored as pair16 (gemm_p16.cuh)
   int ldD = 0, ldH = 0, ld3H = 0;  // row pitches (floats) of the edge state / [E,H] / [E,3H] edge buffers
   int num_sms = 148;
-  struct LayerTc { TcWeight e0, e1, eo, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
+  struct LayerTc { TcWeight e0, e1, eo, eo96, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
   struct LayerMs { MsWeight n0, n1, x0, x2, vp, xv0, xv2, pq; };  // node_chain.cuh (mma.sync fragment order)
   std::vector<LayerMs> Ms;
   std::vector<Lin3U> lin3u;  // per layer, host copies passed by value (constant bank)
@@ -422,6 +423,7 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
       if ((rc = pack(w.e0w + 2 * H, 2 * H + D, H, D, &t.e0))) return rc;
       if ((rc = pack(w.e1w, H, H, H, &t.e1))) return rc;
       if ((rc = pack(w.eow, H, D, H, &t.eo))) return rc;
+      if ((rc = pack(w.eow, H, D, H, &t.eo96, GT_BN3))) return rc;  // 96-column tiles for the fused GCL tail (gcl_tail.cuh)
       if ((rc = pack(w.d0w, D, 3 * H, D, &t.d0))) return rc;
       if ((rc = pack(w.d2w, 3 * H, 3 * H, 3 * H, &t.d2))) return rc;
       if ((rc = pack(w.rbfw, R, 3 * H, R, &t.rbf))) return rc;
@@ -596,7 +598,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
       {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
       {"ew", Ee * (size_t)h->ldD * 4}, {"ew_act", Ee * (size_t)h->ldD * 4}, {"crow", (size_t)h->ldD * 4}, {"g_h_in", Nn * 32 * 4}, {"g_pos", Nn * 12}, {"g_sub", Ee * 8},
-      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * (size_t)h->ldH * 4}, {"m2", Ee * (size_t)h->ldH * 4}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * (size_t)h->ldH * 4}, {"m2", (Ee + 32) * (size_t)h->ldH * 4}, {"agg_src", (Ee + 32) * 4}, {"tail_ts", 16 * 64 * 8}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
       {"d1", Ee * (size_t)h->ld3H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
   };
   for (auto& a : allocs) {
@@ -604,6 +606,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
     if (rc) return rc;
   }
   CU(cudaMemcpy(h->buf<int>("row_ptr"), row_ptr.data(), (Nn + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemset(h->buf<int>("agg_src"), 0xff, (Ee + 32) * 4));  // run table of the fused GCL tail: -1 = no run in this slot
   if (E) {
     CU(cudaMemcpy(h->buf<int>("esrc"), esrc.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->buf<int>("ecol"), ecol.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
@@ -934,6 +937,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     const int ldw0 = 2 * H + D;
     // ---- GCLMessage (leftnet.py:157-183).  W_a = [W_ai | W_aj | W_ae]: the x_i / x_j parts are per-node GEMMs.
     const bool chain = h->use_chain;
+    bool tail_done = false;  // edge_mlp layer 2, the attention gate and edge_out_trans ran in the fused kernel
     GemmArgs g;
     if (chain) {  // x = LN(s + pos_expansion) fused into the staging of the [P | Q] GEMM
       MsGemmArgs m = msa(s, H, H, h->Ms[l].pq, PQ, 2 * H);
@@ -973,15 +977,42 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       }
       if (!fused) {
         if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
-        g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
-        g.bias = w.e1b; g.act = 1;
-        g.hintA = EF;  // last use of hid1
-        if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
+        // Fused tail (gcl_tail.cuh): edge_mlp layer 2 -> attention gate -> edge_out_trans residual in ONE kernel, the hidden
+        // tile m handed to the third contraction through tensor memory.  OARD_GCL_TAIL=0: the three-launch path.
+        static int env_tail = -1;
+        if (env_tail < 0) { const char* e = getenv("OARD_GCL_TAIL"); env_tail = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+        if (P && env_tail && h->use_tc) {
+          GclTailArgs ta;
+          memset(&ta, 0, sizeof ta);
+          ta.hid = hid1; ta.ldh = ldH; ta.P = m2; ta.ldp = ldH; ta.Psrc = h->buf<int>("agg_src"); ta.esrc = esrc;
+          ta.ew = ew; ta.lde = ldD; ta.ew_act = ew_act;
+          ta.c2idx = h->buf<int>("act_pos_t"); ta.b2 = w.e1b; ta.attw = w.attw; ta.attb = w.attb; ta.b3 = w.eob;
+          ta.att = h->buf<float>("att"); ta.E = E; ta.H = H; ta.D = D;
+          ta.ts = (h->debug && l == 0) ? h->buf<long long>("tail_ts") : nullptr;
+          prof_begin(h, "gemm_gcl_tail", 2.0 * E * H * (H + D), 4.0 * E * (1.0 * H + 2.0 * D), false, st);
+          cudaError_t e_ = launch_gcl_tail(ta, h->T[l].e1, h->T[l].eo96, h->num_sms, st);
+          if (e_ == cudaSuccess) { tail_done = true; h->launches++; prof_end(h, st); if (ta.ts) SNAP("tail_ts", ta.ts, 16 * 64 * 8); }
+          else if (e_ == cudaErrorInvalidValue) {  // shape does not fit: drop the profile record, three launches
+            cudaGetLastError();
+            if (h->prof_now) { h->prof_recs.pop_back(); h->ev_used -= 2; }
+          } else return fail(OARD_ECUDA, "%s:%d gcl_tail: %s", __FILE__, __LINE__, cudaGetErrorString(e_));
+        }
+        if (!tail_done) {
+          g = mk(hid1, ldH, w.e1w, H, m2, ldH, E, H, H);
+          g.bias = w.e1b; g.act = 1;
+          g.hintA = EF;  // last use of hid1
+          if (P) GEMM_P16("gemm_gcl_edge2", g, h->T[l].e1, true); else GEMM_TC("gemm_gcl_edge2", g, h->T[l].e1);
+        }
       }
     }
-    PB("k_att_agg", 0, (double)E*(H*4.0+4), 0);
-    if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
-    else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
+    if (tail_done) {  // the fused tail left per-run partial sums of att * m: complete the means
+      PB("k_agg_runs", 0, (double)N*H*4.0*4, 0);
+      k_agg_runs<<<N, HB, 0, st>>>(H, row_ptr, m2, ldH, h->buf<int>("agg_src"), xa, 2 * H);
+    } else {
+      PB("k_att_agg", 0, (double)E*(H*4.0+4), 0);
+      if (P) k_att_agg_p16<<<N, HB, (HB / 32) * ldH * sizeof(float), st>>>(H, ldH, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
+      else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
+    }
     KCHECK();
     // OARD_FORK: from here the node-level chain (node_mlp, x_layernorm, x_proj: reads xa; writes tN, s, tmpH, X) and the
     // edge-level chain (edge_out, dir_proj, rbf_proj: reads m2, att, ew, rbf_act; writes ew, ew_act, d1, RB, G) touch disjoint
@@ -1013,7 +1044,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
     }
     }
-    if (E) {
+    if (E && !tail_done) {
       if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;

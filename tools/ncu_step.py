@@ -18,7 +18,7 @@ def main():
     n_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    B, T = 64, 1000
+    B, T = int(os.environ.get("OARD_B", "64")), 1000
     cfg = dict(cutoff=10.0, num_layers=6, hidden_channels=196, num_radial=96, in_hidden_channels=8, reflect_equiv=True,
                legacy=True, update=True, object_aware=True)
     torch.manual_seed(0)
