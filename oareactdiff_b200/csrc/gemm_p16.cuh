@@ -358,276 +358,6 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
   }
 }
 
-// ------------------------------------------------------------------------------------------------ fused two-layer MLP
-// C = SiLU( SiLU(A W1^T + P[src] + Q[dst]) W2^T + b2 )  — the GCL edge MLP (leftnet.py:160-167) in ONE kernel: the hidden
-// activation never leaves the SM.  Epilogue 1 writes the hidden tile as split-bf16 pairs straight into a shared-memory
-// buffer that has the layout of a TMA-landed pair16 A tile (128-byte rows, SWIZZLE_128B, one 16 KB slab per 32 columns),
-// the MMA warp runs the second contraction from it, epilogue 2 stages its output blocks in the same slabs (they are dead
-// once the second MMA has retired) and TMA-stores them.  One accumulator per layer (TMEM columns 0 / 256): MMA1 of tile
-// t+1 overlaps epilogue 2 of tile t.  Requirements: N1 = K2 <= 256 and N2 <= 256 (one n-tile each), same BN for both.
-// HBM traffic per row: K1 floats in, N2 floats out (the unfused pair moved 2 N1 floats more and cost a second launch).
-template <int SA, int SW, int EW>
-__global__ void __launch_bounds__((EW + 3) * 32, 1)
-gemm_p16_mlp2_kernel(const GemmArgs g, const TcWeight w1, const TcWeight w2, const float* __restrict__ bias2,
-                     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NCG = EW / 4;
-  const int BN = w1.BN;
-  const int W_PART = BN * TC_KC * 2;
-  const int k1_chunks = w1.k_chunks, k2_chunks = w2.k_chunks;
-  uint8_t* a_ring = smem;                                      // [SA][16 KB]
-  uint8_t* hid = smem + (size_t)SA * P16_A_BYTES;              // [k2_chunks][16 KB]  hidden tile = A operand of layer 2
-  uint8_t* w_ring = hid + (size_t)k2_chunks * P16_A_BYTES;     // [SW][hi | lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + (size_t)SW * 2 * W_PART);
-  uint64_t* full_a = bars;
-  uint64_t* empty_a = full_a + SA;
-  uint64_t* full_w = empty_a + SA;
-  uint64_t* empty_w = full_w + SW;
-  uint64_t* acc1_full = empty_w + SW;
-  uint64_t* acc1_empty = acc1_full + 1;   // count EW
-  uint64_t* hid_full = acc1_empty + 1;    // count EW: hidden tile written (generic proxy) and fenced
-  uint64_t* hid_empty = hid_full + 1;     // layer-2 MMAs retired (tcgen05.commit)
-  uint64_t* acc2_full = hid_empty + 1;
-  uint64_t* acc2_empty = acc2_full + 1;   // count EW
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = g.m_dev ? min(*g.m_dev, g.M) : g.M;
-  const int m_tiles = (M + TC_BM - 1) / TC_BM;
-  const int k16_1 = (g.K + 15) / 16, k16_2 = (w2.K + 15) / 16;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SA; s++) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
-    for (int s = 0; s < SW; s++) { ptx::mbar_init(&full_w[s], 1); ptx::mbar_init(&empty_w[s], 1); }
-    ptx::mbar_init(acc1_full, 1); ptx::mbar_init(acc1_empty, EW);
-    ptx::mbar_init(hid_full, EW); ptx::mbar_init(hid_empty, 1);
-    ptx::mbar_init(acc2_full, 1); ptx::mbar_init(acc2_empty, EW);
-    ptx::fence_barrier_init();
-  }
-  if (warp == EW) ptx::tmem_alloc(tmem_slot, 512);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == EW + 1) {
-    // ===================== A loader =====================
-    if (lane == 0) {
-      ptx::tma_prefetch_desc(&tmA);
-      uint32_t gchunk = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-        const int m0 = tile * TC_BM;
-        for (int kc = 0; kc < k1_chunks; kc++, gchunk++) {
-          const int s = gchunk % SA;
-          ptx::mbar_wait(&empty_a[s], ((gchunk / SA) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_a[s], P16_A_BYTES);
-          ptx::tma_load_2d(a_ring + (size_t)s * P16_A_BYTES, &tmA, kc * TC_KC, m0, &full_a[s]);
-        }
-      }
-    }
-  } else if (warp == EW + 2) {
-    // ===================== W loader: the slabs of layer 1, then of layer 2, through one ring =====================
-    if (lane == 0) {
-      uint32_t gchunk = 0;
-      const uint8_t* src1 = reinterpret_cast<const uint8_t*>(w1.data);
-      const uint8_t* src2 = reinterpret_cast<const uint8_t*>(w2.data);
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < k1_chunks + k2_chunks; kc++, gchunk++) {
-          const int s = gchunk % SW;
-          ptx::mbar_wait(&empty_w[s], ((gchunk / SW) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_w[s], 2 * W_PART);
-          const uint8_t* src = kc < k1_chunks ? src1 + (size_t)kc * 2 * W_PART : src2 + (size_t)(kc - k1_chunks) * 2 * W_PART;
-          ptx::bulk_g2s(w_ring + (size_t)s * 2 * W_PART, src, 2 * W_PART, &full_w[s]);
-        }
-      }
-    }
-  } else if (warp == EW) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tc_idesc(TC_BM, BN);
-      uint32_t ga = 0, gw = 0, it = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
-        // ---- layer 1 -> accumulator 1
-        ptx::mbar_wait(acc1_empty, (it & 1) ^ 1);
-        ptx::tc_fence_after();
-        for (int kc = 0; kc < k1_chunks; kc++, ga++, gw++) {
-          const int sa = ga % SA, sw_ = gw % SW;
-          ptx::mbar_wait(&full_w[sw_], (gw / SW) & 1);
-          ptx::mbar_wait(&full_a[sa], (ga / SA) & 1);
-          ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(a_ring + (size_t)sa * P16_A_BYTES);
-          const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * 2 * W_PART), w_lo = w_hi + W_PART;
-          const int steps = min(TC_KC / 16, k16_1 - kc * (TC_KC / 16));
-          for (int j = 0; j < steps; j++) {
-            const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
-            const uint32_t kw = j * 2 * TC_CORE_BYTES;
-            const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-            ptx::umma_bf16(tmem_base, dah, dwh, idesc, (kc | j) != 0);
-            ptx::umma_bf16(tmem_base, dah, dwl, idesc, 1);
-            ptx::umma_bf16(tmem_base, dal, dwh, idesc, 1);
-          }
-          ptx::umma_commit(&empty_a[sa]);
-          ptx::umma_commit(&empty_w[sw_]);
-        }
-        ptx::umma_commit(acc1_full);
-        // ---- layer 2: A = hidden tile in shared memory -> accumulator 2
-        ptx::mbar_wait(hid_full, it & 1);
-        ptx::mbar_wait(acc2_empty, (it & 1) ^ 1);
-        ptx::tc_fence_after();
-        for (int kc = 0; kc < k2_chunks; kc++, gw++) {
-          const int sw_ = gw % SW;
-          ptx::mbar_wait(&full_w[sw_], (gw / SW) & 1);
-          ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(hid + (size_t)kc * P16_A_BYTES);
-          const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * 2 * W_PART), w_lo = w_hi + W_PART;
-          const int steps = min(TC_KC / 16, k16_2 - kc * (TC_KC / 16));
-          for (int j = 0; j < steps; j++) {
-            const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
-            const uint32_t kw = j * 2 * TC_CORE_BYTES;
-            const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-            ptx::umma_bf16(tmem_base + 256, dah, dwh, idesc, (kc | j) != 0);
-            ptx::umma_bf16(tmem_base + 256, dah, dwl, idesc, 1);
-            ptx::umma_bf16(tmem_base + 256, dal, dwh, idesc, 1);
-          }
-          ptx::umma_commit(&empty_w[sw_]);
-        }
-        ptx::umma_commit(hid_empty);
-        ptx::umma_commit(acc2_full);
-      }
-    }
-  } else {
-    // ===================== epilogue warps: thread = row; layer 1 -> hidden slabs, layer 2 -> TMA store =====================
-    const int rq = warp & 3, cg = warp >> 2;
-    const int nb1 = (BN + 31) / 32, nb2 = (BN + 31) / 32;
-    const int sw = lane & 7;
-    if (lane == 0) ptx::tma_prefetch_desc(&tmC);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
-      const int m0r = tile * TC_BM + rq * 32;
-      const int m = m0r + lane;
-      const bool ok = m < M;
-      const float* pr = nullptr;
-      const float* qr = nullptr;
-      if (ok) {
-        pr = g.radd1 + (size_t)(g.ridx1 ? g.ridx1[m] : m) * g.ld1;
-        qr = g.radd2 + (size_t)(g.ridx2 ? g.ridx2[m] : m) * g.ld2;
-      }
-      // the slabs were the staging of this warp's layer-2 stores of the previous tile, and the A operand of its layer-2 MMAs
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      ptx::mbar_wait(hid_empty, (it & 1) ^ 1);
-      __syncwarp();
-      // ---- epilogue 1
-      ptx::mbar_wait(acc1_full, it & 1);
-      ptx::tc_fence_after();
-      for (int blk = cg; blk < nb1; blk += NCG) {
-        uint8_t* iob = hid + (size_t)blk * P16_A_BYTES + (size_t)(rq * 32 + lane) * 128;
-        float v[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
-        const int nblk = blk * 32;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int n = nblk + q * 4;
-          const bool nin = n < w1.N;
-          float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (g.bias && nin) { const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
-          if (nin && ok) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(pr + n));
-            const float4 u = __ldg(reinterpret_cast<const float4*>(qr + n));
-            x.x += t.x + u.x; x.y += t.y + u.y; x.z += t.z + u.z; x.w += t.w + u.w;
-          }
-          x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w);
-          if (!nin || !ok) x = make_float4(0.f, 0.f, 0.f, 0.f);  // K padding of layer 2 / rows beyond M must be exact zeros
-          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        }
-        uint4 cell[8];
-        p16_split8(v, cell[0], cell[2]);
-        p16_split8(v + 8, cell[1], cell[3]);
-        p16_split8(v + 16, cell[4], cell[6]);
-        p16_split8(v + 24, cell[5], cell[7]);
-#pragma unroll
-        for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(iob + ((q ^ sw) << 4)) = cell[q];
-      }
-      // slabs beyond this layer's column blocks (k2_chunks * 32 > nb1 * 32 never happens: both are ceil(N1 / 32))
-      ptx::fence_proxy_async();  // generic smem writes -> visible to the tensor core (async proxy)
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(acc1_empty); ptx::mbar_arrive(hid_full); }
-      // ---- epilogue 2
-      ptx::mbar_wait(acc2_full, it & 1);
-      ptx::tc_fence_after();
-      for (int blk = cg; blk < nb2; blk += NCG) {
-        uint8_t* iob0 = hid + (size_t)blk * P16_A_BYTES + (size_t)(rq * 32) * 128;  // 4 KB staging slab of (blk, rq)
-        uint8_t* iob = iob0 + lane * 128;
-        float v[32];
-        ptx::tmem_ld32(tmem_base + 256 + ((uint32_t)(rq * 32) << 16) + blk * 32, v);  // warp-collective
-        const int nblk = blk * 32;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int n = nblk + q * 4;
-          const bool nin = n < w2.N;
-          float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (bias2 && nin) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias2 + n)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
-          x.x = silu_fast(x.x); x.y = silu_fast(x.y); x.z = silu_fast(x.z); x.w = silu_fast(x.w);
-          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        }
-        uint4 cell[8];
-        p16_split8(v, cell[0], cell[2]);
-        p16_split8(v + 8, cell[1], cell[3]);
-        p16_split8(v + 16, cell[4], cell[6]);
-        p16_split8(v + 24, cell[5], cell[7]);
-#pragma unroll
-        for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(iob + ((q ^ sw) << 4)) = cell[q];
-        ptx::fence_proxy_async();  // generic smem writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&tmC, nblk, m0r, iob0);
-          ptx::bulk_commit();
-        }
-        __syncwarp();
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc2_empty);
-    }
-    if (lane == 0) ptx::bulk_wait_all();
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == EW) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// A: pair16 [M, lda]; C: pair16 [M, ldc]; g carries layer 1 (A, K, radd1/radd2 gathers, optional bias); w1 / w2 packed
-// with the SAME BN, one n-tile each, w2.K == w1.N.  Returns cudaErrorInvalidValue when the shape does not fit.
-inline cudaError_t launch_gemm_p16_mlp2(const GemmArgs& g, const TcWeight& w1, const TcWeight& w2, const float* bias2,
-                                        int num_sms, cudaStream_t st) {
-  if (g.M <= 0) return cudaSuccess;
-  if (w1.n_tiles != 1 || w2.n_tiles != 1 || w1.BN != w2.BN || w2.K != w1.N || g.K != w1.K || w1.BN > 256 || w1.BN % 16 ||
-      g.lda % 16 || g.lda < g.K || g.ldc % 16 || g.ldc < w2.N || !g.radd1 || !g.radd2 || g.aidx || g.mul || g.resid || g.C2 ||
-      g.rowscale || g.prescale || w2.k_chunks * 32 < w1.BN - 31 || ((w1.BN + 31) / 32) > w2.k_chunks)
-    return cudaErrorInvalidValue;
-  const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
-  const int grid = m_tiles < num_sms ? m_tiles : num_sms;
-  CUtensorMap tmA, tmC;
-  memset(&tmA, 0, sizeof tmA); memset(&tmC, 0, sizeof tmC);
-  if (!tc_make_map(&tmA, g.A, g.M, p16_ld(g.K), g.lda, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
-  if (!tc_make_map(&tmC, g.C, g.M, p16_ld(w2.N), g.ldc, 32, 32, true)) return cudaErrorInvalidValue;
-  constexpr int SA = 3, SW = 2, EW = 16;
-  const size_t smem = (size_t)SA * P16_A_BYTES + (size_t)w2.k_chunks * P16_A_BYTES + (size_t)SW * 2 * w1.BN * TC_KC * 2 +
-                      (size_t)(2 * SA + 2 * SW + 6) * 8 + 16;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static PerDeviceOnce attr;
-  if (attr.first_time()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_p16_mlp2_kernel<SA, SW, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-  }
-  gemm_p16_mlp2_kernel<SA, SW, EW><<<grid, (EW + 3) * 32, smem, st>>>(g, w1, w2, bias2, tmA, tmC);
-  return cudaGetLastError();
-}
-
 inline size_t p16_smem_bytes(int BN, int sa, int sw, int ew, int nio) {
   return (size_t)sa * P16_A_BYTES + (size_t)sw * 2 * BN * TC_KC * 2 + (size_t)ew * nio * TC_IO_BYTES +
          (size_t)(2 * sa + 2 * sw + 4 + ew * nio) * 8 + 16;

@@ -23,7 +23,6 @@
 #include "gcl_tail.cuh"
 #include "kernels.cuh"
 #include "dynamics.cuh"
-#include "node_chain.cuh"
 #include "train_core.h"
 
 using namespace oard;
@@ -93,16 +92,14 @@ struct oard_handle {
   std::vector<LayerW> L;
   // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
   bool use_tc = false;
+  bool use_tail = false;  // fused GCL tail kernel (gcl_tail.cuh), OARD_GCL_TAIL=1: same speed as the three launches on B=64 (W-stream bound), 25 % less HBM traffic
   bool use_p16 = false;  // edge-level activations (edge state, GCL hidden, dir_proj hidden) stored as pair16 (gemm_p16.cuh)
   int ldD = 0, ldH = 0, ld3H = 0;  // row pitches (floats) of the edge state / [E,H] / [E,3H] edge buffers
   int num_sms = 148;
   struct LayerTc { TcWeight e0, e1, eo, eo96, d0, d2, rbf, pq, n0, n1, x0, x2, vp, xv0, xv2; };
-  struct LayerMs { MsWeight n0, n1, x0, x2, vp, xv0, xv2, pq; };  // node_chain.cuh (mma.sync fragment order)
-  std::vector<LayerMs> Ms;
   std::vector<Lin3U> lin3u;  // per layer, host copies passed by value (constant bank)
   Lin3E lin3e{};
   bool use_lin3c = false;
-  bool use_chain = false;  // node-level GEMMs on the lean mma.sync kernel with fused LayerNorm / EquiUpdate (node_chain.cuh)
   std::vector<LayerTc> T;
   TcWeight tc_rl0{}, tc_rl2{}, tc_s2v{}, tc_ov1{}, tc_ou0{};
   std::vector<void*> tc_bufs;
@@ -117,12 +114,6 @@ struct oard_handle {
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};  // [0]: subgraph_mask == NULL, [1]: with mask
   int64_t graph_launches = 0;
-  // OARD_FORK=k (off by default): per layer the node-level chain (node_mlp -> x_layernorm -> x_proj) runs on a side stream
-  // next to the edge-level chain (edge_out -> dir_proj / rbf_proj), which then leaves k SMs free; joined before the message
-  // kernel.  Works in eager mode and inside the captured graphs (fork / join become graph edges).
-  int fork_sms = 0;
-  cudaStream_t side_stream = nullptr;
-  std::vector<cudaEvent_t> fork_ev;  // [2 l] fork, [2 l + 1] join
   // profiling: CUDA-event timing per kernel class on sampled forwards
   int prof_every = 0;
   int64_t fwd_count = 0;
@@ -255,25 +246,12 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     h->use_tc = want_tc && dims_ok && prop.major == 10;  // tcgen05 exists on sm_100 only
     const char* ep = getenv("OARD_P16");  // "0": keep fp32 edge activations + the in-kernel-converting GEMM (gemm_tc.cuh)
     h->use_p16 = h->use_tc && !(ep && strcmp(ep, "0") == 0);
+    const char* et = getenv("OARD_GCL_TAIL");
+    h->use_tail = h->use_p16 && et && strcmp(et, "1") == 0;
     const int H_ = cfg->hidden_channels, D_ = 3 * H_ + cfg->num_radial;
     h->ldD = h->use_p16 ? p16_ld(D_) : D_;
     h->ldH = h->use_p16 ? p16_ld(H_) : H_;
     h->ld3H = h->use_p16 ? p16_ld(3 * H_) : 3 * H_;
-    // OARD_CHAIN=1: node-level GEMMs on the mma.sync kernel with fused LayerNorm / EquiUpdate (node_chain.cuh).  Parity-green
-    // but measured SLOWER than the tcgen05 launches (legacy mma.sync issues at ~1/20 of the tcgen05 rate on sm_100:
-    // profiles/r1_node_chain_notes.md), so it is off by default.
-    const char* ec = getenv("OARD_CHAIN");
-    h->use_chain = h->use_tc && cfg->update && cfg->hidden_channels % 4 == 0 && (ec && strcmp(ec, "1") == 0) &&
-                   cfg->hidden_channels <= 256 && ms_gemm_smem<4, 0>(2 * cfg->hidden_channels) <= 227 * 1024;
-    const char* eg = getenv("OARD_GRAPH");  // "0" disables CUDA-graph replay of the forward
-    h->use_graph = !(eg && strcmp(eg, "0") == 0);
-    const char* ef = getenv("OARD_FORK");  // SMs left to the node-level branch (0 / unset: one stream, the measured default)
-    h->fork_sms = ef ? std::max(0, std::min(atoi(ef), h->num_sms - 16)) : 0;
-    if (h->fork_sms > 0 && h->use_tc) {
-      CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
-      h->fork_ev.resize(2 * (size_t)std::max(cfg->num_layers, 1));
-      for (auto& e : h->fork_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    } else h->fork_sms = 0;
   }
   for (size_t i = 0; i < h->specs.size(); i++) CU(cudaMalloc(&h->wdev[i], h->specs[i].numel * sizeof(float)));
   *out = guard.release();
@@ -296,8 +274,6 @@ extern "C" void oard_destroy(oard_handle* h) {
     if (p) cudaFree(p);
   drop_graphs(h);
   h->tctx.release();
-  for (cudaEvent_t e : h->fork_ev) cudaEventDestroy(e);
-  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   free_map(h->ws);
   free_map(h->snaps);
@@ -468,33 +444,6 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
         CU(cudaMemcpy(u.w4, w.l4w, sizeof u.w4, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&u.b4, w.l4b, 4, cudaMemcpyDeviceToHost));
       }
-    }
-  }
-  if (h->use_chain) {
-    cudaStream_t st = (cudaStream_t)stream;
-    auto packms = [&](const float* Wp, int ldw, int N, int K, int nsplit, MsWeight* out) -> int {
-      uint4* buf = nullptr;
-      CU(cudaMalloc(&buf, ms_weight_elems(N, K, nsplit) * sizeof(uint4)));
-      h->tc_bufs.push_back(buf);
-      k_ms_pack<<<128, 256, 0, st>>>(Wp, ldw, N, K, nsplit, buf);
-      CU(cudaGetLastError());
-      *out = MsWeight{buf, N, K, nsplit, N / nsplit, ms_nt8(N, nsplit), ms_k16(K)};
-      return OARD_OK;
-    };
-    const int H = h->cfg.hidden_channels;
-    h->Ms.resize(h->cfg.num_layers);
-    int rc;
-    for (int l = 0; l < h->cfg.num_layers; l++) {
-      const LayerW& w = h->L[l];
-      auto& m = h->Ms[l];
-      if ((rc = packms(w.n0w, 2 * H, H, 2 * H, 1, &m.n0))) return rc;
-      if ((rc = packms(w.n1w, H, H, H, 1, &m.n1))) return rc;
-      if ((rc = packms(w.x0w, H, H, H, 1, &m.x0))) return rc;
-      if ((rc = packms(w.x2w, H, 3 * H, H, 1, &m.x2))) return rc;
-      if ((rc = packms(w.vpw, H, 2 * H, H, 2, &m.vp))) return rc;
-      if ((rc = packms(w.xv0w, 2 * H, H, 2 * H, 1, &m.xv0))) return rc;
-      if ((rc = packms(w.xv2w, H, 3 * H, H, 3, &m.xv2))) return rc;
-      if ((rc = packms(w.pqw, H, 2 * H, H, 1, &m.pq))) return rc;
     }
   }
   h->committed = true;
@@ -800,20 +749,6 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     h->launches++;                                                                                           \
     prof_end(h, st);                                                                                         \
   } while (0)
-#define GEMM_MS(tag, m, MT_, NTW_, MODE_, NW_)                                                                \
-  do {                                                                                                       \
-    prof_begin(h, tag, 2.0 * (m).M * (m).w.N * (m).K * ((MODE_) == 1 ? 3 : 1), 4.0 * (m).M * ((m).K + (m).w.N), false, st); \
-    cudaError_t e_ = launch_ms_gemm<MT_, NTW_, MODE_, NW_>(m, st);                                           \
-    if (e_ != cudaSuccess) return fail(OARD_ECUDA, "%s:%d gemm_ms: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
-    h->launches++;                                                                                           \
-    prof_end(h, st);                                                                                         \
-  } while (0)
-  auto msa = [&](const float* A, int lda, int K, const MsWeight& w_, float* C, int ldc) {
-    MsGemmArgs m;
-    memset(&m, 0, sizeof m);
-    m.M = N; m.K = K; m.A = A; m.lda = lda; m.w = w_; m.C = C; m.ldc = ldc; m.H = H; m.reflect = c.reflect_equiv;
-    return m;
-  };
   const bool P = h->use_p16;
   const int ldD = h->ldD, ldH = h->ldH, ld3H = h->ld3H;
   // L2 residency plan: operands that are streamed once and are too large to stay (the edge state) or are dead after this
@@ -936,52 +871,27 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     const LayerW& w = h->L[l];
     const int ldw0 = 2 * H + D;
     // ---- GCLMessage (leftnet.py:157-183).  W_a = [W_ai | W_aj | W_ae]: the x_i / x_j parts are per-node GEMMs.
-    const bool chain = h->use_chain;
     bool tail_done = false;  // edge_mlp layer 2, the attention gate and edge_out_trans ran in the fused kernel
     GemmArgs g;
-    if (chain) {  // x = LN(s + pos_expansion) fused into the staging of the [P | Q] GEMM
-      MsGemmArgs m = msa(s, H, H, h->Ms[l].pq, PQ, 2 * H);
-      m.ln = 1; m.add = pe; m.gamma = w.glnw; m.beta = w.glnb; m.ln_out = xa; m.ld_ln_out = 2 * H; m.bias = w.pqb;
-      GEMM_MS("gemm_gcl_PQ", m, 4, 2, 0, 4);
-    } else {
-      PB("k_layernorm", 0, N*H*8.0, 0);
-      k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
-      KCHECK();
-      g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
-      g.bias = w.pqb;
-      GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
-    }
+    PB("k_layernorm", 0, N*H*8.0, 0);
+    k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, pe, w.glnw, w.glnb, 0, xa, 2 * H);
+    KCHECK();
+    g = mk(xa, 2 * H, w.pqw, H, PQ, 2 * H, N, 2 * H, H);
+    g.bias = w.pqb;
+    GEMM_TC("gemm_gcl_PQ", g, h->T[l].pq);
     if (E) {
       g = mk(ew, ldD, w.e0w + 2 * H, ldw0, hid1, ldH, E, H, D);
       g.radd1 = PQ; g.ridx1 = esrc; g.ld1 = 2 * H;
       g.radd2 = PQ + H; g.ridx2 = ecol; g.ld2 = 2 * H;
       g.act = 1;
       g.hintA = EF;  // the edge state streams through
-      static int env_mlp2 = -1;
-      // OARD_MLP2=1: both layers of the edge MLP in one kernel (gemm_p16_mlp2_kernel).  Parity-green, but measured slower
-      // (160 vs 97 + 43 us per layer): with 512 TMEM columns and 227 KB of shared memory there is room for ONE accumulator
-      // per layer and ONE hidden tile, so MMA1 of the next tile cannot overlap the epilogues and the A stream (3 x 16 KB
-      // ring) starves; see profiles/r1_tc_notes.md.  Off by default.
-      if (env_mlp2 < 0) { const char* e = getenv("OARD_MLP2"); env_mlp2 = (e && strcmp(e, "1") == 0) ? 1 : 0; }
-      bool fused = false;
-      if (P && env_mlp2) {  // both layers of the edge MLP in one kernel: the hidden activation stays in shared memory
-        GemmArgs g2 = g;
-        g2.C = m2; g2.ldc = ldH;
-        prof_begin(h, "gemm_gcl_edge12", 2.0 * E * H * (D + H), 4.0 * E * (D + H), false, st);
-        cudaError_t e_ = launch_gemm_p16_mlp2(g2, h->T[l].e0, h->T[l].e1, w.e1b, h->num_sms, st);
-        if (e_ == cudaSuccess) { fused = true; h->launches++; prof_end(h, st); }
-        else if (e_ == cudaErrorInvalidValue) {  // shape does not fit the fused kernel: drop the profile record, two launches
-          cudaGetLastError();
-          if (h->prof_now) { h->prof_recs.pop_back(); h->ev_used -= 2; }
-        } else return fail(OARD_ECUDA, "%s:%d gemm_p16_mlp2: %s", __FILE__, __LINE__, cudaGetErrorString(e_));
-      }
-      if (!fused) {
+      {
         if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
-        // Fused tail (gcl_tail.cuh): edge_mlp layer 2 -> attention gate -> edge_out_trans residual in ONE kernel, the hidden
-        // tile m handed to the third contraction through tensor memory.  OARD_GCL_TAIL=0: the three-launch path.
-        static int env_tail = -1;
-        if (env_tail < 0) { const char* e = getenv("OARD_GCL_TAIL"); env_tail = (e && strcmp(e, "0") == 0) ? 0 : 1; }
-        if (P && env_tail && h->use_tc) {
+        // Fused tail (gcl_tail.cuh, OARD_GCL_TAIL=1 at handle creation): edge_mlp layer 2 -> attention gate -> source
+        // aggregation -> edge_out_trans residual in ONE kernel, the hidden tile m handed to the third contraction through
+        // tensor memory.  Parity-green and 25 % lighter on HBM, but not faster at B = 64 (both forms are bound by the
+        // L2 -> shared-memory weight stream: profiles/r2_fused_tail_notes.md), so the three launches stay the default.
+        if (P && h->use_tail) {
           GclTailArgs ta;
           memset(&ta, 0, sizeof ta);
           ta.hid = hid1; ta.ldh = ldH; ta.P = m2; ta.ldp = ldH; ta.Psrc = h->buf<int>("agg_src"); ta.esrc = esrc;
@@ -1014,38 +924,13 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       else k_att_agg<<<N, HB, (HB / 32) * H * sizeof(float), st>>>(H, row_ptr, m2, w.attw, w.attb, h->buf<float>("att"), xa, 2 * H);
     }
     KCHECK();
-    // OARD_FORK: from here the node-level chain (node_mlp, x_layernorm, x_proj: reads xa; writes tN, s, tmpH, X) and the
-    // edge-level chain (edge_out, dir_proj, rbf_proj: reads m2, att, ew, rbf_act; writes ew, ew_act, d1, RB, G) touch disjoint
-    // buffers; they meet again at the message kernel.  The edge-level GEMMs are persistent (one CTA per SM), so they are
-    // launched on num_sms - fork_sms CTAs to leave room for the node-level tiles.
-    const bool fork = h->fork_sms > 0 && E > 0 && !chain && !h->prof_now && !h->debug && 2 * (size_t)l + 1 < h->fork_ev.size();
-    cudaStream_t st_node = st;
-    struct SmGuard { int& v; int keep; ~SmGuard() { v = keep; } } sm_guard{h->num_sms, h->num_sms};
-    if (fork) {
-      CU(cudaEventRecord(h->fork_ev[2 * l], st));
-      CU(cudaStreamWaitEvent(h->side_stream, h->fork_ev[2 * l], 0));
-      st_node = h->side_stream;
-    }
-    {
-    cudaStream_t st = st_node;  // (the launch macros use `st`)
-    if (chain) {
-      MsGemmArgs m = msa(xa, 2 * H, 2 * H, h->Ms[l].n0, tN, H);
-      m.bias = w.n0b; m.act = 1;
-      GEMM_MS("gemm_gcl_node0", m, 4, 2, 0, 4);
-      m = msa(tN, H, H, h->Ms[l].n1, s, H);
-      m.bias = w.n1b; m.act = c.legacy ? 0 : 1; m.resid = xa; m.ldres = 2 * H;
-      GEMM_MS("gemm_gcl_node1", m, 4, 2, 0, 4);
-    } else {
-      g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
-      g.bias = w.n0b; g.act = 1;
-      GEMM_TC("gemm_gcl_node0", g, h->T[l].n0);
-      g = mk(tN, H, w.n1w, H, s, H, N, H, H);
-      g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
-      GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
-    }
-    }
+    g = mk(xa, 2 * H, w.n0w, 2 * H, tN, H, N, H, 2 * H);
+    g.bias = w.n0b; g.act = 1;
+    GEMM_TC("gemm_gcl_node0", g, h->T[l].n0);
+    g = mk(tN, H, w.n1w, H, s, H, N, H, H);
+    g.bias = w.n1b; g.act = c.legacy ? 0 : 1; g.resid = xa; g.ldres = 2 * H;
+    GEMM_TC("gemm_gcl_node1", g, h->T[l].n1);
     if (E && !tail_done) {
-      if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(m2, ldH, w.eow, H, ew, ldD, E, D, H);
       g.bias = w.eob; g.act = 1; g.resid = ew; g.ldres = ldD;
       g.prescale = h->buf<float>("att");  // attention gate of the edge (k_att_agg): W (att m) = att (W m)
@@ -1055,30 +940,17 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       // operand for dir_proj, and the G rows of the messages arriving at one target form one contiguous block
       g.C2 = ew_act; g.c2idx = h->buf<int>("act_pos_t"); g.ldc2 = ldD;
       if (P) GEMM_P16("gemm_gcl_edge_out", g, h->T[l].eo, true); else GEMM_TC("gemm_gcl_edge_out", g, h->T[l].eo);
-      h->num_sms = sm_guard.keep;
     }
     // ---- EquiMessage (leftnet.py:244-289) on active edges only
-    {
-    cudaStream_t st = st_node;
-    if (chain) {  // message x_layernorm fused into the staging of x_proj.0
-      MsGemmArgs m = msa(s, H, H, h->Ms[l].x0, tmpH, H);
-      m.ln = 1; m.gamma = w.mlnw; m.beta = w.mlnb; m.act = 1;
-      GEMM_MS("gemm_xproj0", m, 4, 2, 0, 4);
-      m = msa(tmpH, H, H, h->Ms[l].x2, X, 3 * H);
-      GEMM_MS("gemm_xproj2", m, 4, 2, 0, 4);
-    } else {
-      PB("k_layernorm", 0, N*H*8.0, 0);
-      k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
-      KCHECK();
-      g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
-      g.act = 1;
-      GEMM_TC("gemm_xproj0", g, h->T[l].x0);
-      g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
-      GEMM_TC("gemm_xproj2", g, h->T[l].x2);
-    }
-    }
+    PB("k_layernorm", 0, N*H*8.0, 0);
+    k_layernorm_w<<<(N + 7) / 8, 256, 0, st>>>(N, H, s, H, nullptr, w.mlnw, w.mlnb, 0, tN, H);
+    KCHECK();
+    g = mk(tN, H, w.x0w, H, tmpH, H, N, H, H);
+    g.act = 1;
+    GEMM_TC("gemm_xproj0", g, h->T[l].x0);
+    g = mk(tmpH, H, w.x2w, H, X, 3 * H, N, 3 * H, H);
+    GEMM_TC("gemm_xproj2", g, h->T[l].x2);
     if (E) {
-      if (fork) h->num_sms = sm_guard.keep - h->fork_sms;
       g = mk(ew_act, ldD, w.d0w, D, d1, ld3H, E, 3 * H, D);
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
       g.hintA = EF;  // last use of the compact copy
@@ -1090,11 +962,6 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
       g.hintA = EF; g.hintX = EF;  // last use of d1 and RB; G stays for the message kernel
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
-      h->num_sms = sm_guard.keep;
-    }
-    if (fork) {  // join: the message kernel reads X (node branch) and G (edge branch)
-      CU(cudaEventRecord(h->fork_ev[2 * l + 1], h->side_stream));
-      CU(cudaStreamWaitEvent(st, h->fork_ev[2 * l + 1], 0));
     }
     PB("k_equi_msg", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
     {
@@ -1133,18 +1000,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       SNAP_EDGE("e" + l1);
     }
     // ---- EquiUpdate (leftnet.py:325-346)
-    if (chain) {  // EquiUpdate: scalarisation / lin3 / vec_dot in vec_proj's epilogue, the apply step in xvec_proj.2's
-      MsGemmArgs m = msa(vec, H, H, h->Ms[l].vp, nullptr, 0);
-      m.nodeframe = nodeframe; m.l0w = w.l0w; m.l0b = w.l0b; m.l2w = w.l2w; m.l2b = w.l2b; m.l4w = w.l4w; m.l4b = w.l4b;
-      m.s_in = s; m.sx = sx; m.vd = vd; m.v2 = VP;
-      GEMM_MS("gemm_vec_proj", m, 3, 2, 1, 8);
-      m = msa(sx, 2 * H, 2 * H, h->Ms[l].xv0, tN, H);
-      m.act = 1;
-      GEMM_MS("gemm_xvec0", m, 4, 2, 0, 4);
-      m = msa(tN, H, H, h->Ms[l].xv2, nullptr, 0);
-      m.s = s; m.vec = vec; m.vd = vd; m.v2 = VP;
-      GEMM_MS("gemm_xvec2", m, 4, 3, 2, 4);
-    } else if (c.update) {
+    if (c.update) {
       g = mk(vec, H, w.vpw, H, VP, 2 * H, 3 * N, 2 * H, H);
       GEMM_TC("gemm_vec_proj", g, h->T[l].vp);
       PB("k_upd_scalar", 0, N*H*4.0*9, 0);
