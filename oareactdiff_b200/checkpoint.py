@@ -72,9 +72,9 @@ def load_reference_checkpoint(ddpm: nn.Module, ckpt: Union[str, Dict], prefix: s
             raise KeyError(f"no key starts with '{prefix}' and none matches this module: is this an OA-ReactDiff checkpoint?")
     picked = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     ignored = sorted(k for k in sd if not k.startswith(prefix))
-    res = ddpm.load_state_dict(picked, strict=False)
-    missing, unexpected = list(res.missing_keys), list(res.unexpected_keys)
-    if strict and (missing or unexpected):
+    missing, unexpected = sorted(k for k in own if k not in picked), sorted(k for k in picked if k not in own)
+    if strict and (missing or unexpected):  # validated BEFORE anything is copied: a failed strict load leaves the module untouched
         raise RuntimeError(f"checkpoint does not match the module: missing {missing[:5]}{'...' if len(missing) > 5 else ''}, "
                            f"unexpected {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}")
+    ddpm.load_state_dict(picked, strict=False)
     return {"loaded": len(picked) - len(unexpected), "ignored": ignored, "missing": missing, "unexpected": unexpected}

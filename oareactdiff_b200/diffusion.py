@@ -208,7 +208,16 @@ class EnVariationalDiffusion(nn.Module):
         representations, conditions = batch
         training = self.training if training is None else training
         sizes = [rep["size"] for rep in representations]
-        lt = self.forward(representations, conditions)
+        # forward() keys its t range, t == 0 masking and second (t = 0) denoiser call on self.training: one flag, like the
+        # reference (DDPMModule.training is ddpm.training) — an explicit `training` switches the module mode for the call
+        was_training = self.training
+        if training != was_training:
+            self.train(training)
+        try:
+            lt = self.forward(representations, conditions)
+        finally:
+            if training != was_training:
+                self.train(was_training)
         nfr = len(sizes)
         denoms = [(self.pos_dim if self.pos_only else self.pos_dim + self.node_nfs[ii]) * sizes[ii] for ii in range(nfr)]
         err_norm = [lt["error_t"][ii] / denoms[ii] * scales[ii] for ii in range(nfr)]
@@ -295,9 +304,11 @@ class EnVariationalDiffusion(nn.Module):
         mu_x = self.compute_x_pred(eps, z0_xh, gamma_0, masks)
         x0 = self.sample_normal(mu=mu_x, sigma=sigma_x, masks=masks, fix_noise=fix_noise)
         p = self.pos_dim
-        pos = [self.normalizer.unnormalize(x0[ii][:, :p], 0) for ii in range(len(masks))]
-        cat = [self.normalizer.unnormalize(x0[ii][:, p:-1], 1) for ii in range(len(masks))]
-        charge = [torch.round(self.normalizer.unnormalize(x0[ii][:, -1:], 2)).long() for ii in range(len(masks))]
+        # (the reference indexes the normalizer with the FRAGMENT index here, en_diffusion.py:686-697 — identical for the identity
+        # normalizer of the shipped configurations; mirrored so that a non-default normalizer gives the reference's numbers)
+        pos = [self.normalizer.unnormalize(x0[ii][:, :p], ii) for ii in range(len(masks))]
+        cat = [self.normalizer.unnormalize(x0[ii][:, p:-1], ii) for ii in range(len(masks))]
+        charge = [torch.round(self.normalizer.unnormalize(x0[ii][:, -1:], ii)).long() for ii in range(len(masks))]
         cat = [F.one_hot(torch.argmax(cat[ii], dim=1), self.node_nfs[ii] - 4).long() for ii in range(len(masks))]
         return pos, cat, charge
 

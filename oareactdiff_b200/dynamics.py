@@ -32,6 +32,8 @@ class BaseDynamics(nn.Module):
             assert nf > pos_dim
         model_config = dict(model_config)
         model_config.setdefault("act_fn", "swish")
+        if str(model_config["act_fn"]).lower() not in ("swish", "silu"):  # encoders / decoders and the fused kernels are SiLU
+            raise NotImplementedError(f"act_fn={model_config['act_fn']!r}: only 'swish' (SiLU), the trained configuration, is implemented")
         if "in_node_nf" not in model_config:  # (the reference's own test configs give in_node_nf and no in_hidden_channels)
             model_config["in_node_nf"] = model_config["in_hidden_channels"]
         if model_config.get("in_edge_nf", 0) > 0:

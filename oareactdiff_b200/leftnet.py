@@ -404,10 +404,11 @@ class LEFTNetB200(nn.Module):
         self.inv_sqrt_2 = 1 / math.sqrt(2.0)
         self._engines: Dict[torch.device, _Engine] = {}
         self.assume_static_weights = False  # set True to skip the per-call weight-version check
-        # True: under torch.enable_grad() forward() builds an autograd node (oard_forward_train / oard_backward).  Off by
-        # default: the training kernels are validated in their host-emulation build (tests/test_train_emu.py) but have not
-        # run on hardware yet (tests/test_gpu_train.py, OARD_TRAIN_GPU=1).
+        # True: under torch.enable_grad() forward() builds an autograd node (oard_forward_train / oard_backward: exact-fp32
+        # training kernels, gradients checked against the reference's on the B200 in tests/test_gpu_train.py).  Off by default
+        # (sampling is the hot path); with it off, a forward under autograd warns once that this module gets no gradients.
         self.enable_training_path = False
+        self._warned_no_grad = False
 
     # tensors the C library needs, keyed by reference state-dict name
     def _oard_tensors(self) -> Dict[str, Tensor]:
@@ -429,6 +430,15 @@ class LEFTNetB200(nn.Module):
                 update_coords_mask: Optional[Tensor] = None, subgraph_mask: Optional[Tensor] = None):
         if self.enable_training_path and torch.is_grad_enabled():
             return self._forward_train(h, pos, edge_index, node_mask, update_coords_mask, subgraph_mask)
+        if torch.is_grad_enabled() and not self._warned_no_grad and (h.requires_grad or self.embedding.weight.requires_grad):
+            # the inference kernels return detached outputs: a loss.backward() through this call would still succeed (encoders /
+            # decoders sit around it) and silently train everything EXCEPT this module
+            self._warned_no_grad = True
+            import warnings
+            warnings.warn("LEFTNetB200.forward was called with autograd enabled but enable_training_path is False: the outputs are "
+                          "detached (inference kernels) and this module will receive NO gradients.  Set "
+                          "`model.enable_training_path = True` to train (oard_forward_train / oard_backward), or wrap inference in "
+                          "torch.no_grad().", stacklevel=2)
         return self._forward_infer(h, pos, edge_index, edge_attr, node_mask, edge_mask, update_coords_mask, subgraph_mask)
 
     def _forward_train(self, h, pos, edge_index, node_mask, update_coords_mask, subgraph_mask):

@@ -45,7 +45,7 @@ def test_fused_tail_vs_three_launch_path_and_oracle(cfg_small):
         outs[tail], _ = dyn(*args)
         launches = dyn.model.engine(DEV).launches()
         outs[(tail, "launches")] = launches
-    assert outs[(True, "launches")] == outs[(False, "launches")] - 2 * cfg["num_layers"]  # three launches -> one (+ k_agg_runs for k_att_agg)
+    assert outs[(True, "launches")] == outs[(False, "launches")] - cfg["num_layers"]  # edge2 + k_att_agg + edge_out -> tail + k_agg_runs
     for f in range(3):
         e_ref = rel_err(outs[True][f].cpu(), ref[f])
         e_alt = rel_err(outs[True][f].cpu(), outs[False][f].cpu())

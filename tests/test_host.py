@@ -372,3 +372,43 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         monkeypatch.setattr(_lib, "LIB_PATH", emu)
         with pytest.raises(AttributeError):
             _lib.load()
+
+
+def test_unsupported_activation_is_rejected():
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1, act_fn="relu")
+    with pytest.raises(NotImplementedError, match="act_fn"):
+        ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                        model=ob.LEFTNetB200, device=torch.device("cpu"))
+
+
+def test_forward_under_autograd_without_training_path_warns_once():
+    """With `enable_training_path` off the inference kernels return detached outputs; a training loop would silently update
+    everything but this module, so the first such forward warns (before the engine is even created)."""
+    import warnings
+    m = ob.LEFTNetB200(cutoff=5.0, num_layers=1, hidden_channels=32, num_radial=16, in_hidden_channels=8)
+    h, pos, ei = torch.zeros(3, 8), torch.zeros(3, 3), torch.tensor([[0, 1], [1, 0]])
+    with pytest.warns(UserWarning, match="enable_training_path"), pytest.raises(RuntimeError, match="CUDA"):
+        m(h, pos, ei)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # second call: no second warning
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(h, pos, ei)
+        with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+            ob.LEFTNetB200(cutoff=5.0, num_layers=1, hidden_channels=32, num_radial=16, in_hidden_channels=8)(h, pos, ei)
+
+
+def test_strict_checkpoint_load_validates_before_copying():
+    cfg = dict(oa_ref.TRAINED_CFG, hidden_channels=32, num_radial=16, num_layers=1)
+    dyn = ob.EGNNDynamics(model_config=cfg, fragment_names=["R", "TS", "P"], node_nfs=[9, 9, 9], edge_nf=0, condition_nf=1,
+                          model=ob.LEFTNetB200, device=torch.device("cpu"))
+    ddpm = ob.EnVariationalDiffusion(dynamics=dyn, schdule=ob.DiffSchedule(ob.PredefinedNoiseSchedule("polynomial_2", 5, 1e-5), (1.0, 1.0, 1.0)),
+                                     normalizer=ob.Normalizer(), pos_only=True)
+    before = {k: v.clone() for k, v in ddpm.state_dict().items()}
+    bad = {"ddpm." + k: torch.full_like(v, 7.0) for k, v in before.items()}
+    bad.pop(next(iter(bad)))  # one key missing
+    with pytest.raises(RuntimeError, match="missing"):
+        ob.load_reference_checkpoint(ddpm, bad, strict=True)
+    after = ddpm.state_dict()
+    assert all(torch.equal(after[k], before[k]) for k in before)  # nothing was copied
+    res = ob.load_reference_checkpoint(ddpm, bad, strict=False)
+    assert len(res["missing"]) == 1 and res["loaded"] == len(before) - 1
