@@ -101,8 +101,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
   uint8_t* h_ring = smem;                                        // [SH][16 KB]  hidden activation chunks (A of layer 2)
   uint8_t* r_ring = h_ring + (size_t)SH * P16_A_BYTES;           // [SR][16 KB]  edge-state residual blocks, 128 rows x 32 columns
   uint8_t* w_ring = r_ring + (size_t)SR * P16_A_BYTES;           // [SW][W_SLOT]
-  uint8_t* out_all = w_ring + (size_t)SW * W_SLOT;               // [EW][4 KB]   output staging / transpose scratch per warp
-  float* att_part = reinterpret_cast<float*>(out_all + (size_t)EW * TC_IO_BYTES);  // [3][128]
+  float* att_part = reinterpret_cast<float*>(w_ring + (size_t)SW * W_SLOT);       // [3][128]
   float* b3s = att_part + 3 * TC_BM;                                               // [J * 32] bias of layer 3 (zero padded)
   uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + ((g.D + 31) / 32) * 32);
   uint64_t* full_h = bars;               // [SH]
@@ -117,6 +116,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
   uint64_t* acc3_empty = acc3_full + 2;  // [2] count EW (every epilogue warp arrives for every column tile)
   uint64_t* tile_done = acc3_empty + 2;  // count EW: epilogue 3 of the tile finished (accumulators and m are dead)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 1);
+  volatile uint32_t* r_tag = tmem_slot + 2;  // [SR] index of the block the residual loader last armed the slot for
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.E + TC_BM - 1) / TC_BM;
@@ -133,6 +133,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
     ptx::mbar_init(m_full, EW);
     for (int b = 0; b < 2; b++) { ptx::mbar_init(&acc3_full[b], 1); ptx::mbar_init(&acc3_empty[b], EW); }
     ptx::mbar_init(tile_done, EW);
+    for (int s = 0; s < SR; s++) r_tag[s] = 0xffffffffu;
     ptx::fence_barrier_init();
   }
   if (warp == EW) ptx::tmem_alloc(tmem_slot, 512);
@@ -170,6 +171,8 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           const int s = gi % SR;
           ptx::mbar_wait(&empty_r[s], ((gi / SR) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&full_r[s], P16_A_BYTES);
+          __threadfence_block();
+          r_tag[s] = gi;  // consumers wait for this tag first: a parity wait alone cannot tell phase k from phase k - 2
           ptx::tma_load_2d(r_ring + (size_t)s * P16_A_BYTES, &tmR, f * 32, m0, &full_r[s]);
         }
       }
@@ -270,8 +273,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
     // ===================== epilogue warps: thread = edge row =====================
     const int rq = warp & 3, cg = warp >> 2;  // row quarter, column group (0..2)
     const uint32_t lane_base = (uint32_t)(rq * 32) << 16;
-    uint8_t* stg = out_all + (size_t)warp * TC_IO_BYTES;
-    float* T = reinterpret_cast<float*>(stg);  // 32 x 32 transpose scratch of the aggregation (same 4 KB)
+    int pend_rs = -1;  // ring slot whose quarter is the source of this warp's TMA store in flight (released when it has been read)
     const int sw = lane & 7;
     const int nb2 = (w2.BN + 31) / 32;  // column blocks of the hidden tile (7)
     if (lane == 0) ptx::tma_prefetch_desc(&tmE);
@@ -348,34 +350,38 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
         const int grp = m0r >> 5;
         if (cg == 0 && ((starts >> lane) & 1u) && src >= 0)
           g.Psrc[(size_t)grp * 32 + (__popc(starts & ((2u << lane) - 1u)) - 1)] = src;
-        const unsigned valid_rows = __ballot_sync(0xffffffffu, src >= 0);
+        const int rf = 31 - __clz((int)(starts & ((2u << lane) - 1u)));  // first row (lane) of this row's run
+        const bool run_last = lane == 31 || ((starts >> (lane + 1)) & 1u);
+        const int slot = __popc(starts & ((2u << lane) - 1u)) - 1;
         for (int blk = cg; blk < nb2; blk += 3) {
           uint32_t hw[16], lw[16];
           tmem_ld16_u32(tmem_base + lane_base + GT_COL_MHI + blk * 16, hw);
           tmem_ld16_u32(tmem_base + lane_base + GT_COL_MLO + blk * 16, lw);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the scratch was a store's source
-          __syncwarp();
+          float am[32];
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            const float a = (__uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16)) * att;
-            const float b = (__uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u)) * att;
-            T[lane * 32 + ((2 * j) ^ lane)] = a;
-            T[lane * 32 + ((2 * j + 1) ^ lane)] = b;
+            am[2 * j] = (__uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16)) * att;
+            am[2 * j + 1] = (__uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u)) * att;
           }
-          __syncwarp();
-          const int n = blk * 32 + lane;  // this lane's column
-          float sum = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 32; r++) {
-            sum += T[r * 32 + (lane ^ r)];
-            const bool last = r == 31 || ((starts >> (r + 1)) & 1u);
-            if (last) {
-              if (n < g.H && ((valid_rows >> r) & 1u))
-                g.P[((size_t)grp * 32 + (__popc(starts & ((2u << r) - 1u)) - 1)) * g.ldp + n] = sum;
-              sum = 0.f;
+          // segmented inclusive scan over the rows (lanes) of the warp, per column: the last row of a run ends up with the run's
+          // sum (fixed tree order: bitwise reproducible)
+#pragma unroll
+          for (int c = 0; c < 32; c++) {
+            float v = am[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float t = __shfl_up_sync(0xffffffffu, v, d);
+              if ((int)lane - d >= rf) v += t;
             }
+            am[c] = v;
           }
-          __syncwarp();
+          if (run_last && src >= 0) {
+            float* pp = g.P + ((size_t)grp * 32 + slot) * g.ldp + blk * 32;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              if (blk * 32 + 4 * q < g.H)  // (H % 4 == 0: a float4 never straddles the end)
+                *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(am[4 * q], am[4 * q + 1], am[4 * q + 2], am[4 * q + 3]);
+          }
         }
       }
       GT_TS(4);
@@ -385,24 +391,30 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
         const int buf = g3 & 1;
         const int f = nt * 3 + cg;  // block index inside the row tile
         const int n0 = f * 32;
+        if (pend_rs >= 0) {  // hand back the ring slot of the previous block (see below)
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            ptx::mbar_arrive(&empty_r[pend_rs]);
+          }
+          pend_rs = -1;
+        }
         if (f < J) {
-          // Order matters for the residual ring's phase parity: a warp may only wait for block f of the ring after every warp
-          // has consumed its block of column tile nt - 2 (they hand accumulator nt - 2 back AFTER their ring read, and this
-          // warp is past acc3_full(nt)), so the oldest unconsumed block is at most 5 positions back: less than the 2 * SR = 8
-          // at which a parity wait would be satisfied by a stale phase.
+          // The residual ring has several consumer groups running up to ~3 column tiles apart, more than the 2 * SR blocks a
+          // parity wait can tell apart: a consumer first waits until the loader has armed the slot for ITS block (r_tag), then
+          // for the data (mbarrier phase).
           ptx::mbar_wait(&acc3_full[buf], (g3 >> 1) & 1);
           ptx::tc_fence_after();
           GT_TS(8 + 4 * nt);
           const uint32_t ri = it * (uint32_t)J + (uint32_t)f;
           const int rs = ri % SR;
+          while (r_tag[rs] != ri) {}
           ptx::mbar_wait(&full_r[rs], (ri / SR) & 1);
           GT_TS(9 + 4 * nt);
-          const uint8_t* rb = r_ring + (size_t)rs * P16_A_BYTES + (size_t)(rq * 32 + lane) * 128;
+          uint8_t* rquart = r_ring + (size_t)rs * P16_A_BYTES + (size_t)rq * TC_IO_BYTES;  // this warp's 32 rows of the block
+          uint8_t* rb = rquart + lane * 128;
           uint4 cell[8];
 #pragma unroll
           for (int q = 0; q < 8; q++) cell[q] = *reinterpret_cast<const uint4*>(rb + ((q ^ sw) << 4));
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&empty_r[rs]);
           float e[32];
           p16_join8(cell[0], cell[2], e);
           p16_join8(cell[1], cell[3], e + 8);
@@ -431,20 +443,21 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           p16_split8(v + 16, cell[4], cell[6]);
           p16_split8(v + 24, cell[5], cell[7]);
           GT_TS(10 + 4 * nt);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has read the staging
-          __syncwarp();
+          // The result goes back INTO the ring quarter the residual came from and leaves from there by TMA: no separate staging.
+          // The slot is handed back to the residual loader once the store has read it: at the top of this warp's next block
+          // (before it waits for anything else — the MMAs of the next column tile take longer than the store's read).
+          pend_rs = rs;
           GT_TS(11 + 4 * nt);
-          uint8_t* iob = stg + lane * 128;
 #pragma unroll
           for (int q = 0; q < 8; q++) {
-            *reinterpret_cast<uint4*>(iob + ((q ^ sw) << 4)) = cell[q];
+            *reinterpret_cast<uint4*>(rb + ((q ^ sw) << 4)) = cell[q];
             if (c2 >= 0 && (n0 + (q >> 2) * 16) < g.lde)
               *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.ew_act + (size_t)c2 * g.lde + n0) + q * 16) = cell[q];
           }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&tmE, n0, m0r, stg);
+            ptx::tma_store_2d(&tmE, n0, m0r, rquart);
             ptx::bulk_commit();
           }
           __syncwarp();
@@ -455,6 +468,13 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc3_empty[buf]);
         }
+      }
+      if (pend_rs >= 0) {  // the last block's slot: the next tile's blocks need it before this warp gets back to epilogue 3
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          ptx::mbar_arrive(&empty_r[pend_rs]);
+        }
+        pend_rs = -1;
       }
       GT_TS(40);
       ptx::tc_fence_before();
@@ -473,8 +493,8 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
 }
 
 inline size_t gcl_tail_smem_bytes(int bn2, int D, int sh, int sr, int sw) {
-  return (size_t)(sh + sr) * P16_A_BYTES + (size_t)sw * gcl_tail_wslot(bn2) + (size_t)GT_EW * TC_IO_BYTES + 3 * TC_BM * 4 +
-         (size_t)((D + 31) / 32) * 32 * 4 + (size_t)(2 * sh + 2 * sr + 2 * sw + 7) * 8 + 16;
+  return (size_t)(sh + sr) * P16_A_BYTES + (size_t)sw * gcl_tail_wslot(bn2) + 3 * TC_BM * 4 +
+         (size_t)((D + 31) / 32) * 32 * 4 + (size_t)(2 * sh + 2 * sr + 2 * sw + 7) * 8 + 16 + (size_t)sr * 4;
 }
 
 // hid: pair16 [E, ldh]; w2 packed with one column tile (BN <= 208, K = H); w3 packed with BN = 96 (K = H, N = D).
@@ -492,7 +512,7 @@ inline cudaError_t launch_gcl_tail(const GclTailArgs& g, const TcWeight& w2, con
   if (!tc_make_map(&tmA, g.hid, g.E, p16_ld(g.H), g.ldh, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
   if (!tc_make_map(&tmR, g.ew, g.E, p16_ld(g.D), g.lde, 32, TC_BM, true)) return cudaErrorInvalidValue;
   if (!tc_make_map(&tmE, g.ew, g.E, p16_ld(g.D), g.lde, 32, 32, true)) return cudaErrorInvalidValue;
-  constexpr int SH = 2, SR = 4, SW = 3;
+  constexpr int SH = 2, SR = 4, SW = 4;
   const size_t smem = gcl_tail_smem_bytes(w2.BN, g.D, SH, SR, SW);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static PerDeviceOnce attr;
