@@ -946,7 +946,10 @@ __global__ void k_edge_init_masked(int E, int ld, const int* __restrict__ act_po
 struct EdgeInitIn { int e; float a0, a1, a2, b0, b1, b2, gx, gy, gz, cx, cy, cz, rbe, fv, rv; };
 // Thread h < H evaluates lin3 for BOTH sides (NE1 of the source and of the target) of channel h: the two evaluations share
 // every weight operand, which halves the constant-bank traffic that bounds this kernel.
-template <bool PAIR>
+// HQ4 > 0: the hidden width rounded up to a multiple of 4 as a compile-time loop bound (the padding units have zero weights and
+// contribute SiLU(0) * 0): without the per-group branch the unrolled groups interleave, which hides the MUFU latency of one
+// group's exp2 / rcp chain behind the FMAs of the next (the branchy form ran at IPC 0.75 per SM, 2.4x its MUFU floor).
+template <bool PAIR, int HQ4>
 __global__ void __launch_bounds__(256, 4) k_edge_init_act(
     int H, int R, int reflect, int ld, int cap, const int* __restrict__ n_act, const int* __restrict__ act_idx,
     const int* __restrict__ esrc, const int* __restrict__ ecol, const float4* __restrict__ ecross,
@@ -1002,8 +1005,8 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
       const f32x2 p0 = pk2(s0, r0), p1 = pk2(s1, r1), p2 = pk2(s2, r2);
       f32x2 acc2 = pk2(W.b2, W.b2);
 #pragma unroll
-      for (int k = 0; k < 64; k += 4) {
-        if (k < W.hq) {  // uniform; entries hq .. hq4 are zero-filled on the host
+      for (int k = 0; k < (HQ4 > 0 ? HQ4 : 64); k += 4) {
+        if (HQ4 > 0 || k < W.hq) {  // uniform; entries hq .. hq4 are zero-filled on the host
           f32x2 u[4];
 #pragma unroll
           for (int i = 0; i < 4; i++)

@@ -841,12 +841,13 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     else k_const_row<false><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
     k_edge_init_masked<<<(E + 7) / 8, 256, 0, st>>>(E, ldD, act_pos, crow, ew);
     const int ei_grid = std::min(E, h->num_sms * 4);  // = resident blocks (launch bounds 256 x 4)
-    if (P)
-      k_edge_init_act<true><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                 h->buf<float4>("ecross"), geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
-    else
-      k_edge_init_act<false><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,
-                                                                  h->buf<float4>("ecross"), geo, rb, NE1, f_act, rbf_act, h->lin3e, ew);
+    const int hq4 = (H / 4 + 3) / 4 * 4;
+#define OARD_EI(PV, HQ)                                                                                                \
+    k_edge_init_act<PV, HQ><<<ei_grid, ei_threads, ei_smem, st>>>(H, R, c.reflect_equiv, ldD, E, n_act, act_idx, esrc, ecol,  \
+                                                                  h->buf<float4>("ecross"), geo, rb, NE1, f_act, rbf_act, h->lin3e, ew)
+    if (P) { if (hq4 == 52) OARD_EI(true, 52); else if (hq4 == 8) OARD_EI(true, 8); else if (hq4 == 16) OARD_EI(true, 16); else OARD_EI(true, 0); }
+    else { if (hq4 == 52) OARD_EI(false, 52); else if (hq4 == 8) OARD_EI(false, 8); else if (hq4 == 16) OARD_EI(false, 16); else OARD_EI(false, 0); }
+#undef OARD_EI
     h->launches += 2;
     KCHECK();
   }

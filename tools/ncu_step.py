@@ -1,5 +1,6 @@
-"""Profiling target (not a test): n device-resident reverse steps of the B=64 Transition1x-shaped batch on a compact
-state (every same-fragment edge inside the cutoff, active fraction 0.317), one CUDA graph per step.
+"""Profiling target (not a test): n device-resident reverse steps of the B=64 Transition1x-shaped batch on the state the
+bench times (z_t at t = 501 from the frozen real Transition1x geometries, active fraction 0.317; OARD_GEOM=synthetic: a compact
+random state), one CUDA graph per step.
     python tools/ncu_step.py [n_steps] [eager]
 Used under `ncu --metrics gpu__time_duration.sum` (launch list) and `ncu --set full -k regex:...` (profiles/)."""
 import os
@@ -34,7 +35,14 @@ def main():
     tab = ddpm._tables(T, dev)
     ddpm._seg_setup(masks)
     gen = torch.Generator().manual_seed(1)
-    Z0 = torch.cat([torch.cat([torch.randn(h.size(0), 3, generator=gen) * 1.5, h.cpu()], dim=1) for h in h0]).to(dev)
+    if os.environ.get("OARD_GEOM", "real") == "real" and B <= 512:
+        # the state the bench times: z_t = alpha_t x + sigma_t eps at t = 501 from the frozen real Transition1x geometries
+        x_ref = workloads.real_geometries(0, B, sizes)
+        a, sg = tab["alpha"][501], tab["sigma_abs"][501]
+        Z0 = torch.cat([torch.cat([a * (x - x.mean(0, keepdim=True) * 0) + sg * torch.randn(x.shape, generator=gen), h.cpu()], dim=1)
+                        for x, h in zip(x_ref, h0)]).to(dev)
+    else:
+        Z0 = torch.cat([torch.cat([torch.randn(h.size(0), 3, generator=gen) * 1.5, h.cpu()], dim=1) for h in h0]).to(dev)
     Z = Z0.clone().contiguous()
     ddpm._device_setup(Z, masks, edge_index, nfs, cond, torch.cat(h0))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
