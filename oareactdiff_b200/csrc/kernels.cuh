@@ -612,6 +612,21 @@ __global__ void __launch_bounds__(NG * 64, 1024 / (NG * 64)) k_equi_reduce(
 // row's three 16-byte loads in flight and accumulates in registers — no cross-thread reduction, no shuffles, fixed edge
 // order (bitwise reproducible).  Latency is hidden by the co-resident CTAs (4 per SM), not by an in-CTA pipeline.
 // (Edge slots, deeper register staging, a loader warp and L2 prefetches were all measured slower: profiles/r2_experiments.md.)
+// 16-byte read-only load with an L2 eviction-priority policy (createpolicy): the G rows are written by dir_proj2 with evict_last
+// so that they survive in L2 until this kernel, and are read here with evict_first so that they leave it afterwards.
+__device__ __forceinline__ float4 ldg4_policy(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 template <int CH>
 inline size_t et_smem_bytes(int gmax) {
   return (size_t)gmax * 2 * 3 * CH * 4 + (size_t)((gmax + 3) & ~3) * (4 + 8);
@@ -636,6 +651,7 @@ __global__ void __launch_bounds__(ET_THREADS, 4) k_equi_tgt(
   const int slot = tid / Q, q = tid - slot * Q;
   const float inv_sqrt_3 = 0.57735026918962576f, inv_sqrt_h = rsqrtf((float)H), inv_sqrt_2 = 0.70710678118654752f;
   auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+  const uint64_t polG = l2_evict_first_policy();
   const int total = *n_lead * NS;
   const size_t H3 = (size_t)3 * H;
   for (;;) {
@@ -664,7 +680,7 @@ __global__ void __launch_bounds__(ET_THREADS, 4) k_equi_tgt(
         float4 g0, g1, g2, gm;
         int al = 0;
         if (rap.x < rap.y) {
-          g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+          g0 = ldg4_policy(gp, polG); g1 = ldg4_policy(gp + H, polG); g2 = ldg4_policy(gp + 2 * H, polG);
           al = act_rec[rap.x].y; gm = act_geo[rap.x];
         }
         for (int p = rap.x; p < rap.y; p++) {
@@ -672,7 +688,7 @@ __global__ void __launch_bounds__(ET_THREADS, 4) k_equi_tgt(
           const int ca = al;
           if (p + 1 < rap.y) {  // next row in flight while this one is evaluated
             gp += H3;
-            g0 = ld4(gp); g1 = ld4(gp + H); g2 = ld4(gp + 2 * H);
+            g0 = ldg4_policy(gp, polG); g1 = ldg4_policy(gp + H, polG); g2 = ldg4_policy(gp + 2 * H, polG);
             al = act_rec[p + 1].y; gm = act_geo[p + 1];
           }
           const float ux = -cm.x, uy = -cm.y, uz = -cm.z;  // the message edge (a -> t) has the negated unit vector of (t -> a)

@@ -961,7 +961,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
       g = mk(d1, ld3H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
-      g.hintA = EF; g.hintX = EF;  // last use of d1 and RB; G stays for the message kernel
+      g.hintA = EF; g.hintX = EF; g.hintC = 2 * EF;  // last use of d1 and RB; G (evict_last) stays in L2 for the message kernel, which reads it evict_first
       if (P) GEMM_P16("gemm_dir_proj2", g, h->T[l].d2, false); else GEMM_TC("gemm_dir_proj2", g, h->T[l].d2);
     }
     PB("k_equi_msg", 0, (double)E*(3.0*H*4+24), 1);  // G row + index/geometry per active edge (node rows are L2 / smem traffic)
