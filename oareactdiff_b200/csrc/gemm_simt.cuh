@@ -28,6 +28,10 @@ struct GemmArgs {
   // L2 eviction-priority hints of the tensor-core kernels' TMA streams (gemm_tc.cuh l2_policy): A operand, aux (mul / resid)
   // blocks, C stores.  0 none, 1 evict_first, 2 evict_last.
   int hintA, hintX, hintC;
+  // bring-up only (pair16 kernel, tools/pair_probe.py): bit 0 no A loads, bit 1 no epilogue global traffic, bit 2 no weight
+  // loads, bit 3 no MMAs.  Results are meaningless with any bit set.
+  int ablate;
+  long long* ts;  // bring-up only: clock64 marks of CTA 0 around its 4th tile (pair16 kernel, tools/pair_probe.py timeline)
 };
 
 constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;

@@ -113,6 +113,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Same, for a waiter that usually finds the phase complete (the MMA issuer, whose every cycle is on the critical path):
+// a plain test first, the potentially suspending try_wait only if the phase is still open.
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  if (!done) mbar_wait(bar, parity);
+}
+// One lane of the (converged) warp, the same one every time.  Code that issues tcgen05 / TMA instructions runs warp-uniform
+// and predicates only those instructions with this: inside an `if (lane == 0)` region ptxas cannot prove a single active
+// thread and wraps every UTCHMMA / UTCBAR / UTMALDG in an ELECT ... BRA.U.ANY loop (~40 cycles per instruction, which made
+// the MMA issuer, not the tensor pipe, the bound of the edge GEMMs: profiles/r2_issue_loop_notes.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -238,7 +264,16 @@ __host__ __device__ inline uint32_t tc_idesc(int M, int N) {
 struct TcDebugOpts {  // bring-up / ablation knobs (normally zero)
   int swap_lbo_sbo;
   int ablate;  // bit 0: no A global loads, bit 1: no epilogue global traffic, bit 2: no W bulk copies, bit 3: no MMAs
+  long long* ts;  // timeline probe of CTA 0 (tools/tc_timeline.py): [0] / [15] globaltimer at entry / exit, [1..] clock64 marks
 };
+__device__ __forceinline__ void tc_mark(const TcDebugOpts& dbg, int i) {
+  if (dbg.ts && blockIdx.x == 0) dbg.ts[i] = clock64();
+}
+__device__ __forceinline__ long long tc_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Epilogue modes (compile-time):
 //   0 plain: bias / SiLU / row scale      1: + two gathered row adds (GCL: P[src] + Q[dst])
@@ -273,6 +308,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_chunks = w.k_chunks;
   const int k16_total = (g.K + 15) / 16;
+  if (dbg.ts && blockIdx.x == 0 && threadIdx.x == 0) { dbg.ts[0] = tc_globaltimer(); dbg.ts[1] = clock64(); }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -299,6 +335,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
   const int m_tiles = (M + TC_BM - 1) / TC_BM;
   const int total_tiles = m_tiles * w.n_tiles;
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tc_mark(dbg, 2);  // set-up done
 
   if (warp >= TC_EPI_WARPS + TC_CTRL_WARPS) {
     // ===================== A producer =====================
@@ -365,6 +402,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
       for (uint32_t c = 0; c < nchunks_r; c++) {
         const int r = c % RAW;
         ptx::mbar_wait(&raw_full[r], (c / RAW) & 1);
+        if (c == 0 && pw == 0 && lane == 0) tc_mark(dbg, 4);  // first A box landed
         const uint8_t* raw = raw_base + (size_t)r * TC_RAW_BYTES;
         float4 v[4];
 #pragma unroll
@@ -426,6 +464,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           if (dbg.ablate & 1) { ptx::mbar_arrive(&raw_full[r]); continue; }
           ptx::mbar_arrive_expect_tx(&raw_full[r], TC_RAW_BYTES);
           ptx::tma_load_2d_h(raw_base + (size_t)r * TC_RAW_BYTES, &tmA, kc * TC_KC, m0, &raw_full[r], g.hintA, polA);
+          if (c == 0) tc_mark(dbg, 3);  // first A box requested
         }
       }
     }
@@ -444,7 +483,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           const int s = gchunk % STAGES;
           const uint32_t ph = (gchunk / STAGES) & 1;
           ptx::mbar_wait(&full_a[s], ph);
+          if (gchunk == 0) tc_mark(dbg, 5);  // first converted A stage
           ptx::mbar_wait(&full_w[s], ph);
+          if (gchunk == 0) tc_mark(dbg, 6);  // first weight slab
           ptx::tc_fence_after();
           const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TC_A_PART;
           const uint32_t w_hi = a_hi + 2 * TC_A_PART, w_lo = w_hi + W_PART;
@@ -460,6 +501,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           ptx::umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
         }
         ptx::umma_commit(&acc_full[buf]);
+        tc_mark(dbg, 7);  // last MMA of the (latest) tile issued
       }
     }
   } else {
@@ -518,6 +560,7 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
         ptx::tc_fence_after();
+        if (warp == 0 && lane == 0) tc_mark(dbg, 8);  // accumulator of the (latest) tile complete
         for (int blk = half; blk < nblocks; blk += 2, nb++) {
           const int b = nb % NIO;
           uint8_t* iob = io + (size_t)b * TC_IO_BYTES + lane * 128;
@@ -571,7 +614,9 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
       }
+      if (warp == 0 && lane == 0) tc_mark(dbg, 9);  // last store issued
       if (lane == 0) ptx::bulk_wait_all();
+      if (warp == 0 && lane == 0) tc_mark(dbg, 10);  // stores complete
     } else {
     // thread = row after tcgen05.ld; a padded smem transpose turns that into 4 rows x 128 contiguous bytes per warp access.
     const int rq = warp & 3, half = warp >> 2;
@@ -674,10 +719,12 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tc_mark(dbg, 11);
   if (warp == TC_EPI_WARPS) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
+  if (dbg.ts && blockIdx.x == 0 && threadIdx.x == TC_EPI_WARPS * 32) { dbg.ts[12] = clock64(); dbg.ts[15] = tc_globaltimer(); }
 }
 
 inline size_t tc_smem_bytes(int BN, int stages, int raw, int nio) {
@@ -736,7 +783,7 @@ inline cudaError_t launch_gemm_tc_inst(const GemmArgs& g, const TcWeight& w, int
 
 // ablate bits 4/5 (16, 32) force the LSU paths for the A operand / the epilogue (for A/B comparisons)
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_sms, cudaStream_t st,
-                                  int swap_lbo_sbo = 0, int ablate = 0) {
+                                  int swap_lbo_sbo = 0, int ablate = 0, long long* ts = nullptr) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   if (g.K % 4 || g.lda % 4 || g.N % 4 || g.ldc % 4 || w.BN % 16 || w.BN > 256 || w.BN < 16 || g.K != w.K || g.N != w.N)
     return cudaErrorInvalidValue;
@@ -751,7 +798,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, const TcWeight& w, int num_
     if (env_bits < 0) { const char* e = getenv("OARD_TC_ABLATE"); env_bits = e ? atoi(e) : 0; }
     ablate |= env_bits;
   }
-  TcDebugOpts dbg{swap_lbo_sbo, ablate};
+  TcDebugOpts dbg{swap_lbo_sbo, ablate, ts};
   CUtensorMap tmA, tmC, tmX;
   memset(&tmA, 0, sizeof tmA); memset(&tmC, 0, sizeof tmC); memset(&tmX, 0, sizeof tmX);
   const bool atma = !g.aidx && !(ablate & 16) && tc_make_map(&tmA, g.A, g.M, g.K, g.lda, TC_KC, TC_BM, false);

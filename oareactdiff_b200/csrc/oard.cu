@@ -1562,12 +1562,23 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaError_t e = cudaSuccess;
+  long long* ts = nullptr;  // OARD_TC_TS=1: timeline of CTA 0 of the last launch, printed to stderr (tools/tc_timeline.py)
+  if (use_tc && getenv("OARD_TC_TS")) { CU(cudaMalloc(&ts, 16 * sizeof(long long))); CU(cudaMemsetAsync(ts, 0, 16 * sizeof(long long), st)); }
   for (int r = 0; r < (reps > 1 ? reps + 1 : 1) && e == cudaSuccess; r++) {
     if (r == (reps > 1 ? 1 : 0)) cudaEventRecord(e0, st);
-    e = use_tc ? launch_gemm_tc(g, tw, prop.multiProcessorCount, st, swap_lbo_sbo, ablate) : launch_gemm_simt(g, st);
+    e = use_tc ? launch_gemm_tc(g, tw, prop.multiProcessorCount, st, swap_lbo_sbo, ablate, ts) : launch_gemm_simt(g, st);
   }
   cudaEventRecord(e1, st);
   cudaError_t e2 = cudaStreamSynchronize(st);
+  if (ts) {
+    long long hts[16];
+    if (cudaMemcpy(hts, ts, sizeof hts, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "tc_ts M=%d N=%d K=%d BN=%d span_ns=%lld marks_cycles:", M, N, K, tw.BN, hts[15] - hts[0]);
+      for (int i = 2; i <= 12; i++) fprintf(stderr, " %lld", hts[i] ? hts[i] - hts[1] : -1);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(ts);
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = ms / (reps > 1 ? reps : 1);
@@ -1582,7 +1593,8 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
 // entry packs A (and, for mode 3 with out_pair, the residual) to pair16, runs the kernel and unpacks the result, so the
 // caller compares plain fp32.  mode: 0 plain, 1 gathered adds from aux[M,2N], 2 multiply by aux[M,N], 3 residual aux[M,N]
 // (in place, as the edge state is updated).  c2_out != NULL: rows m % 3 == 0 are also written to the compact copy
-// C2[m / 3] and returned there ([ceil(M/3), N] fp32).  ew: 0 default, 8 or 16 epilogue warps.
+// C2[m / 3] and returned there ([ceil(M/3), N] fp32).  ew: 0 default, 8 or 16 epilogue warps; + 100 / + 200 forces single
+// CTAs / CTA pairs (default: by problem size).
 extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* A, const float* W, const float* bias,
                                   float* C, int mode, const float* aux, int out_pair, int act, float* c2_out, int ew,
                                   int reps, float* ms_out, void* stream) {
@@ -1607,6 +1619,9 @@ extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* 
   const int ldc = out_pair ? Np : N;
   GemmArgs g = mk(Ap, Kp, W, K, out_pair ? Cp : C, ldc, M, N, K);
   g.bias = bias; g.act = act;
+  { const char* ea = getenv("OARD_P16_ABLATE"); g.ablate = ea ? atoi(ea) : 0; }  // timing experiments only
+  long long* ts = nullptr;  // OARD_P16_TS=1: timeline marks of CTA 0 (last launch), printed to stderr
+  if (getenv("OARD_P16_TS")) { CU(cudaMalloc(&ts, 32 * sizeof(long long))); CU(cudaMemsetAsync(ts, 0, 32 * sizeof(long long), st)); g.ts = ts; }
   if (mode == 1) { g.radd1 = aux; g.ld1 = 2 * N; g.radd2 = aux + N; g.ld2 = 2 * N; }
   if (mode == 2) { g.mul = aux; g.ldmul = N; }
   if (mode == 3) {
@@ -1630,7 +1645,7 @@ extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* 
   if (mode == 3 && out_pair) k_p16_pack<<<1024, 256, 0, st>>>(aux, N, M, N, Cp, Np);
   for (int r = 0; r < nrun && e == cudaSuccess; r++) {
     if (r == nrun - (reps > 1 ? reps : 1)) cudaEventRecord(e0, st);
-    e = launch_gemm_p16(g, tw, prop.multiProcessorCount, st, out_pair != 0, ew);
+    e = launch_gemm_p16(g, tw, prop.multiProcessorCount, st, out_pair != 0, ew % 100, ew / 100);
   }
   cudaEventRecord(e1, st);
   if (e == cudaSuccess && out_pair) k_p16_unpack<<<1024, 256, 0, st>>>(Cp, Np, M, N, C, N);
@@ -1643,6 +1658,17 @@ extern "C" int oard_test_gemm_p16(int device, int M, int N, int K, const float* 
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = ms / (reps > 1 ? reps : 1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ts) {
+    long long hts[32];
+    if (cudaMemcpy(hts, ts, sizeof hts, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "p16_ts M=%d N=%d K=%d mode=%d ablate=%d (cycles since mark 0):", M, N, K, mode, g.ablate);
+      for (int i = 0; i < 15; i++) fprintf(stderr, " %lld", hts[i] ? hts[i] - hts[0] : -1);
+      fprintf(stderr, " | chunk 4 (since its start: weights there, A there, MMAs issued, commit 1, commit 2):");
+      for (int i = 17; i < 22; i++) fprintf(stderr, " %lld", hts[i] ? hts[i] - hts[16] : -1);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(ts);
+  }
   cudaFree(Ap); cudaFree(Cp); cudaFree(wbuf);
   if (idx) cudaFree(idx);
   if (C2p) cudaFree(C2p);

@@ -43,3 +43,14 @@ def test_gemm_p16(M, N, K, mode, out_pair):
         res = run_p16(M, N, K, mode, out_pair, act=1, c2=(mode in (0, 3)), ew=ew)
         assert "error" not in res, res
         assert res["nan"] == 0 and res["rel_err"] < 3e-5 and res.get("rel_err_c2", 0.0) < 3e-5, (ew, res)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (300, 196, 684), (257, 588, 588), (1000, 684, 196), (40000, 196, 684)])
+@pytest.mark.parametrize("mode,out_pair,ew", [(0, 1, 16), (0, 0, 16), (1, 1, 16), (2, 0, 8), (3, 1, 16)])
+def test_gemm_p16_cta_pairs(M, N, K, mode, out_pair, ew):
+    """The same kernel on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each CTA holds half of every weight slab, the leader
+    issues the MMAs for both) forced for every shape, incl. ragged last tiles whose second CTA has no valid row (ew + 200)."""
+    from tools.bringup_p16 import run_p16
+    res = run_p16(M, N, K, mode, out_pair, act=1, c2=(mode in (0, 3)), ew=ew + 200)
+    assert "error" not in res, res
+    assert res["nan"] == 0 and res["rel_err"] < 3e-5 and res.get("rel_err_c2", 0.0) < 3e-5, res
