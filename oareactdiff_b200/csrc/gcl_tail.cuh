@@ -201,8 +201,10 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
       }
     }
   } else if (warp == EW) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the warp runs the loop converged, one elected lane issues the tcgen05 instructions
+    // (inside an `if (lane == 0)` region ptxas wraps every UTCHMMA / UTCBAR in an ELECT ... BRA.U.ANY loop; with 336 small
+    // MMAs per row tile in layer 3 that loop, not the tensor pipe, set the pace: 140 cycles per MMA of 48)
+    {
       const uint32_t idesc2 = tc_idesc(TC_BM, w2.BN), idesc3 = tc_idesc(TC_BM, GT_BN3);
       uint32_t ga = 0, gw = 0, it = 0, g3 = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
@@ -220,18 +222,22 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           const uint32_t a0 = ptx::smem_u32(h_ring + (size_t)sa * P16_A_BYTES);
           const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT), w_lo = w_hi + W2_PART;
           const int steps = min(TC_KC / 16, k16_2 - kc * (TC_KC / 16));
-          for (int j = 0; j < steps; j++) {
-            const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
-            const uint32_t kw = j * 2 * TC_CORE_BYTES;
-            const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwh, idesc2, (kc | j) != 0);
-            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwl, idesc2, 1);
-            ptx::umma_bf16(tmem_base + GT_COL_ACC2, dal, dwh, idesc2, 1);
+          if (ptx::elect_one()) {
+            for (int j = 0; j < steps; j++) {
+              const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
+              const uint32_t kw = j * 2 * TC_CORE_BYTES;
+              const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwh, idesc2, (kc | j) != 0);
+              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwl, idesc2, 1);
+              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dal, dwh, idesc2, 1);
+            }
+            ptx::umma_commit(&empty_h[sa]);
+            ptx::umma_commit(&empty_w[sw_]);
           }
-          ptx::umma_commit(&empty_h[sa]);
-          ptx::umma_commit(&empty_w[sw_]);
+          __syncwarp();
         }
-        ptx::umma_commit(acc2_full);
+        if (ptx::elect_one()) ptx::umma_commit(acc2_full);
+        __syncwarp();
         GT_TS(2);
         // ---- layer 3: A = m in tensor memory, 8 column tiles alternating between the accumulators A and B
         ptx::mbar_wait(m_full, it & 1);
@@ -254,17 +260,23 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
             }
             const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT + (size_t)(c & 1) * 2 * W3_PART), w_lo = w_hi + W3_PART;
             const int steps = min(TC_KC / 16, k16_3 - kc * (TC_KC / 16));
-            for (int j = 0; j < steps; j++) {
-              const uint32_t ks = (uint32_t)(kc * (TC_KC / 16) + j) * 8;  // 8 columns per K step of 16
-              const uint32_t kw = j * 2 * TC_CORE_BYTES;
-              const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwh, idesc3, (kc | j) != 0);
-              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwl, idesc3, 1);
-              umma_bf16_ts(d_tmem, tmem_base + GT_COL_MLO + ks, dwh, idesc3, 1);
+            const bool release = (c & 1) == 1 || c == total3 - 1;
+            if (ptx::elect_one()) {
+              for (int j = 0; j < steps; j++) {
+                const uint32_t ks = (uint32_t)(kc * (TC_KC / 16) + j) * 8;  // 8 columns per K step of 16
+                const uint32_t kw = j * 2 * TC_CORE_BYTES;
+                const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwh, idesc3, (kc | j) != 0);
+                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwl, idesc3, 1);
+                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MLO + ks, dwh, idesc3, 1);
+              }
+              if (release) ptx::umma_commit(&empty_w[sw_]);
             }
-            if ((c & 1) == 1 || c == total3 - 1) { ptx::umma_commit(&empty_w[sw_]); gw++; }
+            __syncwarp();
+            if (release) gw++;
           }
-          ptx::umma_commit(&acc3_full[buf]);
+          if (ptx::elect_one()) ptx::umma_commit(&acc3_full[buf]);
+          __syncwarp();
           GT_TS(5 + 2 * nt);
         }
       }
@@ -512,16 +524,25 @@ inline cudaError_t launch_gcl_tail(const GclTailArgs& g, const TcWeight& w2, con
   if (!tc_make_map(&tmA, g.hid, g.E, p16_ld(g.H), g.ldh, TC_KC, TC_BM, true)) return cudaErrorInvalidValue;
   if (!tc_make_map(&tmR, g.ew, g.E, p16_ld(g.D), g.lde, 32, TC_BM, true)) return cudaErrorInvalidValue;
   if (!tc_make_map(&tmE, g.ew, g.E, p16_ld(g.D), g.lde, 32, 32, true)) return cudaErrorInvalidValue;
-  constexpr int SH = 2, SR = 4, SW = 4;
-  const size_t smem = gcl_tail_smem_bytes(w2.BN, g.D, SH, SR, SW);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static PerDeviceOnce attr;
-  if (attr.first_time()) {
-    cudaError_t e = cudaFuncSetAttribute(gcl_tail_kernel<SH, SR, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+  // ring depths (hidden chunks, residual blocks, weight slots); OARD_TAIL_RINGS=<k> picks another instantiated set (A/B runs)
+  static int env_rings = -1;
+  if (env_rings < 0) { const char* e = getenv("OARD_TAIL_RINGS"); env_rings = e ? atoi(e) : 0; }
+#define OARD_TAIL_CASE(IDX, SH, SR, SW)                                                                                   \
+  if (env_rings == IDX) {                                                                                                 \
+    const size_t smem = gcl_tail_smem_bytes(w2.BN, g.D, SH, SR, SW);                                                      \
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;                                                                  \
+    static PerDeviceOnce attr;                                                                                            \
+    if (attr.first_time()) {                                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(gcl_tail_kernel<SH, SR, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e != cudaSuccess) return e;                                                                                     \
+    }                                                                                                                     \
+    gcl_tail_kernel<SH, SR, SW><<<grid, GT_THREADS, smem, st>>>(g, w2, w3, tmA, tmR, tmE);                                \
+    return cudaGetLastError();                                                                                            \
   }
-  gcl_tail_kernel<SH, SR, SW><<<grid, GT_THREADS, smem, st>>>(g, w2, w3, tmA, tmR, tmE);
-  return cudaGetLastError();
+  // measured per layer at B = 64 (us): (3,5,3) 228, (4,5,3) 229, (3,6,3) 230, (2,6,3) 234, (4,4,3) 244, (2,4,4) 249, (3,6,2) 254, (2,7,2) 256
+  OARD_TAIL_CASE(0, 3, 5, 3) OARD_TAIL_CASE(1, 2, 4, 4)
+#undef OARD_TAIL_CASE
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace oard

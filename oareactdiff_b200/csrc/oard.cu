@@ -92,7 +92,7 @@ struct oard_handle {
   std::vector<LayerW> L;
   // tensor-core path: pre-split / pre-tiled bf16 weights (gemm_tc.cuh)
   bool use_tc = false;
-  bool use_tail = false;  // fused GCL tail kernel (gcl_tail.cuh), OARD_GCL_TAIL=1: same speed as the three launches on B=64 (W-stream bound), 25 % less HBM traffic
+  bool use_tail = false;  // fused GCL tail kernel (gcl_tail.cuh) on the pair16 path; OARD_GCL_TAIL=0 keeps edge2 / k_att_agg / edge_out as three launches
   bool use_p16 = false;  // edge-level activations (edge state, GCL hidden, dir_proj hidden) stored as pair16 (gemm_p16.cuh)
   int ldD = 0, ldH = 0, ld3H = 0;  // row pitches (floats) of the edge state / [E,H] / [E,3H] edge buffers
   int num_sms = 148;
@@ -247,7 +247,7 @@ extern "C" int oard_create(const oard_cfg* cfg, int device, oard_handle** out) {
     const char* ep = getenv("OARD_P16");  // "0": keep fp32 edge activations + the in-kernel-converting GEMM (gemm_tc.cuh)
     h->use_p16 = h->use_tc && !(ep && strcmp(ep, "0") == 0);
     const char* et = getenv("OARD_GCL_TAIL");
-    h->use_tail = h->use_p16 && et && strcmp(et, "1") == 0;
+    h->use_tail = h->use_p16 && !(et && strcmp(et, "0") == 0);
     const int H_ = cfg->hidden_channels, D_ = 3 * H_ + cfg->num_radial;
     h->ldD = h->use_p16 ? p16_ld(D_) : D_;
     h->ldH = h->use_p16 ? p16_ld(H_) : H_;
@@ -888,10 +888,11 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.hintA = EF;  // the edge state streams through
       {
         if (P) GEMM_P16("gemm_gcl_edge1", g, h->T[l].e0, true); else GEMM_TC("gemm_gcl_edge1", g, h->T[l].e0);
-        // Fused tail (gcl_tail.cuh, OARD_GCL_TAIL=1 at handle creation): edge_mlp layer 2 -> attention gate -> source
-        // aggregation -> edge_out_trans residual in ONE kernel, the hidden tile m handed to the third contraction through
-        // tensor memory.  Parity-green and 25 % lighter on HBM, but not faster at B = 64 (both forms are bound by the
-        // L2 -> shared-memory weight stream: profiles/r2_fused_tail_notes.md), so the three launches stay the default.
+        // Fused tail (gcl_tail.cuh; OARD_GCL_TAIL=0 at handle creation turns it off): edge_mlp layer 2 -> attention gate ->
+        // source aggregation -> edge_out_trans residual in ONE kernel, the hidden tile m handed to the third contraction
+        // through tensor memory.  25 % lighter on HBM and 228 vs 250 us per layer at B = 64 once its MMA issuer ran
+        // warp-uniform and the residual ring was five deep (profiles/r2_fused_tail_notes.md).  Shapes that do not fit it
+        // (H > 208, ...) fall back to the three launches.
         if (P && h->use_tail) {
           GclTailArgs ta;
           memset(&ta, 0, sizeof ta);

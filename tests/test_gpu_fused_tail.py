@@ -1,6 +1,7 @@
-"""GPU checks of the fused GCL tail kernel (csrc/gcl_tail.cuh, OARD_GCL_TAIL=1 at engine creation): edge_mlp layer 2 ->
-attention gate -> aggregation at the source -> edge_out_trans in one tcgen05 kernel whose third contraction takes its A
-operand from tensor memory.  Against the default three-launch path, against the fp64 oracle, and over many replays (the
+"""GPU checks of the fused GCL tail kernel (csrc/gcl_tail.cuh, the default on the pair16 path; OARD_GCL_TAIL=0 at engine
+creation selects the three launches it replaces): edge_mlp layer 2 -> attention gate -> aggregation at the source ->
+edge_out_trans in one tcgen05 kernel whose third contraction takes its A operand from tensor memory.  Against the
+three-launch path, against the fp64 oracle, and over many replays (the
 kernel's rings are multi-producer / multi-consumer: a phase-parity hazard shows up as a sporadic fault, not on the first call)."""
 import os
 
