@@ -53,8 +53,11 @@ __host__ __device__ inline size_t p16_off_hi(int c) { return (size_t)(c >> 4) * 
 __host__ __device__ inline int p16_ld(int K) { return (K + 15) / 16 * 16; }
 
 // fp32 [M, K] (ld_src) -> pair16 [M, p16_ld(K)] (ld_dst floats); pad columns are written as zeros.  One thread per 8 values.
-__global__ void k_p16_pack(const float* __restrict__ src, int ld_src, int M, int K, float* __restrict__ dst, int ld_dst) {
+// m_dev (optional): the row count lives in device memory (M is then the cap).
+__global__ void k_p16_pack(const float* __restrict__ src, int ld_src, int M, int K, float* __restrict__ dst, int ld_dst,
+                           const int* __restrict__ m_dev = nullptr) {
   const int cells = ld_dst / 8;
+  if (m_dev) M = min(M, *m_dev);
   const size_t total = (size_t)M * cells;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / cells), c8 = (int)(i % cells) * 8;

@@ -547,7 +547,7 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
       {"vecB", Nn * 3 * H * 4}, {"VP", Nn * 6 * H * 4}, {"sx", Nn * 2 * H * 4}, {"vd", Nn * H * 4},
       {"XV", Nn * 3 * H * 4}, {"O1", Nn * 3 * H * 4}, {"sn", Nn * 2 * H * 4}, {"tu", Nn * H * 4},
       {"ew", Ee * (size_t)h->ldD * 4}, {"ew_act", Ee * (size_t)h->ldD * 4}, {"crow", (size_t)h->ldD * 4}, {"g_h_in", Nn * 32 * 4}, {"g_pos", Nn * 12}, {"g_sub", Ee * 8},
-      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * (size_t)h->ldH * 4}, {"m2", (Ee + 32) * (size_t)h->ldH * 4}, {"agg_src", (Ee + 32) * 4}, {"tail_ts", 16 * 64 * 8}, {"rbf_act", Ee * R * 4}, {"f_act", Ee * H * 4},
+      {"g_h_out", Nn * 32 * 4}, {"g_dpos", Nn * 12}, {"hid1", Ee * (size_t)h->ldH * 4}, {"m2", (Ee + 32) * (size_t)h->ldH * 4}, {"agg_src", (Ee + 32) * 4}, {"tail_ts", 16 * 64 * 8}, {"rbf_act", Ee * R * 4}, {"rbf_p16", Ee * (size_t)p16_ld(R) * 4}, {"f_act", Ee * H * 4},
       {"d1", Ee * (size_t)h->ld3H * 4}, {"RB", Ee * 3 * H * 4}, {"G", Ee * 3 * H * 4},
   };
   for (auto& a : allocs) {
@@ -957,9 +957,19 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
       g.m_dev = n_act; g.bias = w.d0b; g.act = 1;
       g.hintA = EF;  // last use of the compact copy
       if (P) GEMM_P16("gemm_dir_proj0", g, h->T[l].d0, true); else GEMM_TC("gemm_dir_proj0", g, h->T[l].d0);
-      g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
-      g.m_dev = n_act;
-      GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
+      static int env_rbf = -1;  // OARD_RBF_P16=0: rbf_proj on the fp32-A kernel (A/B runs)
+      if (env_rbf < 0) { const char* e = getenv("OARD_RBF_P16"); env_rbf = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+      if (P && env_rbf) {  // pair16 copy of the (layer-independent) radial basis, packed once per evaluation: 16 epilogue warps instead of 8
+        float* rbf_p16 = h->buf<float>("rbf_p16");
+        if (l == 0) { k_p16_pack<<<h->num_sms * 4, 256, 0, st>>>(rbf_act, R, E, R, rbf_p16, p16_ld(R), n_act); h->launches++; }
+        g = mk(rbf_p16, p16_ld(R), w.rbfw, R, RB, 3 * H, E, 3 * H, R);
+        g.m_dev = n_act;
+        GEMM_P16("gemm_rbf_proj", g, h->T[l].rbf, false);
+      } else {
+        g = mk(rbf_act, R, w.rbfw, R, RB, 3 * H, E, 3 * H, R);
+        g.m_dev = n_act;
+        GEMM_TC("gemm_rbf_proj", g, h->T[l].rbf);
+      }
       g = mk(d1, ld3H, w.d2w, 3 * H, G, 3 * H, E, 3 * H, 3 * H);
       g.m_dev = n_act; g.bias = w.d2b; g.mul = RB; g.ldmul = 3 * H;
       g.hintA = EF; g.hintX = EF; g.hintC = 2 * EF;  // last use of d1 and RB; G (evict_last) stays in L2 for the message kernel, which reads it evict_first

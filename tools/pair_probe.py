@@ -17,12 +17,12 @@ def main():
     if "ablate" in what:
         # role ablation (results meaningless): 1 no A loads, 4 no weight loads, 2 no epilogue traffic, 8 no MMAs
         E, Ea = 107790, 34188
-        shapes = [("edge_out", E, 684, 196, 3, 1, 16), ("dir0", Ea, 588, 684, 0, 1, 16), ("dir2", Ea, 588, 588, 2, 0, 8),
-                  ("edge2", E, 196, 196, 0, 1, 16), ("edge1_plain", E, 196, 684, 0, 1, 16)]
+        shapes = [("dir0", Ea, 588, 684, 0, 1, 16), ("dir2", Ea, 588, 588, 2, 0, 8), ("edge1_plain", E, 196, 684, 0, 1, 16),
+                  ("edge2", E, 196, 196, 0, 1, 16), ("edge_out", E, 684, 196, 3, 1, 16)]
         for name, M, N, K, mode, op, ew in shapes:
-            for ct in (1,):  # (no-MMA ablations never finish with CTA pairs)
+            for ct in (1, 2):
                 row = {}
-                for ab in (0, 1, 4, 5, 2, 7, 15, 13, 8):
+                for ab in ((0, 1, 4, 5, 2, 7, 15, 13, 8) if ct == 1 else (0, 1, 4, 5, 2, 7)):  # (no-MMA ablations never finish with CTA pairs)
                     os.environ["OARD_P16_ABLATE"] = str(ab)
                     row[ab] = round(1e3 * run_p16(M, N, K, mode, op, 1, c2=False, ew=ew + 100 * ct, reps=20).get("ms", float("nan")), 1)
                 os.environ["OARD_P16_ABLATE"] = "0"
