@@ -222,14 +222,20 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           const uint32_t a0 = ptx::smem_u32(h_ring + (size_t)sa * P16_A_BYTES);
           const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT), w_lo = w_hi + W2_PART;
           const int steps = min(TC_KC / 16, k16_2 - kc * (TC_KC / 16));
+          // descriptors of K step 0; step 1 is a constant further (address field in 16-byte units): the issuing lane's
+          // instruction stream, not the tensor pipe, paces these loops, so everything loop-invariant is hoisted
+          const uint64_t dah0 = p16_a_desc(a0), dal0 = p16_a_desc(a0 + 32);
+          const uint64_t dwh0 = tc_smem_desc(w_hi, TC_CORE_BYTES, TC_SBO), dwl0 = tc_smem_desc(w_lo, TC_CORE_BYTES, TC_SBO);
           if (ptx::elect_one()) {
-            for (int j = 0; j < steps; j++) {
-              const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
-              const uint32_t kw = j * 2 * TC_CORE_BYTES;
-              const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwh, idesc2, (kc | j) != 0);
-              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwl, idesc2, 1);
-              ptx::umma_bf16(tmem_base + GT_COL_ACC2, dal, dwh, idesc2, 1);
+#pragma unroll
+            for (int j = 0; j < TC_KC / 16; j++) {
+              if (j < steps) {
+                const uint64_t dah = dah0 + (uint64_t)(j * (64 >> 4)), dal = dal0 + (uint64_t)(j * (64 >> 4));
+                const uint64_t dwh = dwh0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4)), dwl = dwl0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4));
+                ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwh, idesc2, (kc | j) != 0);
+                ptx::umma_bf16(tmem_base + GT_COL_ACC2, dah, dwl, idesc2, 1);
+                ptx::umma_bf16(tmem_base + GT_COL_ACC2, dal, dwh, idesc2, 1);
+              }
             }
             ptx::umma_commit(&empty_h[sa]);
             ptx::umma_commit(&empty_w[sw_]);
@@ -261,14 +267,17 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
             const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * W_SLOT + (size_t)(c & 1) * 2 * W3_PART), w_lo = w_hi + W3_PART;
             const int steps = min(TC_KC / 16, k16_3 - kc * (TC_KC / 16));
             const bool release = (c & 1) == 1 || c == total3 - 1;
+            const uint64_t dwh0 = tc_smem_desc(w_hi, TC_CORE_BYTES, TC_SBO), dwl0 = tc_smem_desc(w_lo, TC_CORE_BYTES, TC_SBO);
+            const uint32_t ks0 = (uint32_t)(kc * (TC_KC / 16)) * 8;  // 8 columns per K step of 16
             if (ptx::elect_one()) {
-              for (int j = 0; j < steps; j++) {
-                const uint32_t ks = (uint32_t)(kc * (TC_KC / 16) + j) * 8;  // 8 columns per K step of 16
-                const uint32_t kw = j * 2 * TC_CORE_BYTES;
-                const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
-                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwh, idesc3, (kc | j) != 0);
-                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks, dwl, idesc3, 1);
-                umma_bf16_ts(d_tmem, tmem_base + GT_COL_MLO + ks, dwh, idesc3, 1);
+#pragma unroll
+              for (int j = 0; j < TC_KC / 16; j++) {
+                if (j < steps) {
+                  const uint64_t dwh = dwh0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4)), dwl = dwl0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4));
+                  umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks0 + j * 8, dwh, idesc3, (kc | j) != 0);
+                  umma_bf16_ts(d_tmem, tmem_base + GT_COL_MHI + ks0 + j * 8, dwl, idesc3, 1);
+                  umma_bf16_ts(d_tmem, tmem_base + GT_COL_MLO + ks0 + j * 8, dwh, idesc3, 1);
+                }
               }
               if (release) ptx::umma_commit(&empty_w[sw_]);
             }

@@ -286,11 +286,15 @@ gemm_p16_kernel(const GemmArgs g, const TcWeight w, const __grid_constant__ CUte
           const uint32_t a0 = ptx::smem_u32(a_ring + (size_t)sa * P16_A_BYTES);
           const uint32_t w_hi = ptx::smem_u32(w_ring + (size_t)sw_ * 2 * W_MINE), w_lo = w_hi + W_MINE;
           const int steps = (g.ablate & 8) ? 0 : min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
+          // descriptors of K step 0; step 1 is a constant further (the address field counts 16-byte units)
+          const uint64_t dah0 = p16_a_desc(a0), dal0 = p16_a_desc(a0 + 32);
+          const uint64_t dwh0 = tc_smem_desc(w_hi, TC_CORE_BYTES, TC_SBO), dwl0 = tc_smem_desc(w_lo, TC_CORE_BYTES, TC_SBO);
           if (ptx::elect_one()) {
-            for (int j = 0; j < steps; j++) {
-              const uint64_t dah = p16_a_desc(a0 + j * 64), dal = p16_a_desc(a0 + j * 64 + 32);
-              const uint32_t kw = j * 2 * TC_CORE_BYTES;
-              const uint64_t dwh = tc_smem_desc(w_hi + kw, TC_CORE_BYTES, TC_SBO), dwl = tc_smem_desc(w_lo + kw, TC_CORE_BYTES, TC_SBO);
+#pragma unroll
+            for (int j = 0; j < TC_KC / 16; j++) {
+              if (j >= steps) break;
+              const uint64_t dah = dah0 + (uint64_t)(j * (64 >> 4)), dal = dal0 + (uint64_t)(j * (64 >> 4));
+              const uint64_t dwh = dwh0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4)), dwl = dwl0 + (uint64_t)(j * ((2 * TC_CORE_BYTES) >> 4));
               if (CTAS == 2) {
                 ptx::umma_bf16_2cta(d_tmem, dah, dwh, idesc, (kc | j) != 0);
                 ptx::umma_bf16_2cta(d_tmem, dah, dwl, idesc, 1);
