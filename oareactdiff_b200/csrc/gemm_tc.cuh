@@ -408,11 +408,11 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float4*>(raw + roff[i]);
         // cross-proxy WAR: these generic-proxy reads must be ordered before the TMA engine (async proxy) refills the box.
-        // Without this fence the refill can overtake the reads (seen on hardware: stale/corrupt rows in later tiles).
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);  // box consumed (values are in registers)
+        // Without a fence the refill can overtake the reads (seen on hardware: stale/corrupt rows in later tiles).  The fence
+        // consume() issues before it publishes the converted stage orders them too, so the box is handed back after it:
+        // one proxy fence per chunk instead of two (the chunk pipeline of small-M GEMMs runs at the producers' pace).
         consume(c, v);
+        if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);  // box consumed
       }
     } else {
     const int my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -469,8 +469,8 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
       }
     }
   } else if (warp == TC_EPI_WARPS) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp; one elected lane issues the tcgen05 instructions) =====================
+    {
       const uint32_t idesc = tc_idesc(TC_BM, BN);
       const uint32_t wl = dbg.swap_lbo_sbo ? TC_SBO : TC_CORE_BYTES, ws = dbg.swap_lbo_sbo ? TC_CORE_BYTES : TC_SBO;
       uint32_t gchunk = 0, it = 0;
@@ -483,25 +483,31 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
           const int s = gchunk % STAGES;
           const uint32_t ph = (gchunk / STAGES) & 1;
           ptx::mbar_wait(&full_a[s], ph);
-          if (gchunk == 0) tc_mark(dbg, 5);  // first converted A stage
+          if (gchunk == 0 && lane == 0) tc_mark(dbg, 5);  // first converted A stage
           ptx::mbar_wait(&full_w[s], ph);
-          if (gchunk == 0) tc_mark(dbg, 6);  // first weight slab
+          if (gchunk == 0 && lane == 0) tc_mark(dbg, 6);  // first weight slab
           ptx::tc_fence_after();
           const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TC_A_PART;
           const uint32_t w_hi = a_hi + 2 * TC_A_PART, w_lo = w_hi + W_PART;
-          const int steps = min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
-          for (int j = 0; j < ((dbg.ablate & 8) ? 0 : steps); j++) {  // two K-adjacent core matrices per UMMA_K = 16
-            const uint32_t ka = j * 2 * TC_A_LBO, kw = j * 2 * TC_CORE_BYTES;
-            const uint64_t dah = tc_smem_desc(a_hi + ka, TC_A_LBO, TC_A_SBO), dal = tc_smem_desc(a_lo + ka, TC_A_LBO, TC_A_SBO);
-            const uint64_t dwh = tc_smem_desc(w_hi + kw, wl, ws), dwl = tc_smem_desc(w_lo + kw, wl, ws);
-            ptx::umma_bf16(d_tmem, dah, dwh, idesc, (kc | j) != 0);
-            ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
-            ptx::umma_bf16(d_tmem, dal, dwh, idesc, 1);
+          const int steps = (dbg.ablate & 8) ? 0 : min(TC_KC / 16, k16_total - kc * (TC_KC / 16));
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int j = 0; j < TC_KC / 16; j++) {  // two K-adjacent core matrices per UMMA_K = 16
+              if (j >= steps) break;
+              const uint32_t ka = j * 2 * TC_A_LBO, kw = j * 2 * TC_CORE_BYTES;
+              const uint64_t dah = tc_smem_desc(a_hi + ka, TC_A_LBO, TC_A_SBO), dal = tc_smem_desc(a_lo + ka, TC_A_LBO, TC_A_SBO);
+              const uint64_t dwh = tc_smem_desc(w_hi + kw, wl, ws), dwl = tc_smem_desc(w_lo + kw, wl, ws);
+              ptx::umma_bf16(d_tmem, dah, dwh, idesc, (kc | j) != 0);
+              ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
+              ptx::umma_bf16(d_tmem, dal, dwh, idesc, 1);
+            }
+            ptx::umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
           }
-          ptx::umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          __syncwarp();
         }
-        ptx::umma_commit(&acc_full[buf]);
-        tc_mark(dbg, 7);  // last MMA of the (latest) tile issued
+        if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (lane == 0) tc_mark(dbg, 7);  // last MMA of the (latest) tile issued
       }
     }
   } else {
@@ -558,6 +564,10 @@ gemm_tc_kernel(const GemmArgs g, const TcWeight w, const TcDebugOpts dbg, const 
         const float rs = (ok && g.rowscale) ? g.rowscale[g.rsidx ? g.rsidx[m] : m] : 1.f;
         const float ps = (ok && g.prescale) ? g.prescale[m] : 1.f;
         const int c2 = (ok && g.C2) ? g.c2idx[m] : -1;
+        // the bias segment of this warp's first block into L1 while the MMAs run (a cold read costs ~700 cycles of the
+        // epilogue's latency chain; node-level GEMMs have one block per warp and tile)
+        if (g.bias && lane == 0 && n0 + half * 32 < g.N)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(g.bias + n0 + half * 32));
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
         ptx::tc_fence_after();
         if (warp == 0 && lane == 0) tc_mark(dbg, 8);  // accumulator of the (latest) tile complete
