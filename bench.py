@@ -32,7 +32,7 @@ UNIT = "reactions/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="reactions per GPU")
@@ -95,9 +95,16 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[2]))
+            except Exception:
+                pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_mhz_min": sm[0] if sm else None, "sm_mhz_p10": sm[len(sm) // 10] if sm else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def load_workloads():
@@ -546,7 +553,10 @@ def run_b200(args, rank, world, local_rank):
                        "weights": "torch.manual_seed(0) default init (checkpoint is a git-LFS pointer)"},
             "clocks": clk, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "spread": {"ms_per_step_min": srt[0], "ms_per_step_median": srt[len(srt) // 2], "ms_per_step_max": srt[-1],
-                       "repeats": len(srt), "e2e_ms_per_step": [round(x, 1) for x in per_e2e]},
+                       "repeats": len(srt), "resident_ms_per_step": [round(x, 1) for x in per_step],
+                       "e2e_ms_per_step": [round(x, 1) for x in per_e2e],
+                       "note": "per-step CUDA-event times in launch order; this pool's B200s run this workload at the power cap "
+                               "(clocks.reasons), step-to-step differences of a few percent follow the clock"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "outputs_finite": finite},
             "roofline": roof,

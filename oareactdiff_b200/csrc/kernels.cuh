@@ -933,11 +933,10 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
     const float4* __restrict__ geo, const float* __restrict__ rb, const float* __restrict__ NE1,
     const float* __restrict__ f_act, const float* __restrict__ rbf_act, const __grid_constant__ Lin3E W,
     float* __restrict__ ew) {
-  extern __shared__ __align__(16) float sm_ei[];  // row[ld]
+  extern __shared__ __align__(16) float sm_ei[];  // row[2][ld]: the row of edge i leaves while edge i + 1 is evaluated (one barrier per edge)
   const int na = min(*n_act, cap);
-  float* row = sm_ei;
   const int t = threadIdx.x;
-  for (int k = 3 * H + R + t; k < ld; k += blockDim.x) row[k] = 0.f;
+  for (int k = 3 * H + R + t; k < ld; k += blockDim.x) { sm_ei[k] = 0.f; sm_ei[ld + k] = 0.f; }
   auto load = [&](int p) {
     EdgeInitIn in;
     in.e = act_idx[p];
@@ -963,7 +962,8 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
   EdgeInitIn cur{};
   if (p < na) cur = load(p);
   __syncthreads();
-  for (; p < na; p += gridDim.x) {
+  for (int par = 0; p < na; p += gridDim.x, par ^= 1) {
+    float* row = sm_ei + par * ld;
     EdgeInitIn nxt{};
     if (p + (int)gridDim.x < na) nxt = load(p + gridDim.x);
     if (t < H) row[2 * H + t] = cur.fv;
@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(256, 4) k_edge_init_act(
     } else {
       for (int k = t; k < ld; k += blockDim.x) out[k] = row[k];
     }
-    __syncthreads();
+    // (no second barrier: the next edge fills the other buffer, and this one is refilled only after the next barrier)
     cur = nxt;
   }
 }

@@ -835,7 +835,7 @@ static int forward_impl(oard_handle* h, const float* h_in, const float* pos, con
     // initial edge state (leftnet.py:792-809): masked edges get the constant row, active edges the scalarised lin3 terms
     float* crow = h->buf<float>("crow");
     const int ei_threads = HB;  // one thread per channel, both sides
-    const size_t ei_smem = (size_t)ldD * sizeof(float);
+    const size_t ei_smem = 2 * (size_t)ldD * sizeof(float);  // two row buffers
     PB("k_edge_init", 0, (double)E*D*4.0, 0);
     if (P) k_const_row<true><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
     else k_const_row<false><<<1, 128, 0, st>>>(H, R, ldD, f0, c3, crow);
