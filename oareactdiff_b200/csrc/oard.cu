@@ -1585,7 +1585,7 @@ extern "C" int oard_test_gemm_ex(int device, int M, int N, int K, const float* A
     long long hts[16];
     if (cudaMemcpy(hts, ts, sizeof hts, cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "tc_ts M=%d N=%d K=%d BN=%d span_ns=%lld marks_cycles:", M, N, K, tw.BN, hts[15] - hts[0]);
-      for (int i = 2; i <= 12; i++) fprintf(stderr, " %lld", hts[i] ? hts[i] - hts[1] : -1);
+      for (int i = 2; i <= 14; i++) fprintf(stderr, " %lld", hts[i] ? hts[i] - hts[1] : -1);
       fprintf(stderr, "\n");
     }
     cudaFree(ts);

@@ -483,6 +483,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         case_checkpoint()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "inpaint_trained":  # only the trained-configuration RePaint trajectory
+        case_inpaint("inpaint_trained_b4_T12_r2_j3", TRAINED_CFG, [5, 9, 14, 7], seed=44, T=12, resamplings=2, jump_length=3)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "noreflect":  # reflect_equiv=False (reference tests/model/test_equiv.py:40-41)
         case_leftnet("leftnet_small_noreflect", dict(SMALL_CFG, reflect_equiv=False), 11, seed=14, cut=5, pos_scale=3.0)
         sys.exit(0)
@@ -521,6 +524,7 @@ if __name__ == "__main__":
     case_sample("sample_small_T10", SMALL_CFG, [5, 3], seed=41, T=10)
     case_sample("sample_trained_cfg1_T10", TRAINED_CFG, [12], seed=42, T=10)
     case_inpaint("inpaint_small_T12_r2_j3", SMALL_CFG, [4, 6], seed=43, T=12, resamplings=2, jump_length=3)
+    case_inpaint("inpaint_trained_b4_T12_r2_j3", TRAINED_CFG, [5, 9, 14, 7], seed=44, T=12, resamplings=2, jump_length=3)
     case_train_loss("loss_small_train", SMALL_CFG, [5, 3, 4], seed=51, T=20, training=True)
     case_train_loss("loss_small_eval", SMALL_CFG, [5, 3, 4], seed=52, T=20, training=False)
     case_train_loss("loss_trained_train_b4", TRAINED_CFG, [4, 9, 14, 7], seed=53, T=100, training=True)

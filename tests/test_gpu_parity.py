@@ -178,8 +178,11 @@ def test_sample_trajectory_vs_reference_golden(name):
         assert np.array_equal(out[0][f][:, 3:].cpu().numpy(), g[f"out{f}"][:, 3:])
 
 
-def test_inpaint_trajectory_vs_reference_golden():
-    g = load_golden("inpaint_small_T12_r2_j3")
+@pytest.mark.parametrize("name", ["inpaint_small_T12_r2_j3", "inpaint_trained_b4_T12_r2_j3"])
+def test_inpaint_trajectory_vs_reference_golden(name):
+    """RePaint (en_diffusion.py:722-883) against trajectories of the UNMODIFIED reference: the small configuration and the
+    trained one (B = 4 ragged reactions, T = 12, resamplings 2, jump length 3), reactant and product clamped."""
+    g = load_golden(name)
     sizes = [int(x) for x in g["sizes"]]
     ddpm = _make_ddpm(g["cfg"], int(g["seed"]), int(g["T"]), _CpuNoiseDiffusion)
     nodes, h0, cond = oa_ref.synthetic_batch(len(sizes), sizes, int(g["seed"]))
@@ -190,7 +193,7 @@ def test_inpaint_trajectory_vs_reference_golden():
     assert ddpm.n_evals == sum(oa_ref.get_repaint_schedule(2, 3, 12)) + 1
     for f in range(3):
         e = rel_err(out[0][f][:, :3].cpu(), g[f"out{f}"][:, :3])
-        print(f"inpaint frag{f}: {e:.2e}")
+        print(f"{name} frag{f}: {e:.2e}")
         assert e < TRAJ_TOL
 
 

@@ -33,8 +33,9 @@ def test_sample_trajectory_host_logic(oracle_engine, monkeypatch, name, fast):
 
 
 @pytest.mark.parametrize("fast", [True, False])
-@pytest.mark.parametrize("entry", ["inpaint", "inpaint_fixed"])
-def test_inpaint_trajectory_host_logic(oracle_engine, monkeypatch, fast, entry):
+@pytest.mark.parametrize("entry,name", [("inpaint", "inpaint_small_T12_r2_j3"), ("inpaint_fixed", "inpaint_small_T12_r2_j3"),
+                                        ("inpaint", "inpaint_trained_b4_T12_r2_j3")])
+def test_inpaint_trajectory_host_logic(oracle_engine, monkeypatch, fast, entry, name):
     if not fast:
         monkeypatch.setattr(ob.EnVariationalDiffusion, "_fast_ok", lambda self: False)
     if entry == "inpaint_fixed":  # the reference's second entry point with the same body (en_diffusion.py:887-1048)
@@ -47,7 +48,7 @@ def test_inpaint_trajectory_host_logic(oracle_engine, monkeypatch, fast, entry):
                 return ob.EnVariationalDiffusion.inpaint_fixed(self, *a, **k)
             return real(self, *a, **k)
         monkeypatch.setattr(ob.EnVariationalDiffusion, "inpaint", via_fixed)
-    gp.test_inpaint_trajectory_vs_reference_golden()
+    gp.test_inpaint_trajectory_vs_reference_golden(name)
 
 
 def test_schedule_swapped_after_construction_is_honoured(oracle_engine, monkeypatch):

@@ -9,7 +9,8 @@ os.environ["OARD_TC_TS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tools.bringup_p16 import time_tc  # noqa: E402
 
-NAMES = ["setup", "A_req", "A_land", "A_conv", "W_land", "mma_last", "acc_full", "store_last", "stores_done", "sync", "exit"]
+NAMES = ["setup", "A_req", "A_land", "A_conv", "W_land", "mma_last", "acc_full", "store_last", "stores_done", "sync", "exit",
+         "block_in_regs", "block_staged"]
 
 
 def main():
