@@ -132,7 +132,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
     ptx::mbar_init(acc2_full, 1);
     ptx::mbar_init(m_full, EW);
     for (int b = 0; b < 2; b++) { ptx::mbar_init(&acc3_full[b], 1); ptx::mbar_init(&acc3_empty[b], EW); }
-    ptx::mbar_init(tile_done, EW);
+    ptx::mbar_init(tile_done, EW);  // (unused since layer 2 of the next tile is gated by accumulator B alone)
     for (int s = 0; s < SR; s++) r_tag[s] = 0xffffffffu;
     ptx::fence_barrier_init();
   }
@@ -208,9 +208,17 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
       const uint32_t idesc2 = tc_idesc(TC_BM, w2.BN), idesc3 = tc_idesc(TC_BM, GT_BN3);
       uint32_t ga = 0, gw = 0, it = 0, g3 = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, it++) {
-        // the accumulators and the m tile of the previous row tile are dead once its epilogue 3 has finished
+        // Layer 2 of this row tile writes columns [0, 208): accumulator B of layer 3 (the rest of the range is idle during
+        // layer 3).  It may start as soon as the LATEST use of B has been drained by the epilogue — with the column tiles
+        // alternating B, A, B, A, ... the last one of a row tile with an even tile count sits on A, so these MMAs run under
+        // the epilogue of the previous row tile's last column tile instead of waiting for the whole tile.  (The m tile is
+        // rewritten by the epilogue warps themselves, after the last accumulator of the previous tile — hence after the last
+        // MMA that read m — has arrived.)
         GT_TS(0);
-        ptx::mbar_wait(tile_done, (it & 1) ^ 1);
+        if (g3 > 0) {
+          const uint32_t ub = (g3 + 1) / 2 - 1;  // index of B's latest use
+          ptx::mbar_wait(&acc3_empty[1], ub & 1);
+        }
         ptx::tc_fence_after();
         GT_TS(1);
         // ---- layer 2 -> acc2
@@ -252,7 +260,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
         const int total3 = n3_tiles * k3_chunks;
         int sw_ = 0;
         for (int nt = 0; nt < n3_tiles; nt++, g3++) {
-          const int buf = g3 & 1;
+          const int buf = (g3 & 1) ^ 1;  // B first
           ptx::mbar_wait(&acc3_empty[buf], ((g3 >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
           GT_TS(4 + 2 * nt);
@@ -409,7 +417,7 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
       // ---------------- epilogue 3: e += SiLU(att * acc3 + b3) per column tile
       for (int nt = 0; nt < n3_tiles; nt++) {
         const int g3 = (int)it * n3_tiles + nt;
-        const int buf = g3 & 1;
+        const int buf = (g3 & 1) ^ 1;  // B first (see the MMA issuer)
         const int f = nt * 3 + cg;  // block index inside the row tile
         const int n0 = f * 32;
         if (pend_rs >= 0) {  // hand back the ring slot of the previous block (see below)
@@ -498,9 +506,6 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
         pend_rs = -1;
       }
       GT_TS(40);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tile_done);
     }
     if (lane == 0) ptx::bulk_wait_all();
   }
