@@ -434,6 +434,14 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           ptx::mbar_wait(&acc3_full[buf], (g3 >> 1) & 1);
           ptx::tc_fence_after();
           GT_TS(8 + 4 * nt);
+          // The accumulator block goes to registers FIRST and is handed back at once: the MMA warp may refill it as soon as
+          // every warp has arrived, whether or not this warp's residual block is there yet (the residual stream comes from
+          // HBM; waiting for it with the accumulator still held put its latency on the MMA warp's critical path).
+          float v[32];
+          ptx::tmem_ld32(tmem_base + lane_base + (buf ? GT_COL_ACC2 : GT_COL_ACCA) + cg * 32, v);  // warp-collective
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc3_empty[buf]);
           const uint32_t ri = it * (uint32_t)J + (uint32_t)f;
           const int rs = ri % SR;
           while (r_tag[rs] != ri) {}
@@ -449,12 +457,6 @@ gcl_tail_kernel(const GclTailArgs g, const TcWeight w2, const TcWeight w3, const
           p16_join8(cell[1], cell[3], e + 8);
           p16_join8(cell[4], cell[6], e + 16);
           p16_join8(cell[5], cell[7], e + 24);
-          float v[32];
-          ptx::tmem_ld32(tmem_base + lane_base + (buf ? GT_COL_ACC2 : GT_COL_ACCA) + cg * 32, v);  // warp-collective
-          // this accumulator block is in registers: the MMA warp may refill it as soon as every warp has arrived
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&acc3_empty[buf]);
           const f32x2 att2 = pk2(att, att);
           const float2* bp = reinterpret_cast<const float2*>(b3s + n0);
 #pragma unroll
@@ -554,6 +556,7 @@ inline cudaError_t launch_gcl_tail(const GclTailArgs& g, const TcWeight& w2, con
     return cudaGetLastError();                                                                                            \
   }
   // measured per layer at B = 64 (us): (3,5,3) 228, (4,5,3) 229, (3,6,3) 230, (2,6,3) 234, (4,4,3) 244, (2,4,4) 249, (3,6,2) 254, (2,7,2) 256
+  // (after the accumulator hand-back moved ahead of the residual wait: (3,5,3) 218, (4,5,3) 218, (5,4,3) 227)
   OARD_TAIL_CASE(0, 3, 5, 3) OARD_TAIL_CASE(1, 2, 4, 4)
 #undef OARD_TAIL_CASE
   return cudaErrorInvalidValue;
