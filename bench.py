@@ -371,9 +371,12 @@ def run_b200(args, rank, world, local_rank):
     out_host = [torch.empty(h.size(0), 3).pin_memory() for h in h0_h]
 
     # ---- headline step: a full reverse diffusion on trained-model states built from the reference geometries
+    seg_probe = []  # one list of CUDA events (every 100 reverse steps) per resident trajectory
+
     def step_resident():
         torch.manual_seed(4321 + rank)
-        return workloads.replay_trajectory(ddpm, B, nodes_d, cond_d, h0_d, x_d, T)
+        seg_probe.append([])
+        return workloads.replay_trajectory(ddpm, B, nodes_d, cond_d, h0_d, x_d, T, probe=seg_probe[-1])
 
     def step_e2e():  # host (pinned) inputs -> device inside the timed region, result back to the host
         torch.manual_seed(4321 + rank)
@@ -426,8 +429,11 @@ def run_b200(args, rank, world, local_rank):
     l0 = eng.total_launches()
     clocks = ClockSampler(local_rank)
     clocks.start()
+    del seg_probe[:]
     ms, per_step = timed(step_resident, args.steps)
     clk = clocks.stop()
+    # per trajectory: the ten 100-step segments (ms) -> is a slow trajectory uniformly slow (clocks) or slow in bursts (stalls)?
+    segments = [[round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(len(evs) - 1)] for evs in seg_probe[:args.steps]]
     launches = eng.total_launches() - l0
     # per-kernel CUDA-event timing in a SEPARATE, untimed pass over the same step (a profiled forward runs eagerly with an
     # event pair around every kernel: ~10 % slower, so it must not sit inside the timed region)
@@ -554,6 +560,7 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clk, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "spread": {"ms_per_step_min": srt[0], "ms_per_step_median": srt[len(srt) // 2], "ms_per_step_max": srt[-1],
                        "repeats": len(srt), "resident_ms_per_step": [round(x, 1) for x in per_step],
+                       "resident_ms_per_100_reverse_steps": segments,
                        "e2e_ms_per_step": [round(x, 1) for x in per_e2e],
                        "note": "per-step CUDA-event times in launch order; this pool's B200s run this workload at the power cap "
                                "(clocks.reasons), step-to-step differences of a few percent follow the clock"},

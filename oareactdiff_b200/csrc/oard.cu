@@ -66,7 +66,8 @@ struct WeightSpec { std::string name; int64_t numel; };
 
 struct DevBuf {
   void* p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;  // size in use
+  size_t cap = 0;    // size allocated (workspace buffers are kept across re-plans and grown only when needed)
 };
 
 struct LayerW {
@@ -451,13 +452,28 @@ extern "C" int oard_commit_weights(oard_handle* h, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ plan
+// Workspace buffers survive a re-plan: a sampler plans once per trajectory (a new edge list every call), and freeing and
+// re-allocating ~2 GB in ~90 cudaFree / cudaMalloc calls cost 30 ms on a good day and 0.2-0.5 s (driver stalls) on a bad one
+// (tools/setup_probe.py).  A buffer is re-allocated only when the request exceeds its capacity; contents are never assumed
+// to survive, and nothing may assume a fresh buffer either (cudaMalloc does not clear).
 static int ws_alloc(oard_handle* h, const char* name, size_t bytes) {
+  const size_t need = bytes ? bytes : 16;
+  auto it = h->ws.find(name);
+  if (it != h->ws.end() && it->second.p && it->second.cap >= need) {
+    it->second.bytes = need;
+    return OARD_OK;
+  }
+  if (it != h->ws.end()) {
+    if (it->second.p) cudaFree(it->second.p);
+    h->ws_bytes -= it->second.cap;
+    h->ws.erase(it);
+  }
   DevBuf b;
-  b.bytes = bytes ? bytes : 16;
-  cudaError_t e = cudaMalloc(&b.p, b.bytes);
-  if (e != cudaSuccess) return fail(OARD_ECUDA, "cudaMalloc(%s, %zu): %s", name, b.bytes, cudaGetErrorString(e));
+  b.bytes = b.cap = need;
+  cudaError_t e = cudaMalloc(&b.p, b.cap);
+  if (e != cudaSuccess) return fail(OARD_ECUDA, "cudaMalloc(%s, %zu): %s", name, b.cap, cudaGetErrorString(e));
   h->ws[name] = b;
-  h->ws_bytes += b.bytes;
+  h->ws_bytes += b.cap;
   return OARD_OK;
 }
 
@@ -525,10 +541,8 @@ extern "C" int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const
     comp_nodes[fill[c]++] = i;
   }
 
-  drop_graphs(h);
-  free_map(h->ws);
+  drop_graphs(h);  // (captured launches carry N, E and grid sizes)
   free_map(h->snaps);
-  h->ws_bytes = 0;
   h->planned = false;
   h->dyn_planned = false;
   h->train_fwd_done = false;
@@ -1342,10 +1356,6 @@ extern "C" int oard_dyn_plan(oard_handle* h, const int64_t* node_frag, const int
   }
   seg_ptr.push_back(N);
   const int S = (int)seg_frag.size();
-  for (const char* nm : {"dyn_node_frag", "dyn_node_sample", "dyn_seg_ptr", "dyn_seg_frag", "dyn_vel", "dyn_prm", "dyn_flag"}) {
-    auto it = h->ws.find(nm);
-    if (it != h->ws.end()) { cudaFree(it->second.p); h->ws_bytes -= it->second.bytes; h->ws.erase(it); }
-  }
   int rc;
   if ((rc = ws_alloc(h, "dyn_node_frag", (size_t)N * 4)) || (rc = ws_alloc(h, "dyn_node_sample", (size_t)N * 4)) ||
       (rc = ws_alloc(h, "dyn_seg_ptr", (size_t)(S + 1) * 4)) || (rc = ws_alloc(h, "dyn_seg_frag", (size_t)S * 4)) ||

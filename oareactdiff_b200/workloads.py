@@ -71,13 +71,15 @@ def synthetic_geometries(sizes: List[int], seed: int = 0) -> List[torch.Tensor]:
 
 
 @torch.no_grad()
-def replay_trajectory(ddpm, n_samples: int, fragments_nodes, conditions, h0, x_ref, timesteps=None):
+def replay_trajectory(ddpm, n_samples: int, fragments_nodes, conditions, h0, x_ref, timesteps=None, probe=None):
     """A full reverse diffusion (T reverse steps + the p(x | z0) decode = T + 1 denoiser evaluations, posterior sampling,
     CoM projections — the per-step work of `EnVariationalDiffusion.sample`) on the states a TRAINED model would visit: before
     every step the state is re-drawn from q(z_t | x_ref) = alpha_t x_ref + sigma_t eps.  With random weights the literal
     sample() drifts to |x| ~ 1e2 A, the 10 A cutoff empties and the message-passing stages have nothing to do; here every
     same-fragment edge of the reference geometries stays inside the cutoff (active fraction ~0.32 on Transition1x).
-    x_ref / h0: per-fragment [N_f, 3] / [N_f, nf - 3] on the device.  Returns the decoded positions per fragment."""
+    x_ref / h0: per-fragment [N_f, 3] / [N_f, nf - 3] on the device.  Returns the decoded positions per fragment.
+    probe: optional list; a CUDA event is recorded into it every 100 reverse steps (bench.py: is a slow trajectory uniformly
+    slow — clocks — or slow in bursts — stalls?)."""
     T = ddpm.T if timesteps is None else timesteps
     masks, edge_index, nfs = ddpm._setup(n_samples, fragments_nodes)
     dev = x_ref[0].device
@@ -91,6 +93,10 @@ def replay_trajectory(ddpm, n_samples: int, fragments_nodes, conditions, h0, x_r
     if on_device:
         ddpm._device_setup(Z, masks, edge_index, nfs, conditions, H0)
     for s_int in reversed(range(T)):
+        if probe is not None and on_device and (T - 1 - s_int) % 100 == 0:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            probe.append(ev)
         Zt = tab["alpha"][s_int + 1] * X + tab["sigma_abs"][s_int + 1] * ddpm._noise_cat(masks)
         Zt[:, 3:] = H0
         if on_device:  # the device step replays one CUDA graph on a persistent state buffer
