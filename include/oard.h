@@ -68,7 +68,9 @@ int oard_commit_weights(oard_handle* h, void* stream);
 
 /* Build the static per-batch plan from the HOST edge list edge_index[2][E] (int64, edge_index[0] = source):
  * CSR rows, transposed-edge map, connected components (= reactions).  Requirements: edges grouped by source in
- * non-decreasing order, the graph symmetric, no duplicates, components of <= 256 nodes.  Allocates the workspace.
+ * non-decreasing order, the graph symmetric, no duplicates, components of <= 256 nodes.  Allocates the workspace; a later
+ * plan on the same handle (a sampler plans once per trajectory) keeps the buffers and grows only those that are too small, so
+ * the workspace stays at its high-water mark until oard_destroy (oard_workspace_bytes reports the allocated capacity).
  * Components need not be complete graphs: when every component is complete (what get_edges_index builds per sample) the
  * message aggregation takes the group-staged kernel, otherwise the node-per-block kernel, which assumes nothing. */
 int oard_plan(oard_handle* h, int64_t n_nodes, int64_t n_edges, const int64_t* edge_index_host);
