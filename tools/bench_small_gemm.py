@@ -6,7 +6,7 @@ import sys
 
 if len(sys.argv) > 1:  # child: one tile width
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from tests.bringup_p16 import run_p16, time_tc
+    from tools.bringup_p16 import run_p16, time_tc
     bn = sys.argv[1]
     for name, M, N, K, mode in [("node1", 2613, 196, 196, 3), ("x0", 2613, 196, 196, 0), ("node0", 2613, 196, 392, 0),
                                 ("x2", 2613, 588, 196, 0), ("PQ", 2613, 392, 196, 0), ("vec_proj", 7839, 392, 196, 0)]:
